@@ -1,0 +1,337 @@
+/* TEST INFRASTRUCTURE ONLY — never linked into, imported by or called from the
+ * product path (treepl_b200/).  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load the library this
+ * file builds (oracle/_ref/libtreepl_ref.so).
+ *
+ * What it is: a thin extern "C" harness around the UNMODIFIED reference objects
+ * (compiled where they lie under /root/reference/src by oracle/Makefile).  It
+ * replays the setup sequence of the reference's main() (main.cpp:318-497, the
+ * recipe of SURVEY.md Appendix B) and exposes the reference's own
+ *   pl_calc_parallel::calc_pl                  (pl_calc_parallel.cpp:73)
+ *   pl_calc_parallel::calc_gradient            (pl_calc_parallel.cpp:657)
+ *   pl_calc_parallel::calc_function_gradient   (pl_calc_parallel.cpp:132, RAD tape)
+ *   generate_param_order_vector / set_freeparams / set_cv_nodes
+ * so that tests can (1) pin the C restatement in oracle/pl_oracle.c and the
+ * golden vectors under tests/golden/, and (2) time the reference's CPU path on
+ * the GPU box's host cores (bench.py cpu_baseline.kind == "reference").
+ *
+ * NLopt is a third-party consumer of the path that is not built here; the four
+ * optimize_plcp_nlopt* symbols that utils.cpp references are defined below as
+ * stubs that report failure.  Nothing in this harness calls them.
+ */
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <sstream>
+#include <streambuf>
+#include <string>
+#include <vector>
+#include <chrono>
+#include <omp.h>
+
+#include "node.h"
+#include "tree.h"
+#include "tree_reader.h"
+#include "utils.h"
+#include "pl_calc_parallel.h"
+#include "optimize_nlopt.h"
+
+using namespace std;
+
+/* ---- link-only stubs for the NLopt adapters (optimize_nlopt.cpp is not compiled) ---- */
+double function_plcp_nlopt_ad(unsigned, const double*, double*, void*) { return 1e15; }
+double function_plcp_nlopt(unsigned, const double*, double*, void*) { return 1e15; }
+double function_plcp_nlopt_nograd(unsigned, const double*, double*, void*) { return 1e15; }
+double function_plcp_nlopt_ad_parallel(unsigned, const double*, double*, void*) { return 1e15; }
+int optimize_plcp_nlopt(double*, pl_calc_parallel*, int, int, bool, bool, double, double) { return -1; }
+int optimize_plcp_nlopt_ad_parallel(double*, pl_calc_parallel*, int, int, bool, double, double) { return -1; }
+
+namespace {
+
+struct NullBuf : public streambuf { int overflow(int c) override { return c; } };
+
+/* the reference chats on cout; silence it while we are inside reference code */
+struct CoutMute {
+    streambuf* old; NullBuf nb;
+    CoutMute() { old = cout.rdbuf(&nb); }
+    ~CoutMute() { cout.rdbuf(old); }
+};
+
+struct RefProblem {
+    Tree* tree = nullptr;
+    vector<int> free, parents, child_counts;
+    vector<double> c, lf, vmin, vmax, penmin, penmax, sdates, srates, sdur;
+    vector<vector<int> > children;
+    vector<string> names;   /* by node number; "" for unnamed */
+    pl_calc_parallel plp;
+    vector<int> freeparams;
+    vector<int> cv;
+    bool log_pen = false;
+    int numparams = 0;
+    bool islf = false;
+
+    void wire() {
+        plp.setup_starting_bits(&parents, &child_counts, &free, &c, &lf, &vmin, &vmax,
+                                &sdates, &srates, &sdur);          /* main.cpp:483-485 */
+        plp.set_log_pen(log_pen);                                    /* main.cpp:486 */
+        plp.minrate = 0.0;
+        plp.pen_min = &penmin;                                       /* main.cpp:488-490 */
+        plp.pen_max = &penmax;
+        plp.children_vec = &children;
+        plp.paramverbose = false;
+    }
+};
+
+void wire_clone(RefProblem* src, pl_calc_parallel& q) {
+    q.setup_starting_bits(&src->parents, &src->child_counts, &src->free, &src->c, &src->lf,
+                          &src->vmin, &src->vmax, &src->sdates, &src->srates, &src->sdur);
+    q.set_log_pen(src->log_pen);
+    q.minrate = 0.0;
+    q.pen_min = &src->penmin;
+    q.pen_max = &src->penmax;
+    q.children_vec = &src->children;
+    q.paramverbose = false;
+    q.smoothing = src->plp.smoothing;
+    if (!src->cv.empty()) q.set_cv_nodes(src->cv);
+    vector<int> fp(src->freeparams);
+    vector<double> x;
+    q.set_freeparams(src->numparams, src->islf, &fp, &x);
+}
+
+}  // namespace
+
+extern "C" {
+
+/* Build a problem exactly as the reference's main() does (main.cpp:318-490).
+ * Calibrations: cal_tips[k] = space-separated tip names whose MRCA is calibrated. */
+void* ref_from_newick(const char* newick, int numsites, int collapse, int set1,
+                      int ncal, const char** cal_tips, const int* has_min, const double* cmin,
+                      const int* has_max, const double* cmax, int seed, int log_pen) {
+    CoutMute mute;
+    srand(seed);                                                    /* main.cpp:287-293 */
+    RefProblem* p = new RefProblem();
+    p->log_pen = log_pen != 0;
+    TreeReader tr;
+    Tree* tree = tr.readTree(string(newick));                       /* main.cpp:322 */
+    p->tree = tree;
+    process_initial_branch_lengths(tree, collapse != 0, set1 != 0, numsites);   /* :326 */
+    tree->setHeightFromTipToNodes();                                /* :327 */
+    map<Node*, double> mins, maxs;
+    /* mins first, then maxs, as main.cpp:336-387 */
+    for (int k = 0; k < ncal; k++) {
+        if (!has_min[k]) continue;
+        vector<string> tips; Tokenize(string(cal_tips[k]), tips, " ");
+        Node* m = tree->getMRCA(tips);
+        if (!m) { delete p; return nullptr; }
+        mins[m] = cmin[k]; m->min = cmin[k]; m->minb = true; m->pen_minb = true; m->pen_min = cmin[k];
+    }
+    for (int k = 0; k < ncal; k++) {
+        if (!has_max[k]) continue;
+        vector<string> tips; Tokenize(string(cal_tips[k]), tips, " ");
+        Node* m = tree->getMRCA(tips);
+        if (!m) { delete p; return nullptr; }
+        maxs[m] = cmax[k]; m->max = cmax[k]; m->maxb = true;
+        if (m->minb == true) {
+            if (m->min != m->max) { m->pen_maxb = true; m->pen_max = cmax[k]; }
+            else { m->pen_minb = false; m->pen_max = 0; }
+        } else { m->pen_maxb = true; m->pen_max = cmax[k]; }
+    }
+    apply_node_label_preorder(tree);                                /* main.cpp:450 */
+    calc_char_durations(tree, numsites);                            /* :452 */
+    set_mins_maxs(tree, &mins, &maxs);                              /* :454 */
+    setup_date_constraints(tree, &mins, &maxs);                     /* :456 */
+    extract_tree_info(tree, &p->free, &p->parents, &p->child_counts, &p->c, &p->lf,
+                      &p->vmin, &p->vmax, &p->children, &p->penmin, &p->penmax);   /* :467 */
+    set_node_order(tree);                                           /* :472 */
+    get_feasible_start_dates(tree, &p->sdates, &p->srates, &p->sdur);   /* :474 */
+    double start_rate = get_start_rate(tree, &p->sdur);             /* :475 */
+    p->srates[1] = start_rate;                                      /* :477 */
+    int n = (int)p->parents.size();
+    p->names.assign(n, "");
+    for (int i = 0; i < tree->getNodeCount(); i++) {
+        Node* nd = tree->getNode(i);
+        p->names[nd->getNumber()] = nd->getName();
+    }
+    p->wire();
+    return p;
+}
+
+/* Build from flat arrays (bypasses the reference's O(N^2) tree setup). */
+void* ref_from_flat(int n, const int* parents, const int* child_counts, const int* children_flat,
+                    const int* free, const double* c, const double* lf, const double* vmin,
+                    const double* vmax, const double* penmin, const double* penmax,
+                    const double* sdates, const double* srates, const double* sdur, int log_pen) {
+    RefProblem* p = new RefProblem();
+    p->log_pen = log_pen != 0;
+    p->parents.assign(parents, parents + n);
+    p->child_counts.assign(child_counts, child_counts + n);
+    p->free.assign(free, free + n);
+    p->c.assign(c, c + n); p->lf.assign(lf, lf + n);
+    p->vmin.assign(vmin, vmin + n); p->vmax.assign(vmax, vmax + n);
+    p->penmin.assign(penmin, penmin + n); p->penmax.assign(penmax, penmax + n);
+    p->sdates.assign(sdates, sdates + n); p->srates.assign(srates, srates + n);
+    p->sdur.assign(sdur, sdur + n);
+    p->children.resize(n);
+    int k = 0;
+    for (int i = 0; i < n; i++) {
+        p->children[i].assign(children_flat + k, children_flat + k + child_counts[i]);
+        k += child_counts[i];
+    }
+    p->names.assign(n, "");
+    p->wire();
+    return p;
+}
+
+void ref_free(void* h) {
+    RefProblem* p = (RefProblem*)h;
+    if (!p) return;
+    p->plp.delete_ad_arrays();
+    delete p->tree;
+    delete p;
+}
+
+int ref_numnodes(void* h) { return (int)((RefProblem*)h)->parents.size(); }
+
+/* which: 0 parents, 1 child_counts, 2 free, 3 children (flattened in node order), 4 freeparams(2N) */
+int ref_get_ints(void* h, int which, int* out) {
+    RefProblem* p = (RefProblem*)h;
+    const vector<int>* v = nullptr;
+    vector<int> flat;
+    switch (which) {
+        case 0: v = &p->parents; break;
+        case 1: v = &p->child_counts; break;
+        case 2: v = &p->free; break;
+        case 3: for (auto& ch : p->children) for (int x : ch) flat.push_back(x); v = &flat; break;
+        case 4: v = &p->freeparams; break;
+        default: return -1;
+    }
+    if (out) memcpy(out, v->data(), v->size() * sizeof(int));
+    return (int)v->size();
+}
+
+/* which: 0 c, 1 lf, 2 min, 3 max, 4 pen_min, 5 pen_max, 6 start_dates, 7 start_rates,
+ *        8 start_durations, 9 plp.rates, 10 plp.dates, 11 plp.durations */
+int ref_get_doubles(void* h, int which, double* out) {
+    RefProblem* p = (RefProblem*)h;
+    const vector<double>* v = nullptr;
+    switch (which) {
+        case 0: v = &p->c; break;       case 1: v = &p->lf; break;
+        case 2: v = &p->vmin; break;    case 3: v = &p->vmax; break;
+        case 4: v = &p->penmin; break;  case 5: v = &p->penmax; break;
+        case 6: v = &p->sdates; break;  case 7: v = &p->srates; break;
+        case 8: v = &p->sdur; break;    case 9: v = &p->plp.rates; break;
+        case 10: v = &p->plp.dates; break; case 11: v = &p->plp.durations; break;
+        default: return -1;
+    }
+    if (out) memcpy(out, v->data(), v->size() * sizeof(double));
+    return (int)v->size();
+}
+
+/* node name by node number (tips have names); returns length */
+int ref_get_name(void* h, int node, char* out, int cap) {
+    RefProblem* p = (RefProblem*)h;
+    const string& s = p->names[node];
+    if (out && cap > 0) { strncpy(out, s.c_str(), cap - 1); out[cap - 1] = 0; }
+    return (int)s.size();
+}
+
+void ref_set_smoothing(void* h, double s) { ((RefProblem*)h)->plp.smoothing = s; }
+void ref_set_log_pen(void* h, int lp) { RefProblem* p = (RefProblem*)h; p->log_pen = lp != 0; p->plp.set_log_pen(lp != 0); }
+void ref_set_penalty_boundary(void* h, double pb) { ((RefProblem*)h)->plp.penalty_boundary = pb; }
+
+/* overwrite the engine's current rates/dates (what the CV loop does through
+ * setup_starting_bits with the snapshot vectors, main.cpp:701-704) */
+void ref_set_state(void* h, const double* rates, const double* dates) {
+    RefProblem* p = (RefProblem*)h;
+    int n = (int)p->parents.size();
+    for (int i = 0; i < n; i++) { p->plp.rates[i] = rates[i]; p->plp.dates[i] = dates[i]; }
+}
+
+/* cv == NULL clears the mask */
+void ref_set_cv(void* h, const int* cv) {
+    RefProblem* p = (RefProblem*)h;
+    int n = (int)p->parents.size();
+    if (cv) p->cv.assign(cv, cv + n); else p->cv.assign(n, 0);
+    p->plp.set_cv_nodes(p->cv);                                     /* main.cpp:711 */
+}
+
+/* generate_param_order_vector (utils.cpp:295) + set_freeparams (pl_calc_parallel.cpp:920).
+ * x_out may be NULL; returns numparams. */
+int ref_set_freeparams(void* h, int lf, int use_cv, double* x_out) {
+    RefProblem* p = (RefProblem*)h;
+    p->freeparams.clear();
+    vector<int>* cvp = (use_cv && !p->cv.empty()) ? &p->cv : nullptr;
+    int np = generate_param_order_vector(&p->freeparams, lf != 0, cvp, &p->free);
+    vector<double> x;
+    vector<int> fp(p->freeparams);
+    p->plp.set_freeparams(np, lf != 0, &fp, &x);
+    p->numparams = np; p->islf = lf != 0;
+    if (x_out) memcpy(x_out, x.data(), x.size() * sizeof(double));
+    return np;
+}
+
+double ref_calc_pl(void* h, const double* x) {
+    RefProblem* p = (RefProblem*)h;
+    vector<double> v(x, x + p->numparams);
+    return p->plp.calc_pl(v);
+}
+
+/* analytic gradient; the reference requires calc_pl(x) to have run first (it reads
+ * member state), so this harness does both, as function_plcp does (optimize_tnc.cpp:83-93) */
+double ref_calc_pl_and_gradient(void* h, const double* x, double* g) {
+    RefProblem* p = (RefProblem*)h;
+    vector<double> v(x, x + p->numparams), gv(p->numparams, 0.0);
+    double f = p->plp.calc_pl(v);
+    p->plp.calc_gradient(v, &gv);
+    memcpy(g, gv.data(), gv.size() * sizeof(double));
+    return f;
+}
+
+/* RAD reverse-mode f and gradient (pl_calc_parallel.cpp:132). g is pre-filled with NaN so
+ * an early `return LARGE` (which leaves g untouched in the reference) is visible. */
+double ref_calc_function_gradient(void* h, const double* x, double* g) {
+    RefProblem* p = (RefProblem*)h;
+    CoutMute mute;
+    vector<double> v(x, x + p->numparams), gv(p->numparams, numeric_limits<double>::quiet_NaN());
+    double f = p->plp.calc_function_gradient(&v, &gv);
+    memcpy(g, gv.data(), gv.size() * sizeof(double));
+    return f;
+}
+
+/* Wall seconds for `reps` calls of calc_pl (+ calc_gradient if with_grad) per thread on
+ * `nthreads` independent pl_calc_parallel instances (one per OpenMP thread, as the
+ * reference's fold loop does, main.cpp:689-710).  Returns seconds; total evals = reps*nthreads. */
+double ref_time_evals(void* h, const double* x, int reps, int nthreads, int with_grad) {
+    RefProblem* p = (RefProblem*)h;
+    if (nthreads < 1) nthreads = 1;
+    vector<pl_calc_parallel> inst(nthreads);
+    for (int t = 0; t < nthreads; t++) wire_clone(p, inst[t]);
+    double sink = 0.0;
+    auto run = [&](int r) {
+#pragma omp parallel for num_threads(nthreads) reduction(+ : sink) schedule(static, 1)
+        for (int t = 0; t < nthreads; t++) {
+            vector<double> v(x, x + p->numparams), gv(p->numparams, 0.0);
+            for (int k = 0; k < r; k++) {
+                v[0] = x[0] * (1.0 + 1e-12 * k);     /* defeat hoisting; stays feasible */
+                double f = inst[t].calc_pl(v);
+                if (with_grad) { inst[t].calc_gradient(v, &gv); f += gv[k % p->numparams]; }
+                sink += f;
+            }
+        }
+    };
+    run(1);   /* warm-up */
+    auto t0 = chrono::steady_clock::now();
+    run(reps);
+    auto t1 = chrono::steady_clock::now();
+    for (int t = 0; t < nthreads; t++) inst[t].delete_ad_arrays();
+    if (sink == 12345.678) fprintf(stderr, "sink\n");
+    return chrono::duration<double>(t1 - t0).count();
+}
+
+int ref_hw_threads(void) { return omp_get_num_procs(); }
+
+}  /* extern "C" */
