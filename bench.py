@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — PL objective+gradient evaluations per second (fp64) on a synthetic 100k-tip tree.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--tips T] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of B parameter vectors (one launch of the
+batched objective+gradient kernel pair) on the workload BASELINE.json's metric is quoted on:
+a 100,000-tip birth-death tree (N = 199,999 nodes, P = 299,996 parameters).
+
+  value      evaluations/s with X, F, G resident in HBM (CUDA events on the launching stream)
+  e2e        the same through the C-ABI batched entry with pinned HOST buffers: H2D of X and
+             D2H of F and G inside the timed region
+  roofline   main kernel: algorithmic bytes (16 P + 25 N / B per evaluation)
+             / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own calc_pl + calc_gradient (oracle/_ref, built from the
+             reference sources) on the host cores, bounded sample
+
+N > 1 (torchrun): one process per GPU, every rank evaluates its own B vectors of the same tree
+(CV folds / restarts are independent: weak scaling, no data-path collective); barrier + device
+timing, max over ranks.  `--impl reference` times the reference CPU path alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pl_obj_grad_evals_per_sec"
+UNIT = "evals/s"
+
+
+def build_problem(tips, seed=1):
+    from treepl_b200 import treeflat as tf
+    cache = os.path.join(tempfile.gettempdir(), "treepl_b200_synth_%d_%d.npz" % (tips, seed))
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return {k: z[k] for k in z.files}
+    ft, _, _ = tf.synth_problem(tips, seed=seed, ncal=16)
+    d = ft.as_dict()
+    try:
+        np.savez(cache, **d)
+    except OSError:
+        pass
+    return d
+
+
+def make_vectors(flat, P, B, seed, numsites=10000):
+    """B feasible parameter vectors, [P, B] batch innermost: jittered rates, feasible start dates."""
+    n = flat["parents"].shape[0]
+    rng = np.random.RandomState(seed)
+    free = flat["free"] == 1
+    x_dates = flat["start_dates"][free]
+    base = flat["start_rates"][1] * numsites
+    X = np.empty((P, B), dtype=np.float64)
+    X[: n - 1, :] = base * (1.0 + 0.1 * np.sin(np.arange(1, n)[:, None] + np.arange(B)[None, :]))
+    X[n - 1:, :] = x_dates[:, None] * (1.0 - 1e-6 * rng.rand(1, B))
+    return X
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [t.strip() for t in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_rate(flat, x, seconds=12.0, nthreads=None):
+    """Reference calc_pl + calc_gradient on the host cores -> (evals/s, threads, sample description)."""
+    from oracle import refbind as rb
+    if not rb.available():
+        return None
+    nthreads = nthreads or max(1, (os.cpu_count() or 1))
+    rp = rb.RefProblem.from_flat(flat)
+    rp.set_smoothing(1.0)
+    rp.set_freeparams(False)
+    t1 = rp.time_evals(x, 1, nthreads, True)
+    reps = int(max(2, min(2000, seconds / max(t1, 1e-4))))
+    t = rp.time_evals(x, reps, nthreads, True)
+    rate = reps * nthreads / t
+    rp.close()
+    return rate, nthreads, "%d calc_pl+calc_gradient calls on each of %d threads (%.1f s)" % (reps, nthreads, t)
+
+
+def run_reference_arm(args, flat, P):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    X = make_vectors(flat, P, 1, 1234)
+    x = np.ascontiguousarray(X[:, 0])
+    n = flat["parents"].shape[0]
+    steps_total = args.steps + args.warmup
+    budget = min(20.0, 150.0 / max(1, steps_total))
+    res = None
+    times = []
+    from oracle import refbind as rb
+    if not rb.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libtreepl_ref.so is not built"}))
+        return
+    nthreads = max(1, os.cpu_count() or 1)
+    rp = rb.RefProblem.from_flat(flat)
+    rp.set_smoothing(1.0)
+    rp.set_freeparams(False)
+    t1 = rp.time_evals(x, 1, nthreads, True)
+    reps = int(max(1, min(500, budget / max(t1, 1e-4))))
+    for s in range(steps_total):
+        t = rp.time_evals(x, reps, nthreads, True)
+        if s >= args.warmup:
+            times.append(t)
+    rp.close()
+    tsum = sum(times)
+    value = reps * nthreads * len(times) / tsum
+    sample = "%d calc_pl+calc_gradient calls per thread per step, %d threads" % (reps, nthreads)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tsum / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic %d-tip Yule tree, N=%d nodes, P=%d params, PL (lf=false), smoothing=1"
+                                   % (args.tips, n, P)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--tips", type=int, default=100000)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--mode", default="ad", choices=["ad", "analytic"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    flat = build_problem(args.tips)
+    n = flat["parents"].shape[0]
+    from treepl_b200 import treeflat as tf
+    fp, P = tf.generate_param_order_vector(flat["free"], lf=False)
+
+    if args.impl == "reference":
+        run_reference_arm(args, flat, P)
+        return
+
+    import torch
+    from treepl_b200 import engine as eng
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the PL engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B = args.batch
+    mode = eng.GRAD_AD if args.mode == "ad" else eng.GRAD_ANALYTIC
+    plp = eng.PLCalcParallel.from_flat(flat, device=local)
+    plp.set_freeparams(P, False, fp)
+    plp.smoothing = 1.0
+    plp.batch_configure(B)
+    Xh = make_vectors(flat, P, B, 1000 + rank)
+    dev = torch.device("cuda", local)
+    X = torch.from_numpy(Xh).to(dev)
+    F = torch.empty(B, dtype=torch.float64, device=dev)
+    G = torch.empty((P, B), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        plp.calc_pl_grad_batch_dev(B, X.data_ptr(), F.data_ptr(), G.data_ptr(), mode, stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    # correctness guard inside the bench: finite objective for every vector
+    Fh = F.cpu().numpy()
+    if not (np.isfinite(Fh).all() and (Fh < 1e15).all()):
+        raise SystemExit("bench.py: engine returned infeasible/NaN objectives on the bench vectors")
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    plp.set_timing(True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    cnt, main_ms, fin_ms = plp.get_timing()
+    plp.set_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = args.steps * plp.last_launch_count()
+
+    # ---- end to end through the C ABI with pinned host buffers ----
+    e2e_steps = max(1, args.e2e_steps)
+    Xp = torch.from_numpy(Xh).pin_memory()
+    Fp = torch.empty(B, dtype=torch.float64).pin_memory()
+    Gp = torch.empty((P, B), dtype=torch.float64).pin_memory()
+    xp, fpn, gp = Xp.numpy(), Fp.numpy(), Gp.numpy()
+    L = plp._L
+    import ctypes as C
+    dptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    L.tpl_calc_pl_grad_batch(plp._h, B, dptr(xp), dptr(fpn), dptr(gp), mode)     # warm (allocations)
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rc = L.tpl_calc_pl_grad_batch(plp._h, B, dptr(xp), dptr(fpn), dptr(gp), mode)
+        if rc < 0:
+            raise SystemExit("e2e call failed: " + L.tpl_last_error().decode())
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    if not np.allclose(fpn, Fh, rtol=0, atol=0):
+        raise SystemExit("bench.py: host-buffer path and device-buffer path disagree")
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        evals = B * args.steps
+        value = world * evals / (ms * 1e-3)
+        bytes_per_eval = 16.0 * P + 25.0 * n / B
+        main_s = main_ms * 1e-3 / max(cnt, 1)
+        achieved = bytes_per_eval * B / main_s / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "synthetic %d-tip Yule tree, N=%d nodes, P=%d params, PL (lf=false), smoothing=1, "
+                                       "B=%d vectors per step per GPU, gradient=%s; X+G = %.0f MB per step (> 126 MB L2, "
+                                       "no flush needed)" % (args.tips, n, P, B, args.mode, 2 * P * B * 8 / 1e6),
+                           "batch_per_gpu": B, "parallelism": "independent vectors sharded over %d GPU(s)" % world},
+                "gpu_launches": launches,
+                "clocks": clocks,
+                "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(P * B * 8),
+                        "d2h_bytes_per_step": int(P * B * 8 + B * 8), "steps": e2e_steps},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "kernel": "pl_main_kernel",
+                             "kernel_ms": main_ms / max(cnt, 1), "finalize_ms": fin_ms / max(cnt, 1),
+                             "algorithmic_bytes_per_launch": bytes_per_eval * B}}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                r = cpu_reference_rate(flat, np.ascontiguousarray(Xh[:, 0]))
+                if r is not None:
+                    line["cpu_baseline"] = {"value": r[0], "unit": UNIT, "cores": r[1], "kind": "reference", "sample": r[2]}
+            except Exception as ex:      # the baseline must never take the GPU number down with it
+                line["cpu_baseline"] = {"error": repr(ex)}
+        print(json.dumps(line))
+    plp.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

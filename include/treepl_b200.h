@@ -1,0 +1,153 @@
+/* treepl_b200.h — C ABI of the B200-native penalized-likelihood (PL) engine.
+ *
+ * Drop-in boundary for ONE hot path of blackrim/treePL: the objective and gradient that
+ * `class pl_calc_parallel` (reference src/pl_calc_parallel.h:17-82) serves to the TNC / NLopt
+ * callbacks (src/optimize_tnc.cpp:33-105, src/optimize_nlopt.cpp:22-105), to the annealer
+ * (src/siman_calc_par.cpp:154) and to the CV loop (src/main.cpp:689-801).
+ * Plain pointers and sizes only; every entry point cites the reference interface it replaces.
+ * All node-indexed arrays use the REFERENCE node numbering (apply_node_label_preorder,
+ * src/utils.cpp:167-180; root = 0) and the reference parameter layout
+ * (generate_param_order_vector, src/utils.cpp:295-340).
+ *
+ * There is NO CPU fallback: every compute entry point runs sm_100a kernels and fails
+ * (returns TPL_ERR_* / NaN, see tpl_last_error) when no CUDA device is usable.
+ *
+ * Threading: calls on DIFFERENT handles may run concurrently (each handle owns its CUDA
+ * stream and staging buffers, as each OpenMP fold owns its pl_calc_parallel, main.cpp:701);
+ * calls on the same handle must be serialised by the caller, as in the reference.
+ */
+#ifndef TREEPL_B200_H
+#define TREEPL_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPL_LARGE 1e+15              /* infeasible-point sentinel, pl_calc_parallel.cpp:29 */
+
+#define TPL_OK 0
+#define TPL_ERR_CUDA (-1)            /* CUDA runtime / no device */
+#define TPL_ERR_ARG (-2)             /* bad argument */
+#define TPL_ERR_STATE (-3)           /* call order (e.g. gradient before set_freeparams) */
+
+/* gradient flavours: the reference has two mutually inconsistent gradients */
+#define TPL_GRAD_ANALYTIC 0          /* calc_gradient: calc_pl_gradient / calc_lf_gradient  (:657-818) */
+#define TPL_GRAD_AD 1                /* calc_function_gradient: exact adjoint of the RAD / ADOL-C tapes (:132-655) */
+
+typedef struct tpl_engine tpl_engine;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* pl_calc_parallel::setup_starting_bits (pl_calc_parallel.cpp:34-71) plus the member
+ * assignments main() makes right after it (main.cpp:486-490: pen_min, pen_max, children_vec).
+ * `children` is children_vec flattened in node order (node 0's children, node 1's, ...), each
+ * list in Newick order; its length is sum(child_counts) = numnodes-1.  All arrays are COPIED
+ * (the reference borrows them; copying removes the lifetime coupling).  smoothing starts at 1,
+ * penalty_boundary at 0.0025, log_pen off, no CV mask — as in the reference.
+ * `device` = CUDA device ordinal (-1: current device).                                        */
+int tpl_create(tpl_engine** out, int device, int numnodes,
+               const int* parents_nds_ints, const int* child_counts, const int* children,
+               const int* free_, const double* char_durations, const double* log_fact_char_durations,
+               const double* min_, const double* max_, const double* pen_min, const double* pen_max,
+               const double* start_dates, const double* start_rates, const double* start_durations);
+
+/* pl_calc_parallel::delete_ad_arrays + destructor (main.cpp:798) */
+void tpl_destroy(tpl_engine* e);
+
+/* message of the last failing call on this thread */
+const char* tpl_last_error(void);
+
+/* ---- configuration (public data members / setters of pl_calc_parallel) ---------------------- */
+int tpl_set_smoothing(tpl_engine* e, double smoothing);            /* plp.smoothing = ...     main.cpp:490,669 */
+int tpl_set_log_pen(tpl_engine* e, int log_pen);                   /* set_log_pen             pl_calc_parallel.cpp:1000 */
+int tpl_set_penalty_boundary(tpl_engine* e, double pb);            /* penalty_boundary member pl_calc_parallel.cpp:69 */
+int tpl_set_cv_nodes(tpl_engine* e, const int* cvnodes);           /* set_cv_nodes (:959); NULL clears the mask */
+/* overwrite member rates/dates, as the CV loop does by re-running setup_starting_bits on the
+ * snapshot vectors (main.cpp:701-704) */
+int tpl_set_state(tpl_engine* e, const double* rates, const double* dates);
+
+/* generate_param_order_vector (utils.cpp:295-340), host helper: fills freeparams[2*numnodes],
+ * returns numparams.  cvnodes may be NULL.                                                     */
+int tpl_generate_param_order_vector(int numnodes, const int* free_, int lf, const int* cvnodes, int* freeparams);
+
+/* set_freeparams (pl_calc_parallel.cpp:920-955): installs the 2N slot map and the LF/PL switch,
+ * and emits the initial parameter vector from the current member rates/dates into params_out
+ * (capacity >= numparams; may be NULL).  Returns the number of values emitted or TPL_ERR_*.     */
+int tpl_set_freeparams(tpl_engine* e, int numparams, int lf, const int* freeparams, double* params_out);
+
+int tpl_numnodes(const tpl_engine* e);
+int tpl_numparams(const tpl_engine* e);
+
+/* ---- single-point evaluation: what the optimiser callbacks call ------------------------------ */
+
+/* pl_calc_parallel::calc_pl (pl_calc_parallel.cpp:73-130).  x = host pointer, numparams doubles.
+ * Returns the objective, TPL_LARGE for an infeasible point, NaN on engine failure.  Like the
+ * reference it makes x the engine's current state (rates/dates/durations) for later readers.   */
+double tpl_calc_pl(tpl_engine* e, const double* x);
+
+/* pl_calc_parallel::calc_gradient (:657-662).  Like the reference it differentiates at the state
+ * left by the preceding tpl_calc_pl (it does not re-read x, except that it must be the same
+ * vector); g = host pointer, numparams doubles.                                                 */
+int tpl_calc_gradient(tpl_engine* e, const double* x, double* g);
+
+/* pl_calc_parallel::calc_function_gradient (:132-138) == calc_pl_function_gradient_adolc (:622):
+ * objective of the AD expression and its exact gradient.  Does not change the engine state.
+ * An infeasible point returns TPL_LARGE and leaves g untouched, as the reference does.          */
+double tpl_calc_function_gradient(tpl_engine* e, const double* x, double* g);
+
+/* Fused form of function_plcp (optimize_tnc.cpp:75-105): one upload, one launch sequence, one
+ * download.  mode = TPL_GRAD_ANALYTIC gives calc_pl + calc_gradient, TPL_GRAD_AD gives
+ * calc_function_gradient.  g may be NULL (objective only, the annealer's call).                 */
+double tpl_calc_pl_grad(tpl_engine* e, const double* x, double* g, int mode);
+
+/* read-back of the public members main() reads after an optimisation (main.cpp:679-681,749,865-878) */
+int tpl_get_rates(tpl_engine* e, double* out);
+int tpl_get_dates(tpl_engine* e, double* out);
+int tpl_get_durations(tpl_engine* e, double* out);
+
+/* ---- batched evaluation: B independent parameter vectors per launch ---------------------------
+ * The batch dimension is innermost: X[p*B + b] is parameter p of vector b, G likewise, F[b].
+ * Vectors use the FULL parameter layout of the installed slot map (set_freeparams); vector b may
+ * additionally carry its own smoothing value and its own CV mask (folds, main.cpp:693-696):
+ * a masked node's rate row is ignored on input and its gradient row is written as 0.
+ * This is the data-parallel form of the fold loop (main.cpp:689), of the lambda grid
+ * (main.cpp:668) and of multi-start optimisation (utils.cpp:475-553).                           */
+
+/* lane_smoothing: B doubles or NULL (engine smoothing for all).  mask_off/mask_nodes: CSR list
+ * of masked node numbers per vector (mask_off has B+1 entries) or NULL/NULL for no masks.
+ * The configuration stays installed until the next call.                                       */
+int tpl_batch_configure(tpl_engine* e, int B, const double* lane_smoothing,
+                        const int* mask_off, const int* mask_nodes);
+
+/* host buffers: X[P*B] in, F[B] and G[P*B] out (G may be NULL: objective only) */
+int tpl_calc_pl_grad_batch(tpl_engine* e, int B, const double* X, double* F, double* G, int mode);
+
+/* device buffers, asynchronous on `cuda_stream` (a cudaStream_t, NULL = the engine's stream).
+ * No host synchronisation is performed.                                                        */
+int tpl_calc_pl_grad_batch_dev(tpl_engine* e, int B, const double* dX, double* dF, double* dG,
+                               int mode, void* cuda_stream);
+
+/* number of kernels the last evaluation call launched (for bench accounting) */
+int tpl_last_launch_count(const tpl_engine* e);
+
+/* pinned host memory for X/F/G staging */
+void* tpl_host_alloc(unsigned long long bytes);
+void tpl_host_free(void* p);
+
+/* Device timing for roofline accounting (bench.py): while on, every evaluation records CUDA
+ * events around its main kernel and its finalize kernel on the launching stream (up to 4096
+ * evaluations).  tpl_get_timing waits for them, returns the number of evaluations and the summed
+ * kernel milliseconds, and resets the log.                                                     */
+int tpl_set_timing(tpl_engine* e, int on);
+int tpl_get_timing(tpl_engine* e, double* main_ms, double* finalize_ms);
+
+/* test hook: evaluates the kernels' log and reciprocal on n host values (tests only) */
+int tpl_debug_math(int n, const double* x, double* log_out, double* rcp_out);
+
+/* library / device info: returns sm version * 10 (e.g. 1000) of the engine's device, <0 on error */
+int tpl_device_sm(const tpl_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TREEPL_B200_H */

@@ -1,0 +1,63 @@
+"""Build the sm_100a engine library in-tree with nvcc (no JIT cache, the .so travels with the repo)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIB_DIR, "libtreepl_b200.so")
+SOURCES = ["tpl_engine.cu"]
+HEADERS = ["tpl_kernels.cuh", "tpl_math.cuh", os.path.join(ROOT, "include", "treepl_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.sep not in cand or os.path.exists(cand)):
+            return cand
+    return "nvcc"
+
+
+def _host_cxx():
+    # the image's $CXX wrapper links libstdc++ statically, which must not happen inside a .so
+    return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else None
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS
+    cxx = _host_cxx()
+    if cxx:
+        cmd += ["-ccbin", cxx]
+    cmd += ["-I", os.path.join(ROOT, "include"), "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    log = os.path.join(LIB_DIR, "build.log")
+    with open(log, "w") as fh:
+        fh.write(" ".join(cmd) + "\n" + res.stdout)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed (see %s)" % log)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

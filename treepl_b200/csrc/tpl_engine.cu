@@ -1,0 +1,653 @@
+// C ABI of the B200 PL engine (include/treepl_b200.h): handle, device-resident tree,
+// slot maps, staging, launches.  Host-side bookkeeping mirrors pl_calc_parallel's members
+// (reference src/pl_calc_parallel.h:17-82); all arithmetic of the hot path runs in the
+// sm_100a kernels of tpl_kernels.cuh.  There is no CPU evaluation path in this file.
+#include "../../include/treepl_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "tpl_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(TPL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));         \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
+        cudaError_t e = ensure(v.size() ? v.size() : 1);
+        if (e != cudaSuccess) return e;
+        if (v.empty()) return cudaSuccess;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+};
+
+template <class T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost((void**)&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+};
+
+// (invc, logc) table for tpl::fast_log, built in long double (see tpl_math.cuh)
+void build_log_table(std::vector<double2>& tab) {
+    tab.resize(tpl::LOG_TABLE_N);
+    const unsigned long long OFF = 0x3fe6a09e00000000ull;
+    for (int i = 0; i < tpl::LOG_TABLE_N; i++) {
+        unsigned long long bits = OFF + ((unsigned long long)i << (52 - tpl::LOG_TABLE_BITS)) +
+                                  (1ull << (51 - tpl::LOG_TABLE_BITS));
+        // the interval that straddles 1.0 crosses an exponent boundary: centre it in VALUE space
+        unsigned long long lo = OFF + ((unsigned long long)i << (52 - tpl::LOG_TABLE_BITS));
+        unsigned long long hi = lo + (1ull << (52 - tpl::LOG_TABLE_BITS)) - 1;
+        double dlo, dhi, dc;
+        memcpy(&dlo, &lo, 8);
+        memcpy(&dhi, &hi, 8);
+        memcpy(&dc, &bits, 8);
+        if ((lo >> 52) != (hi >> 52)) dc = 0.5 * (dlo + dhi);
+        double invc = (double)(1.0L / (long double)dc);
+        double logc = (double)(-logl((long double)invc));
+        tab[i].x = invc;
+        tab[i].y = logc;
+    }
+}
+
+}  // namespace
+
+struct tpl_engine {
+    int device = 0;
+    int sm = 0;
+    int n = 0;
+    cudaStream_t stream = nullptr;
+    // ---- host mirrors of pl_calc_parallel's inputs / members ----
+    std::vector<int> parent, child_off, children, free_;
+    std::vector<double> c, lf, hmin, hmax, pen_min, pen_max;
+    std::vector<double> rates, dates, durations;     // member state (base values)
+    std::vector<int> cv;                             // cvnodes
+    std::vector<int> freeparams;                     // 2n
+    int numparams = 0;
+    bool lf_mode = false;
+    bool have_fp = false;
+    double smoothing = 1.0;
+    double pb = 0.0025;
+    bool log_pen = false;
+    // last calc_pl vector = contents of the pinned staging buffer h_X (the member state is the
+    // scatter of it over the base member values; materialised lazily, only when someone reads it)
+    bool last_x_valid = false;
+    // ---- device tree ----
+    DevBuf<int> d_parent, d_rslot, d_dslot, d_child_off, d_children, d_bar_node;
+    DevBuf<unsigned char> d_cv;
+    DevBuf<double> d_c, d_lf, d_hfix, d_rfix, d_hmin, d_hmax, d_bar_pmin, d_bar_pmax;
+    DevBuf<double2> d_logtab;
+    int nbar = 0;
+    double sum_c = 0.0;
+    bool static_bad = false;          // a FIXED date violates its own bounds (set_durations :887-896)
+    bool topo_dirty = true, slots_dirty = true, state_dirty = true;
+    // ---- evaluation buffers ----
+    DevBuf<double> d_X, d_G, d_F, d_part_ll, d_part_su, d_part_gr, d_lane_lambda;
+    DevBuf<int> d_part_bad;
+    DevBuf<unsigned long long> d_lanemask;
+    PinBuf<double> h_X, h_G, h_F;
+    // batch configuration
+    int cfg_B = 0;
+    bool cfg_lambda = false, cfg_mask = false;
+    int cfg_nchunks = 0;
+    int last_launches = 0;
+    // optional per-launch device timing (bench.py roofline): events around the main kernel
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;      // triples: before main, after main, after finalize
+    size_t ev_used = 0;
+};
+
+namespace {
+
+void materialize_state(tpl_engine* e) {
+    // scatter the last calc_pl vector into the member rates/dates (pl_calc_parallel.cpp:82-99)
+    if (!e->last_x_valid || !e->have_fp) return;
+    const int n = e->n;
+    for (int i = 0; i < n; i++)
+        if (e->freeparams[i] != -1) e->rates[i] = e->h_X.p[e->freeparams[i]];
+    for (int i = 0; i < n; i++)
+        if (e->freeparams[n + i] != -1) e->dates[i] = e->h_X.p[e->freeparams[n + i]];
+    // set_durations (:883-910), without the early outs
+    for (int i = 0; i < n; i++) {
+        if (i != 0) e->durations[i] = e->dates[e->parent[i]] - e->dates[i];
+        if (e->durations[i] == 0 || std::isnan(e->durations[i]))
+            e->durations[i] = std::numeric_limits<double>::min();
+    }
+    e->last_x_valid = false;
+    // no device refresh needed: hfix/rfix are only READ for slots that are not free, and those
+    // member values are not touched by the scatter; a new slot map re-uploads them (slots_dirty)
+}
+
+int sync_device_tree(tpl_engine* e) {
+    cudaStream_t s = e->stream;
+    const int n = e->n;
+    if (e->topo_dirty) {
+        CK(e->d_parent.upload(e->parent, s));
+        CK(e->d_child_off.upload(e->child_off, s));
+        CK(e->d_children.upload(e->children, s));
+        CK(e->d_c.upload(e->c, s));
+        CK(e->d_lf.upload(e->lf, s));
+        CK(e->d_hmin.upload(e->hmin, s));
+        CK(e->d_hmax.upload(e->hmax, s));
+        std::vector<int> bn;
+        std::vector<double> bmin, bmax;
+        for (int i = 0; i < n; i++)
+            if (e->pen_min[i] != -1 || e->pen_max[i] != -1) {
+                bn.push_back(i);
+                bmin.push_back(e->pen_min[i]);
+                bmax.push_back(e->pen_max[i]);
+            }
+        e->nbar = (int)bn.size();
+        CK(e->d_bar_node.upload(bn, s));
+        CK(e->d_bar_pmin.upload(bmin, s));
+        CK(e->d_bar_pmax.upload(bmax, s));
+        e->sum_c = 0.0;
+        for (int i = 0; i < n; i++) e->sum_c += e->c[i];
+        std::vector<double2> tab;
+        build_log_table(tab);
+        CK(e->d_logtab.upload(tab, s));
+        CK(cudaStreamSynchronize(s));   // the host vectors above are temporaries
+        e->topo_dirty = false;
+    }
+    if (e->slots_dirty) {
+        std::vector<int> rs(n, -1), ds(n, -1);
+        std::vector<unsigned char> cvb(n, 0);
+        if (e->have_fp)
+            for (int i = 0; i < n; i++) {
+                rs[i] = e->freeparams[i];
+                ds[i] = e->freeparams[n + i];
+            }
+        for (int i = 0; i < n; i++) cvb[i] = e->cv[i] ? 1 : 0;
+        CK(e->d_rslot.upload(rs, s));
+        CK(e->d_dslot.upload(ds, s));
+        CK(e->d_cv.upload(cvb, s));
+        CK(cudaStreamSynchronize(s));
+        e->slots_dirty = false;
+        e->state_dirty = true;   // static_bad depends on which dates are fixed
+    }
+    if (e->state_dirty) {
+        CK(e->d_hfix.upload(e->dates, s));
+        CK(e->d_rfix.upload(e->rates, s));
+        CK(cudaStreamSynchronize(s));
+        e->static_bad = false;
+        for (int i = 0; i < n; i++) {
+            bool fixed = !e->have_fp || e->freeparams[n + i] == -1;
+            if (fixed && (e->dates[i] < e->hmin[i] || e->dates[i] > e->hmax[i])) e->static_bad = true;
+        }
+        e->state_dirty = false;
+    }
+    return TPL_OK;
+}
+
+tpl::DevTree dev_tree(tpl_engine* e) {
+    tpl::DevTree t;
+    t.n = e->n;
+    t.parent = e->d_parent.p;
+    t.rslot = e->d_rslot.p;
+    t.dslot = e->d_dslot.p;
+    t.child_off = e->d_child_off.p;
+    t.children = e->d_children.p;
+    t.cv = e->d_cv.p;
+    t.c = e->d_c.p;
+    t.lf = e->d_lf.p;
+    t.hfix = e->d_hfix.p;
+    t.rfix = e->d_rfix.p;
+    t.hmin = e->d_hmin.p;
+    t.hmax = e->d_hmax.p;
+    t.nbar = e->nbar;
+    t.bar_node = e->d_bar_node.p;
+    t.bar_pmin = e->d_bar_pmin.p;
+    t.bar_pmax = e->d_bar_pmax.p;
+    t.sum_c = e->sum_c;
+    double d0 = e->durations[0];
+    if (d0 == 0 || std::isnan(d0)) d0 = std::numeric_limits<double>::min();
+    t.dur0 = d0;
+    return t;
+}
+
+template <int MODE, bool LF, bool LOGPEN, bool WANT_G, bool LANEMASK>
+void launch_pair(const tpl::EvalArgs& a, dim3 grid, dim3 block, cudaStream_t s, cudaEvent_t* ev) {
+    if (ev) cudaEventRecord(ev[0], s);
+    tpl::pl_main_kernel<MODE, LF, LOGPEN, WANT_G, LANEMASK><<<grid, block, 0, s>>>(a);
+    if (ev) cudaEventRecord(ev[1], s);
+    const int fb = 128;
+    tpl::pl_finalize_kernel<MODE, LF, LOGPEN, WANT_G, LANEMASK><<<(a.B + fb - 1) / fb, fb, 0, s>>>(a);
+    if (ev) cudaEventRecord(ev[2], s);
+}
+
+template <int MODE, bool LF, bool LOGPEN, bool WANT_G>
+void launch_m(const tpl::EvalArgs& a, bool lanemask, dim3 g, dim3 b, cudaStream_t s, cudaEvent_t* ev) {
+    if (lanemask) launch_pair<MODE, LF, LOGPEN, WANT_G, true>(a, g, b, s, ev);
+    else launch_pair<MODE, LF, LOGPEN, WANT_G, false>(a, g, b, s, ev);
+}
+template <int MODE, bool LF, bool LOGPEN>
+void launch_g(const tpl::EvalArgs& a, bool want_g, bool lanemask, dim3 g, dim3 b, cudaStream_t s, cudaEvent_t* ev) {
+    if (want_g) launch_m<MODE, LF, LOGPEN, true>(a, lanemask, g, b, s, ev);
+    else launch_m<MODE, LF, LOGPEN, false>(a, lanemask, g, b, s, ev);
+}
+template <int MODE, bool LF>
+void launch_lp(const tpl::EvalArgs& a, bool lp, bool want_g, bool lanemask, dim3 g, dim3 b, cudaStream_t s, cudaEvent_t* ev) {
+    if (lp) launch_g<MODE, LF, true>(a, want_g, lanemask, g, b, s, ev);
+    else launch_g<MODE, LF, false>(a, want_g, lanemask, g, b, s, ev);
+}
+template <int MODE>
+void launch_lf(const tpl::EvalArgs& a, bool lf, bool lp, bool want_g, bool lanemask, dim3 g, dim3 b, cudaStream_t s, cudaEvent_t* ev) {
+    if (lf) launch_lp<MODE, true>(a, false, want_g, lanemask, g, b, s, ev);   // log_pen has no effect on the LF objective
+    else launch_lp<MODE, false>(a, lp, want_g, lanemask, g, b, s, ev);
+}
+
+// Evaluate B vectors resident on the device.  Enqueues 2 kernels on stream s.
+int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, int mode, bool use_cfg,
+                cudaStream_t s) {
+    if (!e->have_fp) return fail(TPL_ERR_STATE, "set_freeparams has not been called");
+    if (mode != TPL_GRAD_ANALYTIC && mode != TPL_GRAD_AD) return fail(TPL_ERR_ARG, "bad gradient mode");
+    if (B < 1) return fail(TPL_ERR_ARG, "B < 1");
+    int rc = sync_device_tree(e);
+    if (rc != TPL_OK) return rc;
+    const int n = e->n;
+    // block shape: LX lanes x NY node rows, 256 threads
+    int LX = 1;
+    while (LX < 32 && LX < B) LX <<= 1;
+    const int NY = 256 / LX;
+    // tile = nodes per block: keep >= ~8 node rows per thread row, and enough blocks to fill 148 SMs
+    int tile = 256;
+    if (LX == 1) tile = 1024;
+    const int ntiles = (n + tile - 1) / tile;
+    const int nlane_blocks = (B + LX - 1) / LX;
+    CK(e->d_part_ll.ensure((size_t)ntiles * B));
+    CK(e->d_part_su.ensure((size_t)ntiles * B));
+    CK(e->d_part_gr.ensure((size_t)ntiles * B));
+    CK(e->d_part_bad.ensure((size_t)ntiles * B));
+    tpl::EvalArgs a;
+    a.t = dev_tree(e);
+    a.X = dX;
+    a.G = dG;
+    a.F = dF;
+    a.B = B;
+    const bool lanemask = use_cfg && e->cfg_mask && e->cfg_B == B;
+    a.lanemask = lanemask ? e->d_lanemask.p : nullptr;
+    a.nchunks = e->cfg_nchunks;
+    a.lane_lambda = (use_cfg && e->cfg_lambda && e->cfg_B == B) ? e->d_lane_lambda.p : nullptr;
+    a.lambda = e->smoothing;
+    a.pb = e->pb;
+    a.part_ll = e->d_part_ll.p;
+    a.part_su = e->d_part_su.p;
+    a.part_gr = e->d_part_gr.p;
+    a.part_bad = e->d_part_bad.p;
+    a.ntiles = ntiles;
+    a.tile_nodes = tile;
+    a.logtab = e->d_logtab.p;
+    dim3 grid(ntiles, nlane_blocks), block(LX, NY);
+    const bool want_g = dG != nullptr;
+    cudaEvent_t* evs = nullptr;
+    if (e->timing && e->ev_used + 3 <= e->ev.size()) { evs = &e->ev[e->ev_used]; e->ev_used += 3; }
+    if (mode == TPL_GRAD_ANALYTIC) launch_lf<0>(a, e->lf_mode, e->log_pen, want_g, lanemask, grid, block, s, evs);
+    else launch_lf<1>(a, e->lf_mode, e->log_pen, want_g, lanemask, grid, block, s, evs);
+    CK(cudaGetLastError());
+    e->last_launches = 2;
+    return TPL_OK;
+}
+
+// single point: host x -> device, evaluate, bring f (and g) back
+double eval_point(tpl_engine* e, const double* x, double* g, int mode, bool keep_state) {
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    if (!e || !x) { fail(TPL_ERR_ARG, "null argument"); return nan; }
+    if (!e->have_fp) { fail(TPL_ERR_STATE, "set_freeparams has not been called"); return nan; }
+    if (cudaSetDevice(e->device) != cudaSuccess) { fail(TPL_ERR_CUDA, "cudaSetDevice failed"); return nan; }
+    const int P = e->numparams;
+    if (!keep_state && e->last_x_valid && x != e->h_X.p) materialize_state(e);   // h_X is about to be overwritten
+    if (e->h_X.ensure(P) != cudaSuccess || e->h_G.ensure(P) != cudaSuccess || e->h_F.ensure(1) != cudaSuccess ||
+        e->d_X.ensure(P) != cudaSuccess || e->d_G.ensure(P) != cudaSuccess || e->d_F.ensure(1) != cudaSuccess) {
+        fail(TPL_ERR_CUDA, "allocation failed");
+        return nan;
+    }
+    if (x != e->h_X.p) memcpy(e->h_X.p, x, sizeof(double) * P);
+    cudaStream_t s = e->stream;
+    if (cudaMemcpyAsync(e->d_X.p, e->h_X.p, sizeof(double) * P, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+        fail(TPL_ERR_CUDA, "H2D copy failed");
+        return nan;
+    }
+    if (eval_device(e, 1, e->d_X.p, e->d_F.p, g ? e->d_G.p : nullptr, mode, false, s) != TPL_OK) return nan;
+    cudaMemcpyAsync(e->h_F.p, e->d_F.p, sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (g) cudaMemcpyAsync(e->h_G.p, e->d_G.p, sizeof(double) * P, cudaMemcpyDeviceToHost, s);
+    cudaError_t err = cudaStreamSynchronize(s);
+    if (err != cudaSuccess) { fail(TPL_ERR_CUDA, std::string("evaluation failed: ") + cudaGetErrorString(err)); return nan; }
+    double f = e->h_F.p[0];
+    if (e->static_bad) f = TPL_LARGE;
+    if (keep_state) e->last_x_valid = true;
+    if (g) {
+        const bool infeasible = (f == TPL_LARGE);
+        if (mode == TPL_GRAD_AD && infeasible) {
+            // the reference returns before touching g (:377,:387,:398)
+        } else {
+            memcpy(g, e->h_G.p, sizeof(double) * P);
+            if (mode == TPL_GRAD_ANALYTIC && e->lf_mode && std::isnan(g[0]))
+                for (int i = 0; i < P; i++) g[i] = 1000000;               // calc_lf_gradient :680-687
+        }
+    }
+    return f;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tpl_last_error(void) { return g_err.c_str(); }
+
+int tpl_create(tpl_engine** out, int device, int numnodes, const int* parents, const int* child_counts,
+               const int* children, const int* free_, const double* c, const double* lf, const double* mn,
+               const double* mx, const double* pen_min, const double* pen_max, const double* start_dates,
+               const double* start_rates, const double* start_durations) {
+    if (!out || numnodes < 1 || !parents || !child_counts || !free_ || !c || !lf || !mn || !mx || !pen_min ||
+        !pen_max || !start_dates || !start_rates || !start_durations || (numnodes > 1 && !children))
+        return fail(TPL_ERR_ARG, "tpl_create: null or empty argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(TPL_ERR_CUDA, "no CUDA device: the PL engine has no CPU fallback");
+    if (device < 0) CK(cudaGetDevice(&device));
+    if (device >= ndev) return fail(TPL_ERR_ARG, "device ordinal out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(TPL_ERR_CUDA, "device is not sm_100 class; this library carries sm_100a code only");
+    tpl_engine* e = new tpl_engine();
+    e->device = device;
+    e->sm = prop.major * 100 + prop.minor * 10;
+    e->n = numnodes;
+    const int n = numnodes;
+    e->parent.assign(parents, parents + n);
+    e->child_off.assign(n + 1, 0);
+    for (int i = 0; i < n; i++) e->child_off[i + 1] = e->child_off[i] + child_counts[i];
+    if (e->child_off[n] != n - 1) { delete e; return fail(TPL_ERR_ARG, "sum(child_counts) != numnodes-1"); }
+    e->children.assign(children, children + (n - 1));
+    for (int i = 0; i < n; i++)
+        for (int j = e->child_off[i]; j < e->child_off[i + 1]; j++) {
+            int ch = e->children[j];
+            if (ch < 1 || ch >= n || e->parent[ch] != i) { delete e; return fail(TPL_ERR_ARG, "children / parents disagree"); }
+        }
+    e->free_.assign(free_, free_ + n);
+    e->c.assign(c, c + n);
+    e->lf.assign(lf, lf + n);
+    e->hmin.assign(mn, mn + n);
+    e->hmax.assign(mx, mx + n);
+    e->pen_min.assign(pen_min, pen_min + n);
+    e->pen_max.assign(pen_max, pen_max + n);
+    e->dates.assign(start_dates, start_dates + n);
+    e->rates.assign(start_rates, start_rates + n);
+    e->durations.assign(start_durations, start_durations + n);
+    e->cv.assign(n, 0);
+    cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) { delete e; return fail(TPL_ERR_CUDA, "cudaStreamCreate failed"); }
+    *out = e;
+    return TPL_OK;
+}
+
+void tpl_destroy(tpl_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+    for (auto& v : e->ev) cudaEventDestroy(v);
+    delete e;
+}
+
+int tpl_set_smoothing(tpl_engine* e, double s) { if (!e) return fail(TPL_ERR_ARG, "null"); e->smoothing = s; return TPL_OK; }
+int tpl_set_log_pen(tpl_engine* e, int lp) { if (!e) return fail(TPL_ERR_ARG, "null"); e->log_pen = lp != 0; return TPL_OK; }
+int tpl_set_penalty_boundary(tpl_engine* e, double pb) { if (!e) return fail(TPL_ERR_ARG, "null"); e->pb = pb; return TPL_OK; }
+
+int tpl_set_cv_nodes(tpl_engine* e, const int* cv) {
+    if (!e) return fail(TPL_ERR_ARG, "null");
+    if (cv) e->cv.assign(cv, cv + e->n); else e->cv.assign(e->n, 0);
+    e->slots_dirty = true;
+    return TPL_OK;
+}
+
+int tpl_set_state(tpl_engine* e, const double* rates, const double* dates) {
+    if (!e || !rates || !dates) return fail(TPL_ERR_ARG, "null");
+    e->last_x_valid = false;
+    e->rates.assign(rates, rates + e->n);
+    e->dates.assign(dates, dates + e->n);
+    e->state_dirty = true;
+    return TPL_OK;
+}
+
+int tpl_generate_param_order_vector(int n, const int* free_, int lf, const int* cv, int* fp) {
+    if (n < 1 || !free_ || !fp) return fail(TPL_ERR_ARG, "null");
+    int icount = 0;                                   /* utils.cpp:295-340 */
+    for (int i = 0; i < n; i++) {
+        if (i == 0) fp[i] = -1;
+        else if (cv) {
+            if (cv[i] == 0) fp[i] = icount++; else fp[i] = -1;
+        } else {
+            fp[i] = icount;
+            if (!lf) icount++;
+        }
+    }
+    if (lf) icount++;
+    for (int i = 0; i < n; i++) fp[n + i] = (free_[i] == 1) ? icount++ : -1;
+    return icount;
+}
+
+int tpl_set_freeparams(tpl_engine* e, int nump, int lf, const int* freep, double* params_out) {
+    if (!e || !freep || nump < 1) return fail(TPL_ERR_ARG, "null or empty");
+    const int n = e->n;
+    for (int i = 0; i < 2 * n; i++)
+        if (freep[i] < -1 || freep[i] >= nump) return fail(TPL_ERR_ARG, "freeparams entry out of range");
+    materialize_state(e);                              // x0 comes from the CURRENT member state
+    e->freeparams.assign(freep, freep + 2 * n);
+    e->numparams = nump;
+    e->lf_mode = lf != 0;
+    e->have_fp = true;
+    e->slots_dirty = true;
+    int k = 0;                                         /* pl_calc_parallel.cpp:930-951 */
+    if (params_out) {
+        for (int i = 0; i < n; i++)
+            if (e->freeparams[i] != -1) {
+                if (k < nump) params_out[k] = e->rates[i];
+                k++;
+                if (e->lf_mode) break;
+            }
+        for (int i = 0; i < n; i++)
+            if (e->freeparams[n + i] != -1) {
+                if (k < nump) params_out[k] = e->dates[i];
+                k++;
+            }
+    }
+    return k;
+}
+
+int tpl_numnodes(const tpl_engine* e) { return e ? e->n : TPL_ERR_ARG; }
+int tpl_numparams(const tpl_engine* e) { return e ? e->numparams : TPL_ERR_ARG; }
+int tpl_device_sm(const tpl_engine* e) { return e ? e->sm : TPL_ERR_ARG; }
+int tpl_last_launch_count(const tpl_engine* e) { return e ? e->last_launches : 0; }
+
+double tpl_calc_pl(tpl_engine* e, const double* x) { return eval_point(e, x, nullptr, TPL_GRAD_ANALYTIC, true); }
+
+int tpl_calc_gradient(tpl_engine* e, const double* x, double* g) {
+    if (!e || !g) return fail(TPL_ERR_ARG, "null");
+    if (!e->last_x_valid) return fail(TPL_ERR_STATE, "calc_gradient needs a preceding calc_pl (it differentiates at the engine state)");
+    (void)x;
+    double f = eval_point(e, e->h_X.p, g, TPL_GRAD_ANALYTIC, true);
+    return std::isnan(f) && !g_err.empty() ? TPL_ERR_CUDA : TPL_OK;
+}
+
+double tpl_calc_function_gradient(tpl_engine* e, const double* x, double* g) {
+    return eval_point(e, x, g, TPL_GRAD_AD, false);
+}
+
+double tpl_calc_pl_grad(tpl_engine* e, const double* x, double* g, int mode) {
+    return eval_point(e, x, g, mode, mode == TPL_GRAD_ANALYTIC);
+}
+
+int tpl_get_rates(tpl_engine* e, double* out) {
+    if (!e || !out) return fail(TPL_ERR_ARG, "null");
+    materialize_state(e);
+    memcpy(out, e->rates.data(), sizeof(double) * e->n);
+    return TPL_OK;
+}
+int tpl_get_dates(tpl_engine* e, double* out) {
+    if (!e || !out) return fail(TPL_ERR_ARG, "null");
+    materialize_state(e);
+    memcpy(out, e->dates.data(), sizeof(double) * e->n);
+    return TPL_OK;
+}
+int tpl_get_durations(tpl_engine* e, double* out) {
+    if (!e || !out) return fail(TPL_ERR_ARG, "null");
+    materialize_state(e);
+    memcpy(out, e->durations.data(), sizeof(double) * e->n);
+    return TPL_OK;
+}
+
+int tpl_batch_configure(tpl_engine* e, int B, const double* lane_smoothing, const int* mask_off, const int* mask_nodes) {
+    if (!e || B < 1) return fail(TPL_ERR_ARG, "null or B < 1");
+    CK(cudaSetDevice(e->device));
+    e->cfg_B = B;
+    e->cfg_lambda = lane_smoothing != nullptr;
+    e->cfg_mask = mask_off != nullptr;
+    if (e->cfg_lambda) {
+        std::vector<double> v(lane_smoothing, lane_smoothing + B);
+        CK(e->d_lane_lambda.upload(v, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    if (e->cfg_mask) {
+        if (!mask_nodes && mask_off[B] > 0) return fail(TPL_ERR_ARG, "mask_nodes is null");
+        const int nch = (B + 63) / 64;
+        std::vector<unsigned long long> bits((size_t)e->n * nch, 0ull);
+        for (int b = 0; b < B; b++)
+            for (int k = mask_off[b]; k < mask_off[b + 1]; k++) {
+                int node = mask_nodes[k];
+                if (node < 0 || node >= e->n) return fail(TPL_ERR_ARG, "mask node out of range");
+                bits[(size_t)node * nch + (b >> 6)] |= 1ull << (b & 63);
+            }
+        e->cfg_nchunks = nch;
+        CK(e->d_lanemask.upload(bits, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return TPL_OK;
+}
+
+int tpl_calc_pl_grad_batch_dev(tpl_engine* e, int B, const double* dX, double* dF, double* dG, int mode, void* stream) {
+    if (!e || !dX || !dF) return fail(TPL_ERR_ARG, "null");
+    CK(cudaSetDevice(e->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    return eval_device(e, B, dX, dF, dG, mode, true, s);
+}
+
+int tpl_calc_pl_grad_batch(tpl_engine* e, int B, const double* X, double* F, double* G, int mode) {
+    if (!e || !X || !F || B < 1) return fail(TPL_ERR_ARG, "null or B < 1");
+    if (!e->have_fp) return fail(TPL_ERR_STATE, "set_freeparams has not been called");
+    CK(cudaSetDevice(e->device));
+    const size_t PB = (size_t)e->numparams * B;
+    CK(e->d_X.ensure(PB));
+    CK(e->d_F.ensure(B));
+    if (G) CK(e->d_G.ensure(PB));
+    cudaStream_t s = e->stream;
+    CK(cudaMemcpyAsync(e->d_X.p, X, PB * sizeof(double), cudaMemcpyHostToDevice, s));
+    int rc = eval_device(e, B, e->d_X.p, e->d_F.p, G ? e->d_G.p : nullptr, mode, true, s);
+    if (rc != TPL_OK) return rc;
+    CK(cudaMemcpyAsync(F, e->d_F.p, B * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (G) CK(cudaMemcpyAsync(G, e->d_G.p, PB * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (e->static_bad) for (int b = 0; b < B; b++) F[b] = TPL_LARGE;
+    return TPL_OK;
+}
+
+int tpl_set_timing(tpl_engine* e, int on) {
+    if (!e) return fail(TPL_ERR_ARG, "null");
+    CK(cudaSetDevice(e->device));
+    e->timing = on != 0;
+    e->ev_used = 0;
+    if (e->timing && e->ev.empty()) {
+        e->ev.resize(3 * 4096);
+        for (auto& v : e->ev) CK(cudaEventCreate(&v));
+    }
+    return TPL_OK;
+}
+
+int tpl_get_timing(tpl_engine* e, double* main_ms, double* finalize_ms) {
+    if (!e || !main_ms || !finalize_ms) return fail(TPL_ERR_ARG, "null");
+    CK(cudaSetDevice(e->device));
+    double m = 0.0, f = 0.0;
+    int cnt = 0;
+    for (size_t k = 0; k + 3 <= e->ev_used; k += 3) {
+        CK(cudaEventSynchronize(e->ev[k + 2]));
+        float a = 0.f, b = 0.f;
+        CK(cudaEventElapsedTime(&a, e->ev[k], e->ev[k + 1]));
+        CK(cudaEventElapsedTime(&b, e->ev[k + 1], e->ev[k + 2]));
+        m += a; f += b; cnt++;
+    }
+    *main_ms = m;
+    *finalize_ms = f;
+    e->ev_used = 0;
+    return cnt;
+}
+
+int tpl_debug_math(int n, const double* x, double* log_out, double* rcp_out) {
+    if (n < 1 || !x || !log_out || !rcp_out) return fail(TPL_ERR_ARG, "null");
+    double *dx = nullptr, *dl = nullptr, *dr = nullptr;
+    double2* dt = nullptr;
+    std::vector<double2> tab;
+    build_log_table(tab);
+    CK(cudaMalloc((void**)&dx, n * sizeof(double)));
+    CK(cudaMalloc((void**)&dl, n * sizeof(double)));
+    CK(cudaMalloc((void**)&dr, n * sizeof(double)));
+    CK(cudaMalloc((void**)&dt, tab.size() * sizeof(double2)));
+    CK(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dt, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    tpl::debug_math_kernel<<<(n + 255) / 256, 256>>>(n, dx, dl, dr, dt);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(log_out, dl, n * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rcp_out, dr, n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dl); cudaFree(dr); cudaFree(dt);
+    return TPL_OK;
+}
+
+void* tpl_host_alloc(unsigned long long bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { fail(TPL_ERR_CUDA, "cudaMallocHost failed"); return nullptr; }
+    return p;
+}
+void tpl_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

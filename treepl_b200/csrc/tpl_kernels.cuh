@@ -1,0 +1,389 @@
+// PL objective + gradient kernels (sm_100a), generation 1: "pull" formulation.
+//
+// Math (reference src/pl_calc_parallel.cpp):
+//   branch i>=1, p = parent[i]:  d_i = h_p - h_i,  x = r_i d_i
+//     objective   += -(c_i ln x - x - lf_i)                        calc_log_like        :821-849
+//     roughness   += (r_i - r_p)^2           (p != root)           calc_roughness_penalty :852-881
+//   rate adjoint   d_i - c_i/r_i + 2L(r_i - r_p)[p!=root] - 2L sum_ch (r_ch - r_i)       :757-811
+//   date adjoint   -(r_i - c_i/d_i) + sum_ch (r_ch - c_ch/d_ch)                          :727-751
+// Every term is 1-hop local (node, parent, children), so there is no level sweep: each
+// (node, vector) pair is owned by exactly one thread which PULLS its parent's and children's
+// rows, recomputes the children's 1/(r d), and writes its own two gradient rows.  No atomics,
+// no inter-thread exchange => bitwise deterministic.  The root-children variance term and the
+// calibration barrier (sparse, order dependent: the reference resets the accumulator on inf,
+// :983-991) are applied per vector by the finalize kernel, which also reduces the per-tile
+// objective partials in fixed order.
+//
+// Layout: X[p*B + b], G[p*B + b] (batch innermost).  Thread block = LX lanes x NY node rows;
+// with LX = 32 a warp reads one 256-byte row per parameter (fully coalesced) and all topology
+// loads are warp-uniform broadcasts.  With B = 1 (the optimiser callbacks) LX = 1 and a warp
+// covers 32 consecutive nodes, whose parameter rows are consecutive in the reference layout.
+#pragma once
+#include "tpl_math.cuh"
+
+namespace tpl {
+
+constexpr double LARGE = 1e15;
+
+struct DevTree {
+    int n;
+    const int* parent;            // [n]
+    const int* rslot;             // [n] row of X with the node's rate, -1 = none
+    const int* dslot;             // [n] row of X with the node's date, -1 = fixed
+    const int* child_off;         // [n+1]
+    const int* children;          // [n-1] Newick order
+    const unsigned char* cv;      // [n] engine-level CV mask (pl_calc_parallel::cvnodes)
+    const double* c;              // [n] char_durations
+    const double* lf;             // [n] log_fact_char_durations
+    const double* hfix;           // [n] member dates[]  (used when dslot < 0)
+    const double* rfix;           // [n] member rates[]  (used when rslot < 0 or masked)
+    const double* hmin;           // [n]
+    const double* hmax;           // [n]
+    // sparse calibration barrier rows, ascending node order (calc_penalty :975-998)
+    int nbar;
+    const int* bar_node;          // [nbar]
+    const double* bar_pmin;       // [nbar] -1 = none
+    const double* bar_pmax;       // [nbar] -1 = none
+    double sum_c;                 // sum of char_durations over ALL nodes (calc_lf_gradient :675)
+    double dur0;                  // member durations[0] after set_durations' fix-up
+};
+
+struct EvalArgs {
+    DevTree t;
+    const double* X;
+    double* G;
+    double* F;
+    int B;
+    const unsigned long long* lanemask;   // [n][nchunks] bit b%64 of word b/64 = node masked for vector b; or null
+    int nchunks;
+    const double* lane_lambda;            // [B] or null
+    double lambda;
+    double pb;                            // penalty_boundary
+    double* part_ll;                      // [ntiles][B]
+    double* part_su;                      // [ntiles][B]
+    double* part_gr;                      // [ntiles][B]  (LF rate-gradient partials)
+    int* part_bad;                        // [ntiles][B]
+    int ntiles;
+    int tile_nodes;
+    const double2* logtab;                // [LOG_TABLE_N]
+};
+
+__device__ __forceinline__ bool in_range400(double v) {      // 2^-400 <= v <= 2^400, v > 0, finite
+    unsigned e = ((unsigned)__double2hiint(v)) >> 20;
+    return (e - 623u) < 800u;
+}
+
+__device__ __forceinline__ double log_any(double x, const double2* tab) {
+    return in_range400(x) ? fast_log(x, tab) : log(x);
+}
+
+template <bool LANEMASK>
+__device__ __forceinline__ bool is_masked(const EvalArgs& a, int node, int lane) {
+    if (LANEMASK) {
+        unsigned long long w = a.lanemask[(size_t)node * a.nchunks + (lane >> 6)];
+        return (w >> (lane & 63)) & 1ull;
+    } else {
+        return a.t.cv[node] != 0;
+    }
+}
+
+// Per-branch quantities.  dr = d(-loglike_i)/d r_i, delta = d(-loglike_i)/d d_i.
+struct Branch {
+    double ll, dr, delta;
+};
+
+// MODE 0: calc_pl / calc_pl_gradient semantics.  MODE 1: the AD expression (tape order).
+// d has already been through the duration rule; dconst = duration replaced by the DBL_MIN constant.
+template <int MODE, bool LF, bool WANT_LL>
+__device__ __forceinline__ Branch branch_terms(double r, double d, double c, double lf, bool dconst,
+                                               const double2* tab) {
+    Branch b;
+    if (in_range400(r) && in_range400(d)) {
+        double xx = r * d;
+        double inv = fast_rcp(xx);
+        double ac = c * inv;
+        b.dr = fma(-ac, d, d);            // d - c/r
+        b.delta = fma(-ac, r, r);         // r - c/d
+        if (WANT_LL) b.ll = fma(-c, fast_log(xx, tab), xx) + lf;
+        else b.ll = 0.0;
+    } else if (MODE == 0) {
+        double xx = r * d;
+        b.ll = 0.0;
+        if (xx > 0.0) b.ll = -(c * log(xx) - xx - lf);                    // :834-835
+        else if (xx == 0.0) b.ll = (c > 0.0) ? LARGE : 0.0;             // :836-840
+        b.dr = -(c / r - d);                                             // :764
+        b.delta = (c == 0.0) ? r : (-c / d + r);                         // :730-734
+    } else {
+        double xx = r * d;
+        if (LF || xx > 0.0) {                                            // :414-417 ; the LF tape has no x>0 guard (:206-210)
+            b.ll = -(c * log(xx) - xx - lf);
+            double au = (1.0 / xx) * (-c);                               // reverse sweep, tape order
+            b.dr = d * au + d;
+            b.delta = dconst ? 0.0 : (r * au + r);
+        } else {                                                         // :418-424
+            b.ll = (c > 0.0) ? LARGE : 0.0;
+            b.dr = 0.0;
+            b.delta = 0.0;
+        }
+    }
+    return b;
+}
+
+// duration rule of set_durations (:898-907) / the AD paths (:396-402)
+template <int MODE, bool LF>
+__device__ __forceinline__ double duration_rule(double hp, double h, int& bad, bool& dconst) {
+    double d = hp - h;
+    dconst = false;
+    if (d < 0.0) bad = 1;
+    if (MODE == 0) {
+        if (d == 0.0 || d != d) d = DBLMIN;
+    } else if (!LF) {
+        if (d == 0.0) { d = DBLMIN; dconst = true; }
+    }
+    return d;
+}
+
+template <int MODE, bool LF, bool LOGPEN, bool WANT_G, bool LANEMASK>
+__global__ void __launch_bounds__(256) pl_main_kernel(const EvalArgs a) {
+    __shared__ double2 s_tab[LOG_TABLE_N];
+    __shared__ double s_red[3][256];
+    __shared__ int s_bad[256];
+    const int LX = blockDim.x, NY = blockDim.y;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * LX + tx;
+    for (int k = tid; k < LOG_TABLE_N; k += LX * NY) s_tab[k] = a.logtab[k];
+    __syncthreads();
+
+    const DevTree& t = a.t;
+    const int B = a.B;
+    const int lane = blockIdx.y * LX + tx;
+    const bool active = lane < B;
+    const int n0 = blockIdx.x * a.tile_nodes;
+    const int n1 = min(t.n, n0 + a.tile_nodes);
+    double acc_ll = 0.0, acc_su = 0.0, acc_gr = 0.0;
+    int bad = 0;
+
+    if (active) {
+        const double lam = a.lane_lambda ? a.lane_lambda[lane] : a.lambda;
+        const double lam2 = 2.0 * lam;
+        const double* __restrict__ X = a.X;
+        for (int i = n0 + ty; i < n1; i += NY) {
+            const int rs = t.rslot[i], ds = t.dslot[i];
+            const bool mi = is_masked<LANEMASK>(a, i, lane);
+            const bool rfree = (rs >= 0) && !mi;
+            const double r = rfree ? X[(size_t)rs * B + lane] : t.rfix[i];
+            const double h = (ds >= 0) ? X[(size_t)ds * B + lane] : t.hfix[i];
+            if (MODE == 0) {                                             // calc_pl :74-78
+                if (rfree && r < 0.0) bad = 1;
+                if (ds >= 0 && h < 0.0) bad = 1;
+            }
+            if (h < t.hmin[i] || h > t.hmax[i]) bad = 1;                 // :887-896
+            double g_r = 0.0, g_h = 0.0;
+            double lr = 0.0;                                             // ln r_i (analytic log_pen only)
+            if (i != 0) {
+                const int p = t.parent[i];
+                const int prs = t.rslot[p], pds = t.dslot[p];
+                const double hp = (pds >= 0) ? X[(size_t)pds * B + lane] : t.hfix[p];
+                bool dconst;
+                const double d = duration_rule<MODE, LF>(hp, h, bad, dconst);
+                const double c = t.c[i];
+                if (LF && MODE == 0) acc_gr += d;                        // sumtimes, all nodes (:676)
+                if (!mi || (MODE == 0 && WANT_G && ds >= 0)) {
+                    Branch b = branch_terms<MODE, LF, true>(r, d, c, t.lf[i], dconst, s_tab);
+                    if (!mi) {
+                        acc_ll += b.ll;
+                        if (LF) { if (MODE == 1) acc_gr += b.dr; }
+                        else g_r = b.dr;
+                        g_h = -b.delta;
+                    } else {
+                        g_h = -b.delta;                                  // analytic: own term regardless of cv (:728-735)
+                    }
+                }
+                if (!LF && !mi) {
+                    if (p != 0) {
+                        const bool pm = is_masked<LANEMASK>(a, p, lane);
+                        const double rp = (prs >= 0 && !pm) ? X[(size_t)prs * B + lane] : t.rfix[p];
+                        const double q = r - rp;
+                        acc_su = fma(q, q, acc_su);                      // :862-864
+                        if (WANT_G) {
+                            if (LOGPEN && MODE == 0) {
+                                lr = log_any(r, s_tab);
+                                g_r += lam2 * (lr - log_any(rp, s_tab)) / r;     // :795-796
+                            } else {
+                                g_r = fma(lam2, q, g_r);                 // :798
+                            }
+                        }
+                    } else if (WANT_G && LOGPEN && MODE == 0) {
+                        lr = log_any(r, s_tab);
+                    }
+                }
+            }
+            if (WANT_G) {
+                const int cb = t.child_off[i], ce = t.child_off[i + 1];
+                double sum_delta = 0.0, sum_q = 0.0;
+                const bool need_q = !LF && rfree && i != 0;
+                if (ds >= 0 || need_q) {
+                    for (int j = cb; j < ce; j++) {
+                        const int ch = t.children[j];
+                        if (is_masked<LANEMASK>(a, ch, lane)) continue;  // :738, :784
+                        const int crs = t.rslot[ch], cds = t.dslot[ch];
+                        const double rc = (crs >= 0) ? X[(size_t)crs * B + lane] : t.rfix[ch];
+                        if (ds >= 0) {
+                            const double hc = (cds >= 0) ? X[(size_t)cds * B + lane] : t.hfix[ch];
+                            bool dconst;
+                            int dummy = 0;
+                            const double dc = duration_rule<MODE, LF>(h, hc, dummy, dconst);
+                            Branch b = branch_terms<MODE, LF, false>(rc, dc, t.c[ch], 0.0, dconst, s_tab);
+                            sum_delta += b.delta;
+                        }
+                        if (need_q) {
+                            if (LOGPEN && MODE == 0) sum_q += (log_any(rc, s_tab) - lr) / r;   // :786, :802
+                            else sum_q += rc - r;
+                        }
+                    }
+                }
+                if (!LF && rs >= 0) a.G[(size_t)rs * B + lane] = rfree ? fma(-lam2, sum_q, g_r) : 0.0;
+                if (ds >= 0) a.G[(size_t)ds * B + lane] = g_h + sum_delta;
+            }
+        }
+    }
+    // fixed-order reduction over the NY node rows of the block
+    s_red[0][tid] = acc_ll;
+    s_red[1][tid] = acc_su;
+    s_red[2][tid] = acc_gr;
+    s_bad[tid] = bad;
+    __syncthreads();
+    if (ty == 0 && active) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        int bb = 0;
+        for (int y = 0; y < NY; y++) {
+            s0 += s_red[0][y * LX + tx];
+            s1 += s_red[1][y * LX + tx];
+            s2 += s_red[2][y * LX + tx];
+            bb |= s_bad[y * LX + tx];
+        }
+        const size_t o = (size_t)blockIdx.x * B + lane;
+        a.part_ll[o] = s0;
+        if (!LF) a.part_su[o] = s1;
+        if (LF) a.part_gr[o] = s2;
+        a.part_bad[o] = bb;
+    }
+}
+
+// One thread per vector: reduce the tile partials in tile order, add the root-children variance
+// term (:866-879) and the calibration barrier (:975-998 / :381-406), write F, and apply the
+// matching sparse gradient corrections to the rows the main kernel has already written.
+template <int MODE, bool LF, bool LOGPEN, bool WANT_G, bool LANEMASK>
+__global__ void __launch_bounds__(128) pl_finalize_kernel(const EvalArgs a) {
+    const DevTree& t = a.t;
+    const int B = a.B;
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= B) return;
+    double ll = 0.0, su = 0.0, gr = 0.0;
+    int bad = 0;
+    for (int k = 0; k < a.ntiles; k++) {
+        const size_t o = (size_t)k * B + lane;
+        ll += a.part_ll[o];
+        if (!LF) su += a.part_su[o];
+        if (LF) gr += a.part_gr[o];
+        bad |= a.part_bad[o];
+    }
+    const double* __restrict__ X = a.X;
+    double f;
+    if (LF) {
+        f = ll;
+        if (WANT_G) {
+            if (MODE == 0) {
+                const double rate = X[lane];                             // params[0]  (:671)
+                a.G[lane] = -(t.sum_c / rate - (gr + t.dur0));           // :678
+            } else {
+                a.G[lane] = gr;
+            }
+        }
+    } else {
+        const double lam = a.lane_lambda ? a.lane_lambda[lane] : a.lambda;
+        // ---- root children block ----
+        const int cb = t.child_off[0], ce = t.child_off[1];
+        double s = 0.0, ss = 0.0, m = 0.0;          // all children (objective; AD gradient)
+        double su_s = 0.0, su_m = 0.0;              // unmasked children (analytic gradient :767-778)
+        for (int j = cb; j < ce; j++) {
+            const int ch = t.children[j];
+            const bool mc = is_masked<LANEMASK>(a, ch, lane);
+            const int crs = t.rslot[ch];
+            const double rc = (crs >= 0 && !mc) ? X[(size_t)crs * B + lane] : t.rfix[ch];
+            const double y = LOGPEN ? log(rc) : rc;
+            s += y;
+            ss += y * y;
+            m += 1.0;
+            if (!mc) { su_s += y; su_m += 1.0; }
+        }
+        const double rp = su + (ss - s * s / m) / m;                     // :878
+        // ---- barrier ----
+        double tpen = 0.0;
+        for (int k = 0; k < t.nbar; k++) {
+            const int i = t.bar_node[k];
+            const int ds = t.dslot[i];
+            const double h = (ds >= 0) ? X[(size_t)ds * B + lane] : t.hfix[i];
+            const double pmn = t.bar_pmin[k], pmx = t.bar_pmax[k];
+            if (MODE == 0) {
+                if (pmn != -1.0) { tpen += 1.0 / (h - pmn); if (isinf(tpen)) tpen = 0.0; }    // :981-985
+                if (pmx != -1.0) { tpen += 1.0 / (pmx - h); if (isinf(tpen)) tpen = 0.0; }    // :988-992
+            } else {
+                if (pmn != -1.0) { const double q = h - pmn; if (q > 0.0) tpen += 1.0 / q; }  // :381-384
+                if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) tpen += 1.0 / q; }  // :391-394
+            }
+        }
+        bool bar_dead = false;
+        if (MODE == 1 && (isinf(tpen) || isnan(tpen))) { tpen = 0.0; bar_dead = true; }      // :405-406
+        if (MODE == 0) f = (ll + a.pb * tpen) + lam * rp;                // :121-123
+        else f = (a.pb * tpen + ll) + lam * rp;                          // :407, :463
+        if (WANT_G) {
+            for (int j = cb; j < ce; j++) {
+                const int ch = t.children[j];
+                const bool mc = is_masked<LANEMASK>(a, ch, lane);
+                const int crs = t.rslot[ch];
+                if (crs < 0 || mc) continue;
+                const double rc = X[(size_t)crs * B + lane];
+                double add;
+                if (MODE == 0) {
+                    const double mean = su_s / su_m;
+                    if (LOGPEN) add = (2.0 * lam / rc) * (log(rc) - mean) / su_m;            // :780
+                    else add = (2.0 * lam) * (rc - mean) / su_m;                             // :782
+                } else {
+                    const double y = LOGPEN ? log(rc) : rc;
+                    add = lam * (2.0 * y - 2.0 * s / m) / m;
+                    if (LOGPEN) add /= rc;
+                }
+                a.G[(size_t)crs * B + lane] += add;
+            }
+            if (MODE == 1 && !bar_dead) {
+                for (int k = 0; k < t.nbar; k++) {
+                    const int i = t.bar_node[k];
+                    const int ds = t.dslot[i];
+                    if (ds < 0) continue;
+                    const double h = X[(size_t)ds * B + lane];
+                    const double pmn = t.bar_pmin[k], pmx = t.bar_pmax[k];
+                    double gb = 0.0;
+                    if (pmn != -1.0) { const double q = h - pmn; if (q > 0.0) gb -= 1.0 / (q * q); }
+                    if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) gb += 1.0 / (q * q); }
+                    a.G[(size_t)ds * B + lane] += a.pb * gb;
+                }
+            }
+        }
+    }
+    a.F[lane] = bad ? LARGE : f;
+}
+
+// test hook: the fast math on its ordinary range (tests/test_engine_gpu.py)
+__global__ void debug_math_kernel(int n, const double* x, double* lo, double* rc, const double2* tab) {
+    __shared__ double2 s_tab[LOG_TABLE_N];
+    for (int k = threadIdx.x; k < LOG_TABLE_N; k += blockDim.x) s_tab[k] = tab[k];
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        lo[i] = log_any(x[i], s_tab);
+        rc[i] = in_range400(x[i]) ? fast_rcp(x[i]) : 1.0 / x[i];
+    }
+}
+
+}  // namespace tpl
