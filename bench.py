@@ -186,7 +186,7 @@ def run_reference_arm(args, flat, P):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--tips", type=int, default=100000)
@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--mode", default="ad", choices=["ad", "analytic"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--min-warm-seconds", type=float, default=1.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -231,22 +232,33 @@ def main():
     X = torch.from_numpy(Xh).to(dev)
     F = torch.empty(B, dtype=torch.float64, device=dev)
     G = torch.empty((P, B), dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default torch stream: its handle is what the C ABI launches on, and what the events time
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step():
         plp.calc_pl_grad_batch_dev(B, X.data_ptr(), F.data_ptr(), G.data_ptr(), mode, stream)
 
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # warm-up: at least W steps and at least ~1 s of load, so that the clock sampler (100 ms period)
+    # sees the GPU under this kernel's load before and during the timed region
+    t_w = time.perf_counter()
+    done = 0
+    while done < args.warmup or (time.perf_counter() - t_w) < args.min_warm_seconds:
         step()
+        done += 1
+        if done % 16 == 0:
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
     # correctness guard inside the bench: finite objective for every vector
     Fh = F.cpu().numpy()
     if not (np.isfinite(Fh).all() and (Fh < 1e15).all()):
         raise SystemExit("bench.py: engine returned infeasible/NaN objectives on the bench vectors")
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     plp.set_timing(True)
     if dist is not None:
         dist.barrier()
