@@ -141,6 +141,11 @@ void tpl_host_free(void* p);
 int tpl_set_timing(tpl_engine* e, int on);
 int tpl_get_timing(tpl_engine* e, double* main_ms, double* finalize_ms);
 
+/* test hooks: pin the kernel generation (0 = automatic, 1 = generic "pull" kernel, 2 = shared-memory
+ * tile kernel whenever it is legal), and report which one the last evaluation used              */
+int tpl_debug_force_kernel(tpl_engine* e, int generation);
+int tpl_last_kernel_generation(const tpl_engine* e);
+
 /* test hook: evaluates the kernels' log and reciprocal on n host values (tests only) */
 int tpl_debug_math(int n, const double* x, double* log_out, double* rcp_out);
 

@@ -168,6 +168,7 @@ def test_large_tree_properties_100k_nodes():
         X[n - 1:, b] = x0[n - 1:]
     plp.batch_configure(B)
     F, G = plp.calc_pl_grad_batch(X, mode=eng.GRAD_AD)
+    assert plp.last_kernel_generation() == 2          # the bench configuration runs the tile kernel
     for b in (0, 17, 63):
         f, g = o.calc_function_gradient(X[:, b])
         assert close_f(F[b], f), (b, F[b], f)
@@ -225,4 +226,91 @@ def test_errors_are_loud():
         plp.calc_pl(np.zeros(P + 1))
     with pytest.raises(eng.EngineError):
         plp.calc_gradient(np.zeros(P))       # no preceding calc_pl
+    plp.close()
+
+
+@pytest.mark.parametrize("name,B", [("big_test", 64), ("big_test", 34), ("clock", 128), ("M1155", 32)])
+@pytest.mark.parametrize("mode", [eng.GRAD_ANALYTIC, eng.GRAD_AD])
+@pytest.mark.parametrize("log_pen", [False, True])
+def test_tile_kernel_equals_generic_kernel(name, B, mode, log_pen):
+    """Generation 2 (shared-memory tiles, cp.async.bulk) against generation 1 on the same vectors, with
+    per-vector smoothing and CV masks, and against the oracle for three vectors."""
+    gd = Golden(name)
+    rng = np.random.RandomState(B + 3 * mode + int(log_pen))
+    n = gd.flat["parents"].shape[0]
+    tips = np.flatnonzero(gd.flat["child_counts"] == 0)
+    tips = tips[gd.flat["parents"][tips] != 0]
+    plp = eng.PLCalcParallel.from_flat(gd.flat)
+    plp.set_log_pen(log_pen)
+    fp, P = eng.generate_param_order_vector(gd.flat["free"], lf=False)
+    x0 = plp.set_freeparams(P, False, fp)
+    nr = n - 1
+    base = gd.flat["start_rates"][1] * gd.meta["numsites"]
+    X = np.empty((P, B))
+    X[:nr, :] = base * np.exp(0.4 * rng.randn(nr, B))
+    X[nr:, :] = x0[nr:, None] * (1 - 1e-4 * rng.rand(P - nr, B))
+    X[nr + 2, 3] = -1.0                                   # one infeasible vector
+    lam = 10.0 ** rng.uniform(-3, 3, B)
+    for use_masks in (False, True):
+        masks = [sorted(rng.choice(tips, rng.randint(0, 1 + len(tips) // 8), replace=False).tolist())
+                 for _ in range(B)] if use_masks else None
+        plp.batch_configure(B, lane_smoothing=lam, masks=masks)
+        plp.force_kernel(1)
+        F1, G1 = plp.calc_pl_grad_batch(X, mode=mode)
+        assert plp.last_kernel_generation() == 1
+        plp.force_kernel(2)
+        F2, G2 = plp.calc_pl_grad_batch(X, mode=mode)
+        assert plp.last_kernel_generation() == 2
+        F2b, G2b = plp.calc_pl_grad_batch(X, mode=mode)
+        assert np.array_equal(F2, F2b) and np.array_equal(G2, G2b, equal_nan=True)     # deterministic
+        F2o, _ = plp.calc_pl_grad_batch(X, mode=mode, want_grad=False)
+        assert np.array_equal(F2, F2o)
+        assert F1[3] == 1e15 and F2[3] == 1e15
+        ok = np.arange(B) != 3
+        assert np.max(np.abs(F1[ok] - F2[ok]) / np.abs(F1[ok])) < 1e-13
+        for b in np.flatnonzero(ok):
+            assert rel_err(G2[:, b], G1[:, b]) < 1e-12, (b, rel_err(G2[:, b], G1[:, b]))
+        o = plo.OracleProblem(gd.flat, log_pen=log_pen)
+        for b in (0, B // 2, B - 1):
+            cv = np.zeros(n, np.int32)
+            if use_masks:
+                cv[masks[b]] = 1
+            o.set_state(gd.flat["start_rates"], gd.flat["start_dates"])
+            o.set_smoothing(lam[b])
+            o.set_cv(cv)
+            o.set_freeparams(False, use_cv=True)
+            xb, keep = _compact(X[:, b], n, masks[b] if use_masks else [])
+            f, g = o.calc_pl_and_gradient(xb) if mode == eng.GRAD_ANALYTIC else o.calc_function_gradient(xb)
+            assert close_f(F2[b], f), (b, F2[b], f)
+            assert rel_err(G2[keep, b], g) < G_TOL
+    plp.force_kernel(0)
+    plp.close()
+
+
+def test_polytomy_and_unary_nodes_use_the_csr_child_path():
+    """Trees that are not strictly binary (collapse, utils.cpp:138-163) must still work in both kernels."""
+    nw = "((a:0.1,b:0.2,c:0.15,(d:0.1,e:0.1):0.05):0.1,(f:0.3,(g:0.1,h:0.1,i:0.1):0.2):0.1,j:0.5);"
+    ft = tf.flatten_newick(nw, 1000, [(["a", "j"], 50, 50), (["g", "h"], 5, 20)], seed=2)
+    flat = ft.as_dict()
+    plp = eng.PLCalcParallel.from_flat(flat)
+    o = plo.OracleProblem(flat)
+    fp, P = eng.generate_param_order_vector(ft.free, lf=False)
+    x0 = plp.set_freeparams(P, False, fp)
+    o.set_freeparams(False)
+    o.set_smoothing(3.0)
+    plp.smoothing = 3.0
+    rng = np.random.RandomState(4)
+    B = 32
+    X = np.repeat(x0[:, None], B, axis=1)
+    X[: ft.numnodes - 1, :] = 2.0 * np.exp(0.3 * rng.randn(ft.numnodes - 1, B))
+    plp.batch_configure(B)
+    for gen in (1, 2):
+        plp.force_kernel(gen)
+        for mode in (eng.GRAD_ANALYTIC, eng.GRAD_AD):
+            F, G = plp.calc_pl_grad_batch(X, mode=mode)
+            assert plp.last_kernel_generation() == gen
+            for b in (0, 31):
+                xb = np.ascontiguousarray(X[:, b])
+                f, g = o.calc_pl_and_gradient(xb) if mode == eng.GRAD_ANALYTIC else o.calc_function_gradient(xb)
+                assert close_f(F[b], f) and rel_err(G[:, b], g) < G_TOL
     plp.close()

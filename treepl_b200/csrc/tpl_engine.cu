@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "tpl_kernels.cuh"
+#include "tpl_tile_kernel.cuh"
 
 namespace {
 
@@ -116,8 +117,19 @@ struct tpl_engine {
     // ---- device tree ----
     DevBuf<int> d_parent, d_rslot, d_dslot, d_child_off, d_children, d_bar_node;
     DevBuf<unsigned char> d_cv;
-    DevBuf<double> d_c, d_lf, d_hfix, d_rfix, d_hmin, d_hmax, d_bar_pmin, d_bar_pmax;
+    DevBuf<double> d_c, d_lf, d_hfix, d_rfix, d_bar_pmin, d_bar_pmax, d_bnd_min, d_bnd_max;
+    DevBuf<int> d_bnd_node;
     DevBuf<double2> d_logtab;
+    int nbnd = 0;
+    // generation-2 (tile kernel) operands
+    DevBuf<int4> d_recs;
+    DevBuf<double2> d_clf;
+    DevBuf<tpl::TileInfo> d_tiles;
+    int tile_hrows = 0;
+    int ntiles2 = 0;
+    bool gen2_ok = false;             // slot map is dense per tile (reference PL layouts are)
+    bool cv_any = false;
+    int force_gen = 0;                // test hook: 1 = always generation 1, 2 = generation 2 when legal
     int nbar = 0;
     double sum_c = 0.0;
     bool static_bad = false;          // a FIXED date violates its own bounds (set_durations :887-896)
@@ -132,6 +144,7 @@ struct tpl_engine {
     bool cfg_lambda = false, cfg_mask = false;
     int cfg_nchunks = 0;
     int last_launches = 0;
+    int last_gen = 0;
     // optional per-launch device timing (bench.py roofline): events around the main kernel
     bool timing = false;
     std::vector<cudaEvent_t> ev;      // triples: before main, after main, after finalize
@@ -168,8 +181,9 @@ int sync_device_tree(tpl_engine* e) {
         CK(e->d_children.upload(e->children, s));
         CK(e->d_c.upload(e->c, s));
         CK(e->d_lf.upload(e->lf, s));
-        CK(e->d_hmin.upload(e->hmin, s));
-        CK(e->d_hmax.upload(e->hmax, s));
+        std::vector<double2> clf(n);
+        for (int i = 0; i < n; i++) clf[i] = make_double2(e->c[i], e->lf[i]);
+        CK(e->d_clf.upload(clf, s));
         std::vector<int> bn;
         std::vector<double> bmin, bmax;
         for (int i = 0; i < n; i++)
@@ -209,12 +223,74 @@ int sync_device_tree(tpl_engine* e) {
     if (e->state_dirty) {
         CK(e->d_hfix.upload(e->dates, s));
         CK(e->d_rfix.upload(e->rates, s));
-        CK(cudaStreamSynchronize(s));
         e->static_bad = false;
         for (int i = 0; i < n; i++) {
             bool fixed = !e->have_fp || e->freeparams[n + i] == -1;
             if (fixed && (e->dates[i] < e->hmin[i] || e->dates[i] > e->hmax[i])) e->static_bad = true;
         }
+        // ---- sparse bound rows: free dates whose [min,max] is not implied by a neighbour ----
+        std::vector<int> bn;
+        std::vector<double> bmin, bmax;
+        for (int i = 0; i < n; i++) {
+            if (!e->have_fp || e->freeparams[n + i] == -1) continue;
+            const int p = e->parent[i];
+            bool max_implied = (p >= 0) && (e->hmax[i] >= e->hmax[p]);
+            bool min_implied = false;
+            for (int j = e->child_off[i]; j < e->child_off[i + 1]; j++)
+                if (e->hmin[e->children[j]] >= e->hmin[i]) { min_implied = true; break; }
+            if (!(max_implied && min_implied)) {
+                bn.push_back(i);
+                bmin.push_back(e->hmin[i]);
+                bmax.push_back(e->hmax[i]);
+            }
+        }
+        e->nbnd = (int)bn.size();
+        CK(e->d_bnd_node.upload(bn, s));
+        CK(e->d_bnd_min.upload(bmin, s));
+        CK(e->d_bnd_max.upload(bmax, s));
+        // ---- generation-2 operands: packed records, tile table ----
+        e->cv_any = false;
+        for (int i = 0; i < n; i++) if (e->cv[i]) e->cv_any = true;
+        std::vector<int4> recs(n);
+        bool ok = e->have_fp && !e->lf_mode;
+        int next_r = -1, next_d = -1;
+        for (int i = 0; i < n && e->have_fp; i++) {
+            int4 r;
+            r.x = e->parent[i];
+            const int rs = e->freeparams[i], ds = e->freeparams[n + i];
+            r.y = rs >= 0 ? rs : -1;
+            r.z = ds >= 0 ? ds : (e->dates[i] == 0.0 ? -1 : -2);
+            const int nc = e->child_off[i + 1] - e->child_off[i];
+            if (nc == 0) r.w = -1;
+            else if (nc == 2 && (e->children[e->child_off[i]] == i + 1 || e->children[e->child_off[i] + 1] == i + 1))
+                r.w = (e->children[e->child_off[i]] == i + 1) ? e->children[e->child_off[i] + 1] : e->children[e->child_off[i]];
+            else r.w = -2;
+            recs[i] = r;
+            if (rs >= 0) { if (next_r >= 0 && rs != next_r) ok = false; next_r = rs + 1; }
+            if (ds >= 0) { if (next_d >= 0 && ds != next_d) ok = false; next_d = ds + 1; }
+        }
+        const int T = tpl::TILE_NODES;
+        const int nt = (n + T - 1) / T;
+        std::vector<tpl::TileInfo> tiles(nt);
+        int hrows = 0;
+        for (int t = 0; t < nt && e->have_fp; t++) {
+            tpl::TileInfo ti = {0, 0, 0, 0};
+            bool fr = true, fd = true;
+            for (int i = t * T; i < std::min(n, (t + 1) * T); i++) {
+                const int rs = e->freeparams[i], ds = e->freeparams[n + i];
+                if (rs >= 0) { if (fr) { ti.rs0 = rs; fr = false; } ti.nrs = rs - ti.rs0 + 1; }
+                if (ds >= 0) { if (fd) { ti.ds0 = ds; fd = false; } ti.nds = ds - ti.ds0 + 1; }
+            }
+            if (ti.nrs > T || ti.nds > T || ti.nrs < 0 || ti.nds < 0) ok = false;
+            hrows = std::max(hrows, ti.nds);
+            tiles[t] = ti;
+        }
+        e->gen2_ok = ok;
+        e->ntiles2 = nt;
+        e->tile_hrows = std::max(hrows, 1);
+        CK(e->d_recs.upload(recs, s));
+        CK(e->d_tiles.upload(tiles, s));
+        CK(cudaStreamSynchronize(s));
         e->state_dirty = false;
     }
     return TPL_OK;
@@ -233,8 +309,10 @@ tpl::DevTree dev_tree(tpl_engine* e) {
     t.lf = e->d_lf.p;
     t.hfix = e->d_hfix.p;
     t.rfix = e->d_rfix.p;
-    t.hmin = e->d_hmin.p;
-    t.hmax = e->d_hmax.p;
+    t.nbnd = e->nbnd;
+    t.bnd_node = e->d_bnd_node.p;
+    t.bnd_min = e->d_bnd_min.p;
+    t.bnd_max = e->d_bnd_max.p;
     t.nbar = e->nbar;
     t.bar_node = e->d_bar_node.p;
     t.bar_pmin = e->d_bar_pmin.p;
@@ -246,35 +324,51 @@ tpl::DevTree dev_tree(tpl_engine* e) {
     return t;
 }
 
-template <int MODE, bool LF, bool LOGPEN, bool WANT_G, bool LANEMASK>
-void launch_pair(const tpl::EvalArgs& a, dim3 grid, dim3 block, cudaStream_t s, cudaEvent_t* ev) {
-    if (ev) cudaEventRecord(ev[0], s);
-    tpl::pl_main_kernel<MODE, LF, LOGPEN, WANT_G, LANEMASK><<<grid, block, 0, s>>>(a);
-    if (ev) cudaEventRecord(ev[1], s);
-    const int fb = 128;
-    tpl::pl_finalize_kernel<MODE, LF, LOGPEN, WANT_G, LANEMASK><<<(a.B + fb - 1) / fb, fb, 0, s>>>(a);
-    if (ev) cudaEventRecord(ev[2], s);
+struct LaunchCfg {
+    bool lf, lp, want_g;
+    int maskmode;          // 0 none, 1 engine cv, 2 per-vector
+    bool gen2;
+    dim3 grid, block;
+    size_t smem;
+    tpl::TileArgs ta;
+    cudaStream_t s;
+    cudaEvent_t* ev;
+};
+
+template <int MODE, bool LF, bool LOGPEN, bool WANT_G, int MASKMODE>
+cudaError_t launch_pair(const tpl::EvalArgs& a, const LaunchCfg& c) {
+    if (c.ev) cudaEventRecord(c.ev[0], c.s);
+    if (c.gen2) {
+        if constexpr (!LF && MASKMODE != 1) {
+            auto kern = tpl::pl_tile_kernel<MODE, LOGPEN, WANT_G, MASKMODE == 2>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+            if (e != cudaSuccess) return e;
+            kern<<<c.grid, c.block, c.smem, c.s>>>(a, c.ta);
+        }
+    } else {
+        tpl::pl_main_kernel<MODE, LF, LOGPEN, WANT_G, MASKMODE><<<c.grid, c.block, 0, c.s>>>(a);
+    }
+    if (c.ev) cudaEventRecord(c.ev[1], c.s);
+    tpl::pl_finalize_kernel<MODE, LF, LOGPEN, WANT_G, MASKMODE>
+        <<<(a.B + 31) / 32, dim3(32, tpl::FIN_SEGS), 0, c.s>>>(a);
+    if (c.ev) cudaEventRecord(c.ev[2], c.s);
+    return cudaGetLastError();
 }
 
 template <int MODE, bool LF, bool LOGPEN, bool WANT_G>
-void launch_m(const tpl::EvalArgs& a, bool lanemask, dim3 g, dim3 b, cudaStream_t s, cudaEvent_t* ev) {
-    if (lanemask) launch_pair<MODE, LF, LOGPEN, WANT_G, true>(a, g, b, s, ev);
-    else launch_pair<MODE, LF, LOGPEN, WANT_G, false>(a, g, b, s, ev);
+cudaError_t launch_m(const tpl::EvalArgs& a, const LaunchCfg& c) {
+    if (c.maskmode == 2) return launch_pair<MODE, LF, LOGPEN, WANT_G, 2>(a, c);
+    if (c.maskmode == 1) return launch_pair<MODE, LF, LOGPEN, WANT_G, 1>(a, c);
+    return launch_pair<MODE, LF, LOGPEN, WANT_G, 0>(a, c);
 }
 template <int MODE, bool LF, bool LOGPEN>
-void launch_g(const tpl::EvalArgs& a, bool want_g, bool lanemask, dim3 g, dim3 b, cudaStream_t s, cudaEvent_t* ev) {
-    if (want_g) launch_m<MODE, LF, LOGPEN, true>(a, lanemask, g, b, s, ev);
-    else launch_m<MODE, LF, LOGPEN, false>(a, lanemask, g, b, s, ev);
-}
-template <int MODE, bool LF>
-void launch_lp(const tpl::EvalArgs& a, bool lp, bool want_g, bool lanemask, dim3 g, dim3 b, cudaStream_t s, cudaEvent_t* ev) {
-    if (lp) launch_g<MODE, LF, true>(a, want_g, lanemask, g, b, s, ev);
-    else launch_g<MODE, LF, false>(a, want_g, lanemask, g, b, s, ev);
+cudaError_t launch_g(const tpl::EvalArgs& a, const LaunchCfg& c) {
+    return c.want_g ? launch_m<MODE, LF, LOGPEN, true>(a, c) : launch_m<MODE, LF, LOGPEN, false>(a, c);
 }
 template <int MODE>
-void launch_lf(const tpl::EvalArgs& a, bool lf, bool lp, bool want_g, bool lanemask, dim3 g, dim3 b, cudaStream_t s, cudaEvent_t* ev) {
-    if (lf) launch_lp<MODE, true>(a, false, want_g, lanemask, g, b, s, ev);   // log_pen has no effect on the LF objective
-    else launch_lp<MODE, false>(a, lp, want_g, lanemask, g, b, s, ev);
+cudaError_t launch_lf(const tpl::EvalArgs& a, const LaunchCfg& c) {
+    if (c.lf) return launch_g<MODE, true, false>(a, c);    // log_pen has no effect on the LF objective
+    return c.lp ? launch_g<MODE, false, true>(a, c) : launch_g<MODE, false, false>(a, c);
 }
 
 // Evaluate B vectors resident on the device.  Enqueues 2 kernels on stream s.
@@ -286,15 +380,33 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
     int rc = sync_device_tree(e);
     if (rc != TPL_OK) return rc;
     const int n = e->n;
-    // block shape: LX lanes x NY node rows, 256 threads
-    int LX = 1;
-    while (LX < 32 && LX < B) LX <<= 1;
-    const int NY = 256 / LX;
-    // tile = nodes per block: keep >= ~8 node rows per thread row, and enough blocks to fill 148 SMs
-    int tile = 256;
-    if (LX == 1) tile = 1024;
-    const int ntiles = (n + tile - 1) / tile;
-    const int nlane_blocks = (B + LX - 1) / LX;
+    const bool lanemask = use_cfg && e->cfg_mask && e->cfg_B == B;
+    const int maskmode = lanemask ? 2 : (e->cv_any ? 1 : 0);
+    // generation 2 (tile kernel): PL, dense slot map, even B, 32-bit element offsets
+    bool gen2 = e->gen2_ok && !e->lf_mode && maskmode != 1 && (B % 2 == 0) && B >= 32 &&
+                (double)e->numparams * (double)B < 2.0e9;
+    if (e->force_gen == 1) gen2 = false;
+    if (e->force_gen == 2)
+        gen2 = e->gen2_ok && !e->lf_mode && maskmode != 1 && (B % 2 == 0) && (double)e->numparams * (double)B < 2.0e9;
+    LaunchCfg c;
+    int ntiles, tile;
+    if (gen2) {
+        tile = tpl::TILE_NODES;
+        ntiles = e->ntiles2;
+        c.grid = dim3(ntiles, (B + tpl::TILE_LANES - 1) / tpl::TILE_LANES);
+        c.block = dim3(256);
+        c.smem = tpl::tile_kernel_smem(e->tile_hrows);
+    } else {
+        // block shape: LX lanes x NY node rows, 256 threads
+        int LX = 1;
+        while (LX < 32 && LX < B) LX <<= 1;
+        const int NY = 256 / LX;
+        tile = (LX == 1) ? 1024 : 256;
+        ntiles = (n + tile - 1) / tile;
+        c.grid = dim3(ntiles, (B + LX - 1) / LX);
+        c.block = dim3(LX, NY);
+        c.smem = 0;
+    }
     CK(e->d_part_ll.ensure((size_t)ntiles * B));
     CK(e->d_part_su.ensure((size_t)ntiles * B));
     CK(e->d_part_gr.ensure((size_t)ntiles * B));
@@ -305,7 +417,6 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
     a.G = dG;
     a.F = dF;
     a.B = B;
-    const bool lanemask = use_cfg && e->cfg_mask && e->cfg_B == B;
     a.lanemask = lanemask ? e->d_lanemask.p : nullptr;
     a.nchunks = e->cfg_nchunks;
     a.lane_lambda = (use_cfg && e->cfg_lambda && e->cfg_B == B) ? e->d_lane_lambda.p : nullptr;
@@ -318,13 +429,20 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
     a.ntiles = ntiles;
     a.tile_nodes = tile;
     a.logtab = e->d_logtab.p;
-    dim3 grid(ntiles, nlane_blocks), block(LX, NY);
-    const bool want_g = dG != nullptr;
-    cudaEvent_t* evs = nullptr;
-    if (e->timing && e->ev_used + 3 <= e->ev.size()) { evs = &e->ev[e->ev_used]; e->ev_used += 3; }
-    if (mode == TPL_GRAD_ANALYTIC) launch_lf<0>(a, e->lf_mode, e->log_pen, want_g, lanemask, grid, block, s, evs);
-    else launch_lf<1>(a, e->lf_mode, e->log_pen, want_g, lanemask, grid, block, s, evs);
-    CK(cudaGetLastError());
+    c.lf = e->lf_mode;
+    c.lp = e->log_pen;
+    c.want_g = dG != nullptr;
+    c.maskmode = maskmode;
+    c.gen2 = gen2;
+    c.ta.recs = e->d_recs.p;
+    c.ta.clf = e->d_clf.p;
+    c.ta.tiles = e->d_tiles.p;
+    c.ta.hrows = e->tile_hrows;
+    c.s = s;
+    c.ev = nullptr;
+    if (e->timing && e->ev_used + 3 <= e->ev.size()) { c.ev = &e->ev[e->ev_used]; e->ev_used += 3; }
+    CK(mode == TPL_GRAD_ANALYTIC ? launch_lf<0>(a, c) : launch_lf<1>(a, c));
+    e->last_gen = gen2 ? 2 : 1;
     e->last_launches = 2;
     return TPL_OK;
 }
@@ -592,6 +710,13 @@ int tpl_calc_pl_grad_batch(tpl_engine* e, int B, const double* X, double* F, dou
     if (e->static_bad) for (int b = 0; b < B; b++) F[b] = TPL_LARGE;
     return TPL_OK;
 }
+
+int tpl_debug_force_kernel(tpl_engine* e, int gen) {
+    if (!e || gen < 0 || gen > 2) return fail(TPL_ERR_ARG, "bad argument");
+    e->force_gen = gen;
+    return TPL_OK;
+}
+int tpl_last_kernel_generation(const tpl_engine* e) { return e ? e->last_gen : TPL_ERR_ARG; }
 
 int tpl_set_timing(tpl_engine* e, int on) {
     if (!e) return fail(TPL_ERR_ARG, "null");

@@ -37,8 +37,13 @@ struct DevTree {
     const double* lf;             // [n] log_fact_char_durations
     const double* hfix;           // [n] member dates[]  (used when dslot < 0)
     const double* rfix;           // [n] member rates[]  (used when rslot < 0 or masked)
-    const double* hmin;           // [n]
-    const double* hmax;           // [n]
+    // sparse date-bound rows (set_durations :887-896).  Only nodes whose [min,max] is NOT implied by
+    // a neighbour are listed: h_i <= h_parent <= max_parent <= max_i makes an inherited max redundant
+    // once every duration is checked to be >= 0, and likewise an inherited min through a child.
+    int nbnd;
+    const int* bnd_node;          // [nbnd]
+    const double* bnd_min;        // [nbnd]
+    const double* bnd_max;        // [nbnd]
     // sparse calibration barrier rows, ascending node order (calc_penalty :975-998)
     int nbar;
     const int* bar_node;          // [nbar]
@@ -77,13 +82,16 @@ __device__ __forceinline__ double log_any(double x, const double2* tab) {
     return in_range400(x) ? fast_log(x, tab) : log(x);
 }
 
-template <bool LANEMASK>
+// MASKMODE 0: no CV mask anywhere (the common case); 1: engine-level cvnodes; 2: per-vector bit masks
+template <int MASKMODE>
 __device__ __forceinline__ bool is_masked(const EvalArgs& a, int node, int lane) {
-    if (LANEMASK) {
+    if (MASKMODE == 2) {
         unsigned long long w = a.lanemask[(size_t)node * a.nchunks + (lane >> 6)];
         return (w >> (lane & 63)) & 1ull;
-    } else {
+    } else if (MASKMODE == 1) {
         return a.t.cv[node] != 0;
+    } else {
+        return false;
     }
 }
 
@@ -143,7 +151,7 @@ __device__ __forceinline__ double duration_rule(double hp, double h, int& bad, b
     return d;
 }
 
-template <int MODE, bool LF, bool LOGPEN, bool WANT_G, bool LANEMASK>
+template <int MODE, bool LF, bool LOGPEN, bool WANT_G, int MASKMODE>
 __global__ void __launch_bounds__(256) pl_main_kernel(const EvalArgs a) {
     __shared__ double2 s_tab[LOG_TABLE_N];
     __shared__ double s_red[3][256];
@@ -169,15 +177,16 @@ __global__ void __launch_bounds__(256) pl_main_kernel(const EvalArgs a) {
         const double* __restrict__ X = a.X;
         for (int i = n0 + ty; i < n1; i += NY) {
             const int rs = t.rslot[i], ds = t.dslot[i];
-            const bool mi = is_masked<LANEMASK>(a, i, lane);
-            const bool rfree = (rs >= 0) && !mi;
+            const bool mi = is_masked<MASKMODE>(a, i, lane);
+            // a per-vector mask ignores the rate row; with the engine-level mask the reference still
+            // scatters x into rates[i] when a slot exists (:82-89)
+            const bool rfree = (rs >= 0) && !(MASKMODE == 2 && mi);
             const double r = rfree ? X[(size_t)rs * B + lane] : t.rfix[i];
             const double h = (ds >= 0) ? X[(size_t)ds * B + lane] : t.hfix[i];
             if (MODE == 0) {                                             // calc_pl :74-78
                 if (rfree && r < 0.0) bad = 1;
                 if (ds >= 0 && h < 0.0) bad = 1;
             }
-            if (h < t.hmin[i] || h > t.hmax[i]) bad = 1;                 // :887-896
             double g_r = 0.0, g_h = 0.0;
             double lr = 0.0;                                             // ln r_i (analytic log_pen only)
             if (i != 0) {
@@ -201,7 +210,7 @@ __global__ void __launch_bounds__(256) pl_main_kernel(const EvalArgs a) {
                 }
                 if (!LF && !mi) {
                     if (p != 0) {
-                        const bool pm = is_masked<LANEMASK>(a, p, lane);
+                        const bool pm = is_masked<MASKMODE>(a, p, lane);
                         const double rp = (prs >= 0 && !pm) ? X[(size_t)prs * B + lane] : t.rfix[p];
                         const double q = r - rp;
                         acc_su = fma(q, q, acc_su);                      // :862-864
@@ -225,7 +234,7 @@ __global__ void __launch_bounds__(256) pl_main_kernel(const EvalArgs a) {
                 if (ds >= 0 || need_q) {
                     for (int j = cb; j < ce; j++) {
                         const int ch = t.children[j];
-                        if (is_masked<LANEMASK>(a, ch, lane)) continue;  // :738, :784
+                        if (is_masked<MASKMODE>(a, ch, lane)) continue;  // :738, :784
                         const int crs = t.rslot[ch], cds = t.dslot[ch];
                         const double rc = (crs >= 0) ? X[(size_t)crs * B + lane] : t.rfix[ch];
                         if (ds >= 0) {
@@ -242,7 +251,7 @@ __global__ void __launch_bounds__(256) pl_main_kernel(const EvalArgs a) {
                         }
                     }
                 }
-                if (!LF && rs >= 0) a.G[(size_t)rs * B + lane] = rfree ? fma(-lam2, sum_q, g_r) : 0.0;
+                if (!LF && rs >= 0) a.G[(size_t)rs * B + lane] = (rfree && !mi) ? fma(-lam2, sum_q, g_r) : 0.0;
                 if (ds >= 0) a.G[(size_t)ds * B + lane] = g_h + sum_delta;
             }
         }
@@ -270,25 +279,55 @@ __global__ void __launch_bounds__(256) pl_main_kernel(const EvalArgs a) {
     }
 }
 
-// One thread per vector: reduce the tile partials in tile order, add the root-children variance
+// Finalize: per vector, reduce the tile partials in fixed order (32 segments of consecutive tiles,
+// then the 32 segment sums in order), check the sparse date bounds, add the root-children variance
 // term (:866-879) and the calibration barrier (:975-998 / :381-406), write F, and apply the
-// matching sparse gradient corrections to the rows the main kernel has already written.
-template <int MODE, bool LF, bool LOGPEN, bool WANT_G, bool LANEMASK>
-__global__ void __launch_bounds__(128) pl_finalize_kernel(const EvalArgs a) {
+// matching sparse gradient corrections to rows the main kernel has already written.
+constexpr int FIN_SEGS = 32;
+template <int MODE, bool LF, bool LOGPEN, bool WANT_G, int MASKMODE>
+__global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const EvalArgs a) {
+    __shared__ double s_sum[3][FIN_SEGS][32];
+    __shared__ int s_bad[FIN_SEGS][32];
     const DevTree& t = a.t;
     const int B = a.B;
-    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane >= B) return;
+    const int tx = threadIdx.x, seg = threadIdx.y;
+    const int lane = blockIdx.x * 32 + tx;
+    const bool active = lane < B;
+    {
+        const int len = (a.ntiles + FIN_SEGS - 1) / FIN_SEGS;
+        const int k0 = seg * len, k1 = min(a.ntiles, k0 + len);
+        double ll = 0.0, su = 0.0, gr = 0.0;
+        int bad = 0;
+        if (active)
+            for (int k = k0; k < k1; k++) {
+                const size_t o = (size_t)k * B + lane;
+                ll += a.part_ll[o];
+                if (!LF) su += a.part_su[o];
+                if (LF) gr += a.part_gr[o];
+                bad |= a.part_bad[o];
+            }
+        s_sum[0][seg][tx] = ll;
+        s_sum[1][seg][tx] = su;
+        s_sum[2][seg][tx] = gr;
+        s_bad[seg][tx] = bad;
+    }
+    __syncthreads();
+    if (seg != 0 || !active) return;
     double ll = 0.0, su = 0.0, gr = 0.0;
     int bad = 0;
-    for (int k = 0; k < a.ntiles; k++) {
-        const size_t o = (size_t)k * B + lane;
-        ll += a.part_ll[o];
-        if (!LF) su += a.part_su[o];
-        if (LF) gr += a.part_gr[o];
-        bad |= a.part_bad[o];
+    for (int k = 0; k < FIN_SEGS; k++) {
+        ll += s_sum[0][k][tx];
+        su += s_sum[1][k][tx];
+        gr += s_sum[2][k][tx];
+        bad |= s_bad[k][tx];
     }
     const double* __restrict__ X = a.X;
+    for (int k = 0; k < t.nbnd; k++) {                                   // set_durations :887-896
+        const int ds = t.dslot[t.bnd_node[k]];
+        if (ds < 0) continue;                                            // fixed dates are checked on the host
+        const double h = X[(size_t)ds * B + lane];
+        if (h < t.bnd_min[k] || h > t.bnd_max[k]) bad = 1;
+    }
     double f;
     if (LF) {
         f = ll;
@@ -308,9 +347,9 @@ __global__ void __launch_bounds__(128) pl_finalize_kernel(const EvalArgs a) {
         double su_s = 0.0, su_m = 0.0;              // unmasked children (analytic gradient :767-778)
         for (int j = cb; j < ce; j++) {
             const int ch = t.children[j];
-            const bool mc = is_masked<LANEMASK>(a, ch, lane);
+            const bool mc = is_masked<MASKMODE>(a, ch, lane);
             const int crs = t.rslot[ch];
-            const double rc = (crs >= 0 && !mc) ? X[(size_t)crs * B + lane] : t.rfix[ch];
+            const double rc = (crs >= 0 && !(MASKMODE == 2 && mc)) ? X[(size_t)crs * B + lane] : t.rfix[ch];
             const double y = LOGPEN ? log(rc) : rc;
             s += y;
             ss += y * y;
@@ -340,7 +379,7 @@ __global__ void __launch_bounds__(128) pl_finalize_kernel(const EvalArgs a) {
         if (WANT_G) {
             for (int j = cb; j < ce; j++) {
                 const int ch = t.children[j];
-                const bool mc = is_masked<LANEMASK>(a, ch, lane);
+                const bool mc = is_masked<MASKMODE>(a, ch, lane);
                 const int crs = t.rslot[ch];
                 if (crs < 0 || mc) continue;
                 const double rc = X[(size_t)crs * B + lane];

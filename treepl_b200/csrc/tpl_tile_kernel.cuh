@@ -1,0 +1,324 @@
+// PL objective + gradient, generation 2 (sm_100a): shared-memory staged node tiles.
+//
+// Why (profiles/r01a_pull_kernel_ncu.md): the generation-1 kernel spends 304 warp instructions per
+// 32-lane node row, ~42 of them fp64 — it is bound by address arithmetic, topology loads and
+// memory latency, not by HBM (21 %) or the fp64 pipe (16 %).  This kernel removes that overhead:
+//
+//  * tile = 64 consecutive nodes (reference preorder) x 64 vectors.  In the reference parameter
+//    layout (generate_param_order_vector, utils.cpp:295-340) the rate rows of consecutive nodes are
+//    consecutive rows of X, and so are their free-date rows: a tile's operands are two dense row
+//    ranges.  One warp issues one cp.async.bulk (TMA, 512 B) per row into shared memory against an
+//    mbarrier; the CTA scheduler overlaps the load phase of one resident CTA with the compute phase
+//    of the others (3 CTAs/SM), so >100 KB of HBM reads are in flight per SM without any registers
+//    being held for them.
+//  * preorder locality: a node's parent is usually a few rows above it and its first child is the
+//    next row, so ~90 % of the parent/child operands are already in the tile; the rest ("halo")
+//    are read from global memory, where the neighbouring tile's CTA has just pulled them into L2.
+//  * each thread owns TWO vectors (one LDS.128 / STG.128 per operand row), so topology decoding,
+//    branches and address arithmetic are amortised over 64 vectors per warp row; node topology is
+//    one packed 16-byte record, element offsets are 32-bit.
+//  * gradient rows are written exactly once by their owner straight from registers (coalesced
+//    512 B per warp), objective partials are reduced in fixed order: bitwise deterministic.
+#pragma once
+#include "tpl_kernels.cuh"
+
+namespace tpl {
+
+constexpr int TILE_NODES = 64;
+constexpr int TILE_LANES = 64;
+
+// packed topology record (one LDS.128 / LDG.128)
+//   x parent
+//   y rslot : >= 0 row of X ; -1 rate = rfix[node]
+//   z dslot : >= 0 row of X ; -1 date is exactly 0 (tips) ; -2 date = hfix[node]
+//   w kid2  : >= 0 binary node with children (node+1, kid2) ; -1 tip ; -2 use the CSR child list
+struct TileInfo {
+    int rs0, nrs, ds0, nds;
+};
+
+struct TileArgs {
+    const int4* recs;          // [n]
+    const double2* clf;        // [n] (char_duration, log_fact)
+    const TileInfo* tiles;     // [ntiles]
+    int hrows;                 // max date rows of any tile (shared-memory sizing)
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg((const double2*)p); }
+
+template <int MODE, bool LOGPEN, bool WANT_G, bool MASK>
+__global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const TileArgs ta) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int T = TILE_NODES, LW = TILE_LANES;
+    double* sR = reinterpret_cast<double*>(smem_raw);                      // [T][LW]
+    double* sH = sR + T * LW;                                              // [hrows][LW]
+    int4* sRec = reinterpret_cast<int4*>(sH + (size_t)ta.hrows * LW);      // [T]
+    double2* sCL = reinterpret_cast<double2*>(sRec + T);                   // [T]
+    unsigned long long* sMask = reinterpret_cast<unsigned long long*>(sCL + T);   // [T]
+    double2* sTab = reinterpret_cast<double2*>(sMask + T);                 // [LOG_TABLE_N]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sTab + LOG_TABLE_N);
+
+    const int tid = threadIdx.x;
+    const int w = tid >> 5, tx = tid & 31;
+    const int tile = blockIdx.x, chunk = blockIdx.y;
+    const unsigned B = (unsigned)a.B;
+    const int lane0 = chunk * LW;
+    const int nl = min(LW, a.B - lane0);                 // even
+    const unsigned rowbytes = (unsigned)nl * 8u;
+    const int n0 = tile * T;
+    const int tn = min(T, a.t.n - n0);
+    const int n1 = n0 + tn;
+    const TileInfo ti = ta.tiles[tile];
+    const double* __restrict__ X = a.X;
+
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (w == 0) {
+        if (tx == 0) mbar_expect_tx(mbar, (unsigned)(ti.nrs + ti.nds) * rowbytes);
+        __syncwarp();
+        for (int k = tx; k < ti.nrs; k += 32)
+            bulk_g2s(sR + k * LW, X + ((size_t)(ti.rs0 + k) * B + lane0), rowbytes, mbar);
+        for (int k = tx; k < ti.nds; k += 32)
+            bulk_g2s(sH + k * LW, X + ((size_t)(ti.ds0 + k) * B + lane0), rowbytes, mbar);
+    }
+    for (int j = tid; j < tn; j += 256) {
+        sRec[j] = ta.recs[n0 + j];
+        sCL[j] = ta.clf[n0 + j];
+        if (MASK) sMask[j] = a.lanemask[(size_t)(n0 + j) * a.nchunks + chunk];
+    }
+    sTab[tid] = a.logtab[tid];
+    __syncthreads();
+    mbar_wait(mbar, 0);
+
+    const int lane = lane0 + 2 * tx;                     // first of this thread's two vectors
+    const bool active = 2 * tx < nl;
+    double acc_ll[2] = {0.0, 0.0}, acc_su[2] = {0.0, 0.0};
+    int bad = 0;                                         // bit l = vector l infeasible
+
+    if (active) {
+        double lam[2];
+        if (a.lane_lambda) { double2 t2 = ldg2(a.lane_lambda + lane); lam[0] = t2.x; lam[1] = t2.y; }
+        else { lam[0] = lam[1] = a.lambda; }
+        const double lam2[2] = {2.0 * lam[0], 2.0 * lam[1]};
+        const int shl = 2 * tx;
+
+        // operand fetch: in-tile rows from shared memory, halo rows from global (L2)
+        auto rate_of = [&](int node, const int4& rc, bool intile, double (&out)[2]) {
+            if (rc.y >= 0) {
+                double2 v = intile ? *reinterpret_cast<const double2*>(sR + (rc.y - ti.rs0) * LW + 2 * tx)
+                                   : ldg2(X + ((unsigned)rc.y * B + (unsigned)lane));
+                out[0] = v.x; out[1] = v.y;
+            } else {
+                out[0] = out[1] = a.t.rfix[node];
+            }
+        };
+        auto date_of = [&](int node, const int4& rc, bool intile, double (&out)[2]) {
+            if (rc.z >= 0) {
+                double2 v = intile ? *reinterpret_cast<const double2*>(sH + (rc.z - ti.ds0) * LW + 2 * tx)
+                                   : ldg2(X + ((unsigned)rc.z * B + (unsigned)lane));
+                out[0] = v.x; out[1] = v.y;
+            } else if (rc.z == -1) {
+                out[0] = out[1] = 0.0;
+            } else {
+                out[0] = out[1] = a.t.hfix[node];
+            }
+        };
+        auto mask_of = [&](int node, bool intile) -> unsigned {
+            if (!MASK) return 0u;
+            unsigned long long mw = intile ? sMask[node - n0] : a.lanemask[(size_t)node * a.nchunks + chunk];
+            return (unsigned)(mw >> shl) & 3u;
+        };
+
+        for (int j = w; j < tn; j += 8) {
+            const int i = n0 + j;
+            const int4 rec = sRec[j];
+            const double2 cl = sCL[j];
+            const unsigned mi = mask_of(i, true);
+            double r[2], h[2];
+            rate_of(i, rec, true, r);
+            date_of(i, rec, true, h);
+            if (MASK && mi && rec.y >= 0) {              // a masked vector ignores its rate row
+                const double rf = a.t.rfix[i];
+                if (mi & 1u) r[0] = rf;
+                if (mi & 2u) r[1] = rf;
+            }
+            if (MODE == 0) {                             // calc_pl :74-78
+#pragma unroll
+                for (int l = 0; l < 2; l++) {
+                    if (rec.y >= 0 && !((mi >> l) & 1u) && r[l] < 0.0) bad |= 1 << l;
+                    if (rec.z >= 0 && h[l] < 0.0) bad |= 1 << l;
+                }
+            }
+            double g_r[2] = {0.0, 0.0}, g_h[2] = {0.0, 0.0}, lr[2] = {0.0, 0.0};
+            if (i != 0) {
+                const int p = rec.x;
+                const bool pin = p >= n0;
+                const int4 prec = pin ? sRec[p - n0] : __ldg(ta.recs + p);
+                double hp[2];
+                date_of(p, prec, pin, hp);
+                double d[2];
+                bool dconst[2];
+#pragma unroll
+                for (int l = 0; l < 2; l++) {
+                    int b1 = 0;
+                    d[l] = duration_rule<MODE, false>(hp[l], h[l], b1, dconst[l]);
+                    bad |= b1 << l;
+                }
+                double rp[2] = {0.0, 0.0};
+                if (p != 0) {
+                    rate_of(p, prec, pin, rp);
+                    if (MASK) {
+                        const unsigned mp = mask_of(p, pin);
+                        if (mp && prec.y >= 0) {
+                            const double rf = a.t.rfix[p];
+                            if (mp & 1u) rp[0] = rf;
+                            if (mp & 2u) rp[1] = rf;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int l = 0; l < 2; l++) {
+                    const bool ml = (mi >> l) & 1u;
+                    if (!ml || (MODE == 0 && WANT_G && rec.z >= 0)) {
+                        Branch b = branch_terms<MODE, false, true>(r[l], d[l], cl.x, cl.y, dconst[l], sTab);
+                        g_h[l] = -b.delta;               // analytic: own term regardless of cv (:728-735)
+                        if (!ml) { acc_ll[l] += b.ll; g_r[l] = b.dr; }
+                        else if (MODE == 1) g_h[l] = 0.0;
+                    }
+                    if (!ml) {
+                        if (p != 0) {
+                            const double q = r[l] - rp[l];
+                            acc_su[l] = fma(q, q, acc_su[l]);                                // :862-864
+                            if (WANT_G) {
+                                if (LOGPEN && MODE == 0) {
+                                    lr[l] = log_any(r[l], sTab);
+                                    g_r[l] += lam2[l] * (lr[l] - log_any(rp[l], sTab)) / r[l];   // :795-796
+                                } else {
+                                    g_r[l] = fma(lam2[l], q, g_r[l]);                          // :798
+                                }
+                            }
+                        } else if (WANT_G && LOGPEN && MODE == 0) {
+                            lr[l] = log_any(r[l], sTab);
+                        }
+                    }
+                }
+            }
+            if (WANT_G) {
+                double sum_delta[2] = {0.0, 0.0}, sum_q[2] = {0.0, 0.0};
+                const bool need_q = (rec.y >= 0) && (i != 0);
+                const bool need_d = rec.z >= 0;
+                auto child = [&](int ch) {
+                    const bool cin = ch < n1;
+                    const int4 crec = cin ? sRec[ch - n0] : __ldg(ta.recs + ch);
+                    const unsigned mc = mask_of(ch, cin);
+                    if (MASK && mc == 3u) return;
+                    double rc[2];
+                    rate_of(ch, crec, cin, rc);
+                    if (need_d) {
+                        const double cc = cin ? sCL[ch - n0].x : __ldg(ta.clf + ch).x;
+                        double hc[2];
+                        date_of(ch, crec, cin, hc);
+#pragma unroll
+                        for (int l = 0; l < 2; l++) {
+                            if (MASK && ((mc >> l) & 1u)) continue;                          // :738
+                            bool dc_const;
+                            int dummy = 0;
+                            const double dc = duration_rule<MODE, false>(h[l], hc[l], dummy, dc_const);
+                            Branch b = branch_terms<MODE, false, false>(rc[l], dc, cc, 0.0, dc_const, sTab);
+                            sum_delta[l] += b.delta;
+                        }
+                    }
+                    if (need_q) {
+#pragma unroll
+                        for (int l = 0; l < 2; l++) {
+                            if (MASK && ((mc >> l) & 1u)) continue;                          // :784
+                            if (LOGPEN && MODE == 0) sum_q[l] += (log_any(rc[l], sTab) - lr[l]) / r[l];   // :786, :802
+                            else sum_q[l] += rc[l] - r[l];
+                        }
+                    }
+                };
+                if (need_q || need_d) {
+                    if (rec.w >= 0) {
+                        child(i + 1);
+                        child(rec.w);
+                    } else if (rec.w == -2) {
+                        for (int k = a.t.child_off[i]; k < a.t.child_off[i + 1]; k++) child(a.t.children[k]);
+                    }
+                }
+                if (rec.y >= 0) {
+                    double2 o;
+                    o.x = ((mi & 1u) ? 0.0 : fma(-lam2[0], sum_q[0], g_r[0]));
+                    o.y = ((mi & 2u) ? 0.0 : fma(-lam2[1], sum_q[1], g_r[1]));
+                    *reinterpret_cast<double2*>(a.G + ((unsigned)rec.y * B + (unsigned)lane)) = o;
+                }
+                if (rec.z >= 0) {
+                    double2 o;
+                    o.x = g_h[0] + sum_delta[0];
+                    o.y = g_h[1] + sum_delta[1];
+                    *reinterpret_cast<double2*>(a.G + ((unsigned)rec.z * B + (unsigned)lane)) = o;
+                }
+            }
+        }
+    }
+    // fixed-order reduction over the 8 warps; the operand tile is dead, reuse it as scratch
+    __syncthreads();
+    double* sRed = sR;                                   // [8][2][LW]
+    int* sBad = reinterpret_cast<int*>(sR + 8 * 2 * LW); // [8][32]
+    sRed[(w * 2 + 0) * LW + 2 * tx] = acc_ll[0];
+    sRed[(w * 2 + 0) * LW + 2 * tx + 1] = acc_ll[1];
+    sRed[(w * 2 + 1) * LW + 2 * tx] = acc_su[0];
+    sRed[(w * 2 + 1) * LW + 2 * tx + 1] = acc_su[1];
+    sBad[w * 32 + tx] = bad;
+    __syncthreads();
+    if (w == 0 && active) {
+        double s0[2] = {0.0, 0.0}, s1[2] = {0.0, 0.0};
+        int bb = 0;
+        for (int y = 0; y < 8; y++) {
+            s0[0] += sRed[(y * 2 + 0) * LW + 2 * tx];
+            s0[1] += sRed[(y * 2 + 0) * LW + 2 * tx + 1];
+            s1[0] += sRed[(y * 2 + 1) * LW + 2 * tx];
+            s1[1] += sRed[(y * 2 + 1) * LW + 2 * tx + 1];
+            bb |= sBad[y * 32 + tx];
+        }
+        const size_t o = (size_t)tile * B + lane;
+        *reinterpret_cast<double2*>(a.part_ll + o) = make_double2(s0[0], s0[1]);
+        *reinterpret_cast<double2*>(a.part_su + o) = make_double2(s1[0], s1[1]);
+        a.part_bad[o] = bb & 1;
+        a.part_bad[o + 1] = (bb >> 1) & 1;
+    }
+}
+
+inline size_t tile_kernel_smem(int hrows) {
+    return (size_t)TILE_NODES * TILE_LANES * 8 + (size_t)hrows * TILE_LANES * 8 + TILE_NODES * (16 + 16 + 8) +
+           LOG_TABLE_N * 16 + 16;
+}
+
+}  // namespace tpl

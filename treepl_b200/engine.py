@@ -68,7 +68,8 @@ def load_library():
                        ("tpl_calc_pl_grad_batch_dev", [vp, ci, vp, vp, vp, ci, vp]),
                        ("tpl_last_launch_count", [vp]), ("tpl_device_sm", [vp]),
                        ("tpl_debug_math", [ci, dp, dp, dp]), ("tpl_set_timing", [vp, ci]),
-                       ("tpl_get_timing", [vp, dp, dp])):
+                       ("tpl_get_timing", [vp, dp, dp]), ("tpl_debug_force_kernel", [vp, ci]),
+                       ("tpl_last_kernel_generation", [vp])):
         fn = getattr(L, name)
         fn.restype = ci
         fn.argtypes = args
@@ -91,7 +92,8 @@ EXPORTED_SYMBOLS = (
     "tpl_set_freeparams", "tpl_numnodes", "tpl_numparams", "tpl_calc_pl", "tpl_calc_gradient",
     "tpl_calc_function_gradient", "tpl_calc_pl_grad", "tpl_get_rates", "tpl_get_dates", "tpl_get_durations",
     "tpl_batch_configure", "tpl_calc_pl_grad_batch", "tpl_calc_pl_grad_batch_dev", "tpl_last_launch_count",
-    "tpl_host_alloc", "tpl_host_free", "tpl_device_sm", "tpl_debug_math", "tpl_set_timing", "tpl_get_timing",
+    "tpl_host_alloc", "tpl_host_free", "tpl_device_sm", "tpl_debug_math", "tpl_set_timing", "tpl_get_timing", "tpl_debug_force_kernel",
+    "tpl_last_kernel_generation",
 )
 
 
@@ -337,6 +339,12 @@ class PLCalcParallel:
         m, f = C.c_double(), C.c_double()
         cnt = self._check(self._L.tpl_get_timing(self._h, C.byref(m), C.byref(f)))
         return cnt, m.value, f.value
+
+    def force_kernel(self, generation):
+        self._check(self._L.tpl_debug_force_kernel(self._h, int(generation)))
+
+    def last_kernel_generation(self):
+        return self._L.tpl_last_kernel_generation(self._h)
 
     def last_launch_count(self):
         return self._L.tpl_last_launch_count(self._h)
