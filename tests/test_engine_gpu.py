@@ -176,7 +176,7 @@ def test_large_tree_properties_100k_nodes():
         f1, g1 = plp.calc_function_gradient(X[:, b].copy())
         # the B=1 launch tiles the node range differently, so the objective's partial sums are
         # grouped differently (a last-bits effect); gradient rows come from the same operands
-        assert close_f(f1, F[b], 1e-14) and rel_err(g1, G[:, b]) < 1e-13
+        assert close_f(f1, F[b], 1e-14) and rel_err(g1, G[:, b]) < G_TOL
     # lane independence: permuting the vectors permutes the results bitwise
     perm = rng.permutation(B)
     Fp, Gp = plp.calc_pl_grad_batch(np.ascontiguousarray(X[:, perm]), mode=eng.GRAD_AD)
@@ -269,7 +269,7 @@ def test_tile_kernel_equals_generic_kernel(name, B, mode, log_pen):
         ok = np.arange(B) != 3
         assert np.max(np.abs(F1[ok] - F2[ok]) / np.abs(F1[ok])) < 1e-13
         for b in np.flatnonzero(ok):
-            assert rel_err(G2[:, b], G1[:, b]) < 1e-12, (b, rel_err(G2[:, b], G1[:, b]))
+            assert rel_err(G2[:, b], G1[:, b]) < G_TOL, (b, rel_err(G2[:, b], G1[:, b]))
         o = plo.OracleProblem(gd.flat, log_pen=log_pen)
         for b in (0, B // 2, B - 1):
             cv = np.zeros(n, np.int32)

@@ -261,10 +261,24 @@ int sync_device_tree(tpl_engine* e) {
             r.y = rs >= 0 ? rs : -1;
             r.z = ds >= 0 ? ds : (e->dates[i] == 0.0 ? -1 : -2);
             const int nc = e->child_off[i + 1] - e->child_off[i];
-            if (nc == 0) r.w = -1;
-            else if (nc == 2 && (e->children[e->child_off[i]] == i + 1 || e->children[e->child_off[i] + 1] == i + 1))
-                r.w = (e->children[e->child_off[i]] == i + 1) ? e->children[e->child_off[i] + 1] : e->children[e->child_off[i]];
-            else r.w = -2;
+            // rec.w: >= 0 second child of a FAST binary node (first child is i+1); -1 FAST tip;
+            // -2 everything else (general path, children through the CSR list)
+            auto plain = [&](int v) { return e->freeparams[v] >= 0; };                     // has a rate row
+            auto dfree = [&](int v) { return e->freeparams[n + v] >= 0; };
+            auto dzero = [&](int v) { return e->freeparams[n + v] < 0 && e->dates[v] == 0.0; };
+            const int p = e->parent[i];
+            const bool par_ok = p > 0 && plain(p) && dfree(p);
+            r.w = -2;
+            if (par_ok && plain(i)) {
+                if (nc == 0 && dzero(i)) r.w = -1;
+                else if (nc == 2 && dfree(i)) {
+                    const int a0 = e->children[e->child_off[i]], a1 = e->children[e->child_off[i] + 1];
+                    const int other = (a0 == i + 1) ? a1 : a0;
+                    if ((a0 == i + 1 || a1 == i + 1) && a0 != a1 && plain(a0) && plain(a1) &&
+                        (dfree(a0) || dzero(a0)) && (dfree(a1) || dzero(a1)))
+                        r.w = other;
+                }
+            }
             recs[i] = r;
             if (rs >= 0) { if (next_r >= 0 && rs != next_r) ok = false; next_r = rs + 1; }
             if (ds >= 0) { if (next_d >= 0 && ds != next_d) ok = false; next_d = ds + 1; }

@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const
     double2* sCL = reinterpret_cast<double2*>(sRec + T);                   // [T]
     unsigned long long* sMask = reinterpret_cast<unsigned long long*>(sCL + T);   // [T]
     double2* sTab = reinterpret_cast<double2*>(sMask + T);                 // [LOG_TABLE_N]
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(sTab + LOG_TABLE_N);
+    double* sZero = reinterpret_cast<double*>(sTab + LOG_TABLE_N);         // [LW] zeros: the date row of every tip
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sZero + LW);
 
     const int tid = threadIdx.x;
     const int w = tid >> 5, tx = tid & 31;
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const
         if (MASK) sMask[j] = a.lanemask[(size_t)(n0 + j) * a.nchunks + chunk];
     }
     sTab[tid] = a.logtab[tid];
+    if (tid < LW) sZero[tid] = 0.0;
     __syncthreads();
     mbar_wait(mbar, 0);
 
@@ -157,11 +159,105 @@ __global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const
             return (unsigned)(mw >> shl) & 3u;
         };
 
+        // ---- fast path: a tip or a binary internal node whose parent and children are ordinary free
+        // parameters (host-classified, rec.w != -2) and whose operands are all in the ordinary range.
+        // Straight-line code: operands through generic pointers (tile row in shared memory or halo row
+        // in global memory), tips' dates from a shared zero row, CV masks as predicates.  Nothing is
+        // committed unless every operand passed the range test; otherwise the general path runs.
+        constexpr bool FASTABLE = !(LOGPEN && MODE == 0);
+        auto fast_row = [&](int j, const int4& rec, const double2& cl, unsigned mi) -> bool {
+            const int i = n0 + j;
+            const bool tip = rec.w == -1;
+            const double2 r2 = *reinterpret_cast<const double2*>(sR + (rec.y - ti.rs0) * LW + 2 * tx);
+            const double* ph = tip ? (sZero + 2 * tx) : (sH + (rec.z - ti.ds0) * LW + 2 * tx);
+            const double2 h2 = *reinterpret_cast<const double2*>(ph);
+            const int p = rec.x;
+            const bool pin = p >= n0;
+            const int4 prec = *(pin ? (const int4*)(sRec + (p - n0)) : (ta.recs + p));
+            const double* php = pin ? (const double*)(sH + (prec.z - ti.ds0) * LW + 2 * tx)
+                                    : (X + ((unsigned)prec.z * B + (unsigned)lane));
+            const double* prp = pin ? (const double*)(sR + (prec.y - ti.rs0) * LW + 2 * tx)
+                                    : (X + ((unsigned)prec.y * B + (unsigned)lane));
+            const double2 hp2 = *reinterpret_cast<const double2*>(php);
+            const double2 rp2 = *reinterpret_cast<const double2*>(prp);
+            const double r[2] = {r2.x, r2.y}, h[2] = {h2.x, h2.y};
+            const double hp[2] = {hp2.x, hp2.y}, rp[2] = {rp2.x, rp2.y};
+            bool ok = true;
+            double ll[2], g_r[2], g_h[2], q[2];
+#pragma unroll
+            for (int l = 0; l < 2; l++) {
+                const double d = hp[l] - h[l];
+                ok = ok && in_range400(r[l]) && in_range400(d);
+                if (MODE == 0 && !tip) ok = ok && (__double2hiint(h[l]) >= 0);       // h < 0 -> LARGE (:74-78)
+                const double xx = r[l] * d;
+                const double ac = cl.x * fast_rcp(xx);
+                g_r[l] = fma(-ac, d, d);                                             // d - c/r
+                g_h[l] = -fma(-ac, r[l], r[l]);                                      // -(r - c/d)
+                ll[l] = fma(-cl.x, fast_log(xx, sTab), xx) + cl.y;
+                q[l] = r[l] - rp[l];
+                if (WANT_G) g_r[l] = fma(lam2[l], q[l], g_r[l]);
+            }
+            if (WANT_G && !tip) {
+                const int c1 = i + 1, c2 = rec.w;
+                const bool in1 = j + 1 < tn, in2 = c2 < n1;
+                const int4 cr1 = *(in1 ? (const int4*)(sRec + j + 1) : (ta.recs + c1));
+                const int4 cr2 = *(in2 ? (const int4*)(sRec + (c2 - n0)) : (ta.recs + c2));
+                const double cc1 = (in1 ? (const double2*)(sCL + j + 1) : (ta.clf + c1))->x;
+                const double cc2 = (in2 ? (const double2*)(sCL + (c2 - n0)) : (ta.clf + c2))->x;
+                const double* pr1 = in1 ? (const double*)(sR + (cr1.y - ti.rs0) * LW + 2 * tx) : (X + ((unsigned)cr1.y * B + (unsigned)lane));
+                const double* pr2 = in2 ? (const double*)(sR + (cr2.y - ti.rs0) * LW + 2 * tx) : (X + ((unsigned)cr2.y * B + (unsigned)lane));
+                const double* ph1 = cr1.z < 0 ? (const double*)(sZero + 2 * tx)
+                                   : (in1 ? (const double*)(sH + (cr1.z - ti.ds0) * LW + 2 * tx) : (X + ((unsigned)cr1.z * B + (unsigned)lane)));
+                const double* ph2 = cr2.z < 0 ? (const double*)(sZero + 2 * tx)
+                                   : (in2 ? (const double*)(sH + (cr2.z - ti.ds0) * LW + 2 * tx) : (X + ((unsigned)cr2.z * B + (unsigned)lane)));
+                const double2 rc1 = *reinterpret_cast<const double2*>(pr1), rc2 = *reinterpret_cast<const double2*>(pr2);
+                const double2 hc1 = *reinterpret_cast<const double2*>(ph1), hc2 = *reinterpret_cast<const double2*>(ph2);
+                const unsigned m1 = mask_of(c1, in1), m2 = mask_of(c2, in2);
+                const double rca[2][2] = {{rc1.x, rc1.y}, {rc2.x, rc2.y}};
+                const double hca[2][2] = {{hc1.x, hc1.y}, {hc2.x, hc2.y}};
+                const double cca[2] = {cc1, cc2};
+                const unsigned mca[2] = {m1, m2};
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+#pragma unroll
+                    for (int l = 0; l < 2; l++) {
+                        const double dc = h[l] - hca[k][l];
+                        ok = ok && in_range400(rca[k][l]) && in_range400(dc);
+                        const double acc = cca[k] * fast_rcp(rca[k][l] * dc);
+                        const double dlt = fma(-acc, rca[k][l], rca[k][l]);         // r_ch - c_ch/d_ch
+                        const double dq = rca[k][l] - r[l];
+                        if (!MASK || !((mca[k] >> l) & 1u)) {
+                            g_h[l] += dlt;
+                            g_r[l] = fma(-lam2[l], dq, g_r[l]);
+                        }
+                    }
+                }
+            }
+            if (!ok) return false;
+#pragma unroll
+            for (int l = 0; l < 2; l++) {
+                if (!MASK || !((mi >> l) & 1u)) {
+                    acc_ll[l] += ll[l];
+                    acc_su[l] = fma(q[l], q[l], acc_su[l]);
+                } else {
+                    g_r[l] = 0.0;
+                }
+            }
+            if (WANT_G) {
+                *reinterpret_cast<double2*>(a.G + ((unsigned)rec.y * B + (unsigned)lane)) = make_double2(g_r[0], g_r[1]);
+                if (!tip) *reinterpret_cast<double2*>(a.G + ((unsigned)rec.z * B + (unsigned)lane)) = make_double2(g_h[0], g_h[1]);
+            }
+            return true;
+        };
+
         for (int j = w; j < tn; j += 8) {
             const int i = n0 + j;
             const int4 rec = sRec[j];
             const double2 cl = sCL[j];
             const unsigned mi = mask_of(i, true);
+            if (FASTABLE && rec.w != -2 && (rec.w == -1 || mi == 0u)) {
+                if (fast_row(j, rec, cl, mi)) continue;
+            }
             double r[2], h[2];
             rate_of(i, rec, true, r);
             date_of(i, rec, true, h);
@@ -318,7 +414,7 @@ __global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const
 
 inline size_t tile_kernel_smem(int hrows) {
     return (size_t)TILE_NODES * TILE_LANES * 8 + (size_t)hrows * TILE_LANES * 8 + TILE_NODES * (16 + 16 + 8) +
-           LOG_TABLE_N * 16 + 16;
+           LOG_TABLE_N * 16 + TILE_LANES * 8 + 16;
 }
 
 }  // namespace tpl
