@@ -115,10 +115,11 @@ struct tpl_engine {
     // scatter of it over the base member values; materialised lazily, only when someone reads it)
     bool last_x_valid = false;
     // ---- device tree ----
-    DevBuf<int> d_parent, d_rslot, d_dslot, d_child_off, d_children, d_bar_node;
+    DevBuf<int> d_parent, d_rslot, d_dslot, d_child_off, d_children, d_bar_ds;
+    DevBuf<double> d_bar_hfix;
     DevBuf<unsigned char> d_cv;
     DevBuf<double> d_c, d_lf, d_hfix, d_rfix, d_bar_pmin, d_bar_pmax, d_bnd_min, d_bnd_max;
-    DevBuf<int> d_bnd_node;
+    DevBuf<int> d_bnd_ds;
     DevBuf<double2> d_logtab;
     int nbnd = 0;
     // generation-2 (tile kernel) operands
@@ -184,18 +185,6 @@ int sync_device_tree(tpl_engine* e) {
         std::vector<double2> clf(n);
         for (int i = 0; i < n; i++) clf[i] = make_double2(e->c[i], e->lf[i]);
         CK(e->d_clf.upload(clf, s));
-        std::vector<int> bn;
-        std::vector<double> bmin, bmax;
-        for (int i = 0; i < n; i++)
-            if (e->pen_min[i] != -1 || e->pen_max[i] != -1) {
-                bn.push_back(i);
-                bmin.push_back(e->pen_min[i]);
-                bmax.push_back(e->pen_max[i]);
-            }
-        e->nbar = (int)bn.size();
-        CK(e->d_bar_node.upload(bn, s));
-        CK(e->d_bar_pmin.upload(bmin, s));
-        CK(e->d_bar_pmax.upload(bmax, s));
         e->sum_c = 0.0;
         for (int i = 0; i < n; i++) e->sum_c += e->c[i];
         std::vector<double2> tab;
@@ -228,6 +217,23 @@ int sync_device_tree(tpl_engine* e) {
             bool fixed = !e->have_fp || e->freeparams[n + i] == -1;
             if (fixed && (e->dates[i] < e->hmin[i] || e->dates[i] > e->hmax[i])) e->static_bad = true;
         }
+        // ---- sparse calibration barrier rows, ascending node order (calc_penalty :975-998) ----
+        {
+            std::vector<int> bds;
+            std::vector<double> bhf, pmin, pmax;
+            for (int i = 0; i < n; i++)
+                if (e->pen_min[i] != -1 || e->pen_max[i] != -1) {
+                    bds.push_back(e->have_fp ? e->freeparams[n + i] : -1);
+                    bhf.push_back(e->dates[i]);
+                    pmin.push_back(e->pen_min[i]);
+                    pmax.push_back(e->pen_max[i]);
+                }
+            e->nbar = (int)bds.size();
+            CK(e->d_bar_ds.upload(bds, s));
+            CK(e->d_bar_hfix.upload(bhf, s));
+            CK(e->d_bar_pmin.upload(pmin, s));
+            CK(e->d_bar_pmax.upload(pmax, s));
+        }
         // ---- sparse bound rows: free dates whose [min,max] is not implied by a neighbour ----
         std::vector<int> bn;
         std::vector<double> bmin, bmax;
@@ -239,13 +245,13 @@ int sync_device_tree(tpl_engine* e) {
             for (int j = e->child_off[i]; j < e->child_off[i + 1]; j++)
                 if (e->hmin[e->children[j]] >= e->hmin[i]) { min_implied = true; break; }
             if (!(max_implied && min_implied)) {
-                bn.push_back(i);
+                bn.push_back(e->freeparams[n + i]);
                 bmin.push_back(e->hmin[i]);
                 bmax.push_back(e->hmax[i]);
             }
         }
         e->nbnd = (int)bn.size();
-        CK(e->d_bnd_node.upload(bn, s));
+        CK(e->d_bnd_ds.upload(bn, s));
         CK(e->d_bnd_min.upload(bmin, s));
         CK(e->d_bnd_max.upload(bmax, s));
         // ---- generation-2 operands: packed records, tile table ----
@@ -267,14 +273,16 @@ int sync_device_tree(tpl_engine* e) {
             auto dfree = [&](int v) { return e->freeparams[n + v] >= 0; };
             auto dzero = [&](int v) { return e->freeparams[n + v] < 0 && e->dates[v] == 0.0; };
             const int p = e->parent[i];
-            const bool par_ok = p > 0 && plain(p) && dfree(p);
+            const int t0 = (i / tpl::TILE_NODES) * tpl::TILE_NODES, t1 = t0 + tpl::TILE_NODES;
+            auto local = [&](int v) { return v >= t0 && v < t1; };                         // same tile
+            const bool par_ok = p > 0 && plain(p) && dfree(p) && local(p);
             r.w = -2;
             if (par_ok && plain(i)) {
                 if (nc == 0 && dzero(i)) r.w = -1;
                 else if (nc == 2 && dfree(i)) {
                     const int a0 = e->children[e->child_off[i]], a1 = e->children[e->child_off[i] + 1];
                     const int other = (a0 == i + 1) ? a1 : a0;
-                    if ((a0 == i + 1 || a1 == i + 1) && a0 != a1 && plain(a0) && plain(a1) &&
+                    if ((a0 == i + 1 || a1 == i + 1) && a0 != a1 && local(a0) && local(a1) && plain(a0) && plain(a1) &&
                         (dfree(a0) || dzero(a0)) && (dfree(a1) || dzero(a1)))
                         r.w = other;
                 }
@@ -324,11 +332,12 @@ tpl::DevTree dev_tree(tpl_engine* e) {
     t.hfix = e->d_hfix.p;
     t.rfix = e->d_rfix.p;
     t.nbnd = e->nbnd;
-    t.bnd_node = e->d_bnd_node.p;
+    t.bnd_ds = e->d_bnd_ds.p;
     t.bnd_min = e->d_bnd_min.p;
     t.bnd_max = e->d_bnd_max.p;
     t.nbar = e->nbar;
-    t.bar_node = e->d_bar_node.p;
+    t.bar_ds = e->d_bar_ds.p;
+    t.bar_hfix = e->d_bar_hfix.p;
     t.bar_pmin = e->d_bar_pmin.p;
     t.bar_pmax = e->d_bar_pmax.p;
     t.sum_c = e->sum_c;

@@ -41,12 +41,13 @@ struct DevTree {
     // a neighbour are listed: h_i <= h_parent <= max_parent <= max_i makes an inherited max redundant
     // once every duration is checked to be >= 0, and likewise an inherited min through a child.
     int nbnd;
-    const int* bnd_node;          // [nbnd]
+    const int* bnd_ds;            // [nbnd] date row of the node (always free)
     const double* bnd_min;        // [nbnd]
     const double* bnd_max;        // [nbnd]
     // sparse calibration barrier rows, ascending node order (calc_penalty :975-998)
     int nbar;
-    const int* bar_node;          // [nbar]
+    const int* bar_ds;            // [nbar] date row of the node, -1 = fixed date
+    const double* bar_hfix;       // [nbar] the fixed date when bar_ds < 0
     const double* bar_pmin;       // [nbar] -1 = none
     const double* bar_pmax;       // [nbar] -1 = none
     double sum_c;                 // sum of char_durations over ALL nodes (calc_lf_gradient :675)
@@ -298,14 +299,31 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const EvalAr
         const int k0 = seg * len, k1 = min(a.ntiles, k0 + len);
         double ll = 0.0, su = 0.0, gr = 0.0;
         int bad = 0;
-        if (active)
-            for (int k = k0; k < k1; k++) {
+        if (active) {
+            // four independent chains so the loads of consecutive tiles overlap; fixed grouping
+            double l4[4] = {0, 0, 0, 0}, s4[4] = {0, 0, 0, 0}, g4[4] = {0, 0, 0, 0};
+            int k = k0;
+            for (; k + 4 <= k1; k += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const size_t o = (size_t)(k + u) * B + lane;
+                    l4[u] += a.part_ll[o];
+                    if (!LF) s4[u] += a.part_su[o];
+                    if (LF) g4[u] += a.part_gr[o];
+                    bad |= a.part_bad[o];
+                }
+            }
+            for (; k < k1; k++) {
                 const size_t o = (size_t)k * B + lane;
-                ll += a.part_ll[o];
-                if (!LF) su += a.part_su[o];
-                if (LF) gr += a.part_gr[o];
+                l4[0] += a.part_ll[o];
+                if (!LF) s4[0] += a.part_su[o];
+                if (LF) g4[0] += a.part_gr[o];
                 bad |= a.part_bad[o];
             }
+            ll = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+            su = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            gr = (g4[0] + g4[1]) + (g4[2] + g4[3]);
+        }
         s_sum[0][seg][tx] = ll;
         s_sum[1][seg][tx] = su;
         s_sum[2][seg][tx] = gr;
@@ -323,9 +341,7 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const EvalAr
     }
     const double* __restrict__ X = a.X;
     for (int k = 0; k < t.nbnd; k++) {                                   // set_durations :887-896
-        const int ds = t.dslot[t.bnd_node[k]];
-        if (ds < 0) continue;                                            // fixed dates are checked on the host
-        const double h = X[(size_t)ds * B + lane];
+        const double h = X[(size_t)t.bnd_ds[k] * B + lane];               // fixed dates are checked on the host
         if (h < t.bnd_min[k] || h > t.bnd_max[k]) bad = 1;
     }
     double f;
@@ -360,9 +376,8 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const EvalAr
         // ---- barrier ----
         double tpen = 0.0;
         for (int k = 0; k < t.nbar; k++) {
-            const int i = t.bar_node[k];
-            const int ds = t.dslot[i];
-            const double h = (ds >= 0) ? X[(size_t)ds * B + lane] : t.hfix[i];
+            const int ds = t.bar_ds[k];
+            const double h = (ds >= 0) ? X[(size_t)ds * B + lane] : t.bar_hfix[k];
             const double pmn = t.bar_pmin[k], pmx = t.bar_pmax[k];
             if (MODE == 0) {
                 if (pmn != -1.0) { tpen += 1.0 / (h - pmn); if (isinf(tpen)) tpen = 0.0; }    // :981-985
@@ -397,8 +412,7 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const EvalAr
             }
             if (MODE == 1 && !bar_dead) {
                 for (int k = 0; k < t.nbar; k++) {
-                    const int i = t.bar_node[k];
-                    const int ds = t.dslot[i];
+                    const int ds = t.bar_ds[k];
                     if (ds < 0) continue;
                     const double h = X[(size_t)ds * B + lane];
                     const double pmn = t.bar_pmin[k], pmx = t.bar_pmax[k];

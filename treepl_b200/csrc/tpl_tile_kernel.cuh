@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const
     double2* sTab = reinterpret_cast<double2*>(sMask + T);                 // [LOG_TABLE_N]
     double* sZero = reinterpret_cast<double*>(sTab + LOG_TABLE_N);         // [LW] zeros: the date row of every tip
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sZero + LW);
+    int* sNext = reinterpret_cast<int*>(mbar + 1);
 
     const int tid = threadIdx.x;
     const int w = tid >> 5, tx = tid & 31;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const
     const double* __restrict__ X = a.X;
 
     if (tid == 0) {
+        *sNext = 0;
         mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -160,26 +162,19 @@ __global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const
         };
 
         // ---- fast path: a tip or a binary internal node whose parent and children are ordinary free
-        // parameters (host-classified, rec.w != -2) and whose operands are all in the ordinary range.
-        // Straight-line code: operands through generic pointers (tile row in shared memory or halo row
-        // in global memory), tips' dates from a shared zero row, CV masks as predicates.  Nothing is
+        // parameters AND lie in this tile (host-classified: rec.w != -2; ~90 % of the rows), and whose
+        // operands are all in the ordinary range.  Straight-line code, shared-memory operands only
+        // (32-bit addressing), tips' dates from a shared zero row, CV masks as predicates.  Nothing is
         // committed unless every operand passed the range test; otherwise the general path runs.
         constexpr bool FASTABLE = !(LOGPEN && MODE == 0);
         auto fast_row = [&](int j, const int4& rec, const double2& cl, unsigned mi) -> bool {
-            const int i = n0 + j;
             const bool tip = rec.w == -1;
             const double2 r2 = *reinterpret_cast<const double2*>(sR + (rec.y - ti.rs0) * LW + 2 * tx);
             const double* ph = tip ? (sZero + 2 * tx) : (sH + (rec.z - ti.ds0) * LW + 2 * tx);
             const double2 h2 = *reinterpret_cast<const double2*>(ph);
-            const int p = rec.x;
-            const bool pin = p >= n0;
-            const int4 prec = *(pin ? (const int4*)(sRec + (p - n0)) : (ta.recs + p));
-            const double* php = pin ? (const double*)(sH + (prec.z - ti.ds0) * LW + 2 * tx)
-                                    : (X + ((unsigned)prec.z * B + (unsigned)lane));
-            const double* prp = pin ? (const double*)(sR + (prec.y - ti.rs0) * LW + 2 * tx)
-                                    : (X + ((unsigned)prec.y * B + (unsigned)lane));
-            const double2 hp2 = *reinterpret_cast<const double2*>(php);
-            const double2 rp2 = *reinterpret_cast<const double2*>(prp);
+            const int4 prec = sRec[rec.x - n0];
+            const double2 hp2 = *reinterpret_cast<const double2*>(sH + (prec.z - ti.ds0) * LW + 2 * tx);
+            const double2 rp2 = *reinterpret_cast<const double2*>(sR + (prec.y - ti.rs0) * LW + 2 * tx);
             const double r[2] = {r2.x, r2.y}, h[2] = {h2.x, h2.y};
             const double hp[2] = {hp2.x, hp2.y}, rp[2] = {rp2.x, rp2.y};
             bool ok = true;
@@ -198,25 +193,20 @@ __global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const
                 if (WANT_G) g_r[l] = fma(lam2[l], q[l], g_r[l]);
             }
             if (WANT_G && !tip) {
-                const int c1 = i + 1, c2 = rec.w;
-                const bool in1 = j + 1 < tn, in2 = c2 < n1;
-                const int4 cr1 = *(in1 ? (const int4*)(sRec + j + 1) : (ta.recs + c1));
-                const int4 cr2 = *(in2 ? (const int4*)(sRec + (c2 - n0)) : (ta.recs + c2));
-                const double cc1 = (in1 ? (const double2*)(sCL + j + 1) : (ta.clf + c1))->x;
-                const double cc2 = (in2 ? (const double2*)(sCL + (c2 - n0)) : (ta.clf + c2))->x;
-                const double* pr1 = in1 ? (const double*)(sR + (cr1.y - ti.rs0) * LW + 2 * tx) : (X + ((unsigned)cr1.y * B + (unsigned)lane));
-                const double* pr2 = in2 ? (const double*)(sR + (cr2.y - ti.rs0) * LW + 2 * tx) : (X + ((unsigned)cr2.y * B + (unsigned)lane));
-                const double* ph1 = cr1.z < 0 ? (const double*)(sZero + 2 * tx)
-                                   : (in1 ? (const double*)(sH + (cr1.z - ti.ds0) * LW + 2 * tx) : (X + ((unsigned)cr1.z * B + (unsigned)lane)));
-                const double* ph2 = cr2.z < 0 ? (const double*)(sZero + 2 * tx)
-                                   : (in2 ? (const double*)(sH + (cr2.z - ti.ds0) * LW + 2 * tx) : (X + ((unsigned)cr2.z * B + (unsigned)lane)));
-                const double2 rc1 = *reinterpret_cast<const double2*>(pr1), rc2 = *reinterpret_cast<const double2*>(pr2);
-                const double2 hc1 = *reinterpret_cast<const double2*>(ph1), hc2 = *reinterpret_cast<const double2*>(ph2);
-                const unsigned m1 = mask_of(c1, in1), m2 = mask_of(c2, in2);
+                const int j2 = rec.w - n0;
+                const int4 cr1 = sRec[j + 1];
+                const int4 cr2 = sRec[j2];
+                const double cca[2] = {sCL[j + 1].x, sCL[j2].x};
+                const double2 rc1 = *reinterpret_cast<const double2*>(sR + (cr1.y - ti.rs0) * LW + 2 * tx);
+                const double2 rc2 = *reinterpret_cast<const double2*>(sR + (cr2.y - ti.rs0) * LW + 2 * tx);
+                const double* ph1 = cr1.z < 0 ? (sZero + 2 * tx) : (sH + (cr1.z - ti.ds0) * LW + 2 * tx);
+                const double* ph2 = cr2.z < 0 ? (sZero + 2 * tx) : (sH + (cr2.z - ti.ds0) * LW + 2 * tx);
+                const double2 hc1 = *reinterpret_cast<const double2*>(ph1);
+                const double2 hc2 = *reinterpret_cast<const double2*>(ph2);
+                unsigned mca[2] = {0u, 0u};
+                if (MASK) { mca[0] = (unsigned)(sMask[j + 1] >> shl) & 3u; mca[1] = (unsigned)(sMask[j2] >> shl) & 3u; }
                 const double rca[2][2] = {{rc1.x, rc1.y}, {rc2.x, rc2.y}};
                 const double hca[2][2] = {{hc1.x, hc1.y}, {hc2.x, hc2.y}};
-                const double cca[2] = {cc1, cc2};
-                const unsigned mca[2] = {m1, m2};
 #pragma unroll
                 for (int k = 0; k < 2; k++) {
 #pragma unroll
@@ -250,6 +240,8 @@ __global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const
             return true;
         };
 
+        // static row assignment (warp w takes rows w, w+8, ...): which warp sums which rows must not
+        // depend on timing, or the objective would not be bitwise reproducible
         for (int j = w; j < tn; j += 8) {
             const int i = n0 + j;
             const int4 rec = sRec[j];
@@ -414,7 +406,7 @@ __global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const
 
 inline size_t tile_kernel_smem(int hrows) {
     return (size_t)TILE_NODES * TILE_LANES * 8 + (size_t)hrows * TILE_LANES * 8 + TILE_NODES * (16 + 16 + 8) +
-           LOG_TABLE_N * 16 + TILE_LANES * 8 + 16;
+           LOG_TABLE_N * 16 + TILE_LANES * 8 + 32;
 }
 
 }  // namespace tpl
