@@ -168,7 +168,7 @@ def test_large_tree_properties_100k_nodes():
         X[n - 1:, b] = x0[n - 1:]
     plp.batch_configure(B)
     F, G = plp.calc_pl_grad_batch(X, mode=eng.GRAD_AD)
-    assert plp.last_kernel_generation() == 2          # the bench configuration runs the tile kernel
+    assert plp.last_kernel_generation() == 3          # the bench configuration runs the persistent tile kernel
     for b in (0, 17, 63):
         f, g = o.calc_function_gradient(X[:, b])
         assert close_f(F[b], f), (b, F[b], f)
@@ -262,9 +262,16 @@ def test_tile_kernel_equals_generic_kernel(name, B, mode, log_pen):
         plp.force_kernel(1)
         F1, G1 = plp.calc_pl_grad_batch(X, mode=mode)
         assert plp.last_kernel_generation() == 1
+        plp.force_kernel(3)                                  # persistent ring kernel
+        F3, G3 = plp.calc_pl_grad_batch(X, mode=mode)
+        assert plp.last_kernel_generation() == 3
+        F3b, G3b = plp.calc_pl_grad_batch(X, mode=mode)
+        assert np.array_equal(F3, F3b) and np.array_equal(G3, G3b, equal_nan=True)     # deterministic
         plp.force_kernel(2)
         F2, G2 = plp.calc_pl_grad_batch(X, mode=mode)
         assert plp.last_kernel_generation() == 2
+        assert np.array_equal(G3, G2, equal_nan=True)        # same row code: gradient rows bitwise equal
+        assert F3[3] == 1e15 and np.max(np.abs(F3[np.arange(B) != 3] - F2[np.arange(B) != 3]) / np.abs(F2[np.arange(B) != 3])) < 1e-13
         F2b, G2b = plp.calc_pl_grad_batch(X, mode=mode)
         assert np.array_equal(F2, F2b) and np.array_equal(G2, G2b, equal_nan=True)     # deterministic
         F2o, _ = plp.calc_pl_grad_batch(X, mode=mode, want_grad=False)
@@ -308,7 +315,7 @@ def test_polytomy_and_unary_nodes_use_the_csr_child_path():
     X = np.repeat(x0[:, None], B, axis=1)
     X[: ft.numnodes - 1, :] = 2.0 * np.exp(0.3 * rng.randn(ft.numnodes - 1, B))
     plp.batch_configure(B)
-    for gen in (1, 2):
+    for gen in (1, 2, 3):
         plp.force_kernel(gen)
         for mode in (eng.GRAD_ANALYTIC, eng.GRAD_AD):
             F, G = plp.calc_pl_grad_batch(X, mode=mode)

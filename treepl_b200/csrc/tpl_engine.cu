@@ -97,6 +97,8 @@ void build_log_table(std::vector<double2>& tab) {
 struct tpl_engine {
     int device = 0;
     int sm = 0;
+    int num_sms = 148;
+    size_t max_smem = 227 * 1024;
     int n = 0;
     cudaStream_t stream = nullptr;
     // ---- host mirrors of pl_calc_parallel's inputs / members ----
@@ -182,7 +184,8 @@ int sync_device_tree(tpl_engine* e) {
         CK(e->d_children.upload(e->children, s));
         CK(e->d_c.upload(e->c, s));
         CK(e->d_lf.upload(e->lf, s));
-        std::vector<double2> clf(n);
+        const int npad = ((n + tpl::TILE_NODES - 1) / tpl::TILE_NODES) * tpl::TILE_NODES;
+        std::vector<double2> clf(npad, make_double2(0.0, 0.0));     // padded: the persistent kernel copies whole tiles
         for (int i = 0; i < n; i++) clf[i] = make_double2(e->c[i], e->lf[i]);
         CK(e->d_clf.upload(clf, s));
         e->sum_c = 0.0;
@@ -257,7 +260,8 @@ int sync_device_tree(tpl_engine* e) {
         // ---- generation-2 operands: packed records, tile table ----
         e->cv_any = false;
         for (int i = 0; i < n; i++) if (e->cv[i]) e->cv_any = true;
-        std::vector<int4> recs(n);
+        const int npad = ((n + tpl::TILE_NODES - 1) / tpl::TILE_NODES) * tpl::TILE_NODES;
+        std::vector<int4> recs(npad, make_int4(-1, -1, -1, -2));
         bool ok = e->have_fp && !e->lf_mode;
         int next_r = -1, next_d = -1;
         for (int i = 0; i < n && e->have_fp; i++) {
@@ -348,6 +352,7 @@ tpl::DevTree dev_tree(tpl_engine* e) {
 }
 
 struct LaunchCfg {
+    int gen;
     bool lf, lp, want_g;
     int maskmode;          // 0 none, 1 engine cv, 2 per-vector
     bool gen2;
@@ -363,10 +368,17 @@ cudaError_t launch_pair(const tpl::EvalArgs& a, const LaunchCfg& c) {
     if (c.ev) cudaEventRecord(c.ev[0], c.s);
     if (c.gen2) {
         if constexpr (!LF && MASKMODE != 1) {
-            auto kern = tpl::pl_tile_kernel<MODE, LOGPEN, WANT_G, MASKMODE == 2>;
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
-            if (e != cudaSuccess) return e;
-            kern<<<c.grid, c.block, c.smem, c.s>>>(a, c.ta);
+            if (c.gen == 3) {
+                auto kern = tpl::pl_persist_kernel<MODE, LOGPEN, WANT_G, MASKMODE == 2>;
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+                if (e != cudaSuccess) return e;
+                kern<<<c.grid, c.block, c.smem, c.s>>>(a, c.ta);
+            } else {
+                auto kern = tpl::pl_tile_kernel<MODE, LOGPEN, WANT_G, MASKMODE == 2>;
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+                if (e != cudaSuccess) return e;
+                kern<<<c.grid, c.block, c.smem, c.s>>>(a, c.ta);
+            }
         }
     } else {
         tpl::pl_main_kernel<MODE, LF, LOGPEN, WANT_G, MASKMODE><<<c.grid, c.block, 0, c.s>>>(a);
@@ -405,20 +417,38 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
     const int n = e->n;
     const bool lanemask = use_cfg && e->cfg_mask && e->cfg_B == B;
     const int maskmode = lanemask ? 2 : (e->cv_any ? 1 : 0);
-    // generation 2 (tile kernel): PL, dense slot map, even B, 32-bit element offsets
-    bool gen2 = e->gen2_ok && !e->lf_mode && maskmode != 1 && (B % 2 == 0) && B >= 32 &&
-                (double)e->numparams * (double)B < 2.0e9;
-    if (e->force_gen == 1) gen2 = false;
-    if (e->force_gen == 2)
-        gen2 = e->gen2_ok && !e->lf_mode && maskmode != 1 && (B % 2 == 0) && (double)e->numparams * (double)B < 2.0e9;
+    // generations 2/3 (tile kernels): PL, dense slot map, even B, 32-bit element offsets
+    const bool tile_legal = e->gen2_ok && !e->lf_mode && maskmode != 1 && (B % 2 == 0) &&
+                            (double)e->numparams * (double)B < 2.0e9;
+    const int nchunks2 = (B + tpl::TILE_LANES - 1) / tpl::TILE_LANES;
+    const long long W = (long long)nchunks2 * e->ntiles2;
+    const int G = (int)std::min<long long>(e->num_sms, W);
+    // generation 3 (persistent ring) additionally needs every CTA's item range to touch <= 2 chunks
+    const bool persist_legal = tile_legal && nchunks2 <= G && tpl::persist_kernel_smem(e->tile_hrows) <= e->max_smem;
+    int gen = 1;
+    if (tile_legal && B >= 32) gen = persist_legal ? 3 : 2;
+    if (e->force_gen == 1) gen = 1;
+    if (e->force_gen == 2 && tile_legal) gen = 2;
+    if (e->force_gen == 3 && persist_legal) gen = 3;
+    const bool gen2 = gen >= 2;
     LaunchCfg c;
+    c.gen = gen;
     int ntiles, tile;
-    if (gen2) {
+    size_t npart;
+    if (gen == 3) {
         tile = tpl::TILE_NODES;
         ntiles = e->ntiles2;
-        c.grid = dim3(ntiles, (B + tpl::TILE_LANES - 1) / tpl::TILE_LANES);
+        c.grid = dim3(G);
+        c.block = dim3(tpl::P_THREADS);
+        c.smem = tpl::persist_kernel_smem(e->tile_hrows);
+        npart = (size_t)G * 2 * tpl::P_CONSUMER_WARPS * tpl::TILE_LANES;
+    } else if (gen == 2) {
+        tile = tpl::TILE_NODES;
+        ntiles = e->ntiles2;
+        c.grid = dim3(ntiles, nchunks2);
         c.block = dim3(256);
         c.smem = tpl::tile_kernel_smem(e->tile_hrows);
+        npart = (size_t)ntiles * B;
     } else {
         // block shape: LX lanes x NY node rows, 256 threads
         int LX = 1;
@@ -429,11 +459,12 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
         c.grid = dim3(ntiles, (B + LX - 1) / LX);
         c.block = dim3(LX, NY);
         c.smem = 0;
+        npart = (size_t)ntiles * B;
     }
-    CK(e->d_part_ll.ensure((size_t)ntiles * B));
-    CK(e->d_part_su.ensure((size_t)ntiles * B));
-    CK(e->d_part_gr.ensure((size_t)ntiles * B));
-    CK(e->d_part_bad.ensure((size_t)ntiles * B));
+    CK(e->d_part_ll.ensure(npart));
+    CK(e->d_part_su.ensure(npart));
+    CK(e->d_part_gr.ensure(npart));
+    CK(e->d_part_bad.ensure(npart));
     tpl::EvalArgs a;
     a.t = dev_tree(e);
     a.X = dX;
@@ -442,6 +473,12 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
     a.B = B;
     a.lanemask = lanemask ? e->d_lanemask.p : nullptr;
     a.nchunks = e->cfg_nchunks;
+    a.mask_stride = e->ntiles2 * tpl::TILE_NODES;
+    a.part_mode = gen == 3 ? 1 : 0;
+    a.p_ncta = G;
+    a.p_ntiles = e->ntiles2;
+    a.p_nchunks = nchunks2;
+    a.p_nwarps = tpl::P_CONSUMER_WARPS;
     a.lane_lambda = (use_cfg && e->cfg_lambda && e->cfg_B == B) ? e->d_lane_lambda.p : nullptr;
     a.lambda = e->smoothing;
     a.pb = e->pb;
@@ -461,11 +498,14 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
     c.ta.clf = e->d_clf.p;
     c.ta.tiles = e->d_tiles.p;
     c.ta.hrows = e->tile_hrows;
+    c.ta.ntiles = e->ntiles2;
+    c.ta.nchunks = nchunks2;
+    c.ta.ncta = G;
     c.s = s;
     c.ev = nullptr;
     if (e->timing && e->ev_used + 3 <= e->ev.size()) { c.ev = &e->ev[e->ev_used]; e->ev_used += 3; }
     CK(mode == TPL_GRAD_ANALYTIC ? launch_lf<0>(a, c) : launch_lf<1>(a, c));
-    e->last_gen = gen2 ? 2 : 1;
+    e->last_gen = gen;
     e->last_launches = 2;
     return TPL_OK;
 }
@@ -536,6 +576,8 @@ int tpl_create(tpl_engine** out, int device, int numnodes, const int* parents, c
     tpl_engine* e = new tpl_engine();
     e->device = device;
     e->sm = prop.major * 100 + prop.minor * 10;
+    e->num_sms = prop.multiProcessorCount;
+    e->max_smem = prop.sharedMemPerBlockOptin;
     e->n = numnodes;
     const int n = numnodes;
     e->parent.assign(parents, parents + n);
@@ -694,12 +736,13 @@ int tpl_batch_configure(tpl_engine* e, int B, const double* lane_smoothing, cons
     if (e->cfg_mask) {
         if (!mask_nodes && mask_off[B] > 0) return fail(TPL_ERR_ARG, "mask_nodes is null");
         const int nch = (B + 63) / 64;
-        std::vector<unsigned long long> bits((size_t)e->n * nch, 0ull);
+        const size_t npad = (size_t)((e->n + tpl::TILE_NODES - 1) / tpl::TILE_NODES) * tpl::TILE_NODES;
+        std::vector<unsigned long long> bits(npad * nch, 0ull);
         for (int b = 0; b < B; b++)
             for (int k = mask_off[b]; k < mask_off[b + 1]; k++) {
                 int node = mask_nodes[k];
                 if (node < 0 || node >= e->n) return fail(TPL_ERR_ARG, "mask node out of range");
-                bits[(size_t)node * nch + (b >> 6)] |= 1ull << (b & 63);
+                bits[(size_t)(b >> 6) * npad + node] |= 1ull << (b & 63);
             }
         e->cfg_nchunks = nch;
         CK(e->d_lanemask.upload(bits, e->stream));
@@ -735,7 +778,7 @@ int tpl_calc_pl_grad_batch(tpl_engine* e, int B, const double* X, double* F, dou
 }
 
 int tpl_debug_force_kernel(tpl_engine* e, int gen) {
-    if (!e || gen < 0 || gen > 2) return fail(TPL_ERR_ARG, "bad argument");
+    if (!e || gen < 0 || gen > 3) return fail(TPL_ERR_ARG, "bad argument");
     e->force_gen = gen;
     return TPL_OK;
 }

@@ -60,8 +60,14 @@ struct EvalArgs {
     double* G;
     double* F;
     int B;
-    const unsigned long long* lanemask;   // [n][nchunks] bit b%64 of word b/64 = node masked for vector b; or null
+    const unsigned long long* lanemask;   // [nchunks][mask_stride] word (b/64, node): bit b%64 = node masked for vector b
     int nchunks;
+    int mask_stride;                      // >= n (padded to whole tiles)
+    // layout of the objective partials: 0 = [ntiles][B] (generations 1, 2);
+    // 1 = generation 3: entry ((cta*2 + slot)*p_nwarps + warp) holds 64 vectors of the chunk that CTA
+    //     was working on
+    int part_mode;
+    int p_ncta, p_ntiles, p_nchunks, p_nwarps;
     const double* lane_lambda;            // [B] or null
     double lambda;
     double pb;                            // penalty_boundary
@@ -87,7 +93,7 @@ __device__ __forceinline__ double log_any(double x, const double2* tab) {
 template <int MASKMODE>
 __device__ __forceinline__ bool is_masked(const EvalArgs& a, int node, int lane) {
     if (MASKMODE == 2) {
-        unsigned long long w = a.lanemask[(size_t)node * a.nchunks + (lane >> 6)];
+        unsigned long long w = a.lanemask[(size_t)(lane >> 6) * a.mask_stride + node];
         return (w >> (lane & 63)) & 1ull;
     } else if (MASKMODE == 1) {
         return a.t.cv[node] != 0;
@@ -294,7 +300,33 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const EvalAr
     const int tx = threadIdx.x, seg = threadIdx.y;
     const int lane = blockIdx.x * 32 + tx;
     const bool active = lane < B;
-    {
+    if (a.part_mode == 1) {
+        // generation-3 partials: CTA c owned work items [c W / G, (c+1) W / G) of the chunk-major list
+        // (chunk k = items [k ntiles, (k+1) ntiles)); slot 1 if the CTA had started in the previous chunk
+        const long long W = (long long)a.p_nchunks * a.p_ntiles, G = a.p_ncta;
+        const int k = lane >> 6, l = lane & 63;
+        const long long c0 = (long long)k * a.p_ntiles, c1 = c0 + a.p_ntiles;
+        const int len = (a.p_ncta + FIN_SEGS - 1) / FIN_SEGS;
+        const int g0 = seg * len, g1 = min(a.p_ncta, g0 + len);
+        double ll = 0.0, su = 0.0;
+        int bad = 0;
+        if (active)
+            for (int c = g0; c < g1; c++) {
+                const long long lo = c * W / G, hi = (c + 1) * W / G;
+                if (lo < c1 && hi > c0 && lo < hi) {
+                    const size_t o = ((size_t)c * 2 + (lo < c0 ? 1 : 0)) * a.p_nwarps * 64 + l;
+                    for (int wv = 0; wv < a.p_nwarps; wv++) {
+                        ll += a.part_ll[o + (size_t)wv * 64];
+                        su += a.part_su[o + (size_t)wv * 64];
+                        bad |= a.part_bad[o + (size_t)wv * 64];
+                    }
+                }
+            }
+        s_sum[0][seg][tx] = ll;
+        s_sum[1][seg][tx] = su;
+        s_sum[2][seg][tx] = 0.0;
+        s_bad[seg][tx] = bad;
+    } else {
         const int len = (a.ntiles + FIN_SEGS - 1) / FIN_SEGS;
         const int k0 = seg * len, k1 = min(a.ntiles, k0 + len);
         double ll = 0.0, su = 0.0, gr = 0.0;

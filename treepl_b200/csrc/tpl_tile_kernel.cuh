@@ -1,24 +1,30 @@
-// PL objective + gradient, generation 2 (sm_100a): shared-memory staged node tiles.
+// PL objective + gradient, generations 2 and 3 (sm_100a): shared-memory staged node tiles.
 //
 // Why (profiles/r01a_pull_kernel_ncu.md): the generation-1 kernel spends 304 warp instructions per
 // 32-lane node row, ~42 of them fp64 — it is bound by address arithmetic, topology loads and
-// memory latency, not by HBM (21 %) or the fp64 pipe (16 %).  This kernel removes that overhead:
+// memory latency, not by HBM (21 %) or the fp64 pipe (16 %).  These kernels remove that overhead:
 //
 //  * tile = 64 consecutive nodes (reference preorder) x 64 vectors.  In the reference parameter
 //    layout (generate_param_order_vector, utils.cpp:295-340) the rate rows of consecutive nodes are
 //    consecutive rows of X, and so are their free-date rows: a tile's operands are two dense row
-//    ranges.  One warp issues one cp.async.bulk (TMA, 512 B) per row into shared memory against an
-//    mbarrier; the CTA scheduler overlaps the load phase of one resident CTA with the compute phase
-//    of the others (3 CTAs/SM), so >100 KB of HBM reads are in flight per SM without any registers
-//    being held for them.
+//    ranges, fetched with one cp.async.bulk (TMA, 512 B) per row into shared memory against an
+//    mbarrier, together with the tile's packed topology records.
 //  * preorder locality: a node's parent is usually a few rows above it and its first child is the
-//    next row, so ~90 % of the parent/child operands are already in the tile; the rest ("halo")
-//    are read from global memory, where the neighbouring tile's CTA has just pulled them into L2.
+//    next row, so ~90 % of the rows find parent and children inside the tile (host-classified
+//    "fast" rows: straight-line code, LDS.128 operands, 32-bit addressing).  The other rows take a
+//    general path that reads halo operands from global memory (L2: the neighbouring tile has just
+//    pulled them) and reproduces every corner of the reference semantics.
 //  * each thread owns TWO vectors (one LDS.128 / STG.128 per operand row), so topology decoding,
-//    branches and address arithmetic are amortised over 64 vectors per warp row; node topology is
-//    one packed 16-byte record, element offsets are 32-bit.
+//    branches and address arithmetic are amortised over 64 vectors per warp row.
 //  * gradient rows are written exactly once by their owner straight from registers (coalesced
-//    512 B per warp), objective partials are reduced in fixed order: bitwise deterministic.
+//    512 B per warp); objective partials are reduced in a fixed order: bitwise deterministic.
+//
+// Generation 2 (pl_tile_kernel): one CTA per tile, load -> barrier -> compute -> barrier.
+//   profiles/r01d: 46 % of its stall samples are barrier waits (load phase + warp imbalance).
+// Generation 3 (pl_persist_kernel): one persistent CTA per SM, 24 consumer warps + 1 producer
+//   warp, 3-stage ring of tiles with full/empty mbarriers.  Consumers never wait for each other:
+//   a warp that finishes its rows of tile k moves on to tile k+1 while the producer refills the
+//   stage that all warps have released.  Objective accumulators stay in registers across tiles.
 #pragma once
 #include "tpl_kernels.cuh"
 
@@ -31,16 +37,21 @@ constexpr int TILE_LANES = 64;
 //   x parent
 //   y rslot : >= 0 row of X ; -1 rate = rfix[node]
 //   z dslot : >= 0 row of X ; -1 date is exactly 0 (tips) ; -2 date = hfix[node]
-//   w kid2  : >= 0 binary node with children (node+1, kid2) ; -1 tip ; -2 use the CSR child list
+//   w kind  : >= 0 FAST binary node, children (node+1, w), parent and children in the same tile
+//             -1   FAST tip, parent in the same tile
+//             -2   general row (children through the CSR list)
 struct TileInfo {
     int rs0, nrs, ds0, nds;
 };
 
 struct TileArgs {
-    const int4* recs;          // [n]
-    const double2* clf;        // [n] (char_duration, log_fact)
+    const int4* recs;          // [ntiles*64] (padded)
+    const double2* clf;        // [ntiles*64] (char_duration, log_fact)
     const TileInfo* tiles;     // [ntiles]
     int hrows;                 // max date rows of any tile (shared-memory sizing)
+    int ntiles;
+    int nchunks;
+    int ncta;                  // generation 3: persistent CTAs
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -50,6 +61,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     asm volatile(
@@ -71,69 +85,35 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg((const double2*)p); }
 
+// One staged tile as the row code sees it.
+struct TileView {
+    const double* sR;                 // [64][64] rate rows
+    const double* sH;                 // [hrows][64] date rows
+    const int4* sRec;                 // [64]
+    const double2* sCL;               // [64]
+    const unsigned long long* sMask;  // [64]
+    int n0, tn;
+    TileInfo ti;
+};
+
+// Rows row0, row0+row_step, ... of the tile, for this thread's two vectors (lane, lane+1).
 template <int MODE, bool LOGPEN, bool WANT_G, bool MASK>
-__global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const TileArgs ta) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int T = TILE_NODES, LW = TILE_LANES;
-    double* sR = reinterpret_cast<double*>(smem_raw);                      // [T][LW]
-    double* sH = sR + T * LW;                                              // [hrows][LW]
-    int4* sRec = reinterpret_cast<int4*>(sH + (size_t)ta.hrows * LW);      // [T]
-    double2* sCL = reinterpret_cast<double2*>(sRec + T);                   // [T]
-    unsigned long long* sMask = reinterpret_cast<unsigned long long*>(sCL + T);   // [T]
-    double2* sTab = reinterpret_cast<double2*>(sMask + T);                 // [LOG_TABLE_N]
-    double* sZero = reinterpret_cast<double*>(sTab + LOG_TABLE_N);         // [LW] zeros: the date row of every tip
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(sZero + LW);
-    int* sNext = reinterpret_cast<int*>(mbar + 1);
-
-    const int tid = threadIdx.x;
-    const int w = tid >> 5, tx = tid & 31;
-    const int tile = blockIdx.x, chunk = blockIdx.y;
+__device__ __forceinline__ void tile_rows(const EvalArgs& a, const TileArgs& ta, const TileView& v,
+                                          const double2* sTab, const double* sZero, int tx, int lane, int chunk,
+                                          const double (&lam2)[2], int row0, int row_step,
+                                          double (&acc_ll)[2], double (&acc_su)[2], int& bad) {
+    constexpr int LW = TILE_LANES;
+    const double* sR = v.sR;
+    const double* sH = v.sH;
+    const int4* sRec = v.sRec;
+    const double2* sCL = v.sCL;
+    const unsigned long long* sMask = v.sMask;
+    const int n0 = v.n0, tn = v.tn, n1 = v.n0 + v.tn;
+    const TileInfo ti = v.ti;
     const unsigned B = (unsigned)a.B;
-    const int lane0 = chunk * LW;
-    const int nl = min(LW, a.B - lane0);                 // even
-    const unsigned rowbytes = (unsigned)nl * 8u;
-    const int n0 = tile * T;
-    const int tn = min(T, a.t.n - n0);
-    const int n1 = n0 + tn;
-    const TileInfo ti = ta.tiles[tile];
     const double* __restrict__ X = a.X;
-
-    if (tid == 0) {
-        *sNext = 0;
-        mbar_init(mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (w == 0) {
-        if (tx == 0) mbar_expect_tx(mbar, (unsigned)(ti.nrs + ti.nds) * rowbytes);
-        __syncwarp();
-        for (int k = tx; k < ti.nrs; k += 32)
-            bulk_g2s(sR + k * LW, X + ((size_t)(ti.rs0 + k) * B + lane0), rowbytes, mbar);
-        for (int k = tx; k < ti.nds; k += 32)
-            bulk_g2s(sH + k * LW, X + ((size_t)(ti.ds0 + k) * B + lane0), rowbytes, mbar);
-    }
-    for (int j = tid; j < tn; j += 256) {
-        sRec[j] = ta.recs[n0 + j];
-        sCL[j] = ta.clf[n0 + j];
-        if (MASK) sMask[j] = a.lanemask[(size_t)(n0 + j) * a.nchunks + chunk];
-    }
-    sTab[tid] = a.logtab[tid];
-    if (tid < LW) sZero[tid] = 0.0;
-    __syncthreads();
-    mbar_wait(mbar, 0);
-
-    const int lane = lane0 + 2 * tx;                     // first of this thread's two vectors
-    const bool active = 2 * tx < nl;
-    double acc_ll[2] = {0.0, 0.0}, acc_su[2] = {0.0, 0.0};
-    int bad = 0;                                         // bit l = vector l infeasible
-
-    if (active) {
-        double lam[2];
-        if (a.lane_lambda) { double2 t2 = ldg2(a.lane_lambda + lane); lam[0] = t2.x; lam[1] = t2.y; }
-        else { lam[0] = lam[1] = a.lambda; }
-        const double lam2[2] = {2.0 * lam[0], 2.0 * lam[1]};
-        const int shl = 2 * tx;
-
+    const int shl = 2 * tx;
+    {
         // operand fetch: in-tile rows from shared memory, halo rows from global (L2)
         auto rate_of = [&](int node, const int4& rc, bool intile, double (&out)[2]) {
             if (rc.y >= 0) {
@@ -157,7 +137,7 @@ __global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const
         };
         auto mask_of = [&](int node, bool intile) -> unsigned {
             if (!MASK) return 0u;
-            unsigned long long mw = intile ? sMask[node - n0] : a.lanemask[(size_t)node * a.nchunks + chunk];
+            unsigned long long mw = intile ? sMask[node - n0] : a.lanemask[(size_t)chunk * a.mask_stride + node];
             return (unsigned)(mw >> shl) & 3u;
         };
 
@@ -242,7 +222,7 @@ __global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const
 
         // static row assignment (warp w takes rows w, w+8, ...): which warp sums which rows must not
         // depend on timing, or the objective would not be bitwise reproducible
-        for (int j = w; j < tn; j += 8) {
+        for (int j = row0; j < tn; j += row_step) {
             const int i = n0 + j;
             const int4 rec = sRec[j];
             const double2 cl = sCL[j];
@@ -376,6 +356,79 @@ __global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const
             }
         }
     }
+}
+
+inline size_t tile_kernel_smem(int hrows) {
+    return (size_t)TILE_NODES * TILE_LANES * 8 + (size_t)hrows * TILE_LANES * 8 + TILE_NODES * (16 + 16 + 8) +
+           LOG_TABLE_N * 16 + TILE_LANES * 8 + 32;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generation 2: one CTA (8 warps) per (tile, 64-vector chunk)
+// ---------------------------------------------------------------------------------------------
+template <int MODE, bool LOGPEN, bool WANT_G, bool MASK>
+__global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const TileArgs ta) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int T = TILE_NODES, LW = TILE_LANES;
+    double* sR = reinterpret_cast<double*>(smem_raw);                      // [T][LW]
+    double* sH = sR + T * LW;                                              // [hrows][LW]
+    int4* sRec = reinterpret_cast<int4*>(sH + (size_t)ta.hrows * LW);      // [T]
+    double2* sCL = reinterpret_cast<double2*>(sRec + T);                   // [T]
+    unsigned long long* sMask = reinterpret_cast<unsigned long long*>(sCL + T);   // [T]
+    double2* sTab = reinterpret_cast<double2*>(sMask + T);                 // [LOG_TABLE_N]
+    double* sZero = reinterpret_cast<double*>(sTab + LOG_TABLE_N);         // [LW] zeros: the date row of every tip
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sZero + LW);
+
+    const int tid = threadIdx.x;
+    const int w = tid >> 5, tx = tid & 31;
+    const int tile = blockIdx.x, chunk = blockIdx.y;
+    const unsigned B = (unsigned)a.B;
+    const int lane0 = chunk * LW;
+    const int nl = min(LW, a.B - lane0);                 // even
+    const unsigned rowbytes = (unsigned)nl * 8u;
+    const int n0 = tile * T;
+    const int tn = min(T, a.t.n - n0);
+    const TileInfo ti = ta.tiles[tile];
+    const double* __restrict__ X = a.X;
+
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (w == 0) {
+        if (tx == 0) mbar_expect_tx(mbar, (unsigned)(ti.nrs + ti.nds) * rowbytes);
+        __syncwarp();
+        for (int k = tx; k < ti.nrs; k += 32)
+            bulk_g2s(sR + k * LW, X + ((size_t)(ti.rs0 + k) * B + lane0), rowbytes, mbar);
+        for (int k = tx; k < ti.nds; k += 32)
+            bulk_g2s(sH + k * LW, X + ((size_t)(ti.ds0 + k) * B + lane0), rowbytes, mbar);
+    }
+    for (int j = tid; j < tn; j += 256) {
+        sRec[j] = ta.recs[n0 + j];
+        sCL[j] = ta.clf[n0 + j];
+        if (MASK) sMask[j] = a.lanemask[(size_t)chunk * a.mask_stride + n0 + j];
+    }
+    sTab[tid] = a.logtab[tid];
+    if (tid < LW) sZero[tid] = 0.0;
+    __syncthreads();
+    mbar_wait(mbar, 0);
+
+    const int lane = lane0 + 2 * tx;                     // first of this thread's two vectors
+    const bool active = 2 * tx < nl;
+    double acc_ll[2] = {0.0, 0.0}, acc_su[2] = {0.0, 0.0};
+    int bad = 0;                                         // bit l = vector l infeasible
+    if (active) {
+        double lam[2];
+        if (a.lane_lambda) { double2 t2 = ldg2(a.lane_lambda + lane); lam[0] = t2.x; lam[1] = t2.y; }
+        else { lam[0] = lam[1] = a.lambda; }
+        const double lam2[2] = {2.0 * lam[0], 2.0 * lam[1]};
+        TileView v;
+        v.sR = sR; v.sH = sH; v.sRec = sRec; v.sCL = sCL; v.sMask = sMask; v.n0 = n0; v.tn = tn; v.ti = ti;
+        // static row assignment (warp w takes rows w, w+8, ...): which warp sums which rows must not
+        // depend on timing, or the objective would not be bitwise reproducible
+        tile_rows<MODE, LOGPEN, WANT_G, MASK>(a, ta, v, sTab, sZero, tx, lane, chunk, lam2, w, 8, acc_ll, acc_su, bad);
+    }
     // fixed-order reduction over the 8 warps; the operand tile is dead, reuse it as scratch
     __syncthreads();
     double* sRed = sR;                                   // [8][2][LW]
@@ -404,9 +457,132 @@ __global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const
     }
 }
 
-inline size_t tile_kernel_smem(int hrows) {
-    return (size_t)TILE_NODES * TILE_LANES * 8 + (size_t)hrows * TILE_LANES * 8 + TILE_NODES * (16 + 16 + 8) +
-           LOG_TABLE_N * 16 + TILE_LANES * 8 + 32;
+// ---------------------------------------------------------------------------------------------
+// generation 3: persistent, warp-specialised, 3-stage ring
+// ---------------------------------------------------------------------------------------------
+constexpr int P_CONSUMER_WARPS = 20;
+constexpr int P_THREADS = (P_CONSUMER_WARPS + 1) * 32;      // + 1 producer warp
+constexpr int P_STAGES = 3;
+
+__host__ __device__ inline size_t persist_stage_bytes(int hrows) {
+    return (size_t)TILE_NODES * TILE_LANES * 8 + (size_t)hrows * TILE_LANES * 8 + TILE_NODES * (16 + 16 + 8);
+}
+inline size_t persist_kernel_smem(int hrows) {
+    return P_STAGES * persist_stage_bytes(hrows) + LOG_TABLE_N * 16 + TILE_LANES * 8 + 2 * P_STAGES * 8 + 64;
+}
+// work item k (0 <= k < nchunks*ntiles) = (chunk k / ntiles, tile k % ntiles); CTA c owns [lo(c), lo(c+1))
+__host__ __device__ inline long long persist_lo(long long c, long long W, long long G) { return c * W / G; }
+
+template <int MODE, bool LOGPEN, bool WANT_G, bool MASK>
+__global__ void __launch_bounds__(P_THREADS, 1) pl_persist_kernel(const EvalArgs a, const TileArgs ta) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int T = TILE_NODES, LW = TILE_LANES, S = P_STAGES, NCW = P_CONSUMER_WARPS;
+    const size_t stage_bytes = persist_stage_bytes(ta.hrows);
+    double2* sTab = reinterpret_cast<double2*>(smem_raw + S * stage_bytes);        // [LOG_TABLE_N]
+    double* sZero = reinterpret_cast<double*>(sTab + LOG_TABLE_N);                 // [LW]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sZero + LW);                      // [S]
+    uint64_t* empty = full + S;                                                    // [S]
+    auto stage_R = [&](int s) { return reinterpret_cast<double*>(smem_raw + s * stage_bytes); };
+    auto stage_H = [&](int s) { return stage_R(s) + T * LW; };
+    auto stage_Rec = [&](int s) { return reinterpret_cast<int4*>(stage_H(s) + (size_t)ta.hrows * LW); };
+    auto stage_CL = [&](int s) { return reinterpret_cast<double2*>(stage_Rec(s) + T); };
+    auto stage_Mask = [&](int s) { return reinterpret_cast<unsigned long long*>(stage_CL(s) + T); };
+
+    const int tid = threadIdx.x;
+    const int w = tid >> 5, tx = tid & 31;
+    const unsigned B = (unsigned)a.B;
+    const long long W = (long long)ta.nchunks * ta.ntiles;
+    const long long G = gridDim.x;
+    const long long k_lo = persist_lo(blockIdx.x, W, G), k_hi = persist_lo(blockIdx.x + 1, W, G);
+    const double* __restrict__ X = a.X;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(full + s, 1); mbar_init(empty + s, NCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < LOG_TABLE_N) sTab[tid] = a.logtab[tid];
+    if (tid < LW) sZero[tid] = 0.0;
+    __syncthreads();
+
+    if (w == NCW) {
+        // ---------------- producer warp ----------------
+        for (long long k = k_lo; k < k_hi; k++) {
+            const int it = (int)(k - k_lo);
+            const int s = it % S;
+            if (it >= S) mbar_wait(empty + s, ((it / S) - 1) & 1);           // all consumer warps released the stage
+            const int chunk = (int)(k / ta.ntiles), tile = (int)(k % ta.ntiles);
+            const int lane0 = chunk * LW;
+            const unsigned rowbytes = (unsigned)min(LW, a.B - lane0) * 8u;
+            const TileInfo ti = ta.tiles[tile];
+            const int n0 = tile * T;
+            if (tx == 0)
+                mbar_expect_tx(full + s, (unsigned)(ti.nrs + ti.nds) * rowbytes + T * 32u + (MASK ? T * 8u : 0u));
+            __syncwarp();
+            double* dR = stage_R(s);
+            double* dH = stage_H(s);
+            for (int r = tx; r < ti.nrs; r += 32)
+                bulk_g2s(dR + r * LW, X + ((size_t)(ti.rs0 + r) * B + lane0), rowbytes, full + s);
+            for (int r = tx; r < ti.nds; r += 32)
+                bulk_g2s(dH + r * LW, X + ((size_t)(ti.ds0 + r) * B + lane0), rowbytes, full + s);
+            if (tx == 0) bulk_g2s(stage_Rec(s), ta.recs + n0, T * 16u, full + s);
+            if (tx == 1) bulk_g2s(stage_CL(s), ta.clf + n0, T * 16u, full + s);
+            if (MASK && tx == 2) bulk_g2s(stage_Mask(s), a.lanemask + ((size_t)chunk * a.mask_stride + n0), T * 8u, full + s);
+        }
+        return;
+    }
+
+    // ---------------- consumer warps ----------------
+    double acc_ll[2] = {0.0, 0.0}, acc_su[2] = {0.0, 0.0};
+    int bad = 0;
+    int cur_chunk = (k_lo < k_hi) ? (int)(k_lo / ta.ntiles) : 0;
+    int slot = 0;
+    double lam2[2] = {0.0, 0.0};
+    auto load_lambda = [&](int chunk) {
+        const int lane = chunk * LW + 2 * tx;
+        if (2 * tx < min(LW, a.B - chunk * LW)) {
+            if (a.lane_lambda) { double2 t2 = ldg2(a.lane_lambda + lane); lam2[0] = 2.0 * t2.x; lam2[1] = 2.0 * t2.y; }
+            else { lam2[0] = lam2[1] = 2.0 * a.lambda; }
+        }
+    };
+    load_lambda(cur_chunk);
+
+    // per-warp partials, entry ((cta*2 + slot)*NCW + warp), 64 vectors each; slot 0 = first chunk this
+    // CTA touches.  No CTA-level reduction (it would need a barrier and scratch): the finalize kernel
+    // sums the entries in fixed (cta, warp) order.
+    auto write_partials = [&](int slot_id) {
+        const size_t o = (((size_t)blockIdx.x * 2 + slot_id) * NCW + w) * LW + 2 * tx;
+        *reinterpret_cast<double2*>(a.part_ll + o) = make_double2(acc_ll[0], acc_ll[1]);
+        *reinterpret_cast<double2*>(a.part_su + o) = make_double2(acc_su[0], acc_su[1]);
+        a.part_bad[o] = bad & 1;
+        a.part_bad[o + 1] = (bad >> 1) & 1;
+    };
+
+    for (long long k = k_lo; k < k_hi; k++) {
+        const int it = (int)(k - k_lo);
+        const int s = it % S;
+        const int chunk = (int)(k / ta.ntiles), tile = (int)(k % ta.ntiles);
+        if (chunk != cur_chunk) {                       // at most once per CTA
+            write_partials(slot);
+            slot = 1;
+            acc_ll[0] = acc_ll[1] = acc_su[0] = acc_su[1] = 0.0;
+            bad = 0;
+            cur_chunk = chunk;
+            load_lambda(chunk);
+        }
+        mbar_wait(full + s, (it / S) & 1);
+        const int lane0 = chunk * LW;
+        const int nl = min(LW, a.B - lane0);
+        if (2 * tx < nl) {
+            TileView v;
+            v.sR = stage_R(s); v.sH = stage_H(s); v.sRec = stage_Rec(s); v.sCL = stage_CL(s); v.sMask = stage_Mask(s);
+            v.n0 = tile * T; v.tn = min(T, a.t.n - tile * T); v.ti = ta.tiles[tile];
+            tile_rows<MODE, LOGPEN, WANT_G, MASK>(a, ta, v, sTab, sZero, tx, lane0 + 2 * tx, chunk, lam2, w, NCW,
+                                                   acc_ll, acc_su, bad);
+        }
+        __syncwarp();
+        if (tx == 0) mbar_arrive(empty + s);             // this warp is done with the stage
+    }
+    if (k_lo < k_hi) write_partials(slot);
 }
 
 }  // namespace tpl
