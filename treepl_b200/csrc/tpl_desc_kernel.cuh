@@ -18,12 +18,15 @@
 // fit the scheme (root, children of the root, fixed calibrations, polytomies, halo overflow, operands
 // outside the ordinary range) take general_row_global(), the exact reference-semantics path.
 #pragma once
+#include <cuda.h>      // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "tpl_tile_kernel.cuh"
 
 namespace tpl {
 
 constexpr int DESC_HALO = 24;                 // halo rows per tile (p94 of the 100k-tip Yule tree; overflow -> general rows)
 constexpr int DESC_INTS = 16;                 // 64-byte descriptor = 4 x int4
+constexpr int DESC_DBOX = 8;                  // rows per TMA box of the date range (rate range: one 64-row box)
 
 // descriptor words (int4 x 4):
 //   q0 = { idx_lo, idx_hi, rslot, dslot }   idx bytes: r_own h_own r_par h_par | r_c1 h_c1 r_c2 h_c2
@@ -42,6 +45,7 @@ struct DescArgs {
     int hrows, ntiles, nchunks, ncta;
 };
 
+// hrows is rounded up to whole date boxes by the host
 __host__ __device__ inline int desc_stage_rows(int hrows) { return TILE_NODES + hrows + DESC_HALO + 1; }
 __host__ __device__ inline size_t desc_stage_bytes(int hrows) {
     return (size_t)desc_stage_rows(hrows) * TILE_LANES * 8 + TILE_NODES * 64 + TILE_NODES * 8;
@@ -53,6 +57,15 @@ inline size_t desc_kernel_smem(int hrows, int stages) {
 // One row entirely through global memory (L2): root, children of the root, fixed calibrations and their
 // neighbours, polytomies, rows whose halo did not fit, and any row with an operand outside the ordinary
 // range.  Reproduces every corner of the reference semantics; ~1 % of the rows.
+// TMA 2-D tiled load: box (64 columns x R rows) of the tensor map at (col, row) -> shared memory
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int col, int row, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(col), "r"(row), "r"(smem_u32(bar))
+        : "memory");
+}
+
 struct RowAcc {
     double ll0, ll1, su0, su1;
     int bad;
@@ -223,7 +236,9 @@ __device__ __noinline__ RowAcc general_row_global(const EvalArgs& a, const TileA
 
 
 template <int MODE, bool LOGPEN, bool WANT_G, bool MASK, int S, int NCW>
-__global__ void __launch_bounds__((NCW + 1) * 32, 1) pl_desc_kernel(const EvalArgs a, const TileArgs ta, const DescArgs da) {
+__global__ void __launch_bounds__((NCW + 1) * 32, 1)
+pl_desc_kernel(const EvalArgs a, const TileArgs ta, const DescArgs da, const __grid_constant__ CUtensorMap tmapR,
+               const __grid_constant__ CUtensorMap tmapD) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int T = TILE_NODES, LW = TILE_LANES;
     const size_t stage_bytes = desc_stage_bytes(da.hrows);
@@ -262,14 +277,20 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) pl_desc_kernel(const EvalAr
             const int lane0 = chunk * LW;
             const unsigned rowbytes = (unsigned)min(LW, a.B - lane0) * 8u;
             const DescTile ti = da.tiles[tile];
+            // Dense row ranges go through 2-D tensor maps of X ([P rows][B columns], fp64): ONE request for
+            // the 64-row rate box and one per 8-row date box.  (Per-row 1-D copies made the single
+            // producer warp the bottleneck: UBLKCP is a uniform-datapath instruction, so a per-lane loop
+            // serialises into ~130 issue sequences per tile — profiles/r01f.)  A box always transfers
+            // its full 64 x rows x 8 bytes; columns beyond B and rows beyond P arrive as zeros.
+            const int ndbox = (ti.nds + DESC_DBOX - 1) / DESC_DBOX;
             if (tx == 0)
-                mbar_expect_tx(full + s, (unsigned)(ti.nrs + ti.nds + ti.nh) * rowbytes + T * 64u + (MASK ? T * 8u : 0u));
+                mbar_expect_tx(full + s, (unsigned)(T * LW * 8) + (unsigned)ndbox * (DESC_DBOX * LW * 8) +
+                                             (unsigned)ti.nh * rowbytes + T * 64u + (MASK ? T * 8u : 0u));
             __syncwarp();
             double* rows = stage_rows(s);
-            for (int r = tx; r < ti.nrs; r += 32)
-                bulk_g2s(rows + r * LW, X + ((size_t)(ti.rs0 + r) * B + lane0), rowbytes, full + s);
-            for (int r = tx; r < ti.nds; r += 32)
-                bulk_g2s(rows + (T + r) * LW, X + ((size_t)(ti.ds0 + r) * B + lane0), rowbytes, full + s);
+            if (tx == 0) tma_load_2d(rows, &tmapR, lane0, ti.rs0, full + s);
+            if (tx >= 1 && tx <= ndbox)
+                tma_load_2d(rows + (T + (tx - 1) * DESC_DBOX) * LW, &tmapD, lane0, ti.ds0 + (tx - 1) * DESC_DBOX, full + s);
             if (tx < ti.nh) {
                 const int xr = da.halo_rows[tile * DESC_HALO + tx];
                 bulk_g2s(rows + (T + da.hrows + tx) * LW, X + ((size_t)xr * B + lane0), rowbytes, full + s);

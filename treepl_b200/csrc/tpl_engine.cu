@@ -320,7 +320,7 @@ int sync_device_tree(tpl_engine* e) {
         }
         e->gen2_ok = ok;
         e->ntiles2 = nt;
-        e->tile_hrows = std::max(hrows, 1);
+        e->tile_hrows = ((std::max(hrows, 1) + tpl::DESC_DBOX - 1) / tpl::DESC_DBOX) * tpl::DESC_DBOX;   // whole date boxes
         CK(e->d_recs.upload(recs, s));
         CK(e->d_tiles.upload(tiles, s));
         // ---- generation-4 operands: every operand of every node as a tile-local row index ----
@@ -438,10 +438,38 @@ tpl::DevTree dev_tree(tpl_engine* e) {
 
 constexpr int G4_NCW = 23;            // consumer warps of the generation-4 kernel
 
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// X viewed as [P rows][B columns] fp64, box = 64 columns x box_rows rows
+bool make_x_map(CUtensorMap* m, const double* X, int P, int B, int box_rows) {
+    EncodeTiledFn enc = get_encoder();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)B, (cuuint64_t)P};
+    cuuint64_t strides[1] = {(cuuint64_t)B * 8};
+    cuuint32_t box[2] = {(cuuint32_t)tpl::TILE_LANES, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)X, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct LaunchCfg {
     int gen;
     int stages = 3;
     tpl::DescArgs da;
+    CUtensorMap tmapR, tmapD;
     bool lf, lp, want_g;
     int maskmode;          // 0 none, 1 engine cv, 2 per-vector
     bool gen2;
@@ -464,12 +492,12 @@ cudaError_t launch_pair(const tpl::EvalArgs& a, const LaunchCfg& c) {
                     auto kern = tpl::pl_desc_kernel<MODE, false, WANT_G, MASKMODE == 2, 3, G4_NCW>;
                     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
                     if (e != cudaSuccess) return e;
-                    kern<<<c.grid, c.block, c.smem, c.s>>>(a, c.ta, c.da);
+                    kern<<<c.grid, c.block, c.smem, c.s>>>(a, c.ta, c.da, c.tmapR, c.tmapD);
                 } else {
                     auto kern = tpl::pl_desc_kernel<MODE, false, WANT_G, MASKMODE == 2, 2, G4_NCW>;
                     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
                     if (e != cudaSuccess) return e;
-                    kern<<<c.grid, c.block, c.smem, c.s>>>(a, c.ta, c.da);
+                    kern<<<c.grid, c.block, c.smem, c.s>>>(a, c.ta, c.da, c.tmapR, c.tmapD);
                 }
             } else if (c.gen == 3) {
                 auto kern = tpl::pl_persist_kernel<MODE, LOGPEN, WANT_G, MASKMODE == 2>;
@@ -628,6 +656,11 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
     c.da.ntiles = e->ntiles2;
     c.da.nchunks = nchunks2;
     c.da.ncta = G;
+    if (gen == 4) {
+        if (!make_x_map(&c.tmapR, dX, e->numparams, B, tpl::TILE_NODES) ||
+            !make_x_map(&c.tmapD, dX, e->numparams, B, tpl::DESC_DBOX))
+            return fail(TPL_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    }
     c.s = s;
     c.ev = nullptr;
     if (e->timing && e->ev_used + 3 <= e->ev.size()) { c.ev = &e->ev[e->ev_used]; e->ev_used += 3; }
