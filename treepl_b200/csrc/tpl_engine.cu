@@ -436,7 +436,7 @@ tpl::DevTree dev_tree(tpl_engine* e) {
     return t;
 }
 
-constexpr int G4_NCW = 23;            // consumer warps of the generation-4 kernel
+constexpr int G4_NCW = 15;            // consumer warps of the generation-4 kernel
 
 // cuTensorMapEncodeTiled through the runtime (no link against libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
