@@ -272,11 +272,13 @@ pl_desc_kernel(const EvalArgs a, const TileArgs ta, const DescArgs da, const __g
         for (long long k = k_lo; k < k_hi; k++) {
             const int it = (int)(k - k_lo);
             const int s = it % S;
-            if (it >= S) mbar_wait(empty + s, ((it / S) - 1) & 1);           // all consumer warps released the stage
             const int chunk = (int)(k / da.ntiles), tile = (int)(k % da.ntiles);
             const int lane0 = chunk * LW;
             const unsigned rowbytes = (unsigned)min(LW, a.B - lane0) * 8u;
+            // tile metadata first (two dependent L2 round trips), THEN wait for the stage: the loads overlap the wait
             const DescTile ti = da.tiles[tile];
+            const int my_halo_row = (tx < ti.nh) ? da.halo_rows[tile * DESC_HALO + tx] : 0;
+            if (it >= S) mbar_wait(empty + s, ((it / S) - 1) & 1);           // all consumer warps released the stage
             // Dense row ranges go through 2-D tensor maps of X ([P rows][B columns], fp64): ONE request for
             // the 64-row rate box and one per 8-row date box.  (Per-row 1-D copies made the single
             // producer warp the bottleneck: UBLKCP is a uniform-datapath instruction, so a per-lane loop
@@ -291,10 +293,8 @@ pl_desc_kernel(const EvalArgs a, const TileArgs ta, const DescArgs da, const __g
             if (tx == 0) tma_load_2d(rows, &tmapR, lane0, ti.rs0, full + s);
             if (tx >= 1 && tx <= ndbox)
                 tma_load_2d(rows + (T + (tx - 1) * DESC_DBOX) * LW, &tmapD, lane0, ti.ds0 + (tx - 1) * DESC_DBOX, full + s);
-            if (tx < ti.nh) {
-                const int xr = da.halo_rows[tile * DESC_HALO + tx];
-                bulk_g2s(rows + (T + da.hrows + tx) * LW, X + ((size_t)xr * B + lane0), rowbytes, full + s);
-            }
+            if (tx < ti.nh)
+                bulk_g2s(rows + (T + da.hrows + tx) * LW, X + ((size_t)my_halo_row * B + lane0), rowbytes, full + s);
             if (tx == 31) bulk_g2s(stage_desc(s), da.desc + (size_t)tile * T * 4, T * 64u, full + s);
             if (MASK && tx == 30)
                 bulk_g2s(stage_mask(s), a.lanemask + ((size_t)chunk * a.mask_stride + (size_t)tile * T), T * 8u, full + s);
