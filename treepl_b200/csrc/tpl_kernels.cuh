@@ -361,102 +361,124 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const EvalAr
         s_sum[2][seg][tx] = gr;
         s_bad[seg][tx] = bad;
     }
-    __syncthreads();
-    if (seg != 0 || !active) return;
-    double ll = 0.0, su = 0.0, gr = 0.0;
-    int bad = 0;
-    for (int k = 0; k < FIN_SEGS; k++) {
-        ll += s_sum[0][k][tx];
-        su += s_sum[1][k][tx];
-        gr += s_sum[2][k][tx];
-        bad |= s_bad[k][tx];
-    }
+    // ---- sparse rows, spread over the 32 segment threads of each vector ----
+    // The barrier sum is order dependent in the reference (accumulator reset on inf, :983-991), so the
+    // segment threads only FETCH: the dependent  slot -> X row  loads run 32-wide, the terms land in
+    // shared memory, and one thread per vector then accumulates them in ascending node order.
+    constexpr int FIN_BAR = 48;                                          // barrier rows staged in shared memory
+    __shared__ double s_bh[FIN_BAR][32];                                 // date of barrier row k
     const double* __restrict__ X = a.X;
-    for (int k = 0; k < t.nbnd; k++) {                                   // set_durations :887-896
-        const double h = X[(size_t)t.bnd_ds[k] * B + lane];               // fixed dates are checked on the host
-        if (h < t.bnd_min[k] || h > t.bnd_max[k]) bad = 1;
+    int bnd_bad = 0;
+    if (active) {
+        for (int k = seg; k < t.nbnd; k += FIN_SEGS) {                   // set_durations :887-896
+            const double h = X[(size_t)t.bnd_ds[k] * B + lane];          // fixed dates are checked on the host
+            if (h < t.bnd_min[k] || h > t.bnd_max[k]) bnd_bad = 1;
+        }
+        if (!LF)
+            for (int k = seg; k < t.nbar && k < FIN_BAR; k += FIN_SEGS) {
+                const int ds = t.bar_ds[k];
+                s_bh[k][tx] = (ds >= 0) ? X[(size_t)ds * B + lane] : t.bar_hfix[k];
+            }
     }
-    double f;
-    if (LF) {
-        f = ll;
-        if (WANT_G) {
-            if (MODE == 0) {
-                const double rate = X[lane];                             // params[0]  (:671)
-                a.G[lane] = -(t.sum_c / rate - (gr + t.dur0));           // :678
-            } else {
-                a.G[lane] = gr;
+    s_bad[seg][tx] |= bnd_bad;
+    __syncthreads();
+    __shared__ int s_dead[32];                                           // AD: barrier sum was inf/NaN -> no barrier gradient
+    if (seg == 0 && active) {
+        double ll = 0.0, su = 0.0, gr = 0.0;
+        int bad = 0;
+        for (int k = 0; k < FIN_SEGS; k++) {
+            ll += s_sum[0][k][tx];
+            su += s_sum[1][k][tx];
+            gr += s_sum[2][k][tx];
+            bad |= s_bad[k][tx];
+        }
+        double f;
+        if (LF) {
+            f = ll;
+            if (WANT_G) {
+                if (MODE == 0) {
+                    const double rate = X[lane];                             // params[0]  (:671)
+                    a.G[lane] = -(t.sum_c / rate - (gr + t.dur0));           // :678
+                } else {
+                    a.G[lane] = gr;
+                }
             }
-        }
-    } else {
-        const double lam = a.lane_lambda ? a.lane_lambda[lane] : a.lambda;
-        // ---- root children block ----
-        const int cb = t.child_off[0], ce = t.child_off[1];
-        double s = 0.0, ss = 0.0, m = 0.0;          // all children (objective; AD gradient)
-        double su_s = 0.0, su_m = 0.0;              // unmasked children (analytic gradient :767-778)
-        for (int j = cb; j < ce; j++) {
-            const int ch = t.children[j];
-            const bool mc = is_masked<MASKMODE>(a, ch, lane);
-            const int crs = t.rslot[ch];
-            const double rc = (crs >= 0 && !(MASKMODE == 2 && mc)) ? X[(size_t)crs * B + lane] : t.rfix[ch];
-            const double y = LOGPEN ? log(rc) : rc;
-            s += y;
-            ss += y * y;
-            m += 1.0;
-            if (!mc) { su_s += y; su_m += 1.0; }
-        }
-        const double rp = su + (ss - s * s / m) / m;                     // :878
-        // ---- barrier ----
-        double tpen = 0.0;
-        for (int k = 0; k < t.nbar; k++) {
-            const int ds = t.bar_ds[k];
-            const double h = (ds >= 0) ? X[(size_t)ds * B + lane] : t.bar_hfix[k];
-            const double pmn = t.bar_pmin[k], pmx = t.bar_pmax[k];
-            if (MODE == 0) {
-                if (pmn != -1.0) { tpen += 1.0 / (h - pmn); if (isinf(tpen)) tpen = 0.0; }    // :981-985
-                if (pmx != -1.0) { tpen += 1.0 / (pmx - h); if (isinf(tpen)) tpen = 0.0; }    // :988-992
-            } else {
-                if (pmn != -1.0) { const double q = h - pmn; if (q > 0.0) tpen += 1.0 / q; }  // :381-384
-                if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) tpen += 1.0 / q; }  // :391-394
-            }
-        }
-        bool bar_dead = false;
-        if (MODE == 1 && (isinf(tpen) || isnan(tpen))) { tpen = 0.0; bar_dead = true; }      // :405-406
-        if (MODE == 0) f = (ll + a.pb * tpen) + lam * rp;                // :121-123
-        else f = (a.pb * tpen + ll) + lam * rp;                          // :407, :463
-        if (WANT_G) {
+        } else {
+            const double lam = a.lane_lambda ? a.lane_lambda[lane] : a.lambda;
+            // ---- root children block ----
+            const int cb = t.child_off[0], ce = t.child_off[1];
+            double s = 0.0, ss = 0.0, m = 0.0;          // all children (objective; AD gradient)
+            double su_s = 0.0, su_m = 0.0;              // unmasked children (analytic gradient :767-778)
             for (int j = cb; j < ce; j++) {
                 const int ch = t.children[j];
                 const bool mc = is_masked<MASKMODE>(a, ch, lane);
                 const int crs = t.rslot[ch];
-                if (crs < 0 || mc) continue;
-                const double rc = X[(size_t)crs * B + lane];
-                double add;
-                if (MODE == 0) {
-                    const double mean = su_s / su_m;
-                    if (LOGPEN) add = (2.0 * lam / rc) * (log(rc) - mean) / su_m;            // :780
-                    else add = (2.0 * lam) * (rc - mean) / su_m;                             // :782
-                } else {
-                    const double y = LOGPEN ? log(rc) : rc;
-                    add = lam * (2.0 * y - 2.0 * s / m) / m;
-                    if (LOGPEN) add /= rc;
-                }
-                a.G[(size_t)crs * B + lane] += add;
+                const double rc = (crs >= 0 && !(MASKMODE == 2 && mc)) ? X[(size_t)crs * B + lane] : t.rfix[ch];
+                const double y = LOGPEN ? log(rc) : rc;
+                s += y;
+                ss += y * y;
+                m += 1.0;
+                if (!mc) { su_s += y; su_m += 1.0; }
             }
-            if (MODE == 1 && !bar_dead) {
-                for (int k = 0; k < t.nbar; k++) {
-                    const int ds = t.bar_ds[k];
-                    if (ds < 0) continue;
-                    const double h = X[(size_t)ds * B + lane];
-                    const double pmn = t.bar_pmin[k], pmx = t.bar_pmax[k];
-                    double gb = 0.0;
-                    if (pmn != -1.0) { const double q = h - pmn; if (q > 0.0) gb -= 1.0 / (q * q); }
-                    if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) gb += 1.0 / (q * q); }
-                    a.G[(size_t)ds * B + lane] += a.pb * gb;
+            const double rp = su + (ss - s * s / m) / m;                     // :878
+            // ---- barrier ----
+            double tpen = 0.0;
+            for (int k = 0; k < t.nbar; k++) {
+                double h;
+                if (k < FIN_BAR) h = s_bh[k][tx];
+                else { const int ds = t.bar_ds[k]; h = (ds >= 0) ? X[(size_t)ds * B + lane] : t.bar_hfix[k]; }
+                const double pmn = t.bar_pmin[k], pmx = t.bar_pmax[k];
+                if (MODE == 0) {
+                    if (pmn != -1.0) { tpen += 1.0 / (h - pmn); if (isinf(tpen)) tpen = 0.0; }    // :981-985
+                    if (pmx != -1.0) { tpen += 1.0 / (pmx - h); if (isinf(tpen)) tpen = 0.0; }    // :988-992
+                } else {
+                    if (pmn != -1.0) { const double q = h - pmn; if (q > 0.0) tpen += 1.0 / q; }  // :381-384
+                    if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) tpen += 1.0 / q; }  // :391-394
+                }
+            }
+            bool bar_dead = false;
+            if (MODE == 1 && (isinf(tpen) || isnan(tpen))) { tpen = 0.0; bar_dead = true; }      // :405-406
+            s_dead[tx] = bar_dead ? 1 : 0;
+            if (MODE == 0) f = (ll + a.pb * tpen) + lam * rp;                // :121-123
+            else f = (a.pb * tpen + ll) + lam * rp;                          // :407, :463
+            if (WANT_G) {
+                for (int j = cb; j < ce; j++) {
+                    const int ch = t.children[j];
+                    const bool mc = is_masked<MASKMODE>(a, ch, lane);
+                    const int crs = t.rslot[ch];
+                    if (crs < 0 || mc) continue;
+                    const double rc = X[(size_t)crs * B + lane];
+                    double add;
+                    if (MODE == 0) {
+                        const double mean = su_s / su_m;
+                        if (LOGPEN) add = (2.0 * lam / rc) * (log(rc) - mean) / su_m;            // :780
+                        else add = (2.0 * lam) * (rc - mean) / su_m;                             // :782
+                    } else {
+                        const double y = LOGPEN ? log(rc) : rc;
+                        add = lam * (2.0 * y - 2.0 * s / m) / m;
+                        if (LOGPEN) add /= rc;
+                    }
+                    a.G[(size_t)crs * B + lane] += add;
                 }
             }
         }
+        a.F[lane] = bad ? LARGE : f;
     }
-    a.F[lane] = bad ? LARGE : f;
+    if (!LF && MODE == 1 && WANT_G) {
+        // barrier gradient (AD expression only): one row per (segment thread, barrier row)
+        __syncthreads();
+        if (active && !s_dead[tx])
+            for (int k = seg; k < t.nbar; k += FIN_SEGS) {
+                const int ds = t.bar_ds[k];
+                if (ds < 0) continue;
+                const double h = (k < FIN_BAR) ? s_bh[k][tx] : X[(size_t)ds * B + lane];
+                const double pmn = t.bar_pmin[k], pmx = t.bar_pmax[k];
+                double gb = 0.0;
+                if (pmn != -1.0) { const double q = h - pmn; if (q > 0.0) gb -= 1.0 / (q * q); }
+                if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) gb += 1.0 / (q * q); }
+                a.G[(size_t)ds * B + lane] += a.pb * gb;
+            }
+    }
 }
 
 // test hook: the fast math on its ordinary range (tests/test_engine_gpu.py)
