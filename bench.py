@@ -127,6 +127,19 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(tips, batch, mode):
+    """DRAM bytes per launch of the main kernel from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        d = json.load(open(p))
+        w = d["workload"]
+        if w["tips"] == tips and w["batch"] == batch and w["mode"] == mode:
+            return d["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def cpu_reference_rate(flat, x, seconds=12.0, nthreads=None):
     """Reference calc_pl + calc_gradient on the host cores -> (evals/s, threads, sample description)."""
     from oracle import refbind as rb
@@ -325,7 +338,9 @@ def main():
                 "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(P * B * 8),
                         "d2h_bytes_per_step": int(P * B * 8 + B * 8), "steps": e2e_steps},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "pl_main_kernel",
+                             "traffic": measured_traffic(args.tips, B, args.mode), "peak_source": peak_src,
+                             "kernel": {4: "pl_desc_kernel", 3: "pl_persist_kernel", 2: "pl_tile_kernel",
+                                        1: "pl_main_kernel"}.get(plp.last_kernel_generation(), "?"),
                              "kernel_ms": main_ms / max(cnt, 1), "finalize_ms": fin_ms / max(cnt, 1),
                              "algorithmic_bytes_per_launch": bytes_per_eval * B}}
         if world == 1 and not args.no_cpu_baseline:

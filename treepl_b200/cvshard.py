@@ -1,0 +1,69 @@
+"""Sharding of independent PL work items over the GPUs of one box.
+
+Work item = one (smoothing value, CV fold) pair or one random restart: the reference runs the folds in an
+OpenMP `parallel for ... reduction(+:chisq)` (src/main.cpp:689) and the restarts one after the other
+(src/utils.cpp:475-553).  They are independent, so each rank (one process per GPU) evaluates its own items
+as the batch dimension of the PL kernels; the tree (~25 N bytes) is replicated.  The only exchanges are
+  * per smoothing value: all-gather of the per-fold chi-square terms (8 bytes x folds), summed in FOLD ORDER on
+    every rank (deterministic, unlike the OpenMP reduction), and
+  * for restarts: all-gather of (best objective, rank), then a broadcast of the winner's parameter vector.
+Both are latency-bound collectives with nothing to fuse into a kernel; NCCL on GPUs, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_items(n_items, rank, world):
+    """Static block-cyclic assignment: item i belongs to rank i % world (folds of similar cost interleave)."""
+    return list(range(rank, n_items, world))
+
+
+def owner_of(item, world):
+    return item % world
+
+
+def gather_fold_scores(local_scores, n_items, dist=None, device=None):
+    """local_scores: {item: chi-square term}.  Returns the full vector (item order) on every rank and its
+    fixed-order sum.  With dist=None (single process) no collective is issued."""
+    import torch
+
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    per = (n_items + world - 1) // world
+    mine = torch.full((per,), float("nan"), dtype=torch.float64, device=device)
+    for k, item in enumerate(shard_items(n_items, rank, world)):
+        mine[k] = float(local_scores[item])
+    if dist is None:
+        parts = [mine]
+    else:
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+    full = np.full(n_items, np.nan)
+    for r, part in enumerate(parts):
+        vals = part.cpu().numpy()
+        for k, item in enumerate(range(r, n_items, world)):
+            full[item] = vals[k]
+    total = 0.0
+    for v in full:                    # fixed item order -> identical on every rank and for every world size
+        total += v
+    return full, total
+
+
+def best_of_restarts(best_f, best_x, dist=None, device=None):
+    """Each rank passes its best (objective, parameter vector); returns the global best on every rank.
+    Ties go to the lowest rank."""
+    import torch
+
+    if dist is None:
+        return float(best_f), np.asarray(best_x, dtype=np.float64), 0
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = torch.tensor([float(best_f)], dtype=torch.float64, device=device)
+    allf = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allf, mine)
+    fs = np.array([t.item() for t in allf])
+    fs_cmp = np.where(np.isnan(fs), np.inf, fs)
+    winner = int(np.argmin(fs_cmp))
+    x = torch.as_tensor(np.asarray(best_x, dtype=np.float64), device=device).clone()
+    dist.broadcast(x, src=winner)
+    return float(fs[winner]), x.cpu().numpy(), winner
