@@ -292,7 +292,7 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    launches = args.steps * plp.last_launch_count()
+    launches = world * args.steps * plp.last_launch_count()
 
     # ---- end to end through the C ABI with pinned host buffers ----
     e2e_steps = max(1, args.e2e_steps)
@@ -316,7 +316,9 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    if not np.allclose(fpn, Fh, rtol=0, atol=0):
+    # the host path evaluates 64-vector sub-batches (pipelined with the copies): the objective partials are
+    # grouped differently, so agreement is to rounding, not bitwise
+    if not np.allclose(fpn, Fh, rtol=1e-13, atol=0):
         raise SystemExit("bench.py: host-buffer path and device-buffer path disagree")
 
     if rank == 0:

@@ -8,6 +8,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -145,8 +146,17 @@ struct tpl_engine {
     bool static_bad = false;          // a FIXED date violates its own bounds (set_durations :887-896)
     bool topo_dirty = true, slots_dirty = true, state_dirty = true;
     // ---- evaluation buffers ----
-    DevBuf<double> d_X, d_G, d_F, d_part_ll, d_part_su, d_part_gr, d_lane_lambda;
-    DevBuf<int> d_part_bad;
+    DevBuf<double> d_X, d_G, d_F, d_lane_lambda;
+    // objective partials: slot 0 for the plain paths, slots 1..3 for the pipelined host path (whose
+    // sub-batches run on separate streams and may overlap)
+    struct PartSet {
+        DevBuf<double> ll, su, gr;
+        DevBuf<int> bad;
+    };
+    PartSet parts[4];
+    // pipelined host path (tpl_calc_pl_grad_batch): 3 slots of (stream, X, G, F) for 64-vector sub-batches
+    cudaStream_t pstream[3] = {nullptr, nullptr, nullptr};
+    DevBuf<double> p_X[3], p_G[3], p_F[3];
     DevBuf<unsigned long long> d_lanemask;
     PinBuf<double> h_X, h_G, h_F;
     // batch configuration
@@ -538,15 +548,18 @@ cudaError_t launch_lf(const tpl::EvalArgs& a, const LaunchCfg& c) {
 }
 
 // Evaluate B vectors resident on the device.  Enqueues 2 kernels on stream s.
+// lane_off / cfg_B: this launch evaluates vectors [lane_off, lane_off + B) of a configured batch of cfg_B
+// vectors (per-vector smoothing and masks are addressed relative to lane_off, a multiple of 64).
 int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, int mode, bool use_cfg,
-                cudaStream_t s) {
+                cudaStream_t s, int lane_off = 0, int cfg_B = -1, int part_slot = 0) {
+    if (cfg_B < 0) cfg_B = B;
     if (!e->have_fp) return fail(TPL_ERR_STATE, "set_freeparams has not been called");
     if (mode != TPL_GRAD_ANALYTIC && mode != TPL_GRAD_AD) return fail(TPL_ERR_ARG, "bad gradient mode");
     if (B < 1) return fail(TPL_ERR_ARG, "B < 1");
     int rc = sync_device_tree(e);
     if (rc != TPL_OK) return rc;
     const int n = e->n;
-    const bool lanemask = use_cfg && e->cfg_mask && e->cfg_B == B;
+    const bool lanemask = use_cfg && e->cfg_mask && e->cfg_B == cfg_B;
     const int maskmode = lanemask ? 2 : (e->cv_any ? 1 : 0);
     // generations 2/3 (tile kernels): PL, dense slot map, even B, 32-bit element offsets
     const bool tile_legal = e->gen2_ok && !e->lf_mode && maskmode != 1 && (B % 2 == 0) &&
@@ -609,17 +622,18 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
         c.smem = 0;
         npart = (size_t)ntiles * B;
     }
-    CK(e->d_part_ll.ensure(npart));
-    CK(e->d_part_su.ensure(npart));
-    CK(e->d_part_gr.ensure(npart));
-    CK(e->d_part_bad.ensure(npart));
+    tpl_engine::PartSet& ps = e->parts[part_slot];
+    CK(ps.ll.ensure(npart));
+    CK(ps.su.ensure(npart));
+    CK(ps.gr.ensure(npart));
+    CK(ps.bad.ensure(npart));
     tpl::EvalArgs a;
     a.t = dev_tree(e);
     a.X = dX;
     a.G = dG;
     a.F = dF;
     a.B = B;
-    a.lanemask = lanemask ? e->d_lanemask.p : nullptr;
+    a.lanemask = lanemask ? e->d_lanemask.p + (size_t)(lane_off / 64) * (size_t)(e->ntiles2 * tpl::TILE_NODES) : nullptr;
     a.nchunks = e->cfg_nchunks;
     a.mask_stride = e->ntiles2 * tpl::TILE_NODES;
     a.part_mode = gen >= 3 ? 1 : 0;
@@ -627,13 +641,13 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
     a.p_ntiles = e->ntiles2;
     a.p_nchunks = nchunks2;
     a.p_nwarps = nwarps;
-    a.lane_lambda = (use_cfg && e->cfg_lambda && e->cfg_B == B) ? e->d_lane_lambda.p : nullptr;
+    a.lane_lambda = (use_cfg && e->cfg_lambda && e->cfg_B == cfg_B) ? e->d_lane_lambda.p + lane_off : nullptr;
     a.lambda = e->smoothing;
     a.pb = e->pb;
-    a.part_ll = e->d_part_ll.p;
-    a.part_su = e->d_part_su.p;
-    a.part_gr = e->d_part_gr.p;
-    a.part_bad = e->d_part_bad.p;
+    a.part_ll = ps.ll.p;
+    a.part_su = ps.su.p;
+    a.part_gr = ps.gr.p;
+    a.part_bad = ps.bad.p;
     a.ntiles = ntiles;
     a.tile_nodes = tile;
     a.logtab = e->d_logtab.p;
@@ -771,6 +785,7 @@ void tpl_destroy(tpl_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+    for (int k = 0; k < 3; k++) if (e->pstream[k]) { cudaStreamSynchronize(e->pstream[k]); cudaStreamDestroy(e->pstream[k]); }
     for (auto& v : e->ev) cudaEventDestroy(v);
     delete e;
 }
@@ -922,7 +937,46 @@ int tpl_calc_pl_grad_batch(tpl_engine* e, int B, const double* X, double* F, dou
     if (!e || !X || !F || B < 1) return fail(TPL_ERR_ARG, "null or B < 1");
     if (!e->have_fp) return fail(TPL_ERR_STATE, "set_freeparams has not been called");
     CK(cudaSetDevice(e->device));
-    const size_t PB = (size_t)e->numparams * B;
+    const int P = e->numparams;
+    if (B >= 128 && B % 2 == 0 && !e->lf_mode) {
+        // Pipelined: 64-vector sub-batches on three streams, so that the upload of sub-batch k+1, the kernels
+        // of sub-batch k and the download of sub-batch k-1 overlap (PCIe is full duplex; a single H2D -> kernel
+        // -> D2H sequence leaves each direction idle half of the time).  X and G are [P][B] on the host, so a
+        // sub-batch is a 2-D copy: P rows of 512 bytes with pitch 8 B.
+        static int sb_env = -1;                        // tuning hook: TPL_PIPE_SB = 64 (default) or 128
+        if (sb_env < 0) { const char* v = getenv("TPL_PIPE_SB"); sb_env = v ? atoi(v) : 64; if (sb_env % 64 || sb_env < 64) sb_env = 64; }
+        const int SB = sb_env;
+        const int nsub = (B + SB - 1) / SB;
+        for (int k = 0; k < 3; k++) {
+            if (!e->pstream[k]) CK(cudaStreamCreateWithFlags(&e->pstream[k], cudaStreamNonBlocking));
+            CK(e->p_X[k].ensure((size_t)P * SB));
+            CK(e->p_F[k].ensure(SB));
+            if (G) CK(e->p_G[k].ensure((size_t)P * SB));
+        }
+        CK(cudaStreamSynchronize(e->stream));          // pending tree uploads of the engine stream
+        int rc0 = sync_device_tree(e);
+        if (rc0 != TPL_OK) return rc0;
+        CK(cudaStreamSynchronize(e->stream));
+        for (int sidx = 0; sidx < nsub; sidx++) {
+            const int k = sidx % 3;
+            const int off = sidx * SB;
+            const int nl = std::min(SB, B - off);
+            cudaStream_t st = e->pstream[k];
+            CK(cudaMemcpy2DAsync(e->p_X[k].p, (size_t)nl * 8, X + off, (size_t)B * 8, (size_t)nl * 8, P,
+                                 cudaMemcpyHostToDevice, st));
+            int rc = eval_device(e, nl, e->p_X[k].p, e->p_F[k].p, G ? e->p_G[k].p : nullptr, mode, true, st, off, B, 1 + k);
+            if (rc != TPL_OK) return rc;
+            CK(cudaMemcpyAsync(F + off, e->p_F[k].p, (size_t)nl * 8, cudaMemcpyDeviceToHost, st));
+            if (G)
+                CK(cudaMemcpy2DAsync(G + off, (size_t)B * 8, e->p_G[k].p, (size_t)nl * 8, (size_t)nl * 8, P,
+                                     cudaMemcpyDeviceToHost, st));
+        }
+        for (int k = 0; k < 3; k++) CK(cudaStreamSynchronize(e->pstream[k]));
+        e->last_launches = 2 * nsub;
+        if (e->static_bad) for (int b = 0; b < B; b++) F[b] = TPL_LARGE;
+        return TPL_OK;
+    }
+    const size_t PB = (size_t)P * B;
     CK(e->d_X.ensure(PB));
     CK(e->d_F.ensure(B));
     if (G) CK(e->d_G.ensure(PB));
