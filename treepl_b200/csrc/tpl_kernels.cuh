@@ -366,7 +366,12 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const EvalAr
     // segment threads only FETCH: the dependent  slot -> X row  loads run 32-wide, the terms land in
     // shared memory, and one thread per vector then accumulates them in ascending node order.
     constexpr int FIN_BAR = 48;                                          // barrier rows staged in shared memory
+    constexpr int FIN_RC = 8;                                            // root children staged in shared memory
     __shared__ double s_bh[FIN_BAR][32];                                 // date of barrier row k
+    __shared__ double s_pmn[FIN_BAR], s_pmx[FIN_BAR];
+    __shared__ double s_rc[FIN_RC][32];                                  // rate of root child j (as the objective sees it)
+    __shared__ int s_rcs[FIN_RC];                                        // its rate row (-1: none)
+    __shared__ unsigned char s_rcm[FIN_RC][32];                          // masked for this vector
     const double* __restrict__ X = a.X;
     int bnd_bad = 0;
     if (active) {
@@ -374,12 +379,24 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const EvalAr
             const double h = X[(size_t)t.bnd_ds[k] * B + lane];          // fixed dates are checked on the host
             if (h < t.bnd_min[k] || h > t.bnd_max[k]) bnd_bad = 1;
         }
-        if (!LF)
+        if (!LF) {
             for (int k = seg; k < t.nbar && k < FIN_BAR; k += FIN_SEGS) {
                 const int ds = t.bar_ds[k];
                 s_bh[k][tx] = (ds >= 0) ? X[(size_t)ds * B + lane] : t.bar_hfix[k];
+                if (tx == 0) { s_pmn[k] = t.bar_pmin[k]; s_pmx[k] = t.bar_pmax[k]; }
             }
+            const int nrc = t.child_off[1] - t.child_off[0];
+            for (int j = seg; j < nrc && j < FIN_RC; j += FIN_SEGS) {
+                const int ch = t.children[t.child_off[0] + j];
+                const bool mc = is_masked<MASKMODE>(a, ch, lane);
+                const int crs = t.rslot[ch];
+                s_rc[j][tx] = (crs >= 0 && !(MASKMODE == 2 && mc)) ? X[(size_t)crs * B + lane] : t.rfix[ch];
+                s_rcm[j][tx] = mc ? 1 : 0;
+                if (tx == 0) s_rcs[j] = crs;
+            }
+        }
     }
+
     s_bad[seg][tx] |= bnd_bad;
     __syncthreads();
     __shared__ int s_dead[32];                                           // AD: barrier sum was inf/NaN -> no barrier gradient
@@ -410,10 +427,15 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const EvalAr
             double s = 0.0, ss = 0.0, m = 0.0;          // all children (objective; AD gradient)
             double su_s = 0.0, su_m = 0.0;              // unmasked children (analytic gradient :767-778)
             for (int j = cb; j < ce; j++) {
-                const int ch = t.children[j];
-                const bool mc = is_masked<MASKMODE>(a, ch, lane);
-                const int crs = t.rslot[ch];
-                const double rc = (crs >= 0 && !(MASKMODE == 2 && mc)) ? X[(size_t)crs * B + lane] : t.rfix[ch];
+                double rc;
+                bool mc;
+                if (j - cb < FIN_RC) { rc = s_rc[j - cb][tx]; mc = s_rcm[j - cb][tx] != 0; }
+                else {
+                    const int ch = t.children[j];
+                    mc = is_masked<MASKMODE>(a, ch, lane);
+                    const int crs = t.rslot[ch];
+                    rc = (crs >= 0 && !(MASKMODE == 2 && mc)) ? X[(size_t)crs * B + lane] : t.rfix[ch];
+                }
                 const double y = LOGPEN ? log(rc) : rc;
                 s += y;
                 ss += y * y;
@@ -425,9 +447,13 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const EvalAr
             double tpen = 0.0;
             for (int k = 0; k < t.nbar; k++) {
                 double h;
-                if (k < FIN_BAR) h = s_bh[k][tx];
-                else { const int ds = t.bar_ds[k]; h = (ds >= 0) ? X[(size_t)ds * B + lane] : t.bar_hfix[k]; }
-                const double pmn = t.bar_pmin[k], pmx = t.bar_pmax[k];
+                double pmn, pmx;
+                if (k < FIN_BAR) { h = s_bh[k][tx]; pmn = s_pmn[k]; pmx = s_pmx[k]; }
+                else {
+                    const int ds = t.bar_ds[k];
+                    h = (ds >= 0) ? X[(size_t)ds * B + lane] : t.bar_hfix[k];
+                    pmn = t.bar_pmin[k]; pmx = t.bar_pmax[k];
+                }
                 if (MODE == 0) {
                     if (pmn != -1.0) { tpen += 1.0 / (h - pmn); if (isinf(tpen)) tpen = 0.0; }    // :981-985
                     if (pmx != -1.0) { tpen += 1.0 / (pmx - h); if (isinf(tpen)) tpen = 0.0; }    // :988-992
@@ -443,11 +469,17 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const EvalAr
             else f = (a.pb * tpen + ll) + lam * rp;                          // :407, :463
             if (WANT_G) {
                 for (int j = cb; j < ce; j++) {
-                    const int ch = t.children[j];
-                    const bool mc = is_masked<MASKMODE>(a, ch, lane);
-                    const int crs = t.rslot[ch];
+                    int crs;
+                    bool mc;
+                    double rc;
+                    if (j - cb < FIN_RC) { crs = s_rcs[j - cb]; mc = s_rcm[j - cb][tx] != 0; rc = s_rc[j - cb][tx]; }
+                    else {
+                        const int ch = t.children[j];
+                        mc = is_masked<MASKMODE>(a, ch, lane);
+                        crs = t.rslot[ch];
+                        rc = (crs >= 0 && !mc) ? X[(size_t)crs * B + lane] : 0.0;
+                    }
                     if (crs < 0 || mc) continue;
-                    const double rc = X[(size_t)crs * B + lane];
                     double add;
                     if (MODE == 0) {
                         const double mean = su_s / su_m;
