@@ -342,3 +342,65 @@ def test_polytomy_and_unary_nodes_use_the_csr_child_path():
                 f, g = o.calc_pl_and_gradient(xb) if mode == eng.GRAD_ANALYTIC else o.calc_function_gradient(xb)
                 assert close_f(F[b], f) and rel_err(G[:, b], g) < G_TOL
     plp.close()
+
+
+@pytest.mark.parametrize("B", [1, 2, 7, 33, 64])
+@pytest.mark.parametrize("mode", [eng.GRAD_ANALYTIC, eng.GRAD_AD])
+def test_langley_fitch_batches_and_ragged_batch_sizes(B, mode):
+    """LF phase (one shared rate, main.cpp:499-552) in batches, odd / tiny batch sizes (generic kernel)."""
+    gd = Golden("vib")
+    rng = np.random.RandomState(B)
+    plp = eng.PLCalcParallel.from_flat(gd.flat)
+    o = plo.OracleProblem(gd.flat)
+    fp, P = eng.generate_param_order_vector(gd.flat["free"], lf=True)
+    x0 = plp.set_freeparams(P, True, fp)
+    o.set_freeparams(True)
+    X = np.repeat(x0[:, None], B, axis=1)
+    X[0, :] = 0.01 * np.exp(rng.randn(B))
+    X[1:, :] *= 1 - 1e-3 * rng.rand(P - 1, B)
+    plp.batch_configure(B)
+    F, G = plp.calc_pl_grad_batch(X, mode=mode)
+    assert plp.last_kernel_generation() == 1
+    for b in range(B):
+        xb = np.ascontiguousarray(X[:, b])
+        f, g = o.calc_pl_and_gradient(xb) if mode == eng.GRAD_ANALYTIC else o.calc_function_gradient(xb)
+        assert close_f(F[b], f), (b, F[b], f)
+        assert rel_err(G[:, b], g) < G_TOL, (b, rel_err(G[:, b], g))
+    # PL on the same engine with the same ragged B
+    fp, P = eng.generate_param_order_vector(gd.flat["free"], lf=False)
+    x0 = plp.set_freeparams(P, False, fp)
+    o.set_freeparams(False)
+    X = np.repeat(x0[:, None], B, axis=1)
+    n = gd.flat["parents"].shape[0]
+    X[: n - 1, :] = 0.01 * np.exp(0.3 * rng.randn(n - 1, B))
+    plp.batch_configure(B)
+    F, G = plp.calc_pl_grad_batch(X, mode=mode)
+    for b in range(B):
+        xb = np.ascontiguousarray(X[:, b])
+        f, g = o.calc_pl_and_gradient(xb) if mode == eng.GRAD_ANALYTIC else o.calc_function_gradient(xb)
+        assert close_f(F[b], f) and rel_err(G[:, b], g) < G_TOL
+    plp.close()
+
+
+def test_smallest_trees():
+    """Two- and three-tip trees: every node is the root or a child of the root (all rows take the general path)."""
+    for nw, cals in (("(a:0.1,b:0.2):0.0;", [(["a", "b"], 10, 10)]),
+                     ("((a:0.1,b:0.2):0.05,c:0.3):0.0;", [(["a", "c"], 5, 5)])):
+        ft = tf.flatten_newick(nw, 100, cals, seed=1)
+        flat = ft.as_dict()
+        plp = eng.PLCalcParallel.from_flat(flat)
+        o = plo.OracleProblem(flat)
+        fp, P = eng.generate_param_order_vector(ft.free, lf=False)
+        x0 = plp.set_freeparams(P, False, fp)
+        o.set_freeparams(False)
+        for B in (1, 32, 64):
+            X = np.repeat(x0[:, None], B, axis=1)
+            X[: ft.numnodes - 1, :] = 1.0 + 0.1 * np.arange(B)[None, :]
+            plp.batch_configure(B)
+            for mode in (eng.GRAD_ANALYTIC, eng.GRAD_AD):
+                F, G = plp.calc_pl_grad_batch(X, mode=mode)
+                for b in (0, B - 1):
+                    xb = np.ascontiguousarray(X[:, b])
+                    f, g = o.calc_pl_and_gradient(xb) if mode == eng.GRAD_ANALYTIC else o.calc_function_gradient(xb)
+                    assert close_f(F[b], f) and rel_err(G[:, b], g) < G_TOL
+        plp.close()
