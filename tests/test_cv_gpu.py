@@ -1,0 +1,84 @@
+"""End-to-end check of the batched device-resident optimiser + LOOCV scoring (first cut):
+the optimum it reaches (objective, dated nodes, chi-square per fold) against an independent CPU optimisation
+of the ORACLE objective (scipy L-BFGS-B) on the reference's example trees."""
+import numpy as np
+import pytest
+
+from golden_util import Golden
+from oracle import plo
+from treepl_b200 import batchopt, cv
+from treepl_b200 import engine as eng
+from treepl_b200 import treeflat as tf
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_fit(flat, lam, tip, x0, lo, hi, nr):
+    from scipy.optimize import minimize
+
+    o = plo.OracleProblem(flat)
+    n = len(flat["parents"])
+    cvm = np.zeros(n, np.int32)
+    keep = np.ones(x0.shape[0], bool)
+    if tip is not None:
+        cvm[tip] = 1
+        keep[tip - 1] = False
+    o.set_smoothing(lam)
+    o.set_cv(cvm if tip is not None else None)
+    o.set_freeparams(False, use_cv=tip is not None)
+    nrc = nr - (0 if tip is None else 1)
+
+    def fun(z):
+        x = z.copy()
+        x[:nrc] = np.exp(z[:nrc])
+        f, g = o.calc_function_gradient(x)
+        if not np.isfinite(f) or f >= 1e15:
+            return 1e15, np.zeros_like(z)
+        g = g.copy()
+        g[:nrc] *= x[:nrc]
+        return f, g
+
+    z0 = x0[keep].copy()
+    z0[:nrc] = np.log(z0[:nrc])
+    lo2, hi2 = lo[keep].copy(), hi[keep].copy()
+    lo2[:nrc] = np.log(lo2[:nrc]); hi2[:nrc] = np.log(hi2[:nrc])
+    # open date bounds, as the batched optimiser keeps them (exactly ON a penalised bound the objective drops
+    # the barrier term: a spurious discontinuous minimum)
+    m = 1e-9 * np.maximum(1.0, np.abs(np.where(hi2[nrc:] < 1e19, hi2[nrc:], lo2[nrc:])))
+    lo2[nrc:] += m
+    hi2[nrc:] -= np.where(hi2[nrc:] < 1e19, m, 0.0)
+    best = None
+    for _ in range(6):           # restart from the last point until it stops improving
+        r = minimize(fun, z0, jac=True, method="L-BFGS-B", bounds=list(zip(lo2, hi2)),
+                     options={"maxiter": 20000, "maxfun": 200000, "ftol": 1e-15, "gtol": 1e-10, "maxcor": 30})
+        z0 = r.x
+        if best is not None and abs(best - r.fun) <= 1e-12 * abs(r.fun):
+            break
+        best = r.fun
+    x = r.x.copy()
+    x[:nrc] = np.exp(x[:nrc])
+    full = np.zeros(x0.shape[0])
+    full[keep] = x
+    return r.fun, full
+
+
+@pytest.mark.parametrize("name,lams", [("test", [0.1, 10.0]), ("pl4203", [1.0, 100.0])])
+def test_batched_loocv_reaches_the_oracle_optimum(name, lams):
+    gd = Golden(name)
+    flat = gd.flat
+    cals = [(t, lo, hi) for t, lo, hi in gd.meta["calibrations"]]
+    ft = tf.flatten_newick(gd.meta["newick"], gd.meta["numsites"], cals, seed=1)
+    tips = ft.tips_postorder
+    res = cv.loocv(flat, lams, tips, max_iter=6000)
+    n = len(flat["parents"])
+    fp, P = tf.generate_param_order_vector(flat["free"], lf=False)
+    lo, hi = batchopt.reference_bounds(flat, fp, P)
+    x0 = cv.start_vector(flat, P, n - 1)
+    for k, lam in enumerate(lams):
+        f_full, x_full = _oracle_fit(flat, lam, None, x0, lo, hi, n - 1)
+        assert abs(res["full_objective"][k] - f_full) <= 1e-7 * abs(f_full), (lam, res["full_objective"][k], f_full)
+        chisq = 0.0
+        for tip in tips:
+            f, x = _oracle_fit(flat, lam, int(tip), x_full, lo, hi, n - 1)
+            chisq += cv.loocv_chisq(flat, x[:, None], [int(tip)], fp)[0]
+        assert abs(res["chisq"][k] - chisq) <= 2e-3 * abs(chisq), (lam, res["chisq"][k], chisq)
