@@ -127,6 +127,42 @@ int tpl_calc_pl_grad_batch(tpl_engine* e, int B, const double* X, double* F, dou
 int tpl_calc_pl_grad_batch_dev(tpl_engine* e, int B, const double* dX, double* dF, double* dG,
                                int mode, void* cuda_stream);
 
+/* ---- device-resident batched optimiser --------------------------------------------------------
+ * Replaces, for B independent problems at once, the host optimiser round trips of the reference:
+ * optimize_plcp_tnc (optimize_tnc.cpp:107-172) / optimize_plcp_nlopt (optimize_nlopt.cpp:116-238) as
+ * driven by optimize_full (utils.cpp:671-763) inside the smoothing-grid / CV-fold loops of main()
+ * (main.cpp:668-682, 689-801).  Projected L-BFGS with Armijo backtracking; rates are optimised as
+ * ln r, dates as h / date_scale; every vector keeps its own line-search and convergence state in HBM
+ * and every trial point of all B vectors is ONE launch of the PL kernels (no host round trip per
+ * evaluation; the host only polls a done counter every `check_every` steps).
+ * X [P][B] host in/out (start must be feasible), F [B] host out.  lower/upper [P]: the bounds the
+ * reference adapters build (optimize_tnc.cpp:116-147).  Uses the batch configuration installed by
+ * tpl_batch_configure when it was made for the same B (per-vector smoothing and CV masks).
+ * status [B] (may be NULL): 1 gradient converged, 2 objective converged, 3 stalled, 4 infeasible start,
+ * 5 non-finite gradient, 0 step cap reached.  iters [B] (may be NULL): accepted steps per vector.      */
+typedef struct tpl_opt_options {
+    int history;        /* L-BFGS pairs kept: 4, 8 or 16 (0 = default 8) */
+    int max_steps;      /* cap on batched objective+gradient evaluations (0 = default 20000) */
+    int patience;       /* stop a vector after this many consecutive relative decreases <= ftol (0 = 5) */
+    int max_ls;         /* halvings per line search (0 = 40) */
+    int check_every;    /* host polls the device-side done counter every this many steps (0 = 32) */
+    int use_graph;      /* 1: replay `check_every` steps as one CUDA graph launch */
+    double ftol;        /* 0 = 1e-12 */
+    double gtol;        /* 0 = 1e-8; on max |projected gradient| relative to max(|f|, 1) */
+    double armijo;      /* 0 = 1e-4 */
+    double date_scale;  /* 0 = 1 */
+} tpl_opt_options;
+
+typedef struct tpl_opt_result {
+    int steps;          /* batched evaluations performed */
+    int n_done;         /* vectors that stopped by themselves */
+    int launches;       /* kernels launched */
+    double device_ms;   /* CUDA-event time of the whole optimisation on the engine stream */
+} tpl_opt_result;
+
+int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, const double* lower, const double* upper,
+                       int mode, const tpl_opt_options* opts, int* status, int* iters, tpl_opt_result* result);
+
 /* number of kernels the last evaluation call launched (for bench accounting) */
 int tpl_last_launch_count(const tpl_engine* e);
 

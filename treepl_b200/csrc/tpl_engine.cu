@@ -17,6 +17,7 @@
 #include "tpl_kernels.cuh"
 #include "tpl_tile_kernel.cuh"
 #include "tpl_desc_kernel.cuh"
+#include "tpl_lbfgs.cuh"
 
 namespace {
 
@@ -165,6 +166,12 @@ struct tpl_engine {
     int cfg_nchunks = 0;
     int last_launches = 0;
     int last_gen = 0;
+    // device-resident optimiser work space (tpl_optimize_batch)
+    struct OptWork {
+        DevBuf<double> Z, Gz, D, X, Gx, S, Y, lo, hi, lane_d, rho, delta, M, part, Ft, Fout;
+        DevBuf<int> lane_i;
+        PinBuf<int> h_done;
+    } opt;
     // optional per-launch device timing (bench.py roofline): events around the main kernel
     bool timing = false;
     std::vector<cudaEvent_t> ev;      // triples: before main, after main, after finalize
@@ -724,6 +731,201 @@ double eval_point(tpl_engine* e, const double* x, double* g, int mode, bool keep
     return f;
 }
 
+
+// ---- device-resident batched L-BFGS (tpl_lbfgs_core.h / tpl_lbfgs.cuh) --------------------------------------
+
+template <int HM>
+int run_optimizer(tpl_engine* e, tplopt::OptArgs a, int B, int mode, int max_steps, int check_every, bool use_graph,
+                  tpl_opt_result* res) {
+    using namespace tplopt;
+    typedef Layout<HM> L;
+    cudaStream_t s = e->stream;
+    const dim3 blk(32, OPT_WY);
+    const dim3 grd((B + 31) / 32, a.nchunks);
+    const dim3 lblk(OPT_LX, OPT_NY);
+    const dim3 lgrd((B + OPT_LX - 1) / OPT_LX);
+    const size_t lsmem = (size_t)(L::NACC + L::NB * L::NB) * OPT_LX * sizeof(double);
+    CK(cudaFuncSetAttribute(opt_lane_kernel<HM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+    int launches = 0;
+    opt_init_kernel<<<grd, blk, 0, s>>>(a);
+    opt_trial_kernel<HM><<<grd, blk, 0, s>>>(a);
+    launches += 2;
+    CK(cudaGetLastError());
+    auto one_step = [&]() -> int {
+        int rc = eval_device(e, B, a.X, const_cast<double*>(a.Ft), const_cast<double*>(a.Gx), mode, true, s);
+        if (rc != TPL_OK) return rc;
+        opt_update_kernel<HM><<<grd, blk, 0, s>>>(a);
+        opt_lane_kernel<HM><<<lgrd, lblk, lsmem, s>>>(a);
+        opt_trial_kernel<HM><<<grd, blk, 0, s>>>(a);
+        CK(cudaGetLastError());
+        return TPL_OK;
+    };
+    int steps = 0;
+    int rc = one_step();               // first step outside any capture: sizes the evaluation work space
+    if (rc != TPL_OK) return rc;
+    steps++;
+    launches += 5;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    const bool was_timing = e->timing;
+    e->timing = false;
+    if (use_graph) {
+        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        for (int k = 0; k < check_every && rc == TPL_OK; k++) rc = one_step();
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc != TPL_OK || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            e->timing = was_timing;
+            return rc != TPL_OK ? rc : fail(TPL_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+        }
+        CK(cudaGraphInstantiate(&gexec, graph, 0));
+    }
+    int ndone = 0;
+    while (steps < max_steps) {
+        if (use_graph) {
+            CK(cudaGraphLaunch(gexec, s));
+        } else {
+            for (int k = 0; k < check_every && rc == TPL_OK; k++) rc = one_step();
+            if (rc != TPL_OK) break;
+        }
+        steps += check_every;
+        launches += 5 * check_every;
+        CK(cudaMemcpyAsync(e->opt.h_done.p, a.ndone, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        ndone = e->opt.h_done.p[0];
+        if (ndone >= B) break;
+    }
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+    e->timing = was_timing;
+    if (rc != TPL_OK) return rc;
+    opt_final_kernel<<<grd, blk, 0, s>>>(a, e->opt.Fout.p);
+    launches++;
+    CK(cudaGetLastError());
+    res->steps = steps;
+    res->n_done = ndone;
+    res->launches = launches;
+    return TPL_OK;
+}
+
+}  // namespace
+
+extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, const double* lower, const double* upper,
+                                  int mode, const tpl_opt_options* opts, int* status, int* iters, tpl_opt_result* result) {
+    using namespace tplopt;
+    if (!e || !X || !F || !lower || !upper || B < 1) return fail(TPL_ERR_ARG, "tpl_optimize_batch: null or B < 1");
+    if (!e->have_fp) return fail(TPL_ERR_STATE, "set_freeparams has not been called");
+    CK(cudaSetDevice(e->device));
+    int rc = sync_device_tree(e);
+    if (rc != TPL_OK) return rc;
+    if (e->static_bad) return fail(TPL_ERR_STATE, "a fixed date violates its own bounds: every point is infeasible");
+    tpl_opt_options o;
+    memset(&o, 0, sizeof(o));
+    if (opts) o = *opts;
+    const int HM = o.history ? o.history : 8;
+    if (HM != 4 && HM != 8 && HM != 16) return fail(TPL_ERR_ARG, "history must be 4, 8 or 16");
+    const int max_steps = o.max_steps > 0 ? o.max_steps : 20000;
+    const int check_every = o.check_every > 0 ? o.check_every : 32;
+    const int P = e->numparams, n = e->n;
+    int nr = 0;
+    for (int i = 0; i < n; i++) nr = std::max(nr, e->freeparams[i] + 1);
+    const double ds = o.date_scale > 0 ? o.date_scale : 1.0;
+    // bounds in the transformed variables.  Date bounds are kept OPEN by a relative margin: exactly ON a penalised
+    // bound the reference's objectives drop the infinite barrier term (calc_penalty resets, the AD paths skip it,
+    // SURVEY.md 8 a13), so a step clamped onto the bound would sit in a spurious discontinuous minimum.
+    std::vector<double> lo(P), hi(P);
+    for (int p = 0; p < P; p++) {
+        if (p < nr) {
+            lo[p] = std::log(std::max(lower[p], 1e-300));
+            hi[p] = std::log(upper[p]);
+        } else {
+            double dlo = lower[p], dhi = upper[p];
+            const double ref = dhi < 1e19 ? dhi : dlo;
+            const double margin = 1e-9 * std::max(1.0, std::fabs(ref));
+            dlo += margin;
+            if (dhi < 1e19) dhi -= margin;
+            lo[p] = dlo / ds;
+            hi[p] = dhi / ds;
+        }
+        if (!(lo[p] <= hi[p])) return fail(TPL_ERR_ARG, "empty bound interval");
+    }
+    const size_t PB = (size_t)P * B;
+    tpl_engine::OptWork& w = e->opt;
+    const int NB = 2 * HM + 1, NACC = 6 * HM + 2;
+    // row chunking: enough blocks to fill the machine, few enough chunks for the per-vector reduction
+    const int groups = (B + 31) / 32;
+    int nchunks = (4 * e->num_sms + groups - 1) / groups;
+    nchunks = std::max(1, std::min(nchunks, std::min(256, (P + OPT_WY - 1) / OPT_WY)));
+    int rows = (P + nchunks - 1) / nchunks;
+    rows = ((rows + OPT_WY - 1) / OPT_WY) * OPT_WY;
+    nchunks = (P + rows - 1) / rows;
+    CK(w.Z.ensure(PB)); CK(w.Gz.ensure(PB)); CK(w.D.ensure(PB)); CK(w.X.ensure(PB)); CK(w.Gx.ensure(PB));
+    CK(w.S.ensure(PB * HM)); CK(w.Y.ensure(PB * HM));
+    CK(w.lo.ensure(P)); CK(w.hi.ensure(P));
+    CK(w.lane_d.ensure((size_t)5 * B)); CK(w.lane_i.ensure((size_t)9 * B + 1));
+    CK(w.rho.ensure((size_t)HM * B)); CK(w.delta.ensure((size_t)NB * B)); CK(w.M.ensure((size_t)NB * NB * B));
+    CK(w.part.ensure((size_t)nchunks * NACC * B)); CK(w.Ft.ensure(B)); CK(w.Fout.ensure(B));
+    CK(w.h_done.ensure(1));
+    cudaStream_t s = e->stream;
+    CK(cudaMemcpyAsync(w.lo.p, lo.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w.hi.p, hi.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w.X.p, X, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(w.lane_d.p, 0, sizeof(double) * 5 * B, s));
+    CK(cudaMemsetAsync(w.lane_i.p, 0, sizeof(int) * (9 * (size_t)B + 1), s));      // st = ST_INIT = 0, t = 0
+    CK(cudaMemsetAsync(w.rho.p, 0, sizeof(double) * HM * B, s));
+    CK(cudaMemsetAsync(w.delta.p, 0, sizeof(double) * NB * B, s));
+    CK(cudaMemsetAsync(w.M.p, 0, sizeof(double) * NB * NB * B, s));
+    CK(cudaMemsetAsync(w.S.p, 0, sizeof(double) * PB * HM, s));
+    CK(cudaMemsetAsync(w.Y.p, 0, sizeof(double) * PB * HM, s));
+    CK(cudaMemsetAsync(w.Gz.p, 0, sizeof(double) * PB, s));
+    OptArgs a;
+    a.o.P = P; a.o.B = B; a.o.nr = nr;
+    a.o.max_ls = o.max_ls > 0 ? o.max_ls : 40;
+    a.o.patience = o.patience > 0 ? o.patience : 5;
+    a.o.ds = ds;
+    a.o.c1 = o.armijo > 0 ? o.armijo : 1e-4;
+    a.o.ftol = o.ftol > 0 ? o.ftol : 1e-12;
+    a.o.gtol = o.gtol > 0 ? o.gtol : 1e-8;
+    a.Z = w.Z.p; a.Gz = w.Gz.p; a.D = w.D.p; a.X = w.X.p; a.Gx = w.Gx.p; a.S = w.S.p; a.Y = w.Y.p;
+    a.lo = w.lo.p; a.hi = w.hi.p;
+    int* li = w.lane_i.p;
+    a.st = li; a.ls = li + B; a.head = li + 2 * (size_t)B; a.stall = li + 3 * (size_t)B; a.flag = li + 4 * (size_t)B;
+    a.newdir = li + 5 * (size_t)B; a.iters = li + 6 * (size_t)B; a.nfail = li + 7 * (size_t)B;
+    a.valid = (unsigned*)(li + 8 * (size_t)B);
+    a.ndone = li + 9 * (size_t)B;
+    double* ld = w.lane_d.p;
+    a.F0 = ld; a.t = ld + B; a.gd = ld + 2 * (size_t)B; a.gamma = ld + 3 * (size_t)B; a.gmax = ld + 4 * (size_t)B;
+    a.Ft = w.Ft.p;
+    a.rho = w.rho.p; a.delta = w.delta.p; a.M = w.M.p; a.part = w.part.p;
+    a.nchunks = nchunks; a.rows_per_chunk = rows;
+    tpl_opt_result res;
+    memset(&res, 0, sizeof(res));
+    cudaEvent_t ev0, ev1;
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, s));
+    const bool graph = o.use_graph != 0;
+    if (HM == 4) rc = run_optimizer<4>(e, a, B, mode, max_steps, check_every, graph, &res);
+    else if (HM == 8) rc = run_optimizer<8>(e, a, B, mode, max_steps, check_every, graph, &res);
+    else rc = run_optimizer<16>(e, a, B, mode, max_steps, check_every, graph, &res);
+    if (rc != TPL_OK) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc; }
+    CK(cudaEventRecord(ev1, s));
+    CK(cudaMemcpyAsync(X, w.X.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(F, w.Fout.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status, a.flag, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+    if (iters) CK(cudaMemcpyAsync(iters, a.iters, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    res.device_ms = ms;
+    e->last_launches = res.launches;
+    if (result) *result = res;
+    return TPL_OK;
+}
+
+namespace {
 }  // namespace
 
 extern "C" {

@@ -54,12 +54,30 @@ def loocv_chisq(flat, X, lane_tip, freeparams):
     return out
 
 
-def loocv(flat, smoothing_grid, tips, device=0, log_pen=False, max_iter=3000, verbose=False):
-    """-> dict(chisq per smoothing value, best smoothing, timings).  tips: node numbers in fold order
-    (externalNodes order, main.cpp:603-608)."""
-    import torch
+def _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose):
+    """-> (X, F, info) with info keys iterations (max accepted steps), nfev (batched evaluations), converged [B]."""
+    P, B = X0.shape
+    if native:
+        X, F, info = plp.optimize_batch(X0, lo, hi, mode=eng.GRAD_AD, history=history, max_steps=20 * max_iter,
+                                        date_scale=dscale, use_graph=1)
+        bad = np.nonzero(info["status"] == 4)[0]
+        if bad.size:
+            raise ValueError("start point infeasible for vectors %s" % bad.tolist()[:8])
+        return X, F, {"iterations": int(info["iterations"].max()), "nfev": info["steps"],
+                      "converged": (info["status"] >= 1) & (info["status"] <= 3), "device_ms": info["device_ms"],
+                      "launches": info["launches"]}
+    opt = batchopt.BatchedLBFGS(plp, P, B, nr, lo, hi, date_scale=dscale)
+    return opt.minimize(X0, max_iter=max_iter, verbose=verbose)
 
-    torch.cuda.set_device(device)
+
+def loocv(flat, smoothing_grid, tips, device=0, log_pen=False, max_iter=3000, verbose=False, native=True, history=8):
+    """-> dict(chisq per smoothing value, best smoothing, timings).  tips: node numbers in fold order
+    (externalNodes order, main.cpp:603-608).  native=True: the optimiser is the library's own device-resident
+    L-BFGS (tpl_optimize_batch); False: the torch-vector-arithmetic prototype of batchopt.py."""
+    if not native:
+        import torch
+
+        torch.cuda.set_device(device)
     n = len(flat["parents"])
     plp = eng.PLCalcParallel.from_flat(flat, device=device)
     plp.set_log_pen(log_pen)
@@ -76,8 +94,7 @@ def loocv(flat, smoothing_grid, tips, device=0, log_pen=False, max_iter=3000, ve
     x0 = start_vector(flat, P, nr)
     par = flat["parents"]
     dscale = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
-    opt = batchopt.BatchedLBFGS(plp, P, B1, nr, lo, hi, date_scale=dscale)
-    Xfull, Ffull, info1 = opt.minimize(np.repeat(x0[:, None], B1, axis=1), max_iter=max_iter, verbose=verbose)
+    Xfull, Ffull, info1 = _minimize(plp, np.repeat(x0[:, None], B1, axis=1), lo, hi, nr, dscale, max_iter, native, history, verbose)
     t1 = time.perf_counter()
     # ---- folds: one vector per (smoothing value, pruned tip) ----
     B2 = K * T
@@ -95,8 +112,7 @@ def loocv(flat, smoothing_grid, tips, device=0, log_pen=False, max_iter=3000, ve
     for b in range(B2, B2p):
         lam2[b] = lam2[B2 - 1]; masks.append(masks[B2 - 1]); lane_tip.append(lane_tip[B2 - 1]); X0[:, b] = X0[:, B2 - 1]
     plp.batch_configure(B2p, lane_smoothing=lam2, masks=masks)
-    opt2 = batchopt.BatchedLBFGS(plp, P, B2p, nr, lo, hi, date_scale=dscale)
-    Xcv, Fcv, info2 = opt2.minimize(X0, max_iter=max_iter, verbose=verbose)
+    Xcv, Fcv, info2 = _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose)
     t2 = time.perf_counter()
     terms = loocv_chisq(flat, Xcv, lane_tip, fp)[:B2].reshape(K, T)
     chisq = terms.sum(axis=1)                      # fold order, fixed
@@ -105,4 +121,6 @@ def loocv(flat, smoothing_grid, tips, device=0, log_pen=False, max_iter=3000, ve
             "full_objective": Ffull[:K].tolist(), "full_seconds": t1 - t0, "cv_seconds": t2 - t1,
             "full_info": {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in info1.items()},
             "cv_iterations": info2["iterations"], "cv_nfev": info2["nfev"], "cv_converged": int(info2["converged"][:B2].sum()),
+            "full_device_ms": info1.get("device_ms"), "cv_device_ms": info2.get("device_ms"),
+            "launches": (info1.get("launches") or 0) + (info2.get("launches") or 0),
             "n_vectors": B2, "terms": terms}

@@ -32,6 +32,17 @@ GRAD_AD = 1
 _lib = None
 
 
+class OptOptions(C.Structure):
+    """tpl_opt_options (include/treepl_b200.h); 0 = library default"""
+    _fields_ = [("history", C.c_int), ("max_steps", C.c_int), ("patience", C.c_int), ("max_ls", C.c_int),
+                ("check_every", C.c_int), ("use_graph", C.c_int), ("ftol", C.c_double), ("gtol", C.c_double),
+                ("armijo", C.c_double), ("date_scale", C.c_double)]
+
+
+class OptResult(C.Structure):
+    _fields_ = [("steps", C.c_int), ("n_done", C.c_int), ("launches", C.c_int), ("device_ms", C.c_double)]
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -78,6 +89,8 @@ def load_library():
         fn = getattr(L, name)
         fn.restype = cd
         fn.argtypes = args
+    L.tpl_optimize_batch.restype = ci
+    L.tpl_optimize_batch.argtypes = [vp, ci, dp, dp, dp, dp, ci, C.POINTER(OptOptions), ip, ip, C.POINTER(OptResult)]
     L.tpl_host_alloc.restype = vp
     L.tpl_host_alloc.argtypes = [C.c_ulonglong]
     L.tpl_host_free.restype = None
@@ -93,7 +106,7 @@ EXPORTED_SYMBOLS = (
     "tpl_calc_function_gradient", "tpl_calc_pl_grad", "tpl_get_rates", "tpl_get_dates", "tpl_get_durations",
     "tpl_batch_configure", "tpl_calc_pl_grad_batch", "tpl_calc_pl_grad_batch_dev", "tpl_last_launch_count",
     "tpl_host_alloc", "tpl_host_free", "tpl_device_sm", "tpl_debug_math", "tpl_set_timing", "tpl_get_timing", "tpl_debug_force_kernel",
-    "tpl_last_kernel_generation",
+    "tpl_last_kernel_generation", "tpl_optimize_batch",
 )
 
 
@@ -330,6 +343,30 @@ class PLCalcParallel:
         self._check(self._L.tpl_calc_pl_grad_batch_dev(self._h, int(B), C.c_void_p(dX), C.c_void_p(dF),
                                                        C.c_void_p(dG) if dG else None, int(mode),
                                                        C.c_void_p(stream) if stream else None))
+
+    def optimize_batch(self, X0, lower, upper, mode=GRAD_AD, **options):
+        """Device-resident batched L-BFGS (tpl_optimize_batch): X0 [P, B] feasible start vectors ->
+        (X [P, B], F [B], info).  options: fields of tpl_opt_options (history, max_steps, patience, max_ls,
+        check_every, use_graph, ftol, gtol, armijo, date_scale)."""
+        X = _f64(X0).copy()
+        P, B = X.shape
+        if P != self.numparams:
+            raise ValueError("X0 has %d rows, engine expects %d" % (P, self.numparams))
+        lo, hi = _f64(lower), _f64(upper)
+        assert lo.shape[0] == P and hi.shape[0] == P
+        F = np.zeros(B)
+        status = np.zeros(B, dtype=np.int32)
+        iters = np.zeros(B, dtype=np.int32)
+        o = OptOptions()
+        for k, v in options.items():
+            if not hasattr(o, k):
+                raise TypeError("unknown optimiser option %r" % k)
+            setattr(o, k, v)
+        res = OptResult()
+        self._check(self._L.tpl_optimize_batch(self._h, B, _dp(X), _dp(F), _dp(lo), _dp(hi), int(mode), C.byref(o),
+                                               _ip(status), _ip(iters), C.byref(res)))
+        return X, F, {"steps": res.steps, "n_done": res.n_done, "launches": res.launches, "device_ms": res.device_ms,
+                      "status": status, "iterations": iters}
 
     def set_timing(self, on):
         self._check(self._L.tpl_set_timing(self._h, int(bool(on))))
