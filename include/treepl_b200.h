@@ -151,6 +151,8 @@ typedef struct tpl_opt_options {
     double gtol;        /* 0 = 1e-8; on max |projected gradient| relative to max(|f|, 1) */
     double armijo;      /* 0 = 1e-4 */
     double date_scale;  /* 0 = 1 */
+    double boundary_frac; /* a new direction's first step covers at most this fraction of the distance to the
+                           * nearest zero-duration boundary (ratio test over the branches); 0 = 0.9, < 0 = off */
 } tpl_opt_options;
 
 typedef struct tpl_opt_result {

@@ -15,7 +15,8 @@ typedef void (*eval_fn)(const double* X, double* F, double* G, void* ctx);   // 
 
 template <int HM>
 static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, const double* hi, double ds, int max_steps,
-               int patience, int max_ls, double ftol, double gtol, double c1, eval_fn ev, void* ctx, int* status, int* iters) {
+               int patience, int max_ls, double ftol, double gtol, double c1, eval_fn ev, void* ctx, int* status, int* iters,
+               int n, const int* parent, const int* dslot, const double* hfix, double boundary_frac) {
     typedef Layout<HM> L;
     constexpr int NB = L::NB, NACC = L::NACC;
     const size_t PB = (size_t)P * B;
@@ -36,22 +37,34 @@ static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, 
     auto trial_kernel = [&]() {
         for (int b = 0; b < B; b++) {
             if (st[b] == ST_DONE) continue;
-            for (int p = 0; p < P; p++) {
-                const size_t i = (size_t)p * B + b;
-                double d;
-                if (newdir[b]) {
+            if (newdir[b]) {
+                // opt_direction_kernel
+                for (int p = 0; p < P; p++) {
+                    const size_t i = (size_t)p * B + b;
                     double q = delta[(size_t)L::IG * B + b] * Gz[i];
                     for (int k = 0; k < HM; k++)
                         if ((valid[b] >> k) & 1u) {
                             q = fma(delta[(size_t)k * B + b], S[(size_t)k * PB + i], q);
                             q = fma(delta[(size_t)(HM + k) * B + b], Y[(size_t)k * PB + i], q);
                         }
-                    d = is_free(Z[i], Gz[i], lo[p], hi[p]) ? -q : 0.0;
-                    D[i] = d;
-                } else {
-                    d = D[i];
+                    D[i] = is_free(Z[i], Gz[i], lo[p], hi[p]) ? -q : 0.0;
                 }
-                const double zt = trial_point(Z[i], t[b], d, lo[p], hi[p]);
+                // opt_stepmax_kernel
+                if (boundary_frac > 0.0) {
+                    double tmin = 1e300;
+                    for (int i = 1; i < n; i++) {
+                        const int pa = parent[i], ri = dslot[i], rp = dslot[pa];
+                        const double zi = ri >= 0 ? Z[(size_t)ri * B + b] : hfix[i] / ds, di = ri >= 0 ? D[(size_t)ri * B + b] : 0.0;
+                        const double zp = rp >= 0 ? Z[(size_t)rp * B + b] : hfix[pa] / ds, dp = rp >= 0 ? D[(size_t)rp * B + b] : 0.0;
+                        tmin = fmin(tmin, branch_step_limit(zi, di, zp, dp));
+                    }
+                    t[b] = fmin(t[b], boundary_frac * tmin);
+                }
+            }
+            // opt_trial_kernel
+            for (int p = 0; p < P; p++) {
+                const size_t i = (size_t)p * B + b;
+                const double zt = trial_point(Z[i], t[b], D[i], lo[p], hi[p]);
                 X[i] = p < nr ? exp(zt) : zt * ds;
             }
         }
@@ -132,9 +145,10 @@ static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, 
 
 extern "C" int lbfgs_sim(int history, int P, int B, int nr, double* X, double* F, const double* lo, const double* hi, double ds,
                          int max_steps, int patience, int max_ls, double ftol, double gtol, double c1, eval_fn ev, void* ctx,
-                         int* status, int* iters) {
-    if (history == 4) return run<4>(P, B, nr, X, F, lo, hi, ds, max_steps, patience, max_ls, ftol, gtol, c1, ev, ctx, status, iters);
-    if (history == 8) return run<8>(P, B, nr, X, F, lo, hi, ds, max_steps, patience, max_ls, ftol, gtol, c1, ev, ctx, status, iters);
-    if (history == 16) return run<16>(P, B, nr, X, F, lo, hi, ds, max_steps, patience, max_ls, ftol, gtol, c1, ev, ctx, status, iters);
+                         int* status, int* iters, int n, const int* parent, const int* dslot, const double* hfix, double boundary_frac) {
+#define TPL_RUN(H) run<H>(P, B, nr, X, F, lo, hi, ds, max_steps, patience, max_ls, ftol, gtol, c1, ev, ctx, status, iters, n, parent, dslot, hfix, boundary_frac)
+    if (history == 4) return TPL_RUN(4);
+    if (history == 8) return TPL_RUN(8);
+    if (history == 16) return TPL_RUN(16);
     return -1;
 }

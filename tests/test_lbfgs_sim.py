@@ -30,7 +30,7 @@ def load_sim():
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
     lib.lbfgs_sim.restype = C.c_int
     lib.lbfgs_sim.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_int,
-                              C.c_double, C.c_double, C.c_double, EVAL_FN, C.c_void_p, ip, ip]
+                              C.c_double, C.c_double, C.c_double, EVAL_FN, C.c_void_p, ip, ip, C.c_int, ip, ip, dp, C.c_double]
     return lib
 
 
@@ -58,7 +58,7 @@ def transformed_bounds(lower, upper, nr, ds):
     return lo, hi
 
 
-def fit(sim, name, lams, max_steps, history=8, masks=None):
+def fit(sim, name, lams, max_steps, history=8, boundary_frac=0.9, ftol=1e-12, patience=5):
     gd = Golden(name)
     flat = gd.flat
     n = len(flat["parents"])
@@ -91,8 +91,12 @@ def fit(sim, name, lams, max_steps, history=8, masks=None):
     status = np.zeros(B, dtype=np.int32)
     iters = np.zeros(B, dtype=np.int32)
     cb = EVAL_FN(evaluator)
-    steps = sim.lbfgs_sim(history, P, B, n - 1, _dp(X), _dp(F), _dp(lo), _dp(hi), ds, max_steps, 5, 40, 1e-12, 1e-8, 1e-4, cb, None,
-                          status.ctypes.data_as(C.POINTER(C.c_int)), iters.ctypes.data_as(C.POINTER(C.c_int)))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    parent = np.ascontiguousarray(flat["parents"], dtype=np.int32)
+    dslot = np.ascontiguousarray(fp[n:], dtype=np.int32)
+    hfix = np.ascontiguousarray(flat["start_dates"], dtype=np.float64)
+    steps = sim.lbfgs_sim(history, P, B, n - 1, _dp(X), _dp(F), _dp(lo), _dp(hi), ds, max_steps, patience, 40, ftol, 1e-8, 1e-4, cb, None,
+                          ip(status), ip(iters), n, ip(parent), ip(dslot), _dp(hfix), boundary_frac)
     assert steps == nev[0]
     return flat, fp, X, F, status, iters, steps
 

@@ -119,5 +119,5 @@ def test_loocv_m1155_chisq_table_matches_the_reference_run():
     res = cv.loocv(dict(gd.flat), [1000.0, 100.0, 10.0, 1.0, 0.1], ft.tips_postorder, max_iter=6000, native=True)
     ref = np.array([2730.97, 2365.8, 2130.28, 2178.18, 2187.12])
     assert res["cv_converged"] == res["n_vectors"]
-    assert np.all(np.abs(np.array(res["chisq"]) - ref) <= 1e-4 * ref), res["chisq"]
+    assert np.all(np.abs(np.array(res["chisq"]) - ref) <= 5e-5 * ref), res["chisq"]      # the reference prints 6 digits; at smoothing 0.1 chi-square moves by ~2e-5 between equally converged optima
     assert res["best"] == 10.0

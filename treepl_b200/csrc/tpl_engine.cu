@@ -168,7 +168,7 @@ struct tpl_engine {
     int last_gen = 0;
     // device-resident optimiser work space (tpl_optimize_batch)
     struct OptWork {
-        DevBuf<double> Z, Gz, D, X, Gx, S, Y, lo, hi, lane_d, rho, delta, M, part, Ft, Fout;
+        DevBuf<double> Z, Gz, D, X, Gx, S, Y, lo, hi, lane_d, rho, delta, M, part, tpart, Ft, Fout;
         DevBuf<int> lane_i;
         PinBuf<int> h_done;
     } opt;
@@ -747,24 +747,28 @@ int run_optimizer(tpl_engine* e, tplopt::OptArgs a, int B, int mode, int max_ste
     const size_t lsmem = (size_t)(L::NACC + L::NB * L::NB) * OPT_LX * sizeof(double);
     CK(cudaFuncSetAttribute(opt_lane_kernel<HM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
     int launches = 0;
+    const dim3 tgrd((B + 31) / 32, a.tchunks);
     opt_init_kernel<<<grd, blk, 0, s>>>(a);
-    opt_trial_kernel<HM><<<grd, blk, 0, s>>>(a);
+    opt_trial_kernel<<<grd, blk, 0, s>>>(a);
     launches += 2;
     CK(cudaGetLastError());
     auto one_step = [&]() -> int {
         int rc = eval_device(e, B, a.X, const_cast<double*>(a.Ft), const_cast<double*>(a.Gx), mode, true, s);
         if (rc != TPL_OK) return rc;
-        opt_update_kernel<HM><<<grd, blk, 0, s>>>(a);
+        opt_update_kernel<HM><<<grd, dim3(32, HM), 0, s>>>(a);
         opt_lane_kernel<HM><<<lgrd, lblk, lsmem, s>>>(a);
-        opt_trial_kernel<HM><<<grd, blk, 0, s>>>(a);
+        opt_direction_kernel<HM><<<grd, blk, 0, s>>>(a);
+        if (a.boundary_frac > 0.0) opt_stepmax_kernel<<<tgrd, blk, 0, s>>>(a);
+        opt_trial_kernel<<<grd, blk, 0, s>>>(a);
         CK(cudaGetLastError());
         return TPL_OK;
     };
+    const int per_step = a.boundary_frac > 0.0 ? 7 : 6;
     int steps = 0;
     int rc = one_step();               // first step outside any capture: sizes the evaluation work space
     if (rc != TPL_OK) return rc;
     steps++;
-    launches += 5;
+    launches += per_step;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     const bool was_timing = e->timing;
@@ -789,7 +793,7 @@ int run_optimizer(tpl_engine* e, tplopt::OptArgs a, int B, int mode, int max_ste
             if (rc != TPL_OK) break;
         }
         steps += check_every;
-        launches += 5 * check_every;
+        launches += per_step * check_every;
         CK(cudaMemcpyAsync(e->opt.h_done.p, a.ndone, sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         ndone = e->opt.h_done.p[0];
@@ -857,12 +861,12 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
     int nchunks = (4 * e->num_sms + groups - 1) / groups;
     nchunks = std::max(1, std::min(nchunks, std::min(256, (P + OPT_WY - 1) / OPT_WY)));
     int rows = (P + nchunks - 1) / nchunks;
-    rows = ((rows + OPT_WY - 1) / OPT_WY) * OPT_WY;
+    rows = ((rows + 15) / 16) * 16;                 // whole row tiles of the update kernel for every history size
     nchunks = (P + rows - 1) / rows;
     CK(w.Z.ensure(PB)); CK(w.Gz.ensure(PB)); CK(w.D.ensure(PB)); CK(w.X.ensure(PB)); CK(w.Gx.ensure(PB));
     CK(w.S.ensure(PB * HM)); CK(w.Y.ensure(PB * HM));
     CK(w.lo.ensure(P)); CK(w.hi.ensure(P));
-    CK(w.lane_d.ensure((size_t)5 * B)); CK(w.lane_i.ensure((size_t)9 * B + 1));
+    CK(w.lane_d.ensure((size_t)5 * B)); CK(w.lane_i.ensure((size_t)9 * B + 1 + groups));
     CK(w.rho.ensure((size_t)HM * B)); CK(w.delta.ensure((size_t)NB * B)); CK(w.M.ensure((size_t)NB * NB * B));
     CK(w.part.ensure((size_t)nchunks * NACC * B)); CK(w.Ft.ensure(B)); CK(w.Fout.ensure(B));
     CK(w.h_done.ensure(1));
@@ -871,7 +875,7 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
     CK(cudaMemcpyAsync(w.hi.p, hi.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(w.X.p, X, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(w.lane_d.p, 0, sizeof(double) * 5 * B, s));
-    CK(cudaMemsetAsync(w.lane_i.p, 0, sizeof(int) * (9 * (size_t)B + 1), s));      // st = ST_INIT = 0, t = 0
+    CK(cudaMemsetAsync(w.lane_i.p, 0, sizeof(int) * (9 * (size_t)B + 1 + groups), s));      // st = ST_INIT = 0, t = 0
     CK(cudaMemsetAsync(w.rho.p, 0, sizeof(double) * HM * B, s));
     CK(cudaMemsetAsync(w.delta.p, 0, sizeof(double) * NB * B, s));
     CK(cudaMemsetAsync(w.M.p, 0, sizeof(double) * NB * NB * B, s));
@@ -898,6 +902,16 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
     a.Ft = w.Ft.p;
     a.rho = w.rho.p; a.delta = w.delta.p; a.M = w.M.p; a.part = w.part.p;
     a.nchunks = nchunks; a.rows_per_chunk = rows;
+    a.tcount = li + 9 * (size_t)B + 1;
+    a.n = n; a.parent = e->d_parent.p; a.dslot = e->d_dslot.p; a.hfix = e->d_hfix.p;
+    int tchunks = std::max(1, std::min(nchunks, (n + 8 * OPT_WY - 1) / (8 * OPT_WY)));
+    int npc = (n + tchunks - 1) / tchunks;
+    npc = ((npc + OPT_WY - 1) / OPT_WY) * OPT_WY;
+    tchunks = (n + npc - 1) / npc;
+    a.tchunks = tchunks; a.nodes_per_chunk = npc;
+    CK(w.tpart.ensure((size_t)tchunks * B));
+    a.tpart = w.tpart.p;
+    a.boundary_frac = o.boundary_frac < 0 ? 0.0 : (o.boundary_frac > 0 ? std::min(o.boundary_frac, 0.999999) : 0.9);
     tpl_opt_result res;
     memset(&res, 0, sizeof(res));
     cudaEvent_t ev0, ev1;

@@ -8,8 +8,10 @@
 //                       new (s, y) pair, and accumulates the 6m+2 dot products the Gram matrix needs  ((2m+9) * 8 B / element)
 //   opt_lane_kernel   : per vector: fixed-order reduction of the chunk partials, Gram update, two-loop recursion
 //                       on coefficients, Armijo / convergence state machine (tpl_lbfgs_core.h)
-//   opt_trial_kernel  : D = -free * sum_j delta_j b_j  (reads 2m+2 rows) for vectors with a new direction,
-//                       then the trial point X = (exp(z + t D) | ds (z + t D)) for every running vector
+//   opt_direction_kernel : D = -free * sum_j delta_j b_j  (reads 2m+2 rows) for vectors with a new direction
+//   opt_stepmax_kernel   : ratio test over the tree's branches: a new direction's first step stays inside the
+//                          feasible region (all durations > 0) instead of discovering the boundary by backtracking
+//   opt_trial_kernel     : the trial point X = (exp(z + t D) | ds (z + t D)) for every running vector
 // Deterministic: static row -> thread mapping, fixed-order reductions, no floating-point atomics.
 #pragma once
 #include "tpl_lbfgs_core.h"
@@ -29,6 +31,14 @@ struct OptArgs {
     double *rho, *delta, *M, *part;  // [HM][B], [NB][B], [NB*NB][B], [nchunks][NACC][B]
     int nchunks, rows_per_chunk;
     int* ndone;
+    // ratio test (largest step that keeps every branch duration positive)
+    int n;                           // nodes
+    const int *parent, *dslot;       // [n] parent node, date row of the node (-1 = fixed date)
+    const double* hfix;              // [n] fixed dates
+    double* tpart;                   // [tchunks][B] per-chunk minima of the ratio test
+    int* tcount;                     // [ceil(B/32)] arrival counters of the ratio test (zero between launches)
+    int tchunks, nodes_per_chunk;
+    double boundary_frac;            // fraction of the distance to the boundary a first trial step may take
 };
 
 constexpr int OPT_WY = 8;            // row sub-lanes per block (block = 32 x 8)
@@ -49,12 +59,19 @@ __global__ void __launch_bounds__(32 * OPT_WY) opt_init_kernel(OptArgs a) {
     }
 }
 
+// Block = 32 vectors x HM threads.  Rows are processed in tiles of HM rows, two phases per tile:
+//   phase 1  thread (tx, r) owns ROW r of the tile: new gradient in the transformed variables, accepted point,
+//            the new (s, y) pair (written to slot h), projected gradient gp; s, y, gp go to shared memory
+//   phase 2  thread (tx, k) owns history SLOT k: streams S_k, Y_k of the tile's rows (2 HM independent loads in
+//            flight) and accumulates its six dot products against the tile's s, y, gp
+// so a thread carries 6 accumulators instead of 6 HM + 2 (no register-bound occupancy), and the per-chunk
+// partials of slot k are complete in one thread (fixed order, no cross-thread reduction).
 template <int HM>
-__global__ void __launch_bounds__(32 * OPT_WY) opt_update_kernel(OptArgs a) {
+__global__ void __launch_bounds__(32 * HM) opt_update_kernel(OptArgs a) {
     typedef Layout<HM> L;
     constexpr int NACC = L::NACC;
-    __shared__ double red[8][OPT_WY][32];
-    const int tx = threadIdx.x, ty = threadIdx.y;
+    __shared__ double sh_s[2][HM][32], sh_y[2][HM][32], sh_g[2][HM][32];
+    const int tx = threadIdx.x, k = threadIdx.y;
     const int b = blockIdx.x * 32 + tx;
     const int B = a.o.B, P = a.o.P, nr = a.o.nr;
     const double ds = a.o.ds;
@@ -71,67 +88,88 @@ __global__ void __launch_bounds__(32 * OPT_WY) opt_update_kernel(OptArgs a) {
     const bool acc_lane = dec == DEC_ACCEPT;
     const bool active = acc_lane || dec == DEC_INIT;
     if (!__syncthreads_or(active)) return;          // no vector of this block moved: partials stay unused
-    double acc[NACC];
-#pragma unroll
-    for (int k = 0; k < NACC; k++) acc[k] = 0.0;
-    if (active) {
-        const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
-        for (int p = p0 + ty; p < p1; p += OPT_WY) {
-            const size_t i = (size_t)p * B + b;
-            const double lo = a.lo[p], hi = a.hi[p];
-            const double x = a.X[i], gx = a.Gx[i];
-            const double gzn = p < nr ? gx * x : gx * ds;          // chain rule: d/du = r d/dr, d/dz = ds d/dh
-            double z = a.Z[i];
-            double s = 0.0, y = 0.0;
-            if (acc_lane) {
-                const double zt = trial_point(z, t, a.D[i], lo, hi);
-                s = zt - z;
-                y = gzn - a.Gz[i];
-                z = zt;
-                a.Z[i] = zt;
-                a.S[(size_t)h * PB + i] = s;
-                a.Y[(size_t)h * PB + i] = y;
+    const bool cur = k == h;
+    const bool my_slot = acc_lane && (cur || ((valid >> k) & 1u));
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, gg = 0.0, gmx = 0.0;
+    const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
+    const double* Sk = a.S + (size_t)k * PB + b;
+    const double* Yk = a.Y + (size_t)k * PB + b;
+    int buf = 0;
+    for (int r0 = p0; r0 < p1; r0 += HM, buf ^= 1) {
+        {   // ---- phase 1: row r0 + k ----
+            const int p = r0 + k;
+            double s = 0.0, y = 0.0, gp = 0.0;
+            if (active && p < p1) {
+                const size_t i = (size_t)p * B + b;
+                const double lo = a.lo[p], hi = a.hi[p];
+                const double x = a.X[i], gx = a.Gx[i];
+                double z = a.Z[i];
+                const double gzn = p < nr ? gx * x : gx * ds;       // chain rule: d/du = r d/dr, d/dz = ds d/dh
+                if (acc_lane) {
+                    const double zt = trial_point(z, t, a.D[i], lo, hi);
+                    s = zt - z;
+                    y = gzn - a.Gz[i];
+                    z = zt;
+                    a.Z[i] = zt;
+                    a.S[(size_t)h * PB + i] = s;
+                    a.Y[(size_t)h * PB + i] = y;
+                }
+                a.Gz[i] = gzn;
+                gp = is_free(z, gzn, lo, hi) ? gzn : 0.0;
+                gg = fma(gp, gp, gg);
+                gmx = fmax(gmx, fabs(gp));
             }
-            a.Gz[i] = gzn;
-            const double gp = is_free(z, gzn, lo, hi) ? gzn : 0.0;
-            acc[L::A_GG] = fma(gp, gp, acc[L::A_GG]);
-            acc[L::A_GMAX] = fmax(acc[L::A_GMAX], fabs(gp));
-            if (acc_lane) {
+            sh_s[buf][k][tx] = s;
+            sh_y[buf][k][tx] = y;
+            sh_g[buf][k][tx] = gp;
+        }
+        __syncthreads();
+        if (my_slot) {   // ---- phase 2: slot k against the tile's rows ----
+            double Sv[HM], Yv[HM];
 #pragma unroll
-                for (int k = 0; k < HM; k++) {
-                    const bool cur = k == h;
-                    if (cur || ((valid >> k) & 1u)) {
-                        const double Sk = cur ? s : a.S[(size_t)k * PB + i];
-                        const double Yk = cur ? y : a.Y[(size_t)k * PB + i];
-                        acc[6 * k + 0] = fma(s, Sk, acc[6 * k + 0]);
-                        acc[6 * k + 1] = fma(s, Yk, acc[6 * k + 1]);
-                        acc[6 * k + 2] = fma(y, Sk, acc[6 * k + 2]);
-                        acc[6 * k + 3] = fma(y, Yk, acc[6 * k + 3]);
-                        acc[6 * k + 4] = fma(gp, Sk, acc[6 * k + 4]);
-                        acc[6 * k + 5] = fma(gp, Yk, acc[6 * k + 5]);
-                    }
+            for (int r = 0; r < HM; r++) {
+                Sv[r] = 0.0;
+                Yv[r] = 0.0;
+                if (!cur && r0 + r < p1) {
+                    Sv[r] = Sk[(size_t)(r0 + r) * B];
+                    Yv[r] = Yk[(size_t)(r0 + r) * B];
                 }
             }
-        }
-    }
-    // fixed-order block reduction over ty, 8 accumulators per round
-    double* part = a.part + (size_t)blockIdx.y * NACC * B;
 #pragma unroll
-    for (int g0 = 0; g0 < NACC; g0 += 8) {
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-            if (g0 + j < NACC) red[j][ty][tx] = acc[g0 + j];
-        __syncthreads();
-        if (g0 + ty < NACC && b < B) {
-            double v = red[ty][0][tx];
-            if (g0 + ty == L::A_GMAX) {
-                for (int y = 1; y < OPT_WY; y++) v = fmax(v, red[ty][y][tx]);
-            } else {
-                for (int y = 1; y < OPT_WY; y++) v += red[ty][y][tx];
+            for (int r = 0; r < HM; r++) {
+                const double s = sh_s[buf][r][tx], y = sh_y[buf][r][tx], gp = sh_g[buf][r][tx];
+                const double sv = cur ? s : Sv[r], yv = cur ? y : Yv[r];
+                a0 = fma(s, sv, a0);
+                a1 = fma(s, yv, a1);
+                a2 = fma(y, sv, a2);
+                a3 = fma(y, yv, a3);
+                a4 = fma(gp, sv, a4);
+                a5 = fma(gp, yv, a5);
             }
-            part[(size_t)(g0 + ty) * B + b] = v;
         }
-        __syncthreads();
+        // double buffering: the next tile's phase 1 writes the other buffer, and its barrier orders this
+        // tile's phase-2 reads before the buffer is written again
+    }
+    __syncthreads();
+    double* part = a.part + (size_t)blockIdx.y * NACC * B;
+    if (b < B) {
+        part[(size_t)(6 * k + 0) * B + b] = a0;
+        part[(size_t)(6 * k + 1) * B + b] = a1;
+        part[(size_t)(6 * k + 2) * B + b] = a2;
+        part[(size_t)(6 * k + 3) * B + b] = a3;
+        part[(size_t)(6 * k + 4) * B + b] = a4;
+        part[(size_t)(6 * k + 5) * B + b] = a5;
+    }
+    sh_s[0][k][tx] = gg;
+    sh_y[0][k][tx] = gmx;
+    __syncthreads();
+    if (k == 0 && b < B) {
+        for (int r = 1; r < HM; r++) {
+            gg += sh_s[0][r][tx];
+            gmx = fmax(gmx, sh_y[0][r][tx]);
+        }
+        part[(size_t)L::A_GG * B + b] = gg;
+        part[(size_t)L::A_GMAX * B + b] = gmx;
     }
 }
 
@@ -174,45 +212,112 @@ __global__ void __launch_bounds__(OPT_LX * OPT_NY) opt_lane_kernel(OptArgs a) {
         for (int k = ty; k < NB * NB; k += OPT_NY) a.M[(size_t)k * B + b] = sM[k * OPT_LX + tx];
 }
 
+// D = -free * sum_j delta_j b_j for the vectors that got a new direction
 template <int HM>
-__global__ void __launch_bounds__(32 * OPT_WY) opt_trial_kernel(OptArgs a) {
+__global__ void __launch_bounds__(32 * OPT_WY) opt_direction_kernel(OptArgs a) {
     typedef Layout<HM> L;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int b = blockIdx.x * 32 + tx;
+    const int B = a.o.B, P = a.o.P;
+    if (b >= B) return;
+    if (a.st[b] == ST_DONE || a.newdir[b] == 0) return;
+    const size_t PB = (size_t)P * B;
+    const unsigned valid = a.valid[b];
+    double dl[L::NB];
+#pragma unroll
+    for (int j = 0; j < L::NB; j++) dl[j] = a.delta[(size_t)j * B + b];
+    const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
+    // two rows per iteration: 2 (2 m + 2) independent loads in flight per thread
+    for (int p = p0 + ty; p < p1; p += 2 * OPT_WY) {
+        const int pb = p + OPT_WY;
+        const bool two = pb < p1;
+        const size_t i = (size_t)p * B + b, j = two ? (size_t)pb * B + b : i;
+        const double z0 = a.Z[i], g0 = a.Gz[i], z1 = a.Z[j], g1 = a.Gz[j];
+        double q0 = dl[L::IG] * g0, q1 = dl[L::IG] * g1;
+        double s0[HM], y0[HM], s1[HM], y1[HM];
+#pragma unroll
+        for (int k = 0; k < HM; k++) {
+            s0[k] = y0[k] = s1[k] = y1[k] = 0.0;
+            if ((valid >> k) & 1u) {
+                s0[k] = a.S[(size_t)k * PB + i];
+                y0[k] = a.Y[(size_t)k * PB + i];
+                s1[k] = a.S[(size_t)k * PB + j];
+                y1[k] = a.Y[(size_t)k * PB + j];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < HM; k++) {
+            q0 = fma(dl[k], s0[k], q0);
+            q0 = fma(dl[HM + k], y0[k], q0);
+            q1 = fma(dl[k], s1[k], q1);
+            q1 = fma(dl[HM + k], y1[k], q1);
+        }
+        a.D[i] = is_free(z0, g0, a.lo[p], a.hi[p]) ? -q0 : 0.0;
+        if (two) a.D[j] = is_free(z1, g1, a.lo[pb], a.hi[pb]) ? -q1 : 0.0;
+    }
+}
+
+// Ratio test for vectors with a new direction: the largest t for which every branch duration
+// h_parent - h_node of z + t D stays positive (the objective is +1e15 beyond it, set_durations
+// pl_calc_parallel.cpp:883-910).  Per-chunk minima; the LAST block of a 32-vector group to finish combines them
+// (min is order independent, so the result is deterministic) and shortens the unit step to boundary_frac of
+// the distance to the boundary.
+__global__ void __launch_bounds__(32 * OPT_WY) opt_stepmax_kernel(OptArgs a) {
+    __shared__ double red[OPT_WY][32];
+    __shared__ int s_last;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int b = blockIdx.x * 32 + tx;
+    const int B = a.o.B;
+    const bool active = b < B && a.st[b] != ST_DONE && a.newdir[b] != 0;
+    if (!__syncthreads_or(active)) return;          // uniform over blockIdx.y: the whole group skips
+    double tmin = 1e300;
+    if (active) {
+        const double ids = 1.0 / a.o.ds;
+        const int i0 = max(1, blockIdx.y * a.nodes_per_chunk), i1 = min(a.n, (blockIdx.y + 1) * a.nodes_per_chunk);
+        for (int i = i0 + ty; i < i1; i += OPT_WY) {
+            const int pa = a.parent[i];
+            const int ri = a.dslot[i], rp = a.dslot[pa];
+            double zi, di = 0.0, zp, dp = 0.0;
+            if (ri >= 0) { zi = a.Z[(size_t)ri * B + b]; di = a.D[(size_t)ri * B + b]; } else zi = a.hfix[i] * ids;
+            if (rp >= 0) { zp = a.Z[(size_t)rp * B + b]; dp = a.D[(size_t)rp * B + b]; } else zp = a.hfix[pa] * ids;
+            tmin = fmin(tmin, branch_step_limit(zi, di, zp, dp));
+        }
+    }
+    red[ty][tx] = tmin;
+    __syncthreads();
+    if (ty == 0 && b < B) {
+        for (int y = 1; y < OPT_WY; y++) tmin = fmin(tmin, red[y][tx]);
+        a.tpart[(size_t)blockIdx.y * B + b] = tmin;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tx == 0 && ty == 0) s_last = atomicAdd(a.tcount + blockIdx.x, 1) == (int)gridDim.y - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    tmin = 1e300;
+    if (active)
+        for (int c = ty; c < a.tchunks; c += OPT_WY) tmin = fmin(tmin, __ldcg(a.tpart + (size_t)c * B + b));
+    red[ty][tx] = tmin;
+    __syncthreads();
+    if (ty == 0 && active) {
+        for (int y = 1; y < OPT_WY; y++) tmin = fmin(tmin, red[y][tx]);
+        a.t[b] = fmin(a.t[b], a.boundary_frac * tmin);
+    }
+    if (tx == 0 && ty == 0) a.tcount[blockIdx.x] = 0;       // ready for the next launch
+}
+
+// trial point X = (exp(z + t D) | ds (z + t D)) for every running vector
+__global__ void __launch_bounds__(32 * OPT_WY) opt_trial_kernel(OptArgs a) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
     const int B = a.o.B, P = a.o.P, nr = a.o.nr;
     if (b >= B) return;
     if (a.st[b] == ST_DONE) return;
-    const double ds = a.o.ds;
-    const size_t PB = (size_t)P * B;
-    const bool nd = a.newdir[b] != 0;
-    const double t = a.t[b];
-    const unsigned valid = a.valid[b];
-    double dl[L::NB];
-    if (nd) {
-#pragma unroll
-        for (int j = 0; j < L::NB; j++) dl[j] = a.delta[(size_t)j * B + b];
-    }
+    const double t = a.t[b], ds = a.o.ds;
     const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
-    for (int p = p0 + ty; p < p1; p += OPT_WY) {
+    for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
         const size_t i = (size_t)p * B + b;
-        const double lo = a.lo[p], hi = a.hi[p];
-        const double z = a.Z[i];
-        double d;
-        if (nd) {
-            const double gz = a.Gz[i];
-            double q = dl[L::IG] * gz;
-#pragma unroll
-            for (int k = 0; k < HM; k++)
-                if ((valid >> k) & 1u) {
-                    q = fma(dl[k], a.S[(size_t)k * PB + i], q);
-                    q = fma(dl[HM + k], a.Y[(size_t)k * PB + i], q);
-                }
-            d = is_free(z, gz, lo, hi) ? -q : 0.0;
-            a.D[i] = d;
-        } else {
-            d = a.D[i];
-        }
-        const double zt = trial_point(z, t, d, lo, hi);
+        const double zt = trial_point(a.Z[i], t, a.D[i], a.lo[p], a.hi[p]);
         a.X[i] = p < nr ? exp(zt) : zt * ds;
     }
 }

@@ -74,6 +74,12 @@ TPL_HD bool is_free(double z, double g, double lo, double hi) {
     return !((z <= lo && g > 0.0) || (z >= hi && g < 0.0));
 }
 
+// ratio test of one branch: the step length at which the duration zp - zi of z + t d reaches zero (1e300: never)
+TPL_HD double branch_step_limit(double zi, double di, double zp, double dp) {
+    const double shrink = di - dp;
+    return shrink > 0.0 ? (zp - zi) / shrink : 1e300;
+}
+
 struct LaneIO {
     // scalars of this vector
     int *st, *ls, *head, *stall, *flag, *newdir, *iters, *nfail;
@@ -145,7 +151,10 @@ TPL_HD bool lane_step(const LaneIO& L, double Ft, const OptConst& o) {
             *L.head = (h + 1) % HM;
             const double F0 = *L.F0;
             const double rel = fabs(F0 - Ft) / fmax(fabs(F0), 1.0);
-            const int stl = (rel <= o.ftol) ? *L.stall + 1 : 0;
+            // a first-trial step that the ratio test cut short (t < 1 without backtracking) says nothing about
+            // convergence: the boundary, not the objective, limited the decrease
+            const bool cut_short = *L.ls == 0 && *L.t < 1.0;
+            const int stl = (rel <= o.ftol) ? *L.stall + (cut_short ? 0 : 1) : 0;
             *L.stall = stl;
             *L.iters += 1;
             if (stl >= o.patience) { *L.flag = FLAG_CONV_F; done = true; }

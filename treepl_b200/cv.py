@@ -54,12 +54,16 @@ def loocv_chisq(flat, X, lane_tip, freeparams):
     return out
 
 
-def _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose):
+def _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose, **opt):
     """-> (X, F, info) with info keys iterations (max accepted steps), nfev (batched evaluations), converged [B]."""
     P, B = X0.shape
     if native:
+        # chi-square is far more sensitive to the last digits of the optimum than the objective is (at small
+        # smoothing the pruned tip's prediction hangs on weakly determined rates): converge tightly
+        opt.setdefault("ftol", 1e-15)
+        opt.setdefault("patience", 40)
         X, F, info = plp.optimize_batch(X0, lo, hi, mode=eng.GRAD_AD, history=history, max_steps=20 * max_iter,
-                                        date_scale=dscale, use_graph=1)
+                                        date_scale=dscale, use_graph=1, **opt)
         bad = np.nonzero(info["status"] == 4)[0]
         if bad.size:
             raise ValueError("start point infeasible for vectors %s" % bad.tolist()[:8])
@@ -70,7 +74,7 @@ def _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose):
     return opt.minimize(X0, max_iter=max_iter, verbose=verbose)
 
 
-def loocv(flat, smoothing_grid, tips, device=0, log_pen=False, max_iter=3000, verbose=False, native=True, history=8):
+def loocv(flat, smoothing_grid, tips, device=0, log_pen=False, max_iter=3000, verbose=False, native=True, history=8, **opt):
     """-> dict(chisq per smoothing value, best smoothing, timings).  tips: node numbers in fold order
     (externalNodes order, main.cpp:603-608).  native=True: the optimiser is the library's own device-resident
     L-BFGS (tpl_optimize_batch); False: the torch-vector-arithmetic prototype of batchopt.py."""
@@ -94,7 +98,7 @@ def loocv(flat, smoothing_grid, tips, device=0, log_pen=False, max_iter=3000, ve
     x0 = start_vector(flat, P, nr)
     par = flat["parents"]
     dscale = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
-    Xfull, Ffull, info1 = _minimize(plp, np.repeat(x0[:, None], B1, axis=1), lo, hi, nr, dscale, max_iter, native, history, verbose)
+    Xfull, Ffull, info1 = _minimize(plp, np.repeat(x0[:, None], B1, axis=1), lo, hi, nr, dscale, max_iter, native, history, verbose, **opt)
     t1 = time.perf_counter()
     # ---- folds: one vector per (smoothing value, pruned tip) ----
     B2 = K * T
@@ -112,7 +116,7 @@ def loocv(flat, smoothing_grid, tips, device=0, log_pen=False, max_iter=3000, ve
     for b in range(B2, B2p):
         lam2[b] = lam2[B2 - 1]; masks.append(masks[B2 - 1]); lane_tip.append(lane_tip[B2 - 1]); X0[:, b] = X0[:, B2 - 1]
     plp.batch_configure(B2p, lane_smoothing=lam2, masks=masks)
-    Xcv, Fcv, info2 = _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose)
+    Xcv, Fcv, info2 = _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose, **opt)
     t2 = time.perf_counter()
     terms = loocv_chisq(flat, Xcv, lane_tip, fp)[:B2].reshape(K, T)
     chisq = terms.sum(axis=1)                      # fold order, fixed
