@@ -18,6 +18,13 @@ a 100,000-tip birth-death tree (N = 199,999 nodes, P = 299,996 parameters).
 N > 1 (torchrun): one process per GPU, every rank evaluates its own B vectors of the same tree
 (CV folds / restarts are independent: weak scaling, no data-path collective); barrier + device
 timing, max over ranks.  `--impl reference` times the reference CPU path alone (rank 0 only).
+
+Second workload (BASELINE.json: "LOO-CV wall time at 1/8 B200"), not the driver's default:
+    python bench.py --workload loocv [--gpus N] [--steps K] [--impl reference]
+one step = the complete leave-one-out cross-validation of examples/M1155.cppr8s (59 folds x 5 smoothing values,
+tests/golden/M1155.npz) with the library's device-resident batched L-BFGS; the (smoothing, fold) vectors are
+dealt to the ranks and the chi-square terms all-gathered over NCCL (strong scaling).  The reference arm replays
+the reference's own CV loop around its optimize_full (annealer + TNC) on the host cores (oracle/_ref).
 """
 import argparse
 import json
@@ -193,7 +200,123 @@ def run_reference_arm(args, flat, P):
                                    % (args.tips, n, P)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_loocv:
+        # second half of BASELINE.json's metric: LOO-CV wall time (one run of the reference's CV loop, all host threads)
+        try:
+            gd, cals, tips = load_m1155()
+            p = rb.RefProblem.from_newick(gd.meta["newick"], gd.meta["numsites"], cals, seed=1)
+            t = time.perf_counter()
+            r = p.cross_validate(M1155_GRID, [[t_] for t_ in tips], nthreads=nthreads)
+            line["loocv"] = {"workload": "examples/M1155.cppr8s LOOCV (59 folds x 5 smoothing values)",
+                             "wall_s": time.perf_counter() - t, "cores": nthreads,
+                             "kind": "reference CV loop replayed around the reference's optimize_full (annealer + TNC)",
+                             "full_objective": r["full_pl"].tolist()}
+            p.close()
+        except Exception as ex:
+            line["loocv"] = {"error": repr(ex)}
     print(json.dumps(line))
+
+
+M1155_GRID = [1000.0, 100.0, 10.0, 1.0, 0.1]
+M1155_REF_CHISQ = [2730.97, 2365.8, 2130.28, 2178.18, 2187.12]      # reference run, seed 1, nthreads 1
+
+
+def load_m1155():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import Golden
+    from treepl_b200 import treeflat as tf
+    gd = Golden("M1155")
+    cals = [(t, lo, hi) for t, lo, hi in gd.meta["calibrations"]]
+    ft = tf.flatten_newick(gd.meta["newick"], gd.meta["numsites"], cals, seed=1)
+    return gd, cals, [int(t) for t in ft.tips_postorder]
+
+
+def run_loocv(args):
+    """--workload loocv: wall time of the complete M1155 leave-one-out cross-validation."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    gd, cals, tips = load_m1155()
+    workload = "examples/M1155.cppr8s: LOOCV, %d folds x %d smoothing values = %d optimisations of P=170 parameters" % (
+        len(tips), len(M1155_GRID), len(tips) * len(M1155_GRID))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import refbind as rb
+        if not rb.available():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libtreepl_ref.so is not built"}))
+            return
+        nthreads = max(1, os.cpu_count() or 1)
+        times, last = [], None
+        for s in range(args.warmup + args.steps):
+            p = rb.RefProblem.from_newick(gd.meta["newick"], gd.meta["numsites"], cals, seed=1)
+            t = time.perf_counter()
+            last = p.cross_validate(M1155_GRID, [[t_] for t_ in tips], nthreads=nthreads)
+            dt = time.perf_counter() - t
+            p.close()
+            if s >= args.warmup:
+                times.append(dt)
+        val = sum(times) / len(times)
+        sample = ("the whole workload: reference Langley-Fitch fit + CV loop (main.cpp:497-822 replayed) around the "
+                  "reference's optimize_full (annealer + TNC; NLopt not built), %d OpenMP threads over folds" % nthreads)
+        print(json.dumps({"impl": "reference", "metric": "loocv_wall_seconds", "value": val, "unit": "s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * val, "higher_is_better": False,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "examples/M1155.tre",
+                          "config": {"workload": workload},
+                          "chisq": last["chisq"].tolist(), "full_objective": last["full_pl"].tolist(),
+                          "note": "TNC-only replay: its optimiser stops short of the optimum (compare full_objective with the "
+                                  "b200 arm's), so its chi-square table is NOT the parity reference; SURVEY.md 8c's is",
+                          "cpu_baseline": {"value": val, "unit": "s", "cores": nthreads, "kind": "reference", "sample": sample},
+                          "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    from treepl_b200 import cv
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the PL engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    times, res = [], None
+    for s in range(args.warmup + args.steps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        res = cv.loocv(dict(gd.flat), M1155_GRID, tips, device=local, max_iter=6000, dist=dist)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        dt = time.perf_counter() - t
+        if dist is not None:
+            tt = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        if s >= args.warmup:
+            times.append(dt)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        val = sum(times) / len(times)
+        chisq = res["chisq"]
+        rel = [abs(a - b) / b for a, b in zip(chisq, M1155_REF_CHISQ)]
+        print(json.dumps({"metric": "loocv_wall_seconds", "value": val, "unit": "s", "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * val, "higher_is_better": False, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "examples/M1155.tre (tests/golden/M1155.npz)",
+                          "config": {"workload": workload, "optimizer": "tpl_optimize_batch (L-BFGS, history 8, CUDA graph)",
+                                     "parallelism": "(smoothing, fold) vectors dealt to %d GPU(s), chi-square all-gather" % world},
+                          "gpu_launches": int(res["launches"]) * world, "clocks": clocks,
+                          "chisq": chisq, "chisq_reference_run": M1155_REF_CHISQ, "chisq_max_rel_diff": max(rel),
+                          "best_smoothing": res["best"], "full_objective": res["full_objective"],
+                          "device_ms": {"full_fits": res["full_device_ms"], "folds": res["cv_device_ms"]},
+                          "batched_evaluations": {"full_fits": res["full_info"]["nfev"], "folds": res["cv_nfev"]},
+                          "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": int(2 * 170 * 8 * (6 + res["n_local_vectors"])),
+                                  "d2h_bytes_per_step": int(2 * 170 * 8 * (6 + res["n_local_vectors"]))}}))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():
@@ -208,7 +331,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--min-warm-seconds", type=float, default=1.0)
+    ap.add_argument("--workload", default="evals", choices=["evals", "loocv"])
+    ap.add_argument("--no-loocv", action="store_true", help="skip the LOO-CV summary attached to the default line")
     args = ap.parse_args()
+    if args.workload == "loocv":
+        if args.steps == 200:
+            args.steps = 1 if args.impl == "reference" else 5
+        if args.impl == "reference" and args.warmup == 3:
+            args.warmup = 0
+        run_loocv(args)
+        return
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
     flat = build_problem(args.tips)
@@ -352,6 +484,21 @@ def main():
                     line["cpu_baseline"] = {"value": r[0], "unit": UNIT, "cores": r[1], "kind": "reference", "sample": r[2]}
             except Exception as ex:      # the baseline must never take the GPU number down with it
                 line["cpu_baseline"] = {"error": repr(ex)}
+        if world == 1 and not args.no_loocv:
+            try:
+                from treepl_b200 import cv
+                gd, cals, tips = load_m1155()
+                cv.loocv(dict(gd.flat), M1155_GRID, tips, device=local, max_iter=6000)        # warm (allocations, graphs)
+                t = time.perf_counter()
+                r = cv.loocv(dict(gd.flat), M1155_GRID, tips, device=local, max_iter=6000)
+                wall = time.perf_counter() - t
+                line["loocv"] = {"workload": "examples/M1155.cppr8s LOOCV (59 folds x 5 smoothing values), device-resident batched L-BFGS",
+                                 "wall_s": wall, "chisq": r["chisq"], "chisq_reference_run": M1155_REF_CHISQ,
+                                 "chisq_max_rel_diff": max(abs(a - b) / b for a, b in zip(r["chisq"], M1155_REF_CHISQ)),
+                                 "best_smoothing": r["best"], "full_objective": r["full_objective"],
+                                 "gpu_launches": int(r["launches"]), "batched_evaluations": r["full_info"]["nfev"] + r["cv_nfev"]}
+            except Exception as ex:
+                line["loocv"] = {"error": repr(ex)}
         print(json.dumps(line))
     plp.close()
     if dist is not None:

@@ -11,6 +11,8 @@
  *   pl_calc_parallel::calc_gradient            (pl_calc_parallel.cpp:657)
  *   pl_calc_parallel::calc_function_gradient   (pl_calc_parallel.cpp:132, RAD tape)
  *   generate_param_order_vector / set_freeparams / set_cv_nodes
+ *   optimize_full (utils.cpp:671: annealer + TNC rounds) inside a replay of main()'s
+ *   Langley-Fitch fit and cross-validation loop (ref_cv below)
  * so that tests can (1) pin the C restatement in oracle/pl_oracle.c and the
  * golden vectors under tests/golden/, and (2) time the reference's CPU path on
  * the GPU box's host cores (bench.py cpu_baseline.kind == "reference").
@@ -39,6 +41,7 @@
 #include "utils.h"
 #include "pl_calc_parallel.h"
 #include "optimize_nlopt.h"
+#include "optim_options.h"
 
 using namespace std;
 
@@ -330,6 +333,105 @@ double ref_time_evals(void* h, const double* x, int reps, int nthreads, int with
     for (int t = 0; t < nthreads; t++) inst[t].delete_ad_arrays();
     if (sink == 12345.678) fprintf(stderr, "sink\n");
     return chrono::duration<double>(t1 - t0).count();
+}
+
+/* The reference's cross-validation run (main.cpp:497-822) replayed around the reference's OWN optimiser
+ * stack: optimize_full (utils.cpp:671-763) = siman_calc_par annealing + optimize_best (TNC, tnc.c) rounds.
+ *   1. Langley-Fitch fit of the full data (main.cpp:499-578)
+ *   2. for each smoothing value (main.cpp:668-682): PL fit of the full data, warm-started from the previous state
+ *   3. for each fold (main.cpp:689-801, OpenMP over folds with `nthreads`): prune the fold's tips (CV mask),
+ *      re-optimise from the full-data optimum, chi-square of the pruned branches (LOOCV :737-757, random :769-793)
+ * groups: CSR lists of tip node numbers per fold.  OptimOptions are the constructor defaults (optim_options.cpp)
+ * with the TNC optimiser (opt = optad = 0; NLopt is not built here, see the stubs above).
+ * The caller seeds libc rand() through ref_from_newick(seed) exactly as main() does; with nthreads = 1 the run
+ * is then reproducible.  Returns 0, fills chisq[nlam], fullpl[nlam], seconds[3] = {LF, full fits, folds}. */
+int ref_cv(void* h, int nlam, const double* lams, int ngroups, const int* goff, const int* gnodes, int randomcv,
+           int nthreads, double* chisq_out, double* fullpl_out, double* seconds) {
+    RefProblem* p = (RefProblem*)h;
+    CoutMute mute;
+    OptimOptions oopt;
+    oopt.nthreads = nthreads < 1 ? 1 : nthreads;
+    pl_calc_parallel& plp = p->plp;
+    auto now = [] { return chrono::steady_clock::now(); };
+    auto secs = [](chrono::steady_clock::time_point a, chrono::steady_clock::time_point b) {
+        return chrono::duration<double>(b - a).count();
+    };
+    auto t0 = now();
+    vector<int> freeparams;
+    vector<double> params;
+    int numparams = generate_param_order_vector(&freeparams, true, NULL, &p->free);
+    plp.set_freeparams(numparams, true, &freeparams, &params);
+    double init = plp.calc_pl(params);
+    if (std::isnan(init) || std::isinf(init) || init == 1e15) return -1;
+    optimize_full(plp, &params, &oopt, false);
+    plp.calc_pl(params);
+    auto t1 = now();
+    vector<double> strates(p->srates.size(), params[0]), stdates(plp.dates), stdur(plp.durations);
+    double tfull = 0.0, tfold = 0.0;
+    const int n = (int)p->parents.size();
+    for (int li = 0; li < nlam; li++) {
+        auto a = now();
+        freeparams.clear();
+        numparams = generate_param_order_vector(&freeparams, false, NULL, &p->free);
+        plp.smoothing = lams[li];
+        plp.set_freeparams(numparams, false, &freeparams, &params);
+        plp.calc_pl(params);
+        optimize_full(plp, &params, &oopt, false);
+        fullpl_out[li] = plp.calc_pl(params);
+        stdates = plp.dates;
+        stdur = plp.durations;
+        strates = plp.rates;
+        auto b = now();
+        tfull += secs(a, b);
+        double chisq = 0.0;
+#pragma omp parallel for reduction(+ : chisq) num_threads(oopt.nthreads)
+        for (int g = 0; g < ngroups; g++) {
+            vector<int> cvnodes(n, 0);
+            for (int j = goff[g]; j < goff[g + 1]; j++) cvnodes[gnodes[j]] = 1;
+            pl_calc_parallel q;
+            q.setup_starting_bits(&p->parents, &p->child_counts, &p->free, &p->c, &p->lf, &p->vmin, &p->vmax,
+                                  &stdates, &strates, &stdur);
+            q.set_log_pen(p->log_pen);
+            q.children_vec = &p->children;
+            q.pen_min = &p->penmin;
+            q.pen_max = &p->penmax;
+            q.smoothing = lams[li];
+            q.paramverbose = false;
+            q.set_cv_nodes(cvnodes);
+            vector<int> fpcv;
+            int npcv = generate_param_order_vector(&fpcv, false, &cvnodes, &p->free);
+            vector<double> xcv;
+            q.set_freeparams(npcv, false, &fpcv, &xcv);
+            q.calc_pl(xcv);
+            optimize_full(q, &xcv, &oopt, true);
+            q.calc_pl(xcv);
+            double tch = 0.0;
+            for (int j = goff[g]; j < goff[g + 1]; j++) {
+                const int tip = gnodes[j];
+                const int par = p->parents[tip];
+                double ratees = 0.0;
+                if (par == 0) {
+                    for (int v = 0; v < n; v++)
+                        if (p->parents[v] == par && v != tip) ratees = q.rates[v];
+                } else {
+                    ratees = q.rates[par];
+                }
+                const double d = q.durations[tip];
+                const double expe = ratees * d;
+                const double len = p->c[tip];
+                const double sq = (len - expe) * (len - expe);
+                if (!(d < 1e-100 || expe < 1e-100)) tch += sq / expe;
+            }
+            chisq += randomcv ? tch / (float)(goff[g + 1] - goff[g]) : tch;
+            q.delete_ad_arrays();
+        }
+        chisq_out[li] = chisq;
+        tfold += secs(b, now());
+    }
+    seconds[0] = secs(t0, t1);
+    seconds[1] = tfull;
+    seconds[2] = tfold;
+    return 0;
 }
 
 int ref_hw_threads(void) { return omp_get_num_procs(); }

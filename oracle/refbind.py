@@ -50,6 +50,8 @@ def lib():
         L.ref_calc_function_gradient.argtypes = [vp, dp, dp]
         L.ref_time_evals.restype = cd
         L.ref_time_evals.argtypes = [vp, dp, ci, ci, ci]
+        L.ref_cv.restype = ci
+        L.ref_cv.argtypes = [vp, ci, dp, ci, ip, ip, ci, ci, dp, dp, dp]
         L.ref_hw_threads.restype = ci
         _lib = L
     return _lib
@@ -187,6 +189,24 @@ class RefProblem:
         g = np.zeros_like(x)
         f = lib().ref_calc_function_gradient(self.h, _dp(x), _dp(g))
         return f, g
+
+    def cross_validate(self, smoothing_grid, groups, randomcv=False, nthreads=1):
+        """The reference's Langley-Fitch fit + cross-validation loop (main.cpp:497-822) around its own
+        optimize_full (annealer + TNC).  groups: list of lists of tip node numbers.  Call right after
+        from_newick(seed=...) for the libc rand() sequence of a reference run.
+        -> dict(chisq [K], full_pl [K], seconds {lf, full, folds})."""
+        lam = np.ascontiguousarray(smoothing_grid, dtype=np.float64)
+        off = np.zeros(len(groups) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(g) for g in groups])
+        nodes = np.ascontiguousarray([v for g in groups for v in g], dtype=np.int32)
+        chisq = np.zeros(len(lam))
+        full = np.zeros(len(lam))
+        secs = np.zeros(3)
+        rc = lib().ref_cv(self.h, len(lam), _dp(lam), len(groups), _ip(off), _ip(nodes), int(bool(randomcv)),
+                          int(nthreads), _dp(chisq), _dp(full), _dp(secs))
+        if rc != 0:
+            raise RuntimeError("reference cross-validation failed to initialise (rc=%d)" % rc)
+        return {"chisq": chisq, "full_pl": full, "seconds": {"lf": secs[0], "full": secs[1], "folds": secs[2]}}
 
     def time_evals(self, x, reps, nthreads, with_grad=True):
         x = np.ascontiguousarray(x, dtype=np.float64)

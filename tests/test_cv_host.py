@@ -1,0 +1,59 @@
+"""Host logic of the CV driver (treepl_b200/cv.py) on the CPU: fold sampling and chi-square scoring
+(reference src/main.cpp:603-656, 737-793)."""
+import numpy as np
+
+from golden_util import Golden
+from treepl_b200 import cv
+from treepl_b200 import treeflat as tf
+
+
+def _m1155():
+    gd = Golden("M1155")
+    cals = [(t, lo, hi) for t, lo, hi in gd.meta["calibrations"]]
+    ft = tf.flatten_newick(gd.meta["newick"], gd.meta["numsites"], cals, seed=1)
+    return gd.flat, [int(t) for t in ft.tips_postorder]
+
+
+def test_random_groups_are_sister_free_and_avoid_root_children():
+    flat, tips = _m1155()
+    par = flat["parents"]
+    groups = cv.sample_random_groups(flat, tips, n_groups=10, frac=0.1, seed=3)
+    assert len(groups) == 10
+    size = int(len(tips) * 0.1 + 0.5)
+    for g in groups:
+        assert len(g) == size and len(set(g)) == size
+        assert all(par[t] != 0 for t in g)                       # main.cpp:621
+        assert len({par[t] for t in g}) == size                  # no two sisters
+        assert all(flat["child_counts"][t] == 0 for t in g)
+    assert groups == cv.sample_random_groups(flat, tips, 10, 0.1, seed=3)      # reproducible
+
+
+def test_chisq_terms_follow_the_reference_formula():
+    """(c - r_parent d)^2 / (r_parent d); a child of the root is predicted with its sibling's rate (main.cpp:739-748);
+    random-subsample folds average over the group (main.cpp:792)."""
+    flat, tips = _m1155()
+    n = len(flat["parents"])
+    par = flat["parents"]
+    fp, P = tf.generate_param_order_vector(flat["free"], lf=False)
+    rng = np.random.RandomState(0)
+    x = cv.start_vector(flat, P, n - 1)
+    x[: n - 1] *= np.exp(0.2 * rng.randn(n - 1))
+    dates = flat["start_dates"].copy()
+    for i in range(n):
+        if fp[n + i] != -1:
+            dates[i] = x[fp[n + i]]
+    want = []
+    for t in tips[:12]:
+        p = par[t]
+        if p == 0:
+            sib = [j for j in range(n) if par[j] == 0 and j != t][-1]
+            r = x[fp[sib]]
+        else:
+            r = x[fp[p]]
+        e = r * (dates[p] - dates[t])
+        want.append((flat["c"][t] - e) ** 2 / e)
+    got = [cv.group_chisq(flat, x, [t], fp, False) for t in tips[:12]]
+    assert np.allclose(got, want, rtol=1e-14)
+    grp = tips[:12]
+    assert np.isclose(cv.group_chisq(flat, x, grp, fp, True), np.sum(want) / 12, rtol=1e-13)
+    assert np.isclose(cv.group_chisq(flat, x, grp, fp, False), np.sum(want), rtol=1e-13)

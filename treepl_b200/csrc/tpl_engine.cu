@@ -168,7 +168,7 @@ struct tpl_engine {
     int last_gen = 0;
     // device-resident optimiser work space (tpl_optimize_batch)
     struct OptWork {
-        DevBuf<double> Z, Gz, D, X, Gx, S, Y, lo, hi, lane_d, rho, delta, M, part, tpart, Ft, Fout;
+        DevBuf<double> Z, Gz, D, X, Gx, S, Y, lo, hi, lane_d, rho, delta, M, part, part_red, tpart, Ft, Fout;
         DevBuf<int> lane_i;
         PinBuf<int> h_done;
     } opt;
@@ -748,22 +748,24 @@ int run_optimizer(tpl_engine* e, tplopt::OptArgs a, int B, int mode, int max_ste
     CK(cudaFuncSetAttribute(opt_lane_kernel<HM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
     int launches = 0;
     const dim3 tgrd((B + 31) / 32, a.tchunks);
-    opt_init_kernel<<<grd, blk, 0, s>>>(a);
-    opt_trial_kernel<<<grd, blk, 0, s>>>(a);
+    const dim3 fgrd((B + 31) / 32, a.light_chunks);
+    opt_init_kernel<<<fgrd, blk, 0, s>>>(a);
+    opt_trial_kernel<<<fgrd, blk, 0, s>>>(a);
     launches += 2;
     CK(cudaGetLastError());
     auto one_step = [&]() -> int {
         int rc = eval_device(e, B, a.X, const_cast<double*>(a.Ft), const_cast<double*>(a.Gx), mode, true, s);
         if (rc != TPL_OK) return rc;
         opt_update_kernel<HM><<<grd, dim3(32, HM), 0, s>>>(a);
+        if (a.lane_part == a.part_red) opt_reduce_kernel<HM><<<dim3((B + 31) / 32, L::NACC), blk, 0, s>>>(a);
         opt_lane_kernel<HM><<<lgrd, lblk, lsmem, s>>>(a);
         opt_direction_kernel<HM><<<grd, blk, 0, s>>>(a);
         if (a.boundary_frac > 0.0) opt_stepmax_kernel<<<tgrd, blk, 0, s>>>(a);
-        opt_trial_kernel<<<grd, blk, 0, s>>>(a);
+        opt_trial_kernel<<<fgrd, blk, 0, s>>>(a);
         CK(cudaGetLastError());
         return TPL_OK;
     };
-    const int per_step = a.boundary_frac > 0.0 ? 7 : 6;
+    const int per_step = (a.boundary_frac > 0.0 ? 7 : 6) + (a.lane_part == a.part_red ? 1 : 0);
     int steps = 0;
     int rc = one_step();               // first step outside any capture: sizes the evaluation work space
     if (rc != TPL_OK) return rc;
@@ -803,7 +805,7 @@ int run_optimizer(tpl_engine* e, tplopt::OptArgs a, int B, int mode, int max_ste
     if (graph) cudaGraphDestroy(graph);
     e->timing = was_timing;
     if (rc != TPL_OK) return rc;
-    opt_final_kernel<<<grd, blk, 0, s>>>(a, e->opt.Fout.p);
+    opt_final_kernel<<<fgrd, blk, 0, s>>>(a, e->opt.Fout.p);
     launches++;
     CK(cudaGetLastError());
     res->steps = steps;
@@ -902,9 +904,22 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
     a.Ft = w.Ft.p;
     a.rho = w.rho.p; a.delta = w.delta.p; a.M = w.M.p; a.part = w.part.p;
     a.nchunks = nchunks; a.rows_per_chunk = rows;
+    CK(w.part_red.ensure((size_t)NACC * B));
+    a.part_red = w.part_red.p;
+    const bool two_level = nchunks > 32;            // many chunks: reduce them with a grid of blocks first
+    a.lane_part = two_level ? w.part_red.p : w.part.p;
+    a.lane_nchunks = two_level ? 1 : nchunks;
     a.tcount = li + 9 * (size_t)B + 1;
     a.n = n; a.parent = e->d_parent.p; a.dslot = e->d_dslot.p; a.hfix = e->d_hfix.p;
-    int tchunks = std::max(1, std::min(nchunks, (n + 8 * OPT_WY - 1) / (8 * OPT_WY)));
+    {   // light kernels carry ~40 registers: give the machine ~16 blocks per SM
+        int lc = (16 * e->num_sms + groups - 1) / groups;
+        lc = std::max(1, std::min(lc, (P + 4 * OPT_WY - 1) / (4 * OPT_WY)));
+        int lr = (P + lc - 1) / lc;
+        lr = ((lr + OPT_WY - 1) / OPT_WY) * OPT_WY;
+        a.light_rows = lr;
+        a.light_chunks = (P + lr - 1) / lr;
+    }
+    int tchunks = std::max(1, std::min(4 * nchunks, (n + 8 * OPT_WY - 1) / (8 * OPT_WY)));
     int npc = (n + tchunks - 1) / tchunks;
     npc = ((npc + OPT_WY - 1) / OPT_WY) * OPT_WY;
     tchunks = (n + npc - 1) / npc;

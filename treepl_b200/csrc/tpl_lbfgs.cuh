@@ -30,6 +30,10 @@ struct OptArgs {
     const double* Ft;                // [B] objective of the trial point
     double *rho, *delta, *M, *part;  // [HM][B], [NB][B], [NB*NB][B], [nchunks][NACC][B]
     int nchunks, rows_per_chunk;
+    int light_chunks, light_rows;    // finer row chunking for the light streaming kernels (init, trial, final)
+    double* part_red;                // [NACC][B] reduced partials (opt_reduce_kernel)
+    const double* lane_part;         // what the lane kernel reduces: part (few chunks) or part_red
+    int lane_nchunks;
     int* ndone;
     // ratio test (largest step that keeps every branch duration positive)
     int n;                           // nodes
@@ -49,7 +53,7 @@ constexpr int OPT_NY = 32;
 __global__ void __launch_bounds__(32 * OPT_WY) opt_init_kernel(OptArgs a) {
     const int b = blockIdx.x * 32 + threadIdx.x;
     if (b >= a.o.B) return;
-    const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(a.o.P, p0 + a.rows_per_chunk);
+    const int p0 = blockIdx.y * a.light_rows, p1 = min(a.o.P, p0 + a.light_rows);
     for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
         const size_t i = (size_t)p * a.o.B + b;
         const double x = a.X[i];
@@ -95,6 +99,21 @@ __global__ void __launch_bounds__(32 * HM) opt_update_kernel(OptArgs a) {
     const double* Sk = a.S + (size_t)k * PB + b;
     const double* Yk = a.Y + (size_t)k * PB + b;
     int buf = 0;
+    // phase-1 operands of the NEXT tile are fetched before phase 2 of the current one (software pipeline)
+    double nx = 0.0, ngx = 0.0, nz = 0.0, nd = 0.0, ngz = 0.0;
+    auto fetch = [&](int p) {
+        if (active && p < p1) {
+            const size_t i = (size_t)p * B + b;
+            nx = a.X[i];
+            ngx = a.Gx[i];
+            nz = a.Z[i];
+            if (acc_lane) {
+                nd = a.D[i];
+                ngz = a.Gz[i];
+            }
+        }
+    };
+    fetch(p0 + k);
     for (int r0 = p0; r0 < p1; r0 += HM, buf ^= 1) {
         {   // ---- phase 1: row r0 + k ----
             const int p = r0 + k;
@@ -102,13 +121,12 @@ __global__ void __launch_bounds__(32 * HM) opt_update_kernel(OptArgs a) {
             if (active && p < p1) {
                 const size_t i = (size_t)p * B + b;
                 const double lo = a.lo[p], hi = a.hi[p];
-                const double x = a.X[i], gx = a.Gx[i];
-                double z = a.Z[i];
-                const double gzn = p < nr ? gx * x : gx * ds;       // chain rule: d/du = r d/dr, d/dz = ds d/dh
+                double z = nz;
+                const double gzn = p < nr ? ngx * nx : ngx * ds;    // chain rule: d/du = r d/dr, d/dz = ds d/dh
                 if (acc_lane) {
-                    const double zt = trial_point(z, t, a.D[i], lo, hi);
+                    const double zt = trial_point(z, t, nd, lo, hi);
                     s = zt - z;
-                    y = gzn - a.Gz[i];
+                    y = gzn - ngz;
                     z = zt;
                     a.Z[i] = zt;
                     a.S[(size_t)h * PB + i] = s;
@@ -123,6 +141,7 @@ __global__ void __launch_bounds__(32 * HM) opt_update_kernel(OptArgs a) {
             sh_y[buf][k][tx] = y;
             sh_g[buf][k][tx] = gp;
         }
+        fetch(r0 + HM + k);
         __syncthreads();
         if (my_slot) {   // ---- phase 2: slot k against the tile's rows ----
             double Sv[HM], Yv[HM];
@@ -173,6 +192,35 @@ __global__ void __launch_bounds__(32 * HM) opt_update_kernel(OptArgs a) {
     }
 }
 
+// fixed-order reduction of the chunk partials, one block per (32 vectors, accumulator): used when there are many chunks
+template <int HM>
+__global__ void __launch_bounds__(32 * OPT_WY) opt_reduce_kernel(OptArgs a) {
+    typedef Layout<HM> L;
+    constexpr int NACC = L::NACC;
+    __shared__ double red[OPT_WY][32];
+    const int tx = threadIdx.x, ty = threadIdx.y, k = blockIdx.y;
+    const int b = blockIdx.x * 32 + tx;
+    const int B = a.o.B;
+    double v = 0.0;
+    if (b < B) {
+        if (k == L::A_GMAX) {
+            for (int c = ty; c < a.nchunks; c += OPT_WY) v = fmax(v, a.part[((size_t)c * NACC + k) * B + b]);
+        } else {
+            for (int c = ty; c < a.nchunks; c += OPT_WY) v += a.part[((size_t)c * NACC + k) * B + b];
+        }
+    }
+    red[ty][tx] = v;
+    __syncthreads();
+    if (ty == 0 && b < B) {
+        if (k == L::A_GMAX) {
+            for (int y = 1; y < OPT_WY; y++) v = fmax(v, red[y][tx]);
+        } else {
+            for (int y = 1; y < OPT_WY; y++) v += red[y][tx];
+        }
+        a.part_red[(size_t)k * B + b] = v;
+    }
+}
+
 template <int HM>
 __global__ void __launch_bounds__(OPT_LX * OPT_NY) opt_lane_kernel(OptArgs a) {
     typedef Layout<HM> L;
@@ -187,9 +235,9 @@ __global__ void __launch_bounds__(OPT_LX * OPT_NY) opt_lane_kernel(OptArgs a) {
         for (int k = ty; k < NACC; k += OPT_NY) {
             double v = 0.0;
             if (k == L::A_GMAX) {
-                for (int c = 0; c < a.nchunks; c++) v = fmax(v, a.part[((size_t)c * NACC + k) * B + b]);
+                for (int c = 0; c < a.lane_nchunks; c++) v = fmax(v, a.lane_part[((size_t)c * NACC + k) * B + b]);
             } else {
-                for (int c = 0; c < a.nchunks; c++) v += a.part[((size_t)c * NACC + k) * B + b];
+                for (int c = 0; c < a.lane_nchunks; c++) v += a.lane_part[((size_t)c * NACC + k) * B + b];
             }
             sacc[k * OPT_LX + tx] = v;
         }
@@ -314,7 +362,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) opt_trial_kernel(OptArgs a) {
     if (b >= B) return;
     if (a.st[b] == ST_DONE) return;
     const double t = a.t[b], ds = a.o.ds;
-    const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
+    const int p0 = blockIdx.y * a.light_rows, p1 = min(P, p0 + a.light_rows);
     for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
         const size_t i = (size_t)p * B + b;
         const double zt = trial_point(a.Z[i], t, a.D[i], a.lo[p], a.hi[p]);
@@ -327,7 +375,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) opt_final_kernel(OptArgs a, doubl
     const int b = blockIdx.x * 32 + threadIdx.x;
     if (b >= a.o.B) return;
     if (blockIdx.y == 0 && threadIdx.y == 0) F[b] = a.F0[b];
-    const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(a.o.P, p0 + a.rows_per_chunk);
+    const int p0 = blockIdx.y * a.light_rows, p1 = min(a.o.P, p0 + a.light_rows);
     for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
         const size_t i = (size_t)p * a.o.B + b;
         const double z = a.Z[i];

@@ -1,5 +1,5 @@
-"""Leave-one-out cross-validation over a smoothing grid as ONE batched device-resident optimisation
-(SURVEY.md §8 f1 + f4; reference: the CV loop of src/main.cpp:588-822).
+"""Cross-validation over a smoothing grid (leave-one-out or random-subsample folds) as ONE batched device-resident
+optimisation, sharded over the GPUs of a box (SURVEY.md §8 e, f1, f4; reference: the CV loop of src/main.cpp:588-822).
 
 Reference flow: for each smoothing value (sequentially, warm-started from the previous one) fit the full data,
 then for each tip prune it (CV mask), re-optimise from the full-data optimum, and score
@@ -74,14 +74,59 @@ def _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose, *
     return opt.minimize(X0, max_iter=max_iter, verbose=verbose)
 
 
-def loocv(flat, smoothing_grid, tips, device=0, log_pen=False, max_iter=3000, verbose=False, native=True, history=8, **opt):
-    """-> dict(chisq per smoothing value, best smoothing, timings).  tips: node numbers in fold order
-    (externalNodes order, main.cpp:603-608).  native=True: the optimiser is the library's own device-resident
-    L-BFGS (tpl_optimize_batch); False: the torch-vector-arithmetic prototype of batchopt.py."""
+def sample_random_groups(flat, tips, n_groups, frac, seed=1):
+    """Random-subsample folds (src/main.cpp:609-656): n_groups groups of round(frac * #tips) tips drawn without
+    replacement among the tips that are not children of the root, no two of them sisters (the reference's
+    check_possible_cv_nodes has an uninitialised index; the intent — never prune both children
+    of a node — is what is implemented).  numpy RNG instead of libc rand(): groups are not the reference's."""
+    par = flat["parents"]
+    rng = np.random.RandomState(seed)
+    size = int(len(tips) * frac + 0.5)
+    poss_all = [int(t) for t in tips if par[t] != 0]
+    groups = []
+    for _ in range(n_groups):
+        poss = list(poss_all)
+        taken_parents = set()
+        g = []
+        fails = 0
+        while len(g) < size and poss:
+            k = int(rng.randint(len(poss)))
+            t = poss[k]
+            if par[t] in taken_parents:
+                fails += 1
+                if fails > 1000:
+                    raise RuntimeError("could not sample a sister-free fold")
+                continue
+            g.append(t)
+            taken_parents.add(par[t])
+            poss.pop(k)
+        groups.append(g)
+    return groups
+
+
+def group_chisq(flat, x, group, freeparams, randomcv):
+    """chi-square contribution of one fold from its optimised vector x [P] (src/main.cpp:737-757 LOOCV,
+    :769-793 random-subsample: mean over the group's tips)."""
+    t = loocv_chisq(flat, np.repeat(x[:, None], len(group), axis=1), list(group), freeparams)
+    return float(np.sum(t)) / (len(group) if randomcv else 1.0)
+
+
+def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_pen=False, max_iter=3000, verbose=False,
+                   native=True, history=8, dist=None, **opt):
+    """-> dict(chisq per smoothing value, best smoothing, timings).  groups: list of folds, each a list of tip node
+    numbers (LOOCV: one tip per fold in externalNodes order, main.cpp:603-608).
+    Every (smoothing value, fold) pair is one work item.  With `dist` (torch.distributed, one process per GPU) the
+    items are dealt block-cyclically to the ranks (cvshard.shard_items), each rank optimises its share as one batch,
+    and the per-item chi-square terms are all-gathered and summed in item order (deterministic for every world size).
+    native=True: the library's own device-resident L-BFGS (tpl_optimize_batch); False: the torch prototype."""
+    from . import cvshard
+
     if not native:
         import torch
 
         torch.cuda.set_device(device)
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
     n = len(flat["parents"])
     plp = eng.PLCalcParallel.from_flat(flat, device=device)
     plp.set_log_pen(log_pen)
@@ -89,9 +134,9 @@ def loocv(flat, smoothing_grid, tips, device=0, log_pen=False, max_iter=3000, ve
     plp.set_freeparams(P, False, fp)
     nr = n - 1
     lo, hi = batchopt.reference_bounds(flat, fp, P)
-    K, T = len(smoothing_grid), len(tips)
+    K, T = len(smoothing_grid), len(groups)
     t0 = time.perf_counter()
-    # ---- full-data fits: one vector per smoothing value (padded to an even batch) ----
+    # ---- full-data fits: one vector per smoothing value (padded to an even batch), replicated on every rank ----
     B1 = K + (K % 2)
     lam1 = np.array(list(smoothing_grid) + [smoothing_grid[-1]] * (B1 - K), dtype=np.float64)
     plp.batch_configure(B1, lane_smoothing=lam1)
@@ -100,31 +145,46 @@ def loocv(flat, smoothing_grid, tips, device=0, log_pen=False, max_iter=3000, ve
     dscale = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
     Xfull, Ffull, info1 = _minimize(plp, np.repeat(x0[:, None], B1, axis=1), lo, hi, nr, dscale, max_iter, native, history, verbose, **opt)
     t1 = time.perf_counter()
-    # ---- folds: one vector per (smoothing value, pruned tip) ----
-    B2 = K * T
-    B2p = B2 + (B2 % 2)
+    # ---- folds: one vector per (smoothing value, fold); this rank's share ----
+    n_items = K * T
+    mine = cvshard.shard_items(n_items, rank, world)
+    B2 = len(mine)
+    B2p = max(2, B2 + (B2 % 2))
     lam2 = np.empty(B2p)
-    masks, lane_tip = [], []
+    masks = []
     X0 = np.empty((P, B2p))
-    for k in range(K):
-        for j, tip in enumerate(tips):
-            b = k * T + j
-            lam2[b] = smoothing_grid[k]
-            masks.append([int(tip)])
-            lane_tip.append(int(tip))
-            X0[:, b] = Xfull[:, k]
-    for b in range(B2, B2p):
-        lam2[b] = lam2[B2 - 1]; masks.append(masks[B2 - 1]); lane_tip.append(lane_tip[B2 - 1]); X0[:, b] = X0[:, B2 - 1]
+    for b in range(B2p):
+        item = mine[min(b, B2 - 1)] if B2 else 0           # padding repeats the last item
+        k, g = divmod(item, T)
+        lam2[b] = smoothing_grid[k]
+        masks.append([int(t) for t in groups[g]])
+        X0[:, b] = Xfull[:, k]
     plp.batch_configure(B2p, lane_smoothing=lam2, masks=masks)
     Xcv, Fcv, info2 = _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose, **opt)
     t2 = time.perf_counter()
-    terms = loocv_chisq(flat, Xcv, lane_tip, fp)[:B2].reshape(K, T)
-    chisq = terms.sum(axis=1)                      # fold order, fixed
+    local = {item: group_chisq(flat, Xcv[:, b], groups[item % T], fp, randomcv) for b, item in enumerate(mine)}
+    dev = None
+    if dist is not None and dist.get_backend() == "nccl":
+        import torch
+
+        dev = torch.device("cuda", device)
+    full, _ = cvshard.gather_fold_scores(local, n_items, dist=dist, device=dev)
+    terms = full.reshape(K, T)
+    chisq = np.zeros(K)
+    for k in range(K):
+        for g in range(T):            # fold order, fixed
+            chisq[k] += terms[k, g]
+    t3 = time.perf_counter()
     plp.close()
     return {"smoothing": list(smoothing_grid), "chisq": chisq.tolist(), "best": float(smoothing_grid[int(np.argmin(chisq))]),
-            "full_objective": Ffull[:K].tolist(), "full_seconds": t1 - t0, "cv_seconds": t2 - t1,
+            "full_objective": Ffull[:K].tolist(), "full_seconds": t1 - t0, "cv_seconds": t2 - t1, "gather_seconds": t3 - t2,
             "full_info": {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in info1.items()},
             "cv_iterations": info2["iterations"], "cv_nfev": info2["nfev"], "cv_converged": int(info2["converged"][:B2].sum()),
             "full_device_ms": info1.get("device_ms"), "cv_device_ms": info2.get("device_ms"),
             "launches": (info1.get("launches") or 0) + (info2.get("launches") or 0),
-            "n_vectors": B2, "terms": terms}
+            "n_vectors": n_items, "n_local_vectors": B2, "terms": terms}
+
+
+def loocv(flat, smoothing_grid, tips, **kw):
+    """Leave-one-out CV: one fold per tip (tips in externalNodes order, main.cpp:603-608)."""
+    return cross_validate(flat, smoothing_grid, [[int(t)] for t in tips], randomcv=False, **kw)
