@@ -160,6 +160,7 @@ typedef struct tpl_opt_result {
     int n_done;         /* vectors that stopped by themselves */
     int launches;       /* kernels launched */
     double device_ms;   /* CUDA-event time of the whole optimisation on the engine stream */
+    double mean_log10_step; /* diagnostic: mean log10 of the accepted step lengths over all vectors (0 = unit steps) */
 } tpl_opt_result;
 
 int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, const double* lower, const double* upper,

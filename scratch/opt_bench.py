@@ -94,6 +94,37 @@ if "big" in what:
             print(json.dumps(r), flush=True)
         plp.close()
 
+if "conv" in what:
+    import bench
+    flat = bench.build_problem(100000)
+    fp, P = tf.generate_param_order_vector(flat["free"], lf=False)
+    n = flat["parents"].shape[0]
+    lo, hi = batchopt.reference_bounds(flat, fp, P)
+    par = flat["parents"]
+    ds = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
+    B = 16
+    lam = 10.0 ** np.linspace(3, -1, 16)
+    x0 = cv.start_vector(flat, P, n - 1)
+    X0 = np.repeat(x0[:, None], B, axis=1)
+    for hist in (8,):
+        plp = eng.PLCalcParallel.from_flat(flat, device=0)
+        plp.set_freeparams(P, False, fp)
+        plp.batch_configure(B, lane_smoothing=lam)
+        Xc = X0
+        tot = 0
+        for rnd in range(2):
+            t = time.perf_counter()
+            X, F, info = plp.optimize_batch(Xc, lo, hi, date_scale=ds, history=hist, max_steps=5000, check_every=50, use_graph=1)
+            wall = time.perf_counter() - t
+            tot += info["steps"]
+            print(json.dumps({"history": hist, "round": rnd, "steps": info["steps"], "total_steps": tot, "wall_s": wall, "ms_per_step": info["device_ms"] / info["steps"],
+                              "status": np.bincount(info["status"], minlength=6).tolist(), "iters": [int(info["iterations"].min()), int(info["iterations"].max())],
+                              "mean_log10_step": info["mean_log10_step"], "F": [float(F[0]), float(F[5]), float(F[10]), float(F[15])]}), flush=True)
+            Xc = X
+            if (info["status"] > 0).all():
+                break
+        plp.close()
+
 if "ncubig" in what or "ncusmall" in what:
     import bench
     if "ncubig" in what:

@@ -14,25 +14,25 @@ using namespace tplopt;
 typedef void (*eval_fn)(const double* X, double* F, double* G, void* ctx);   // X, G: [P][B]; F: [B]
 
 template <int HM>
-static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, const double* hi, double ds, int max_steps,
+static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, const double* hi, const double* SC, int max_steps,
                int patience, int max_ls, double ftol, double gtol, double c1, eval_fn ev, void* ctx, int* status, int* iters,
                int n, const int* parent, const int* dslot, const double* hfix, double boundary_frac) {
     typedef Layout<HM> L;
     constexpr int NB = L::NB, NACC = L::NACC;
     const size_t PB = (size_t)P * B;
     OptConst o;
-    o.P = P; o.B = B; o.nr = nr; o.max_ls = max_ls; o.patience = patience; o.ds = ds; o.c1 = c1; o.ftol = ftol; o.gtol = gtol;
+    o.P = P; o.B = B; o.nr = nr; o.max_ls = max_ls; o.patience = patience; o.c1 = c1; o.ftol = ftol; o.gtol = gtol;
     std::vector<double> Z(PB), Gz(PB, 0.0), D(PB, 0.0), Gx(PB), S(PB * HM, 0.0), Y(PB * HM, 0.0), Ft(B);
     std::vector<int> st(B, ST_INIT), ls(B, 0), head(B, 0), stall(B, 0), flag(B, 0), newdir(B, 0), it(B, 0), nfail(B, 0);
     std::vector<unsigned> valid(B, 0u);
-    std::vector<double> F0(B, 0.0), t(B, 0.0), gd(B, 0.0), gamma(B, 0.0), gmax(B, 0.0);
+    std::vector<double> F0(B, 0.0), t(B, 0.0), gd(B, 0.0), gamma(B, 0.0), gmax(B, 0.0), tlog(B, 0.0);
     std::vector<double> rho((size_t)HM * B, 0.0), delta((size_t)NB * B, 0.0), M((size_t)NB * NB * B, 0.0), acc((size_t)NACC * B, 0.0);
     // opt_init_kernel
     for (int p = 0; p < P; p++)
         for (int b = 0; b < B; b++) {
             const size_t i = (size_t)p * B + b;
-            const double z = p < nr ? log(X[i]) : X[i] / ds;
-            Z[i] = fmin(fmax(z, lo[p]), hi[p]);
+            const double w = p < nr ? log(X[i]) : X[i];
+            Z[i] = fmin(fmax(w, lo[p]), hi[p]) / SC[i];
         }
     auto trial_kernel = [&]() {
         for (int b = 0; b < B; b++) {
@@ -47,15 +47,18 @@ static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, 
                             q = fma(delta[(size_t)k * B + b], S[(size_t)k * PB + i], q);
                             q = fma(delta[(size_t)(HM + k) * B + b], Y[(size_t)k * PB + i], q);
                         }
-                    D[i] = is_free(Z[i], Gz[i], lo[p], hi[p]) ? -q : 0.0;
+                    D[i] = is_free(Z[i], Gz[i], lo[p], hi[p], SC[i]) ? -q : 0.0;
                 }
                 // opt_stepmax_kernel
                 if (boundary_frac > 0.0) {
                     double tmin = 1e300;
                     for (int i = 1; i < n; i++) {
                         const int pa = parent[i], ri = dslot[i], rp = dslot[pa];
-                        const double zi = ri >= 0 ? Z[(size_t)ri * B + b] : hfix[i] / ds, di = ri >= 0 ? D[(size_t)ri * B + b] : 0.0;
-                        const double zp = rp >= 0 ? Z[(size_t)rp * B + b] : hfix[pa] / ds, dp = rp >= 0 ? D[(size_t)rp * B + b] : 0.0;
+                        // in date units: h = z sc, dh/dt = d sc
+                        const double zi = ri >= 0 ? Z[(size_t)ri * B + b] * SC[(size_t)ri * B + b] : hfix[i];
+                        const double di = ri >= 0 ? D[(size_t)ri * B + b] * SC[(size_t)ri * B + b] : 0.0;
+                        const double zp = rp >= 0 ? Z[(size_t)rp * B + b] * SC[(size_t)rp * B + b] : hfix[pa];
+                        const double dp = rp >= 0 ? D[(size_t)rp * B + b] * SC[(size_t)rp * B + b] : 0.0;
                         tmin = fmin(tmin, branch_step_limit(zi, di, zp, dp));
                     }
                     t[b] = fmin(t[b], boundary_frac * tmin);
@@ -64,8 +67,8 @@ static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, 
             // opt_trial_kernel
             for (int p = 0; p < P; p++) {
                 const size_t i = (size_t)p * B + b;
-                const double zt = trial_point(Z[i], t[b], D[i], lo[p], hi[p]);
-                X[i] = p < nr ? exp(zt) : zt * ds;
+                const double zt = trial_point(Z[i], t[b], D[i], lo[p], hi[p], SC[i]);
+                X[i] = to_param(p < nr, zt, SC[i]);
             }
         }
     };
@@ -84,10 +87,10 @@ static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, 
             for (int k = 0; k < NACC; k++) a[k] = 0.0;
             for (int p = 0; p < P; p++) {
                 const size_t i = (size_t)p * B + b;
-                const double gzn = p < nr ? Gx[i] * X[i] : Gx[i] * ds;
+                const double gzn = chain_grad(p < nr, Gx[i], X[i], SC[i]);
                 double z = Z[i], s = 0.0, y = 0.0;
                 if (al) {
-                    const double zt = trial_point(z, t[b], D[i], lo[p], hi[p]);
+                    const double zt = trial_point(z, t[b], D[i], lo[p], hi[p], SC[i]);
                     s = zt - z;
                     y = gzn - Gz[i];
                     z = zt;
@@ -96,7 +99,7 @@ static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, 
                     Y[(size_t)h * PB + i] = y;
                 }
                 Gz[i] = gzn;
-                const double gp = is_free(z, gzn, lo[p], hi[p]) ? gzn : 0.0;
+                const double gp = is_free(z, gzn, lo[p], hi[p], SC[i]) ? gzn : 0.0;
                 a[L::A_GG] = fma(gp, gp, a[L::A_GG]);
                 a[L::A_GMAX] = fmax(a[L::A_GMAX], fabs(gp));
                 if (al)
@@ -120,7 +123,7 @@ static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, 
             LaneIO io;
             io.st = &st[b]; io.ls = &ls[b]; io.head = &head[b]; io.stall = &stall[b]; io.flag = &flag[b];
             io.newdir = &newdir[b]; io.iters = &it[b]; io.nfail = &nfail[b]; io.valid = &valid[b];
-            io.F0 = &F0[b]; io.t = &t[b]; io.gd = &gd[b]; io.gamma = &gamma[b]; io.gmax = &gmax[b];
+            io.F0 = &F0[b]; io.t = &t[b]; io.gd = &gd[b]; io.gamma = &gamma[b]; io.gmax = &gmax[b]; io.tlog = &tlog[b];
             io.rho = &rho[b]; io.rho_s = B;
             io.delta = &delta[b]; io.delta_s = B;
             io.M = &M[b]; io.M_s = B;
@@ -133,7 +136,7 @@ static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, 
     for (int p = 0; p < P; p++)
         for (int b = 0; b < B; b++) {
             const size_t i = (size_t)p * B + b;
-            X[i] = p < nr ? exp(Z[i]) : Z[i] * ds;
+            X[i] = to_param(p < nr, Z[i], SC[i]);
         }
     for (int b = 0; b < B; b++) {
         Fout[b] = F0[b];
@@ -143,10 +146,10 @@ static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, 
     return steps;
 }
 
-extern "C" int lbfgs_sim(int history, int P, int B, int nr, double* X, double* F, const double* lo, const double* hi, double ds,
+extern "C" int lbfgs_sim(int history, int P, int B, int nr, double* X, double* F, const double* lo, const double* hi, const double* SC,
                          int max_steps, int patience, int max_ls, double ftol, double gtol, double c1, eval_fn ev, void* ctx,
                          int* status, int* iters, int n, const int* parent, const int* dslot, const double* hfix, double boundary_frac) {
-#define TPL_RUN(H) run<H>(P, B, nr, X, F, lo, hi, ds, max_steps, patience, max_ls, ftol, gtol, c1, ev, ctx, status, iters, n, parent, dslot, hfix, boundary_frac)
+#define TPL_RUN(H) run<H>(P, B, nr, X, F, lo, hi, SC, max_steps, patience, max_ls, ftol, gtol, c1, ev, ctx, status, iters, n, parent, dslot, hfix, boundary_frac)
     if (history == 4) return TPL_RUN(4);
     if (history == 8) return TPL_RUN(8);
     if (history == 16) return TPL_RUN(16);

@@ -29,7 +29,7 @@ def load_sim():
     lib = C.CDLL(SIM_SO)
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
     lib.lbfgs_sim.restype = C.c_int
-    lib.lbfgs_sim.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_int,
+    lib.lbfgs_sim.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int,
                               C.c_double, C.c_double, C.c_double, EVAL_FN, C.c_void_p, ip, ip, C.c_int, ip, ip, dp, C.c_double]
     return lib
 
@@ -43,8 +43,8 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def transformed_bounds(lower, upper, nr, ds):
-    """the bound transform of tpl_optimize_batch (tpl_engine.cu), restated"""
+def transformed_bounds(lower, upper, nr):
+    """the bound transform of tpl_optimize_batch (tpl_engine.cu), restated: bounds in w = ln r | h"""
     lo = np.array(lower, dtype=np.float64)
     hi = np.array(upper, dtype=np.float64)
     lo[:nr] = np.log(np.maximum(lo[:nr], 1e-300))
@@ -53,14 +53,43 @@ def transformed_bounds(lower, upper, nr, ds):
     margin = 1e-9 * np.maximum(1.0, np.abs(np.where(dhi < 1e19, dhi, dlo)))
     dlo += margin
     dhi -= np.where(dhi < 1e19, margin, 0.0)
-    lo[nr:] /= ds
-    hi[nr:] /= ds
     return lo, hi
 
 
-def fit(sim, name, lams, max_steps, history=8, boundary_frac=0.9, ftol=1e-12, patience=5):
-    gd = Golden(name)
-    flat = gd.flat
+def diagonal_scales(flat, fp, X, lams):
+    """the per-element scales of opt_scale_kernel (tpl_lbfgs.cuh), restated in numpy: sc = 1 / sqrt(H_ww) with
+    H_ww = r d + 2 lambda r^2 (1 + #children) for w = ln r, and the sum of c / d^2 over the adjacent branches for w = h"""
+    n = len(flat["parents"])
+    par = flat["parents"]
+    P, B = X.shape
+    SC = np.ones((P, B))
+    c = flat["c"]
+    nch = flat["child_counts"]
+    for b in range(B):
+        dates = flat["start_dates"].astype(np.float64).copy()
+        rates = np.zeros(n)
+        for i in range(n):
+            if fp[n + i] != -1:
+                dates[i] = X[fp[n + i], b]
+            if fp[i] != -1:
+                rates[i] = X[fp[i], b]
+        dur = np.maximum(dates[par[1:]] - dates[1:], 2.2250738585072014e-308)
+        hd = np.zeros(n)
+        w = c[1:] / dur ** 2
+        np.add.at(hd, np.arange(1, n), w)
+        np.add.at(hd, par[1:], w)
+        for i in range(1, n):
+            if fp[i] != -1:
+                r = rates[i]
+                SC[fp[i], b] = 1.0 / np.sqrt(max(r * dur[i - 1] + 2.0 * lams[b] * r * r * (1 + nch[i]), 1e-300))
+        for i in range(n):
+            if fp[n + i] != -1:
+                SC[fp[n + i], b] = 1.0 / np.sqrt(max(hd[i], 1e-300))
+    return SC
+
+
+def fit(sim, name, lams, max_steps, history=8, boundary_frac=0.9, ftol=1e-12, patience=5, scaling="global", flat=None, x0=None):
+    flat = Golden(name).flat if flat is None else flat
     n = len(flat["parents"])
     fp, P = tf.generate_param_order_vector(flat["free"], lf=False)
     lower, upper = batchopt.reference_bounds(flat, fp, P)
@@ -82,11 +111,16 @@ def fit(sim, name, lams, max_steps, history=8, boundary_frac=0.9, ftol=1e-12, pa
             if f < 1e15:
                 G[:, b] = g
 
-    x0 = cv.start_vector(flat, P, n - 1)
+    x0 = cv.start_vector(flat, P, n - 1) if x0 is None else x0
     par = flat["parents"]
-    ds = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
-    lo, hi = transformed_bounds(lower, upper, n - 1, ds)
-    X = np.ascontiguousarray(np.repeat(x0[:, None], B, axis=1))
+    lo, hi = transformed_bounds(lower, upper, n - 1)
+    X = np.ascontiguousarray(np.repeat(x0[:, None], B, axis=1)) if x0.ndim == 1 else np.ascontiguousarray(x0)
+    if scaling == "diag":
+        SC = np.ascontiguousarray(diagonal_scales(flat, fp, X, lams))
+    else:
+        ds = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
+        SC = np.ones((P, B))
+        SC[n - 1:] = ds
     F = np.zeros(B)
     status = np.zeros(B, dtype=np.int32)
     iters = np.zeros(B, dtype=np.int32)
@@ -95,7 +129,7 @@ def fit(sim, name, lams, max_steps, history=8, boundary_frac=0.9, ftol=1e-12, pa
     parent = np.ascontiguousarray(flat["parents"], dtype=np.int32)
     dslot = np.ascontiguousarray(fp[n:], dtype=np.int32)
     hfix = np.ascontiguousarray(flat["start_dates"], dtype=np.float64)
-    steps = sim.lbfgs_sim(history, P, B, n - 1, _dp(X), _dp(F), _dp(lo), _dp(hi), ds, max_steps, patience, 40, ftol, 1e-8, 1e-4, cb, None,
+    steps = sim.lbfgs_sim(history, P, B, n - 1, _dp(X), _dp(F), _dp(lo), _dp(hi), _dp(SC), max_steps, patience, 40, ftol, 1e-8, 1e-4, cb, None,
                           ip(status), ip(iters), n, ip(parent), ip(dslot), _dp(hfix), boundary_frac)
     assert steps == nev[0]
     return flat, fp, X, F, status, iters, steps

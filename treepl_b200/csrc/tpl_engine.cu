@@ -168,7 +168,7 @@ struct tpl_engine {
     int last_gen = 0;
     // device-resident optimiser work space (tpl_optimize_batch)
     struct OptWork {
-        DevBuf<double> Z, Gz, D, X, Gx, S, Y, lo, hi, lane_d, rho, delta, M, part, part_red, tpart, Ft, Fout;
+        DevBuf<double> Z, Gz, D, X, Gx, S, Y, lo, hi, sc, lane_d, rho, delta, M, part, part_red, tpart, Ft, Fout;
         DevBuf<int> lane_i;
         PinBuf<int> h_done;
     } opt;
@@ -839,8 +839,9 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
     // bounds in the transformed variables.  Date bounds are kept OPEN by a relative margin: exactly ON a penalised
     // bound the reference's objectives drop the infinite barrier term (calc_penalty resets, the AD paths skip it,
     // SURVEY.md 8 a13), so a step clamped onto the bound would sit in a spurious discontinuous minimum.
-    std::vector<double> lo(P), hi(P);
+    std::vector<double> lo(P), hi(P), sc(P);
     for (int p = 0; p < P; p++) {
+        sc[p] = p < nr ? 1.0 : ds;
         if (p < nr) {
             lo[p] = std::log(std::max(lower[p], 1e-300));
             hi[p] = std::log(upper[p]);
@@ -850,8 +851,8 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
             const double margin = 1e-9 * std::max(1.0, std::fabs(ref));
             dlo += margin;
             if (dhi < 1e19) dhi -= margin;
-            lo[p] = dlo / ds;
-            hi[p] = dhi / ds;
+            lo[p] = dlo;
+            hi[p] = dhi;
         }
         if (!(lo[p] <= hi[p])) return fail(TPL_ERR_ARG, "empty bound interval");
     }
@@ -867,16 +868,17 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
     nchunks = (P + rows - 1) / rows;
     CK(w.Z.ensure(PB)); CK(w.Gz.ensure(PB)); CK(w.D.ensure(PB)); CK(w.X.ensure(PB)); CK(w.Gx.ensure(PB));
     CK(w.S.ensure(PB * HM)); CK(w.Y.ensure(PB * HM));
-    CK(w.lo.ensure(P)); CK(w.hi.ensure(P));
-    CK(w.lane_d.ensure((size_t)5 * B)); CK(w.lane_i.ensure((size_t)9 * B + 1 + groups));
+    CK(w.lo.ensure(P)); CK(w.hi.ensure(P)); CK(w.sc.ensure(P));
+    CK(w.lane_d.ensure((size_t)6 * B)); CK(w.lane_i.ensure((size_t)9 * B + 1 + groups));
     CK(w.rho.ensure((size_t)HM * B)); CK(w.delta.ensure((size_t)NB * B)); CK(w.M.ensure((size_t)NB * NB * B));
     CK(w.part.ensure((size_t)nchunks * NACC * B)); CK(w.Ft.ensure(B)); CK(w.Fout.ensure(B));
     CK(w.h_done.ensure(1));
     cudaStream_t s = e->stream;
     CK(cudaMemcpyAsync(w.lo.p, lo.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(w.hi.p, hi.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w.sc.p, sc.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(w.X.p, X, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(w.lane_d.p, 0, sizeof(double) * 5 * B, s));
+    CK(cudaMemsetAsync(w.lane_d.p, 0, sizeof(double) * 6 * B, s));
     CK(cudaMemsetAsync(w.lane_i.p, 0, sizeof(int) * (9 * (size_t)B + 1 + groups), s));      // st = ST_INIT = 0, t = 0
     CK(cudaMemsetAsync(w.rho.p, 0, sizeof(double) * HM * B, s));
     CK(cudaMemsetAsync(w.delta.p, 0, sizeof(double) * NB * B, s));
@@ -888,19 +890,18 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
     a.o.P = P; a.o.B = B; a.o.nr = nr;
     a.o.max_ls = o.max_ls > 0 ? o.max_ls : 40;
     a.o.patience = o.patience > 0 ? o.patience : 5;
-    a.o.ds = ds;
     a.o.c1 = o.armijo > 0 ? o.armijo : 1e-4;
     a.o.ftol = o.ftol > 0 ? o.ftol : 1e-12;
     a.o.gtol = o.gtol > 0 ? o.gtol : 1e-8;
     a.Z = w.Z.p; a.Gz = w.Gz.p; a.D = w.D.p; a.X = w.X.p; a.Gx = w.Gx.p; a.S = w.S.p; a.Y = w.Y.p;
-    a.lo = w.lo.p; a.hi = w.hi.p;
+    a.lo = w.lo.p; a.hi = w.hi.p; a.sc = w.sc.p;
     int* li = w.lane_i.p;
     a.st = li; a.ls = li + B; a.head = li + 2 * (size_t)B; a.stall = li + 3 * (size_t)B; a.flag = li + 4 * (size_t)B;
     a.newdir = li + 5 * (size_t)B; a.iters = li + 6 * (size_t)B; a.nfail = li + 7 * (size_t)B;
     a.valid = (unsigned*)(li + 8 * (size_t)B);
     a.ndone = li + 9 * (size_t)B;
     double* ld = w.lane_d.p;
-    a.F0 = ld; a.t = ld + B; a.gd = ld + 2 * (size_t)B; a.gamma = ld + 3 * (size_t)B; a.gmax = ld + 4 * (size_t)B;
+    a.F0 = ld; a.t = ld + B; a.gd = ld + 2 * (size_t)B; a.gamma = ld + 3 * (size_t)B; a.gmax = ld + 4 * (size_t)B; a.tlog = ld + 5 * (size_t)B;
     a.Ft = w.Ft.p;
     a.rho = w.rho.p; a.delta = w.delta.p; a.M = w.M.p; a.part = w.part.p;
     a.nchunks = nchunks; a.rows_per_chunk = rows;
@@ -943,7 +944,17 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
     CK(cudaMemcpyAsync(F, w.Fout.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
     if (status) CK(cudaMemcpyAsync(status, a.flag, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
     if (iters) CK(cudaMemcpyAsync(iters, a.iters, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+    std::vector<double> tlog(B);
+    std::vector<int> nit(B);
+    CK(cudaMemcpyAsync(tlog.data(), a.tlog, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(nit.data(), a.iters, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    {
+        double ts = 0.0;
+        long long ni = 0;
+        for (int b = 0; b < B; b++) { ts += tlog[b]; ni += nit[b]; }
+        res.mean_log10_step = ni > 0 ? ts / (double)ni : 0.0;
+    }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     cudaEventDestroy(ev0);

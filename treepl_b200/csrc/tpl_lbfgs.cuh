@@ -11,7 +11,7 @@
 //   opt_direction_kernel : D = -free * sum_j delta_j b_j  (reads 2m+2 rows) for vectors with a new direction
 //   opt_stepmax_kernel   : ratio test over the tree's branches: a new direction's first step stays inside the
 //                          feasible region (all durations > 0) instead of discovering the boundary by backtracking
-//   opt_trial_kernel     : the trial point X = (exp(z + t D) | ds (z + t D)) for every running vector
+//   opt_trial_kernel     : the trial point X = to_param(z + t D) for every running vector
 // Deterministic: static row -> thread mapping, fixed-order reductions, no floating-point atomics.
 #pragma once
 #include "tpl_lbfgs_core.h"
@@ -23,10 +23,11 @@ struct OptArgs {
     double *Z, *Gz, *D, *X;          // [P][B]
     const double* Gx;                // [P][B] gradient of the trial point in the ORIGINAL parameters (PL kernels)
     double *S, *Y;                   // [HM][P][B]
-    const double *lo, *hi;           // [P] bounds in the transformed variables
+    const double *lo, *hi;           // [P] bounds in the unscaled transformed variable w = ln r | h
+    const double* sc;                // [P] per-row scale: the optimiser's variable is z = w / sc
     int *st, *ls, *head, *stall, *flag, *newdir, *iters, *nfail;
     unsigned* valid;
-    double *F0, *t, *gd, *gamma, *gmax;
+    double *F0, *t, *gd, *gamma, *gmax, *tlog;
     const double* Ft;                // [B] objective of the trial point
     double *rho, *delta, *M, *part;  // [HM][B], [NB][B], [NB*NB][B], [nchunks][NACC][B]
     int nchunks, rows_per_chunk;
@@ -57,8 +58,8 @@ __global__ void __launch_bounds__(32 * OPT_WY) opt_init_kernel(OptArgs a) {
     for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
         const size_t i = (size_t)p * a.o.B + b;
         const double x = a.X[i];
-        const double z = p < a.o.nr ? log(x) : x / a.o.ds;
-        a.Z[i] = fmin(fmax(z, a.lo[p]), a.hi[p]);
+        const double w = p < a.o.nr ? log(x) : x;
+        a.Z[i] = fmin(fmax(w, a.lo[p]), a.hi[p]) / a.sc[p];
         a.D[i] = 0.0;
     }
 }
@@ -78,7 +79,6 @@ __global__ void __launch_bounds__(32 * HM) opt_update_kernel(OptArgs a) {
     const int tx = threadIdx.x, k = threadIdx.y;
     const int b = blockIdx.x * 32 + tx;
     const int B = a.o.B, P = a.o.P, nr = a.o.nr;
-    const double ds = a.o.ds;
     const size_t PB = (size_t)P * B;
     int dec = DEC_SKIP, h = 0;
     unsigned valid = 0;
@@ -120,11 +120,11 @@ __global__ void __launch_bounds__(32 * HM) opt_update_kernel(OptArgs a) {
             double s = 0.0, y = 0.0, gp = 0.0;
             if (active && p < p1) {
                 const size_t i = (size_t)p * B + b;
-                const double lo = a.lo[p], hi = a.hi[p];
+                const double lo = a.lo[p], hi = a.hi[p], sc = a.sc[p];
                 double z = nz;
-                const double gzn = p < nr ? ngx * nx : ngx * ds;    // chain rule: d/du = r d/dr, d/dz = ds d/dh
+                const double gzn = chain_grad(p < nr, ngx, nx, sc);
                 if (acc_lane) {
-                    const double zt = trial_point(z, t, nd, lo, hi);
+                    const double zt = trial_point(z, t, nd, lo, hi, sc);
                     s = zt - z;
                     y = gzn - ngz;
                     z = zt;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(32 * HM) opt_update_kernel(OptArgs a) {
                     a.Y[(size_t)h * PB + i] = y;
                 }
                 a.Gz[i] = gzn;
-                gp = is_free(z, gzn, lo, hi) ? gzn : 0.0;
+                gp = is_free(z, gzn, lo, hi, sc) ? gzn : 0.0;
                 gg = fma(gp, gp, gg);
                 gmx = fmax(gmx, fabs(gp));
             }
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(OPT_LX * OPT_NY) opt_lane_kernel(OptArgs a) {
         LaneIO io;
         io.st = a.st + b; io.ls = a.ls + b; io.head = a.head + b; io.stall = a.stall + b; io.flag = a.flag + b;
         io.newdir = a.newdir + b; io.iters = a.iters + b; io.nfail = a.nfail + b; io.valid = a.valid + b;
-        io.F0 = a.F0 + b; io.t = a.t + b; io.gd = a.gd + b; io.gamma = a.gamma + b; io.gmax = a.gmax + b;
+        io.F0 = a.F0 + b; io.t = a.t + b; io.gd = a.gd + b; io.gamma = a.gamma + b; io.gmax = a.gmax + b; io.tlog = a.tlog + b;
         io.rho = a.rho + b; io.rho_s = B;
         io.delta = a.delta + b; io.delta_s = B;
         io.M = sM + tx; io.M_s = OPT_LX;
@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(32 * OPT_WY) opt_direction_kernel(OptArgs a) {
             q1 = fma(dl[k], s1[k], q1);
             q1 = fma(dl[HM + k], y1[k], q1);
         }
-        a.D[i] = is_free(z0, g0, a.lo[p], a.hi[p]) ? -q0 : 0.0;
-        if (two) a.D[j] = is_free(z1, g1, a.lo[pb], a.hi[pb]) ? -q1 : 0.0;
+        a.D[i] = is_free(z0, g0, a.lo[p], a.hi[p], a.sc[p]) ? -q0 : 0.0;
+        if (two) a.D[j] = is_free(z1, g1, a.lo[pb], a.hi[pb], a.sc[pb]) ? -q1 : 0.0;
     }
 }
 
@@ -320,14 +320,14 @@ __global__ void __launch_bounds__(32 * OPT_WY) opt_stepmax_kernel(OptArgs a) {
     if (!__syncthreads_or(active)) return;          // uniform over blockIdx.y: the whole group skips
     double tmin = 1e300;
     if (active) {
-        const double ids = 1.0 / a.o.ds;
         const int i0 = max(1, blockIdx.y * a.nodes_per_chunk), i1 = min(a.n, (blockIdx.y + 1) * a.nodes_per_chunk);
         for (int i = i0 + ty; i < i1; i += OPT_WY) {
             const int pa = a.parent[i];
             const int ri = a.dslot[i], rp = a.dslot[pa];
             double zi, di = 0.0, zp, dp = 0.0;
-            if (ri >= 0) { zi = a.Z[(size_t)ri * B + b]; di = a.D[(size_t)ri * B + b]; } else zi = a.hfix[i] * ids;
-            if (rp >= 0) { zp = a.Z[(size_t)rp * B + b]; dp = a.D[(size_t)rp * B + b]; } else zp = a.hfix[pa] * ids;
+            // in date units: h = z sc, dh/dt = d sc
+            if (ri >= 0) { const double sc = a.sc[ri]; zi = a.Z[(size_t)ri * B + b] * sc; di = a.D[(size_t)ri * B + b] * sc; } else zi = a.hfix[i];
+            if (rp >= 0) { const double sc = a.sc[rp]; zp = a.Z[(size_t)rp * B + b] * sc; dp = a.D[(size_t)rp * B + b] * sc; } else zp = a.hfix[pa];
             tmin = fmin(tmin, branch_step_limit(zi, di, zp, dp));
         }
     }
@@ -355,18 +355,19 @@ __global__ void __launch_bounds__(32 * OPT_WY) opt_stepmax_kernel(OptArgs a) {
     if (tx == 0 && ty == 0) a.tcount[blockIdx.x] = 0;       // ready for the next launch
 }
 
-// trial point X = (exp(z + t D) | ds (z + t D)) for every running vector
+// trial point X = to_param(z + t D) for every running vector
 __global__ void __launch_bounds__(32 * OPT_WY) opt_trial_kernel(OptArgs a) {
     const int b = blockIdx.x * 32 + threadIdx.x;
     const int B = a.o.B, P = a.o.P, nr = a.o.nr;
     if (b >= B) return;
     if (a.st[b] == ST_DONE) return;
-    const double t = a.t[b], ds = a.o.ds;
+    const double t = a.t[b];
     const int p0 = blockIdx.y * a.light_rows, p1 = min(P, p0 + a.light_rows);
     for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
         const size_t i = (size_t)p * B + b;
-        const double zt = trial_point(a.Z[i], t, a.D[i], a.lo[p], a.hi[p]);
-        a.X[i] = p < nr ? exp(zt) : zt * ds;
+        const double sc = a.sc[p];
+        const double zt = trial_point(a.Z[i], t, a.D[i], a.lo[p], a.hi[p], sc);
+        a.X[i] = to_param(p < nr, zt, sc);
     }
 }
 
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) opt_final_kernel(OptArgs a, doubl
     for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
         const size_t i = (size_t)p * a.o.B + b;
         const double z = a.Z[i];
-        a.X[i] = p < a.o.nr ? exp(z) : z * a.o.ds;
+        a.X[i] = to_param(p < a.o.nr, z, a.sc[p]);
     }
 }
 

@@ -38,7 +38,6 @@ enum { FLAG_RUNNING = 0, FLAG_CONV_GRAD = 1, FLAG_CONV_F = 2, FLAG_STALLED = 3, 
 struct OptConst {
     int P, B, nr;            // parameters, vectors, leading rate rows (optimised as ln r)
     int max_ls, patience;
-    double ds;               // dates are optimised as h / ds
     double c1, ftol, gtol;
 };
 
@@ -65,13 +64,23 @@ TPL_HD int decide(int st, double Ft, double F0, double t, double gd, double c1) 
     return DEC_REJECT;
 }
 
-// trial point in the transformed variables, clamped into the (open) box
-TPL_HD double trial_point(double z, double t, double d, double lo, double hi) {
-    return fmin(fmax(fma(t, d, z), lo), hi);
+// Transformed variables.  Row p of vector b is optimised as z = w / sc with w = ln r (rate rows) or w = h (date rows)
+// and sc > 0 a per-element scale (a diagonal preconditioner: sc ~ 1 / sqrt(d2f/dw2), see opt_scale_kernel).
+TPL_HD double to_param(bool rate_row, double z, double sc) {
+    const double w = z * sc;
+    return rate_row ? exp(w) : w;
+}
+// chain rule: df/dz = df/dx * dx/dw * sc, dx/dw = x for rate rows, 1 for date rows
+TPL_HD double chain_grad(bool rate_row, double gx, double x, double sc) {
+    return (rate_row ? gx * x : gx) * sc;
+}
+// trial point z + t d, clamped into the (open) box lo <= w <= hi given in the unscaled variable w
+TPL_HD double trial_point(double z, double t, double d, double lo, double hi, double sc) {
+    return fmin(fmax(fma(t, d, z), lo / sc), hi / sc);
 }
 // a variable on a bound whose gradient pushes outward is frozen (projected gradient)
-TPL_HD bool is_free(double z, double g, double lo, double hi) {
-    return !((z <= lo && g > 0.0) || (z >= hi && g < 0.0));
+TPL_HD bool is_free(double z, double g, double lo, double hi, double sc) {
+    return !((z <= lo / sc && g > 0.0) || (z >= hi / sc && g < 0.0));
 }
 
 // ratio test of one branch: the step length at which the duration zp - zi of z + t d reaches zero (1e300: never)
@@ -84,7 +93,7 @@ struct LaneIO {
     // scalars of this vector
     int *st, *ls, *head, *stall, *flag, *newdir, *iters, *nfail;
     unsigned* valid;
-    double *F0, *t, *gd, *gamma, *gmax;
+    double *F0, *t, *gd, *gamma, *gmax, *tlog;   // tlog: sum of log10(accepted step lengths), a diagnostic
     double* rho;   int rho_s;       // rho[k * rho_s], k < HM
     double* delta; int delta_s;     // delta[j * delta_s], j < 2 HM + 1
     double* M;     int M_s;         // Gram matrix M[(i * NB + j) * M_s]
@@ -157,6 +166,7 @@ TPL_HD bool lane_step(const LaneIO& L, double Ft, const OptConst& o) {
             const int stl = (rel <= o.ftol) ? *L.stall + (cut_short ? 0 : 1) : 0;
             *L.stall = stl;
             *L.iters += 1;
+            *L.tlog += log10(*L.t);
             if (stl >= o.patience) { *L.flag = FLAG_CONV_F; done = true; }
         } else {
             *L.gamma = 1.0;

@@ -40,7 +40,8 @@ class OptOptions(C.Structure):
 
 
 class OptResult(C.Structure):
-    _fields_ = [("steps", C.c_int), ("n_done", C.c_int), ("launches", C.c_int), ("device_ms", C.c_double)]
+    _fields_ = [("steps", C.c_int), ("n_done", C.c_int), ("launches", C.c_int), ("device_ms", C.c_double),
+                ("mean_log10_step", C.c_double)]
 
 
 class EngineError(RuntimeError):
@@ -366,7 +367,7 @@ class PLCalcParallel:
         self._check(self._L.tpl_optimize_batch(self._h, B, _dp(X), _dp(F), _dp(lo), _dp(hi), int(mode), C.byref(o),
                                                _ip(status), _ip(iters), C.byref(res)))
         return X, F, {"steps": res.steps, "n_done": res.n_done, "launches": res.launches, "device_ms": res.device_ms,
-                      "status": status, "iterations": iters}
+                      "mean_log10_step": res.mean_log10_step, "status": status, "iterations": iters}
 
     def set_timing(self, on):
         self._check(self._L.tpl_set_timing(self._h, int(bool(on))))
