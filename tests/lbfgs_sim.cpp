@@ -32,7 +32,7 @@ static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, 
         for (int b = 0; b < B; b++) {
             const size_t i = (size_t)p * B + b;
             const double w = p < nr ? log(X[i]) : X[i];
-            Z[i] = fmin(fmax(w, lo[p]), hi[p]) / SC[i];
+            Z[i] = fmin(fmax(w / SC[i], lo[p] / SC[i]), hi[p] / SC[i]);
         }
     auto trial_kernel = [&]() {
         for (int b = 0; b < B; b++) {
@@ -47,7 +47,7 @@ static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, 
                             q = fma(delta[(size_t)k * B + b], S[(size_t)k * PB + i], q);
                             q = fma(delta[(size_t)(HM + k) * B + b], Y[(size_t)k * PB + i], q);
                         }
-                    D[i] = is_free(Z[i], Gz[i], lo[p], hi[p], SC[i]) ? -q : 0.0;
+                    D[i] = is_free(Z[i], Gz[i], lo[p] / SC[i], hi[p] / SC[i]) ? -q : 0.0;
                 }
                 // opt_stepmax_kernel
                 if (boundary_frac > 0.0) {
@@ -67,7 +67,7 @@ static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, 
             // opt_trial_kernel
             for (int p = 0; p < P; p++) {
                 const size_t i = (size_t)p * B + b;
-                const double zt = trial_point(Z[i], t[b], D[i], lo[p], hi[p], SC[i]);
+                const double zt = trial_point(Z[i], t[b], D[i], lo[p] / SC[i], hi[p] / SC[i]);
                 X[i] = to_param(p < nr, zt, SC[i]);
             }
         }
@@ -90,7 +90,7 @@ static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, 
                 const double gzn = chain_grad(p < nr, Gx[i], X[i], SC[i]);
                 double z = Z[i], s = 0.0, y = 0.0;
                 if (al) {
-                    const double zt = trial_point(z, t[b], D[i], lo[p], hi[p], SC[i]);
+                    const double zt = trial_point(z, t[b], D[i], lo[p] / SC[i], hi[p] / SC[i]);
                     s = zt - z;
                     y = gzn - Gz[i];
                     z = zt;
@@ -99,7 +99,7 @@ static int run(int P, int B, int nr, double* X, double* Fout, const double* lo, 
                     Y[(size_t)h * PB + i] = y;
                 }
                 Gz[i] = gzn;
-                const double gp = is_free(z, gzn, lo[p], hi[p], SC[i]) ? gzn : 0.0;
+                const double gp = is_free(z, gzn, lo[p] / SC[i], hi[p] / SC[i]) ? gzn : 0.0;
                 a[L::A_GG] = fma(gp, gp, a[L::A_GG]);
                 a[L::A_GMAX] = fmax(a[L::A_GMAX], fabs(gp));
                 if (al)

@@ -35,6 +35,16 @@ int main() {
         std::vector<double> g(np);
         plp.calc_gradient(x, &g);
         printf("GPU f=%.6f np=%d g0=%.6f\n", f, np, g[0]);
+        // device-resident batched optimiser: two copies of the problem at smoothing 0.1 (examples/test.cppr8s)
+        plp.set_smoothing(0.1);
+        const double f01 = plp.calc_pl(x);
+        const int B = 2;
+        std::vector<double> X(np * B), F(B), lo(np), up(np);
+        for (int p = 0; p < np; p++) { X[p * B] = X[p * B + 1] = x[p]; lo[p] = 1e-40; up[p] = 1e15; }
+        for (int i = 0; i < 13; i++) if (fp[13 + i] != -1) { lo[fp[13 + i]] = mn[i] == 0 ? 1e-40 : mn[i]; up[fp[13 + i]] = mx[i]; }
+        std::vector<int> status(B);
+        tpl_opt_result r = plp.optimize_batch(B, X.data(), F.data(), lo.data(), up.data(), TPL_GRAD_AD, nullptr, status.data());
+        printf("OPT F=%.6f F0=%.6f status=%d steps=%d\n", F[0], f01, status[0], r.steps);
     } catch (const std::exception& ex) {
         printf("EXCEPTION %s\n", ex.what());
         return 3;
@@ -60,5 +70,7 @@ def test_cpp_host_mirror_compiles_links_and_fails_loudly_without_gpu():
         has_gpu = False
     if has_gpu:
         assert res.returncode == 0 and res.stdout.startswith("GPU f="), res.stdout
+        opt = [ln for ln in res.stdout.splitlines() if ln.startswith("OPT ")][0].split()
+        assert float(opt[1].split("=")[1]) < float(opt[2].split("=")[1]) and opt[3] in ("status=1", "status=2", "status=3"), res.stdout
     else:
         assert res.returncode == 3 and "EXCEPTION" in res.stdout and "no CUDA device" in res.stdout, res.stdout

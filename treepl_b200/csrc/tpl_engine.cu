@@ -759,7 +759,7 @@ int run_optimizer(tpl_engine* e, tplopt::OptArgs a, int B, int mode, int max_ste
         opt_update_kernel<HM><<<grd, dim3(32, HM), 0, s>>>(a);
         if (a.lane_part == a.part_red) opt_reduce_kernel<HM><<<dim3((B + 31) / 32, L::NACC), blk, 0, s>>>(a);
         opt_lane_kernel<HM><<<lgrd, lblk, lsmem, s>>>(a);
-        opt_direction_kernel<HM><<<grd, blk, 0, s>>>(a);
+        opt_direction_kernel<HM><<<dim3((B + 31) / 32, a.dir_chunks), blk, 0, s>>>(a);
         if (a.boundary_frac > 0.0) opt_stepmax_kernel<<<tgrd, blk, 0, s>>>(a);
         opt_trial_kernel<<<fgrd, blk, 0, s>>>(a);
         CK(cudaGetLastError());
@@ -843,29 +843,48 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
     for (int p = 0; p < P; p++) {
         sc[p] = p < nr ? 1.0 : ds;
         if (p < nr) {
-            lo[p] = std::log(std::max(lower[p], 1e-300));
-            hi[p] = std::log(upper[p]);
+            lo[p] = std::log(std::max(lower[p], 1e-300)) / sc[p];
+            hi[p] = std::log(upper[p]) / sc[p];
         } else {
             double dlo = lower[p], dhi = upper[p];
             const double ref = dhi < 1e19 ? dhi : dlo;
             const double margin = 1e-9 * std::max(1.0, std::fabs(ref));
             dlo += margin;
             if (dhi < 1e19) dhi -= margin;
-            lo[p] = dlo;
-            hi[p] = dhi;
+            lo[p] = dlo / sc[p];
+            hi[p] = dhi / sc[p];
         }
         if (!(lo[p] <= hi[p])) return fail(TPL_ERR_ARG, "empty bound interval");
     }
     const size_t PB = (size_t)P * B;
     tpl_engine::OptWork& w = e->opt;
     const int NB = 2 * HM + 1, NACC = 6 * HM + 2;
-    // row chunking: enough blocks to fill the machine, few enough chunks for the per-vector reduction
+    // Row chunking.  The two heavy kernels run as exactly ONE wave of equally loaded blocks (blocks = resident
+    // slots of the kernel's own occupancy): with a few hundred long blocks a partial second wave would cost up to
+    // half of the kernel's time (ncu: 1.14 waves -> 68 % of the HBM rate, profiles/r01j).
     const int groups = (B + 31) / 32;
-    int nchunks = (4 * e->num_sms + groups - 1) / groups;
-    nchunks = std::max(1, std::min(nchunks, std::min(256, (P + OPT_WY - 1) / OPT_WY)));
-    int rows = (P + nchunks - 1) / nchunks;
-    rows = ((rows + 15) / 16) * 16;                 // whole row tiles of the update kernel for every history size
-    nchunks = (P + rows - 1) / rows;
+    int occ_upd = 1, occ_dir = 1;
+    if (HM == 4) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_upd, tplopt::opt_update_kernel<4>, 32 * 4, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dir, tplopt::opt_direction_kernel<4>, 32 * OPT_WY, 0);
+    } else if (HM == 8) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_upd, tplopt::opt_update_kernel<8>, 32 * 8, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dir, tplopt::opt_direction_kernel<8>, 32 * OPT_WY, 0);
+    } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_upd, tplopt::opt_update_kernel<16>, 32 * 16, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dir, tplopt::opt_direction_kernel<16>, 32 * OPT_WY, 0);
+    }
+    auto one_wave = [&](int occ, int align, int* nch, int* rws) {
+        int c = std::max(1, (e->num_sms * std::max(occ, 1)) / groups);
+        c = std::min(c, (P + align - 1) / align);
+        int r = (P + c - 1) / c;
+        r = ((r + align - 1) / align) * align;
+        *rws = r;
+        *nch = (P + r - 1) / r;
+    };
+    int nchunks, rows, dir_chunks, dir_rows;
+    one_wave(occ_upd, 16, &nchunks, &rows);          // whole row tiles of the update kernel for every history size
+    one_wave(occ_dir, 2 * OPT_WY, &dir_chunks, &dir_rows);
     CK(w.Z.ensure(PB)); CK(w.Gz.ensure(PB)); CK(w.D.ensure(PB)); CK(w.X.ensure(PB)); CK(w.Gx.ensure(PB));
     CK(w.S.ensure(PB * HM)); CK(w.Y.ensure(PB * HM));
     CK(w.lo.ensure(P)); CK(w.hi.ensure(P)); CK(w.sc.ensure(P));
@@ -905,6 +924,7 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
     a.Ft = w.Ft.p;
     a.rho = w.rho.p; a.delta = w.delta.p; a.M = w.M.p; a.part = w.part.p;
     a.nchunks = nchunks; a.rows_per_chunk = rows;
+    a.dir_chunks = dir_chunks; a.dir_rows = dir_rows;
     CK(w.part_red.ensure((size_t)NACC * B));
     a.part_red = w.part_red.p;
     const bool two_level = nchunks > 32;            // many chunks: reduce them with a grid of blocks first

@@ -23,14 +23,15 @@ struct OptArgs {
     double *Z, *Gz, *D, *X;          // [P][B]
     const double* Gx;                // [P][B] gradient of the trial point in the ORIGINAL parameters (PL kernels)
     double *S, *Y;                   // [HM][P][B]
-    const double *lo, *hi;           // [P] bounds in the unscaled transformed variable w = ln r | h
-    const double* sc;                // [P] per-row scale: the optimiser's variable is z = w / sc
+    const double* sc;                // [P] per-row scale: the optimiser's variable is z = w / sc, w = ln r | h
+    const double *lo, *hi;           // [P] bounds of z (bounds of w divided by sc)
     int *st, *ls, *head, *stall, *flag, *newdir, *iters, *nfail;
     unsigned* valid;
     double *F0, *t, *gd, *gamma, *gmax, *tlog;
     const double* Ft;                // [B] objective of the trial point
     double *rho, *delta, *M, *part;  // [HM][B], [NB][B], [NB*NB][B], [nchunks][NACC][B]
     int nchunks, rows_per_chunk;
+    int dir_chunks, dir_rows;        // row chunking of the direction kernel (one full wave of its own occupancy)
     int light_chunks, light_rows;    // finer row chunking for the light streaming kernels (init, trial, final)
     double* part_red;                // [NACC][B] reduced partials (opt_reduce_kernel)
     const double* lane_part;         // what the lane kernel reduces: part (few chunks) or part_red
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) opt_init_kernel(OptArgs a) {
         const size_t i = (size_t)p * a.o.B + b;
         const double x = a.X[i];
         const double w = p < a.o.nr ? log(x) : x;
-        a.Z[i] = fmin(fmax(w, a.lo[p]), a.hi[p]) / a.sc[p];
+        a.Z[i] = fmin(fmax(w / a.sc[p], a.lo[p]), a.hi[p]);
         a.D[i] = 0.0;
     }
 }
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(32 * HM) opt_update_kernel(OptArgs a) {
                 double z = nz;
                 const double gzn = chain_grad(p < nr, ngx, nx, sc);
                 if (acc_lane) {
-                    const double zt = trial_point(z, t, nd, lo, hi, sc);
+                    const double zt = trial_point(z, t, nd, lo, hi);
                     s = zt - z;
                     y = gzn - ngz;
                     z = zt;
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(32 * HM) opt_update_kernel(OptArgs a) {
                     a.Y[(size_t)h * PB + i] = y;
                 }
                 a.Gz[i] = gzn;
-                gp = is_free(z, gzn, lo, hi, sc) ? gzn : 0.0;
+                gp = is_free(z, gzn, lo, hi) ? gzn : 0.0;
                 gg = fma(gp, gp, gg);
                 gmx = fmax(gmx, fabs(gp));
             }
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) opt_direction_kernel(OptArgs a) {
     double dl[L::NB];
 #pragma unroll
     for (int j = 0; j < L::NB; j++) dl[j] = a.delta[(size_t)j * B + b];
-    const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
+    const int p0 = blockIdx.y * a.dir_rows, p1 = min(P, p0 + a.dir_rows);
     // two rows per iteration: 2 (2 m + 2) independent loads in flight per thread
     for (int p = p0 + ty; p < p1; p += 2 * OPT_WY) {
         const int pb = p + OPT_WY;
@@ -300,8 +301,8 @@ __global__ void __launch_bounds__(32 * OPT_WY) opt_direction_kernel(OptArgs a) {
             q1 = fma(dl[k], s1[k], q1);
             q1 = fma(dl[HM + k], y1[k], q1);
         }
-        a.D[i] = is_free(z0, g0, a.lo[p], a.hi[p], a.sc[p]) ? -q0 : 0.0;
-        if (two) a.D[j] = is_free(z1, g1, a.lo[pb], a.hi[pb], a.sc[pb]) ? -q1 : 0.0;
+        a.D[i] = is_free(z0, g0, a.lo[p], a.hi[p]) ? -q0 : 0.0;
+        if (two) a.D[j] = is_free(z1, g1, a.lo[pb], a.hi[pb]) ? -q1 : 0.0;
     }
 }
 
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) opt_trial_kernel(OptArgs a) {
     for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
         const size_t i = (size_t)p * B + b;
         const double sc = a.sc[p];
-        const double zt = trial_point(a.Z[i], t, a.D[i], a.lo[p], a.hi[p], sc);
+        const double zt = trial_point(a.Z[i], t, a.D[i], a.lo[p], a.hi[p]);
         a.X[i] = to_param(p < nr, zt, sc);
     }
 }

@@ -74,13 +74,13 @@ TPL_HD double to_param(bool rate_row, double z, double sc) {
 TPL_HD double chain_grad(bool rate_row, double gx, double x, double sc) {
     return (rate_row ? gx * x : gx) * sc;
 }
-// trial point z + t d, clamped into the (open) box lo <= w <= hi given in the unscaled variable w
-TPL_HD double trial_point(double z, double t, double d, double lo, double hi, double sc) {
-    return fmin(fmax(fma(t, d, z), lo / sc), hi / sc);
+// trial point z + t d, clamped into the (open) box lo <= z <= hi (bounds already divided by the row's scale)
+TPL_HD double trial_point(double z, double t, double d, double lo, double hi) {
+    return fmin(fmax(fma(t, d, z), lo), hi);
 }
 // a variable on a bound whose gradient pushes outward is frozen (projected gradient)
-TPL_HD bool is_free(double z, double g, double lo, double hi, double sc) {
-    return !((z <= lo / sc && g > 0.0) || (z >= hi / sc && g < 0.0));
+TPL_HD bool is_free(double z, double g, double lo, double hi) {
+    return !((z <= lo && g > 0.0) || (z >= hi && g < 0.0));
 }
 
 // ratio test of one branch: the step length at which the duration zp - zi of z + t d reaches zero (1e300: never)

@@ -107,6 +107,17 @@ public:
         check(tpl_batch_configure(e_, B, lane_smoothing, mask_off, mask_nodes));
     }
 
+    // Device-resident batched optimiser: B independent problems (folds, smoothing values, restarts) minimised in one
+    // call instead of B x optimize_full / optimize_plcp_tnc round trips (utils.cpp:671-763, optimize_tnc.cpp:107-172).
+    // X [P][B] in/out, F [B] out; lower/upper as the reference adapters build them (optimize_tnc.cpp:116-147).
+    tpl_opt_result optimize_batch(int B, double* X, double* F, const double* lower, const double* upper, int mode,
+                                  const tpl_opt_options* opts = nullptr, int* status = nullptr, int* iters = nullptr) {
+        ensure();
+        tpl_opt_result res;
+        check(tpl_optimize_batch(e_, B, X, F, lower, upper, mode, opts, status, iters, &res));
+        return res;
+    }
+
     void delete_ad_arrays() { if (e_) { tpl_destroy(e_); e_ = nullptr; } }     // main.cpp:798
     tpl_engine* handle() { ensure(); return e_; }
 
