@@ -147,6 +147,10 @@ typedef struct tpl_opt_options {
     int max_ls;         /* halvings per line search (0 = 40) */
     int check_every;    /* host polls the device-side done counter every this many steps (0 = 32) */
     int use_graph;      /* 1: replay `check_every` steps as one CUDA graph launch */
+    int method;         /* 0: L-BFGS (any layout); 1: truncated Newton, CG on the ANALYTIC Hessian-vector product with a
+                         * Jacobi preconditioner — what the reference's TNC approximates with finite differences
+                         * (tnc.c:483-827).  PL layout, AD gradient, no log penalty. */
+    int max_cg;         /* method 1: CG iterations per Newton step (0 = 100) */
     double ftol;        /* 0 = 1e-12 */
     double gtol;        /* 0 = 1e-8; on max |projected gradient| relative to max(|f|, 1) */
     double armijo;      /* 0 = 1e-4 */
@@ -159,6 +163,7 @@ typedef struct tpl_opt_result {
     int steps;          /* batched evaluations performed */
     int n_done;         /* vectors that stopped by themselves */
     int launches;       /* kernels launched */
+    int cg_iterations;  /* method 1: Hessian-vector products used, summed over the vectors */
     double device_ms;   /* CUDA-event time of the whole optimisation on the engine stream */
     double mean_log10_step; /* diagnostic: mean log10 of the accepted step lengths over all vectors (0 = unit steps) */
 } tpl_opt_result;
@@ -184,6 +189,10 @@ int tpl_get_timing(tpl_engine* e, double* main_ms, double* finalize_ms);
  * tile kernel whenever it is legal), and report which one the last evaluation used              */
 int tpl_debug_force_kernel(tpl_engine* e, int generation);
 int tpl_last_kernel_generation(const tpl_engine* e);
+
+/* test hook: W = H_z V and DG = diag(H_z) at X through the truncated-Newton kernels (z = w / sc_rows[p], w = ln r | h);
+ * X, V, W, DG: host [P][B].  Uses the installed batch configuration (per-vector smoothing and masks) when made for B. */
+int tpl_debug_hessvec(tpl_engine* e, int B, const double* X, const double* V, const double* sc_rows, double* W, double* DG);
 
 /* test hook: evaluates the kernels' log and reciprocal on n host values (tests only) */
 int tpl_debug_math(int n, const double* x, double* log_out, double* rcp_out);

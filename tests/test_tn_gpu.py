@@ -1,0 +1,113 @@
+"""Batched truncated Newton (tpl_optimize_batch, method = 1) on the GPU through the C ABI:
+  * the CUDA Hessian-vector kernel equals the CPU emulation of the same node function (tests/tn_sim.cpp), which
+    tests/test_tn_sim.py pins against finite differences of the oracle's gradient;
+  * the optimiser reaches the reference's END-TO-END results and the CPU emulation's optimum;
+  * graph replay == plain launches, bitwise; per-vector CV masks and smoothing values are honoured."""
+import numpy as np
+import pytest
+
+from golden_util import Golden
+from treepl_b200 import batchopt, cv
+from treepl_b200 import engine as eng
+from treepl_b200 import treeflat as tf
+import test_tn_sim as TS
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(pr, flat):
+    plp = eng.PLCalcParallel.from_flat(flat, device=0)
+    plp.set_freeparams(pr.P, False, pr.fp)
+    masks = None
+    if pr.mask is not None:
+        masks = [list(np.flatnonzero(pr.mask[b])) for b in range(pr.B)]
+    plp.batch_configure(pr.B, lane_smoothing=pr.lams, masks=masks)
+    return plp
+
+
+@pytest.mark.parametrize("name,lams,masked", [("test", [0.1, 10.0], False), ("M1155", [10.0, 0.1, 1000.0, 1.0], True),
+                                              ("big_test", [1.0] * 33, True)])
+def test_hessvec_kernel_equals_cpu_emulation(name, lams, masked):
+    sim = TS.load_sim()
+    flat = Golden(name).flat
+    n = len(flat["parents"])
+    tips = np.flatnonzero(flat["child_counts"] == 0)
+    masks = None
+    if masked:
+        masks = [[int(tips[(3 + 2 * b) % len(tips)])] for b in range(len(lams))]
+        masks[0] = []
+    pr = TS.Problem(flat, lams, masks)
+    P, B = pr.P, pr.B
+    rng = np.random.RandomState(11)
+    x0 = cv.start_vector(flat, P, n - 1)
+    X = np.repeat(x0[:, None], B, axis=1)
+    X[: n - 1] *= np.exp(0.2 * rng.randn(n - 1, B))
+    V = rng.randn(P, B)
+    plp = _engine(pr, flat)
+    F, G = plp.calc_pl_grad_batch(X, mode=eng.GRAD_AD)
+    W, DG = plp.debug_hessvec(X, V, pr.sc)
+    Ws, DGs = np.zeros((P, B)), np.zeros((P, B))
+    Xc, Gc, Vc = np.ascontiguousarray(X), np.ascontiguousarray(G), np.ascontiguousarray(V)
+    sim.tn_sim_hessvec(P, B, *pr.tree_args(), TS._d(pr.sc), TS._d(pr.lams), 0.0025, TS._d(Xc), TS._d(Gc), TS._d(Vc), TS._d(Ws), TS._d(DGs))
+    scale = np.abs(Ws).max(axis=0)
+    assert np.all(np.abs(W - Ws).max(axis=0) <= 1e-11 * scale), np.abs(W - Ws).max(axis=0) / scale
+    assert np.allclose(DG, DGs, rtol=1e-11, atol=0)
+    plp.close()
+
+
+def _run(name, lams, masks=None, **opt):
+    flat = Golden(name).flat
+    pr = TS.Problem(flat, lams, masks)
+    plp = _engine(pr, flat)
+    lower, upper = batchopt.reference_bounds(flat, pr.fp, pr.P)
+    x0 = cv.start_vector(flat, pr.P, pr.n - 1)
+    X0 = np.repeat(x0[:, None], pr.B, axis=1)
+    X, F, info = plp.optimize_batch(X0, lower, upper, method=1, date_scale=float(pr.sc[-1]), **opt)
+    return pr, plp, X, F, info
+
+
+def test_tn_reproduces_reference_final_pl_and_cpu_emulation():
+    sim = TS.load_sim()
+    for name, lams, ref in (("test", [0.1, 0.1], 234.23049), ("pl4203", [100.0, 1.0], 390.04656), ("M1155", [10.0, 1000.0, 0.1, 1.0], 252.3558)):
+        pr, plp, X, F, info = _run(name, lams, max_steps=20000)
+        assert ((info["status"] >= 1) & (info["status"] <= 2)).all(), info
+        assert abs(F[0] - ref) <= (1e-4 if name == "test" else 2e-6) * ref and F[0] <= ref + 1e-6 * ref, (name, F)
+        _, Xs, Fs, ss, its, ncg, steps = TS.fit(sim, name, lams)
+        assert np.all(np.abs(F - Fs) <= 1e-9 * np.abs(Fs)), (name, F, Fs)
+        assert 0.5 * steps <= info["steps"] <= 2.0 * steps + 64, (info["steps"], steps)
+        # a stationary point of the engine's own objective
+        f, g = plp.calc_pl_grad_batch(X, mode=eng.GRAD_AD)
+        assert np.all(np.abs(f - F) <= 1e-12 * np.abs(F))
+        plp.close()
+
+
+def test_tn_graph_replay_is_bitwise_and_uses_fewer_evaluations_than_lbfgs():
+    lams = [1000.0, 100.0, 10.0, 1.0, 0.1, 0.1]
+    runs = []
+    for graph in (0, 1, 1):
+        pr, plp, X, F, info = _run("M1155", lams, max_steps=20000, use_graph=graph)
+        runs.append((X, F, info))
+        plp.close()
+    assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][0], runs[1][0])
+    assert np.array_equal(runs[1][1], runs[2][1]) and np.array_equal(runs[1][0], runs[2][0])
+    flat = Golden("M1155").flat
+    pr = TS.Problem(flat, lams)
+    plp = _engine(pr, flat)
+    lower, upper = batchopt.reference_bounds(flat, pr.fp, pr.P)
+    x0 = cv.start_vector(flat, pr.P, pr.n - 1)
+    Xl, Fl, il = plp.optimize_batch(np.repeat(x0[:, None], pr.B, axis=1), lower, upper, method=0, date_scale=float(pr.sc[-1]), max_steps=20000,
+                                    ftol=1e-15, patience=40)
+    plp.close()
+    assert np.all(runs[0][1] <= Fl + 1e-9 * np.abs(Fl)), (runs[0][1], Fl)
+    assert runs[0][2]["steps"] < 0.7 * il["steps"], (runs[0][2]["steps"], il["steps"])
+
+
+def test_tn_loocv_m1155_chisq_table():
+    gd = Golden("M1155")
+    cals = [(t, lo, hi) for t, lo, hi in gd.meta["calibrations"]]
+    ft = tf.flatten_newick(gd.meta["newick"], gd.meta["numsites"], cals, seed=1)
+    res = cv.loocv(dict(gd.flat), [1000.0, 100.0, 10.0, 1.0, 0.1], ft.tips_postorder, method=1)
+    ref = np.array([2730.97, 2365.8, 2130.28, 2178.18, 2187.12])
+    assert res["cv_converged"] == res["n_vectors"]
+    assert np.all(np.abs(np.array(res["chisq"]) - ref) <= 2e-5 * ref), res["chisq"]
+    assert res["best"] == 10.0

@@ -18,6 +18,7 @@
 #include "tpl_tile_kernel.cuh"
 #include "tpl_desc_kernel.cuh"
 #include "tpl_lbfgs.cuh"
+#include "tpl_tn.cuh"
 
 namespace {
 
@@ -171,6 +172,9 @@ struct tpl_engine {
         DevBuf<double> Z, Gz, D, X, Gx, S, Y, lo, hi, sc, lane_d, rho, delta, M, part, part_red, tpart, Ft, Fout;
         DevBuf<int> lane_i;
         PinBuf<int> h_done;
+        // truncated Newton
+        DevBuf<double> R, ZZ, Pv, Hp, Minv, DG, pmin_n, pmax_n, tn_part, tn_lane_d;
+        DevBuf<int> tn_lane_i;
     } opt;
     // optional per-launch device timing (bench.py roofline): events around the main kernel
     bool timing = false;
@@ -814,6 +818,203 @@ int run_optimizer(tpl_engine* e, tplopt::OptArgs a, int B, int mode, int max_ste
     return TPL_OK;
 }
 
+// ---- batched truncated Newton (tpl_tn_core.h / tpl_tn.cuh) ---------------------------------------------------------
+
+// work space, tree operands and chunking of the truncated-Newton kernels; uploads lo / hi / sc and X
+int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>& lo, const std::vector<double>& hi,
+               const std::vector<double>& sc, int nr, const tpl_opt_options& o, tpltn::TnArgs& a) {
+    using namespace tpltn;
+    if (e->lf_mode) return fail(TPL_ERR_ARG, "truncated Newton needs the PL layout (one rate per branch)");
+    if (e->log_pen) return fail(TPL_ERR_ARG, "truncated Newton does not carry the log-penalty Hessian; use method 0");
+    if (e->cv_any) return fail(TPL_ERR_ARG, "truncated Newton takes CV masks per vector (tpl_batch_configure), not set_cv_nodes");
+    const int P = e->numparams, n = e->n;
+    const size_t PB = (size_t)P * B;
+    tpl_engine::OptWork& w = e->opt;
+    cudaStream_t s = e->stream;
+    const int groups = (B + 31) / 32;
+    const int WY = tplopt::OPT_WY;
+    auto one_wave = [&](int occ, int total, int align, int* nch, int* per) {
+        int c = std::max(1, (e->num_sms * std::max(occ, 1)) / groups);
+        c = std::min(c, (total + align - 1) / align);
+        int r = (total + c - 1) / c;
+        r = ((r + align - 1) / align) * align;
+        *per = r;
+        *nch = (total + r - 1) / r;
+    };
+    int occ_row = 1, occ_node = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_row, tn_update_kernel, 32 * WY, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_node, tn_hv_kernel, 32 * WY, 0);
+    one_wave(occ_row, P, WY, &a.row_chunks, &a.rows_per_chunk);
+    one_wave(occ_node, n, WY, &a.node_chunks, &a.nodes_per_chunk);
+    CK(w.Z.ensure(PB)); CK(w.Gz.ensure(PB)); CK(w.D.ensure(PB)); CK(w.X.ensure(PB)); CK(w.Gx.ensure(PB));
+    CK(w.R.ensure(PB)); CK(w.ZZ.ensure(PB)); CK(w.Pv.ensure(PB)); CK(w.Hp.ensure(PB)); CK(w.Minv.ensure(PB)); CK(w.DG.ensure(PB));
+    CK(w.lo.ensure(P)); CK(w.hi.ensure(P)); CK(w.sc.ensure(P)); CK(w.Ft.ensure(B)); CK(w.Fout.ensure(B)); CK(w.h_done.ensure(1));
+    const size_t npart = (size_t)(3 + 1 + 1) * a.row_chunks * B + (size_t)(2 + 1) * a.node_chunks * B;
+    CK(w.tn_part.ensure(npart));
+    CK(w.tn_lane_d.ensure((size_t)11 * B));
+    CK(w.tn_lane_i.ensure((size_t)8 * B + 1 + 5 * (size_t)groups));
+    CK(w.pmin_n.upload(e->pen_min, s));
+    CK(w.pmax_n.upload(e->pen_max, s));
+    CK(cudaMemcpyAsync(w.lo.p, lo.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w.hi.p, hi.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w.sc.p, sc.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w.X.p, X, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(w.tn_lane_d.p, 0, sizeof(double) * 11 * B, s));
+    CK(cudaMemsetAsync(w.tn_lane_i.p, 0, sizeof(int) * (8 * (size_t)B + 1 + 5 * (size_t)groups), s));     // st = TS_INIT, t = 0
+    for (DevBuf<double>* buf : {&w.Gz, &w.D, &w.R, &w.ZZ, &w.Pv, &w.Hp, &w.Minv, &w.DG, &w.Gx})
+        CK(cudaMemsetAsync(buf->p, 0, sizeof(double) * PB, s));
+    CK(cudaStreamSynchronize(s));       // pen_min / pen_max uploads read host vectors of the engine; lo / hi / sc are the caller's
+    a.o.P = P; a.o.B = B; a.o.nr = nr;
+    a.o.max_ls = o.max_ls > 0 ? o.max_ls : 40;
+    a.o.max_cg = o.max_cg > 0 ? o.max_cg : 100;
+    a.o.patience = o.patience > 0 ? o.patience : 3;
+    a.o.c1 = o.armijo > 0 ? o.armijo : 1e-4;
+    a.o.ftol = o.ftol > 0 ? o.ftol : 1e-13;
+    a.o.gtol = o.gtol > 0 ? o.gtol : 1e-8;
+    a.o.boundary_frac = o.boundary_frac < 0 ? 0.0 : (o.boundary_frac > 0 ? std::min(o.boundary_frac, 0.999999) : 0.9);
+    a.t = dev_tree(e);
+    a.pmin_n = w.pmin_n.p; a.pmax_n = w.pmax_n.p;
+    const bool lanemask = e->cfg_mask && e->cfg_B == B;
+    a.lanemask = lanemask ? e->d_lanemask.p : nullptr;
+    a.mask_stride = e->ntiles2 * tpl::TILE_NODES;
+    a.lane_lambda = (e->cfg_lambda && e->cfg_B == B) ? e->d_lane_lambda.p : nullptr;
+    a.lambda = e->smoothing;
+    a.pb = e->pb;
+    a.sc = w.sc.p; a.lo = w.lo.p; a.hi = w.hi.p;
+    a.Z = w.Z.p; a.Gz = w.Gz.p; a.S = w.D.p; a.X = w.X.p; a.R = w.R.p; a.ZZ = w.ZZ.p; a.Pv = w.Pv.p; a.Hp = w.Hp.p;
+    a.Minv = w.Minv.p; a.DG = w.DG.p; a.Gx = w.Gx.p; a.Ft = w.Ft.p;
+    int* li = w.tn_lane_i.p;
+    const size_t Bs = (size_t)B;
+    a.st = li; a.ls = li + Bs; a.cgit = li + 2 * Bs; a.flag = li + 3 * Bs; a.stall = li + 4 * Bs; a.iters = li + 5 * Bs;
+    a.ncg = li + 6 * Bs; a.act = li + 7 * Bs; a.ndone = li + 8 * Bs;
+    int* cnt = li + 8 * Bs + 1;
+    a.cnt_setup = cnt; a.cnt_hv = cnt + groups; a.cnt_upd = cnt + 2 * groups; a.cnt_gd = cnt + 3 * groups; a.cnt_tm = cnt + 4 * groups;
+    double* ld = w.tn_lane_d.p;
+    a.F0 = ld; a.t_ = ld + Bs; a.gd = ld + 2 * Bs; a.rz = ld + 3 * Bs; a.rz0 = ld + 4 * Bs; a.tol2 = ld + 5 * Bs; a.alpha = ld + 6 * Bs;
+    a.beta = ld + 7 * Bs; a.gmax = ld + 8 * Bs; a.tlog = ld + 9 * Bs; a.gdtmp = ld + 10 * Bs;
+    double* pp = w.tn_part.p;
+    a.part_setup = pp; pp += (size_t)3 * a.row_chunks * B;
+    a.part_upd = pp; pp += (size_t)a.row_chunks * B;
+    a.part_gd = pp; pp += (size_t)a.row_chunks * B;
+    a.part_hv = pp; pp += (size_t)2 * a.node_chunks * B;
+    a.part_tm = pp;
+    return TPL_OK;
+}
+
+int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<double>& lo, const std::vector<double>& hi,
+                const std::vector<double>& sc, int nr, int mode, const tpl_opt_options& o, int* status, int* iters,
+                tpl_opt_result* result) {
+    using namespace tpltn;
+    if (mode != TPL_GRAD_AD) return fail(TPL_ERR_ARG, "truncated Newton differentiates the AD objective (TPL_GRAD_AD)");
+    TnArgs a;
+    int prc = tn_prepare(e, B, X, lo, hi, sc, nr, o, a);
+    if (prc != TPL_OK) return prc;
+    const int P = e->numparams;
+    const size_t PB = (size_t)P * B;
+    tpl_engine::OptWork& w = e->opt;
+    cudaStream_t s = e->stream;
+    const int groups = (B + 31) / 32;
+    const int WY = tplopt::OPT_WY;
+    const int max_steps = o.max_steps > 0 ? o.max_steps : 20000;
+    const int check_every = o.check_every > 0 ? o.check_every : 32;
+    const dim3 blk(32, WY);
+    const dim3 rgrd(groups, a.row_chunks), ngrd(groups, a.node_chunks);
+    cudaEvent_t ev0, ev1;
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, s));
+    int launches = 0;
+    tn_init_kernel<<<rgrd, blk, 0, s>>>(a);
+    tn_trial_kernel<<<rgrd, blk, 0, s>>>(a);
+    launches += 2;
+    CK(cudaGetLastError());
+    auto one_step = [&]() -> int {
+        int rc = eval_device(e, B, a.X, const_cast<double*>(a.Ft), const_cast<double*>(a.Gx), mode, true, s);
+        if (rc != TPL_OK) return rc;
+        tn_diag_kernel<<<ngrd, blk, 0, s>>>(a);
+        tn_setup_kernel<<<rgrd, blk, 0, s>>>(a);
+        tn_hv_kernel<<<ngrd, blk, 0, s>>>(a);
+        tn_update_kernel<<<rgrd, blk, 0, s>>>(a);
+        tn_dir_kernel<<<rgrd, blk, 0, s>>>(a);
+        tn_gd_kernel<<<rgrd, blk, 0, s>>>(a);
+        tn_stepmax_kernel<<<ngrd, blk, 0, s>>>(a);
+        tn_trial_kernel<<<rgrd, blk, 0, s>>>(a);
+        CK(cudaGetLastError());
+        return TPL_OK;
+    };
+    const int per_step = 10;
+    int steps = 0;
+    int rc = one_step();               // first step outside any capture: sizes the evaluation work space
+    if (rc != TPL_OK) return rc;
+    steps++;
+    launches += per_step;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    const bool was_timing = e->timing;
+    e->timing = false;
+    if (o.use_graph) {
+        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        for (int k = 0; k < check_every && rc == TPL_OK; k++) rc = one_step();
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc != TPL_OK || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            e->timing = was_timing;
+            return rc != TPL_OK ? rc : fail(TPL_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+        }
+        CK(cudaGraphInstantiate(&gexec, graph, 0));
+    }
+    int ndone = 0;
+    while (steps < max_steps) {
+        if (o.use_graph) {
+            CK(cudaGraphLaunch(gexec, s));
+        } else {
+            for (int k = 0; k < check_every && rc == TPL_OK; k++) rc = one_step();
+            if (rc != TPL_OK) break;
+        }
+        steps += check_every;
+        launches += per_step * check_every;
+        CK(cudaMemcpyAsync(w.h_done.p, a.ndone, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        ndone = w.h_done.p[0];
+        if (ndone >= B) break;
+    }
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+    e->timing = was_timing;
+    if (rc != TPL_OK) return rc;
+    tn_final_kernel<<<rgrd, blk, 0, s>>>(a, w.Fout.p);
+    launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev1, s));
+    CK(cudaMemcpyAsync(X, w.X.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(F, w.Fout.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status, a.flag, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+    std::vector<double> tlog(B);
+    std::vector<int> nit(B), ncg(B);
+    CK(cudaMemcpyAsync(tlog.data(), a.tlog, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(nit.data(), a.iters, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ncg.data(), a.ncg, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    tpl_opt_result res;
+    memset(&res, 0, sizeof(res));
+    double ts = 0.0;
+    long long ni = 0, nc = 0;
+    for (int b = 0; b < B; b++) { ts += tlog[b]; ni += nit[b]; nc += ncg[b]; if (iters) iters[b] = nit[b]; }
+    res.steps = steps;
+    res.n_done = ndone;
+    res.launches = launches;
+    res.cg_iterations = (int)std::min<long long>(nc, 2147483647LL);
+    res.device_ms = ms;
+    res.mean_log10_step = ni > 0 ? ts / (double)ni : 0.0;
+    e->last_launches = launches;
+    if (result) *result = res;
+    return TPL_OK;
+}
+
 }  // namespace
 
 extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, const double* lower, const double* upper,
@@ -856,6 +1057,8 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
         }
         if (!(lo[p] <= hi[p])) return fail(TPL_ERR_ARG, "empty bound interval");
     }
+    if (o.method == 1) return optimize_tn(e, B, X, F, lo, hi, sc, nr, mode, o, status, iters, result);
+    if (o.method != 0) return fail(TPL_ERR_ARG, "method must be 0 (L-BFGS) or 1 (truncated Newton)");
     const size_t PB = (size_t)P * B;
     tpl_engine::OptWork& w = e->opt;
     const int NB = 2 * HM + 1, NACC = 6 * HM + 2;
@@ -982,6 +1185,42 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
     res.device_ms = ms;
     e->last_launches = res.launches;
     if (result) *result = res;
+    return TPL_OK;
+}
+
+
+extern "C" int tpl_debug_hessvec(tpl_engine* e, int B, const double* X, const double* V, const double* sc_rows, double* W, double* DG) {
+    using namespace tpltn;
+    if (!e || !X || !V || !sc_rows || !W || !DG || B < 1) return fail(TPL_ERR_ARG, "null or B < 1");
+    if (!e->have_fp) return fail(TPL_ERR_STATE, "set_freeparams has not been called");
+    CK(cudaSetDevice(e->device));
+    int rc = sync_device_tree(e);
+    if (rc != TPL_OK) return rc;
+    const int P = e->numparams;
+    const size_t PB = (size_t)P * B;
+    int nr = 0;
+    for (int i = 0; i < e->n; i++) nr = std::max(nr, e->freeparams[i] + 1);
+    std::vector<double> lo(P, -1e300), hi(P, 1e300), sc(sc_rows, sc_rows + P);
+    tpl_opt_options o;
+    memset(&o, 0, sizeof(o));
+    TnArgs a;
+    rc = tn_prepare(e, B, X, lo, hi, sc, nr, o, a);
+    if (rc != TPL_OK) return rc;
+    cudaStream_t s = e->stream;
+    tpl_engine::OptWork& w = e->opt;
+    rc = eval_device(e, B, a.X, const_cast<double*>(a.Ft), const_cast<double*>(a.Gx), TPL_GRAD_AD, true, s);
+    if (rc != TPL_OK) return rc;
+    const dim3 blk(32, tplopt::OPT_WY);
+    const dim3 ngrd((B + 31) / 32, a.node_chunks);
+    CK(cudaMemcpyAsync(w.Pv.p, V, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
+    tn_diag_kernel<<<ngrd, blk, 0, s>>>(a);                     // st = TS_INIT and a finite objective: every vector "accepts"
+    std::vector<int> cg(B, TS_CG);
+    CK(cudaMemcpyAsync(a.st, cg.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+    tn_hv_kernel<<<ngrd, blk, 0, s>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(W, w.Hp.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(DG, w.DG.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return TPL_OK;
 }
 

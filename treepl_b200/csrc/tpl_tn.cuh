@@ -1,0 +1,349 @@
+// Streaming kernels of the batched truncated-Newton optimiser (sm_100a).  Method, math and what it replaces in the
+// reference (TNC, src/tnc.c:483-827 behind src/optimize_tnc.cpp:107-172): tpl_tn_core.h.
+//
+// One optimiser step = one PL evaluation of the trial points (for the vectors in their line search) + one analytic
+// Hessian-vector product (for the vectors inside their CG solve) + the CG vector updates.  Vectors advance
+// independently; each kernel skips the 32-vector groups that have nothing to do in it.  Every per-vector reduction
+// (p.Hp, r.M^-1 r, gp.s, the ratio test) is finished by the LAST block of the vector group to arrive (fixed-order
+// sums over the chunk partials, so the result does not depend on which block that is), and that block also runs the
+// vector's state machine (tpl_tn_core.h::phase_*): no separate reduction or bookkeeping launches.
+//
+//   tn_diag_kernel    node-indexed   diagonal of H_z at a newly accepted point (Jacobi preconditioner)
+//   tn_setup_kernel   row-indexed    accept the step: Z, Gz, M^-1, r = -gp, zz = M^-1 r, p = zz, s = 0      -> phase_setup
+//   tn_hv_kernel      node-indexed   Hp = H_z p (pull: node, parent, children)                               -> phase_hv
+//   tn_update_kernel  row-indexed    s += alpha p, r -= alpha Hp, zz = M^-1 r                                 -> phase_update
+//   tn_dir_kernel     row-indexed    p = zz + beta p
+//   tn_gd_kernel      row-indexed    gd = Gz.s  (s = p when CG stopped at its first iteration)
+//   tn_stepmax_kernel node-indexed   largest step keeping all durations positive                             -> phase_finish
+//   tn_trial_kernel   row-indexed    X = to_param(z + t s)
+#pragma once
+#include "tpl_kernels.cuh"
+#include "tpl_lbfgs.cuh"
+#include "tpl_tn_core.h"
+
+namespace tpltn {
+
+using tplopt::OPT_WY;
+
+struct TnArgs {
+    TnConst o;
+    tpl::DevTree t;
+    const double *pmin_n, *pmax_n;           // [n] node-indexed calibration penalties (-1 = none)
+    const unsigned long long* lanemask;      // per-vector CV masks (EvalArgs layout) or null
+    int mask_stride;
+    const double* lane_lambda;               // [B] or null
+    double lambda, pb;
+    const double *sc, *lo, *hi;              // [P]
+    double *Z, *Gz, *S, *X, *R, *ZZ, *Pv, *Hp, *Minv, *DG;   // [P][B]
+    const double* Gx;                        // [P][B] gradient of the evaluated point, original parameters
+    const double* Ft;                        // [B]
+    int *st, *ls, *cgit, *flag, *stall, *iters, *ncg, *act;
+    double *F0, *t_, *gd, *rz, *rz0, *tol2, *alpha, *beta, *gmax, *tlog, *gdtmp;
+    int row_chunks, rows_per_chunk;          // row-indexed kernels
+    int node_chunks, nodes_per_chunk;        // node-indexed kernels
+    double *part_setup, *part_hv, *part_upd, *part_gd, *part_tm;
+    int *cnt_setup, *cnt_hv, *cnt_upd, *cnt_gd, *cnt_tm;      // [groups] arrival counters, zero between launches
+    int* ndone;
+};
+
+__device__ __forceinline__ Lane lane_of(const TnArgs& a, int b) {
+    Lane L;
+    L.st = a.st + b; L.ls = a.ls + b; L.cgit = a.cgit + b; L.flag = a.flag + b; L.stall = a.stall + b; L.iters = a.iters + b;
+    L.ncg = a.ncg + b; L.act = a.act + b;
+    L.F0 = a.F0 + b; L.t = a.t_ + b; L.gd = a.gd + b; L.rz = a.rz + b; L.rz0 = a.rz0 + b; L.tol2 = a.tol2 + b; L.alpha = a.alpha + b;
+    L.beta = a.beta + b; L.gmax = a.gmax + b; L.tlog = a.tlog + b;
+    return L;
+}
+
+// Per-vector reduction across the blocks (blockIdx.y) of a 32-vector group.  v[k]: this thread's partial; bit k of MAXM /
+// MINM selects max / min instead of sum.  Returns true in the last block to arrive, with the group totals in v[] of the
+// ty == 0 threads.  Deterministic: partials are combined in chunk order, then in ty order.
+template <int K, unsigned MAXM, unsigned MINM>
+__device__ __forceinline__ bool group_reduce(double (&v)[K], double* part, int* counter, int B, int b) {
+    __shared__ double red[OPT_WY][K][32];
+    __shared__ int s_last;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    auto comb = [](int k, double x, double y) {
+        if ((MAXM >> k) & 1u) return fmax(x, y);
+        if ((MINM >> k) & 1u) return fmin(x, y);
+        return x + y;
+    };
+#pragma unroll
+    for (int k = 0; k < K; k++) red[ty][k][tx] = v[k];
+    __syncthreads();
+    if (ty == 0 && b < B) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double x = red[0][k][tx];
+            for (int y = 1; y < OPT_WY; y++) x = comb(k, x, red[y][k][tx]);
+            part[((size_t)blockIdx.y * K + k) * B + b] = x;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tx == 0 && ty == 0) s_last = atomicAdd(counter + blockIdx.x, 1) == (int)gridDim.y - 1;
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    const int nch = gridDim.y;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double x = ((MAXM >> k) & 1u) ? 0.0 : (((MINM >> k) & 1u) ? 1e300 : 0.0);
+        if (b < B)
+            for (int c = ty; c < nch; c += OPT_WY) x = comb(k, x, __ldcg(part + ((size_t)c * K + k) * B + b));
+        red[ty][k][tx] = x;
+    }
+    __syncthreads();
+    if (ty == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double x = red[0][k][tx];
+            for (int y = 1; y < OPT_WY; y++) x = comb(k, x, red[y][k][tx]);
+            v[k] = x;
+        }
+    }
+    if (tx == 0 && ty == 0) counter[blockIdx.x] = 0;        // ready for the next launch
+    return true;
+}
+
+struct DevView {
+    const TnArgs& a;
+    int B, b;
+    const double* Vv;
+    double* W;
+    double lam, pb;
+    __device__ int parent(int i) const { return a.t.parent[i]; }
+    __device__ int child_begin(int i) const { return a.t.child_off[i]; }
+    __device__ int child_end(int i) const { return a.t.child_off[i + 1]; }
+    __device__ int child(int j) const { return a.t.children[j]; }
+    __device__ int rslot(int i) const { return a.t.rslot[i]; }
+    __device__ int dslot(int i) const { return a.t.dslot[i]; }
+    __device__ double c(int i) const { return a.t.c[i]; }
+    __device__ double hfix(int i) const { return a.t.hfix[i]; }
+    __device__ double rfix(int i) const { return a.t.rfix[i]; }
+    __device__ double pmin(int i) const { return a.pmin_n[i]; }
+    __device__ double pmax(int i) const { return a.pmax_n[i]; }
+    __device__ bool masked(int i) const {
+        if (!a.lanemask) return false;
+        return (a.lanemask[(size_t)(b >> 6) * a.mask_stride + i] >> (b & 63)) & 1ull;
+    }
+    __device__ double sc(int row) const { return a.sc[row]; }
+    __device__ double x(int row) const { return a.X[(size_t)row * B + b]; }
+    __device__ double v(int row) const { return Vv[(size_t)row * B + b]; }
+    __device__ double gx(int row) const { return a.Gx[(size_t)row * B + b]; }
+    __device__ void put(int row, double val) { W[(size_t)row * B + b] = val; }
+};
+
+__device__ __forceinline__ int lane_decision(const TnArgs& a, int b) {
+    return decide(a.st[b], a.Ft[b], a.F0[b], a.t_[b], a.gd[b], a.o.c1);
+}
+
+// Z = clamp(w / sc), S = 0
+__global__ void __launch_bounds__(32 * OPT_WY) tn_init_kernel(TnArgs a) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    if (b >= a.o.B) return;
+    if (blockIdx.y == 0 && threadIdx.y == 0) a.act[b] = ACT_TRIAL;      // the first trial point is the start itself (t = 0)
+    const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(a.o.P, p0 + a.rows_per_chunk);
+    for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
+        const size_t i = (size_t)p * a.o.B + b;
+        const double x = a.X[i];
+        const double w = p < a.o.nr ? log(x) : x;
+        a.Z[i] = fmin(fmax(w / a.sc[p], a.lo[p]), a.hi[p]);
+        a.S[i] = 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(32 * OPT_WY) tn_trial_kernel(TnArgs a) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    const int B = a.o.B, P = a.o.P, nr = a.o.nr;
+    if (b >= B) return;
+    const int act = a.act[b];
+    if (a.st[b] == TS_DONE || !(act & ACT_TRIAL)) return;
+    const bool sd = (act & ACT_SD) != 0;
+    const double t = a.t_[b];
+    const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
+    for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
+        const size_t i = (size_t)p * B + b;
+        double s;
+        if (sd) {
+            s = -a.Gz[i] * a.Minv[i];
+            a.S[i] = s;
+        } else {
+            s = a.S[i];
+        }
+        a.X[i] = tplopt::to_param(p < nr, tplopt::trial_point(a.Z[i], t, s, a.lo[p], a.hi[p]), a.sc[p]);
+    }
+}
+
+__global__ void __launch_bounds__(32 * OPT_WY) tn_diag_kernel(TnArgs a) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    const int B = a.o.B;
+    if (b >= B) return;
+    const int dec = lane_decision(a, b);
+    if (dec != DEC_ACCEPT && dec != DEC_INIT) return;
+    DevView V = {a, B, b, a.Pv, a.DG, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb};
+    const int i0 = blockIdx.y * a.nodes_per_chunk, i1 = min(a.t.n, i0 + a.nodes_per_chunk);
+    for (int i = i0 + threadIdx.y; i < i1; i += OPT_WY) diag_node(V, i);
+}
+
+__global__ void __launch_bounds__(32 * OPT_WY) tn_setup_kernel(TnArgs a) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int b = blockIdx.x * 32 + tx;
+    const int B = a.o.B, P = a.o.P, nr = a.o.nr;
+    int dec = DEC_SKIP;
+    double t = 0.0;
+    if (b < B) {
+        dec = lane_decision(a, b);
+        t = a.t_[b];
+    }
+    if (!__syncthreads_or(dec != DEC_SKIP)) return;          // uniform over blockIdx.y
+    double v[3] = {0.0, 0.0, 0.0};
+    if (dec == DEC_ACCEPT || dec == DEC_INIT) {
+        const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
+        for (int p = p0 + ty; p < p1; p += OPT_WY) {
+            const size_t i = (size_t)p * B + b;
+            const double lo = a.lo[p], hi = a.hi[p];
+            double z = a.Z[i];
+            if (dec == DEC_ACCEPT) z = tplopt::trial_point(z, t, a.S[i], lo, hi);
+            const double gz = tplopt::chain_grad(p < nr, a.Gx[i], a.X[i], a.sc[p]);
+            const double mi = precond_inverse(a.DG[i], tplopt::is_free(z, gz, lo, hi));
+            const double gp = mi > 0.0 ? gz : 0.0;
+            const double zz = -gp * mi;
+            a.Z[i] = z;
+            a.Gz[i] = gz;
+            a.Minv[i] = mi;
+            a.R[i] = -gp;
+            a.ZZ[i] = zz;
+            a.Pv[i] = zz;
+            a.S[i] = 0.0;
+            v[0] = fma(gp * mi, gp, v[0]);
+            v[1] = fmax(v[1], fabs(gp));
+            v[2] = fma(gp, gp, v[2]);
+        }
+    }
+    if (!group_reduce<3, 2u, 0u>(v, a.part_setup, a.cnt_setup, B, b)) return;
+    if (ty == 0 && b < B)
+        if (phase_setup(lane_of(a, b), a.Ft[b], v, a.o)) atomicAdd(a.ndone, 1);
+}
+
+__global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int b = blockIdx.x * 32 + tx;
+    const int B = a.o.B;
+    const bool active = b < B && a.st[b] == TS_CG;
+    if (!__syncthreads_or(active)) return;
+    double v[2] = {0.0, 0.0};
+    if (active) {
+        DevView V = {a, B, b, a.Pv, a.Hp, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb};
+        const int i0 = blockIdx.y * a.nodes_per_chunk, i1 = min(a.t.n, i0 + a.nodes_per_chunk);
+        for (int i = i0 + ty; i < i1; i += OPT_WY) {
+            double vw, vv;
+            hess_node(V, i, vw, vv);
+            v[0] += vw;
+            v[1] += vv;
+        }
+    }
+    if (!group_reduce<2, 0u, 0u>(v, a.part_hv, a.cnt_hv, B, b)) return;
+    if (ty == 0 && active) phase_hv(lane_of(a, b), v, a.o);
+}
+
+__global__ void __launch_bounds__(32 * OPT_WY) tn_update_kernel(TnArgs a) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int b = blockIdx.x * 32 + tx;
+    const int B = a.o.B, P = a.o.P;
+    const bool active = b < B && a.st[b] == TS_CG && (a.act[b] & ACT_CG);
+    if (!__syncthreads_or(active)) return;
+    double v[1] = {0.0};
+    if (active) {
+        const double alpha = a.alpha[b];
+        const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
+        for (int p = p0 + ty; p < p1; p += OPT_WY) {
+            const size_t i = (size_t)p * B + b;
+            const double pv = a.Pv[i];
+            a.S[i] = fma(alpha, pv, a.S[i]);
+            const double r = fma(-alpha, a.Hp[i], a.R[i]);
+            a.R[i] = r;
+            const double zz = r * a.Minv[i];
+            a.ZZ[i] = zz;
+            v[0] = fma(r, zz, v[0]);
+        }
+    }
+    if (!group_reduce<1, 0u, 0u>(v, a.part_upd, a.cnt_upd, B, b)) return;
+    if (ty == 0 && active) phase_update(lane_of(a, b), v, a.o);
+}
+
+__global__ void __launch_bounds__(32 * OPT_WY) tn_dir_kernel(TnArgs a) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    const int B = a.o.B, P = a.o.P;
+    if (b >= B) return;
+    if (a.st[b] != TS_CG || !(a.act[b] & ACT_DIR)) return;
+    const double beta = a.beta[b];
+    const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
+    for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
+        const size_t i = (size_t)p * B + b;
+        a.Pv[i] = fma(beta, a.Pv[i], a.ZZ[i]);
+    }
+}
+
+__global__ void __launch_bounds__(32 * OPT_WY) tn_gd_kernel(TnArgs a) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int b = blockIdx.x * 32 + tx;
+    const int B = a.o.B, P = a.o.P;
+    int act = 0;
+    if (b < B && a.st[b] == TS_CG) act = a.act[b];
+    const bool active = (act & ACT_FIN) != 0;
+    if (!__syncthreads_or(active)) return;
+    double v[1] = {0.0};
+    if (active) {
+        const bool takep = (act & ACT_TAKEP) != 0;
+        const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
+        for (int p = p0 + ty; p < p1; p += OPT_WY) {
+            const size_t i = (size_t)p * B + b;
+            double s;
+            if (takep) {
+                s = a.Pv[i];
+                a.S[i] = s;
+            } else {
+                s = a.S[i];
+            }
+            v[0] = fma(a.Gz[i], s, v[0]);
+        }
+    }
+    if (!group_reduce<1, 0u, 0u>(v, a.part_gd, a.cnt_gd, B, b)) return;
+    if (ty == 0 && active) a.gdtmp[b] = v[0];
+}
+
+__global__ void __launch_bounds__(32 * OPT_WY) tn_stepmax_kernel(TnArgs a) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int b = blockIdx.x * 32 + tx;
+    const int B = a.o.B;
+    const bool active = b < B && a.st[b] == TS_CG && (a.act[b] & ACT_FIN);
+    if (!__syncthreads_or(active)) return;
+    double v[1] = {1e300};
+    if (active) {
+        const int i0 = max(1, blockIdx.y * a.nodes_per_chunk), i1 = min(a.t.n, (blockIdx.y + 1) * a.nodes_per_chunk);
+        for (int i = i0 + ty; i < i1; i += OPT_WY) {
+            const int pa = a.t.parent[i];
+            const int ri = a.t.dslot[i], rp = a.t.dslot[pa];
+            double zi, di = 0.0, zp, dp = 0.0;
+            if (ri >= 0) { const double sc = a.sc[ri]; zi = a.Z[(size_t)ri * B + b] * sc; di = a.S[(size_t)ri * B + b] * sc; } else zi = a.t.hfix[i];
+            if (rp >= 0) { const double sc = a.sc[rp]; zp = a.Z[(size_t)rp * B + b] * sc; dp = a.S[(size_t)rp * B + b] * sc; } else zp = a.t.hfix[pa];
+            v[0] = fmin(v[0], tplopt::branch_step_limit(zi, di, zp, dp));
+        }
+    }
+    if (!group_reduce<1, 0u, 1u>(v, a.part_tm, a.cnt_tm, B, b)) return;
+    if (ty == 0 && active) phase_finish(lane_of(a, b), a.gdtmp[b], v[0], a.o);
+}
+
+__global__ void __launch_bounds__(32 * OPT_WY) tn_final_kernel(TnArgs a, double* F) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    if (b >= a.o.B) return;
+    if (blockIdx.y == 0 && threadIdx.y == 0) F[b] = a.F0[b];
+    const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(a.o.P, p0 + a.rows_per_chunk);
+    for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
+        const size_t i = (size_t)p * a.o.B + b;
+        a.X[i] = tplopt::to_param(p < a.o.nr, a.Z[i], a.sc[p]);
+    }
+}
+
+}  // namespace tpltn

@@ -60,8 +60,9 @@ def _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose, *
     if native:
         # chi-square is far more sensitive to the last digits of the optimum than the objective is (at small
         # smoothing the pruned tip's prediction hangs on weakly determined rates): converge tightly
-        opt.setdefault("ftol", 1e-15)
-        opt.setdefault("patience", 40)
+        if opt.get("method", 0) == 0:
+            opt.setdefault("ftol", 1e-15)
+            opt.setdefault("patience", 40)
         X, F, info = plp.optimize_batch(X0, lo, hi, mode=eng.GRAD_AD, history=history, max_steps=20 * max_iter,
                                         date_scale=dscale, use_graph=1, **opt)
         bad = np.nonzero(info["status"] == 4)[0]

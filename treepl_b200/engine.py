@@ -35,12 +35,12 @@ _lib = None
 class OptOptions(C.Structure):
     """tpl_opt_options (include/treepl_b200.h); 0 = library default"""
     _fields_ = [("history", C.c_int), ("max_steps", C.c_int), ("patience", C.c_int), ("max_ls", C.c_int),
-                ("check_every", C.c_int), ("use_graph", C.c_int), ("ftol", C.c_double), ("gtol", C.c_double),
+                ("check_every", C.c_int), ("use_graph", C.c_int), ("method", C.c_int), ("max_cg", C.c_int), ("ftol", C.c_double), ("gtol", C.c_double),
                 ("armijo", C.c_double), ("date_scale", C.c_double), ("boundary_frac", C.c_double)]
 
 
 class OptResult(C.Structure):
-    _fields_ = [("steps", C.c_int), ("n_done", C.c_int), ("launches", C.c_int), ("device_ms", C.c_double),
+    _fields_ = [("steps", C.c_int), ("n_done", C.c_int), ("launches", C.c_int), ("cg_iterations", C.c_int), ("device_ms", C.c_double),
                 ("mean_log10_step", C.c_double)]
 
 
@@ -92,6 +92,8 @@ def load_library():
         fn.argtypes = args
     L.tpl_optimize_batch.restype = ci
     L.tpl_optimize_batch.argtypes = [vp, ci, dp, dp, dp, dp, ci, C.POINTER(OptOptions), ip, ip, C.POINTER(OptResult)]
+    L.tpl_debug_hessvec.restype = ci
+    L.tpl_debug_hessvec.argtypes = [vp, ci, dp, dp, dp, dp, dp]
     L.tpl_host_alloc.restype = vp
     L.tpl_host_alloc.argtypes = [C.c_ulonglong]
     L.tpl_host_free.restype = None
@@ -107,7 +109,7 @@ EXPORTED_SYMBOLS = (
     "tpl_calc_function_gradient", "tpl_calc_pl_grad", "tpl_get_rates", "tpl_get_dates", "tpl_get_durations",
     "tpl_batch_configure", "tpl_calc_pl_grad_batch", "tpl_calc_pl_grad_batch_dev", "tpl_last_launch_count",
     "tpl_host_alloc", "tpl_host_free", "tpl_device_sm", "tpl_debug_math", "tpl_set_timing", "tpl_get_timing", "tpl_debug_force_kernel",
-    "tpl_last_kernel_generation", "tpl_optimize_batch",
+    "tpl_last_kernel_generation", "tpl_optimize_batch", "tpl_debug_hessvec",
 )
 
 
@@ -348,7 +350,7 @@ class PLCalcParallel:
     def optimize_batch(self, X0, lower, upper, mode=GRAD_AD, **options):
         """Device-resident batched L-BFGS (tpl_optimize_batch): X0 [P, B] feasible start vectors ->
         (X [P, B], F [B], info).  options: fields of tpl_opt_options (history, max_steps, patience, max_ls,
-        check_every, use_graph, ftol, gtol, armijo, date_scale)."""
+        check_every, use_graph, method (0 L-BFGS, 1 truncated Newton), max_cg, ftol, gtol, armijo, date_scale, boundary_frac)."""
         X = _f64(X0).copy()
         P, B = X.shape
         if P != self.numparams:
@@ -367,7 +369,15 @@ class PLCalcParallel:
         self._check(self._L.tpl_optimize_batch(self._h, B, _dp(X), _dp(F), _dp(lo), _dp(hi), int(mode), C.byref(o),
                                                _ip(status), _ip(iters), C.byref(res)))
         return X, F, {"steps": res.steps, "n_done": res.n_done, "launches": res.launches, "device_ms": res.device_ms,
-                      "mean_log10_step": res.mean_log10_step, "status": status, "iterations": iters}
+                      "mean_log10_step": res.mean_log10_step, "cg_iterations": res.cg_iterations, "status": status, "iterations": iters}
+
+    def debug_hessvec(self, X, V, sc_rows):
+        """-> (H_z V, diag H_z) at X through the truncated-Newton kernels (test hook)."""
+        X, V, sc = _f64(X), _f64(V), _f64(sc_rows)
+        P, B = X.shape
+        W, DG = np.zeros((P, B)), np.zeros((P, B))
+        self._check(self._L.tpl_debug_hessvec(self._h, B, _dp(X), _dp(V), _dp(sc), _dp(W), _dp(DG)))
+        return W, DG
 
     def set_timing(self, on):
         self._check(self._L.tpl_set_timing(self._h, int(bool(on))))
