@@ -125,6 +125,53 @@ if "conv" in what:
                 break
         plp.close()
 
+if "tn" in what:
+    gd = Golden("M1155")
+    cals = [(t, lo, hi) for t, lo, hi in gd.meta["calibrations"]]
+    ft = tf.flatten_newick(gd.meta["newick"], gd.meta["numsites"], cals, seed=1)
+    grid = [1000.0, 100.0, 10.0, 1.0, 0.1]
+    for method in (1, 0):
+        for rep in range(2):
+            t = time.perf_counter()
+            res = cv.loocv(dict(gd.flat), grid, ft.tips_postorder, max_iter=6000, method=method)
+            wall = time.perf_counter() - t
+        r = {k: v for k, v in res.items() if k not in ("terms", "full_info")}
+        r["wall_s"] = wall
+        r["full_nfev"] = res["full_info"]["nfev"]
+        out["m1155_method%d" % method] = r
+        print(method, json.dumps(r), flush=True)
+    import bench
+    flat = bench.build_problem(100000)
+    fp, P = tf.generate_param_order_vector(flat["free"], lf=False)
+    n = flat["parents"].shape[0]
+    lo, hi = batchopt.reference_bounds(flat, fp, P)
+    par = flat["parents"]
+    ds = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
+    B = 16
+    lam = 10.0 ** np.linspace(3, -1, 16)
+    x0 = cv.start_vector(flat, P, n - 1)
+    X0 = np.repeat(x0[:, None], B, axis=1)
+    plp = eng.PLCalcParallel.from_flat(flat, device=0)
+    plp.set_freeparams(P, False, fp)
+    plp.batch_configure(B, lane_smoothing=lam)
+    Xc = X0
+    tot = 0
+    for rnd in range(6):
+        t = time.perf_counter()
+        X, F, info = plp.optimize_batch(Xc, lo, hi, date_scale=ds, method=1, max_cg=int(sys.argv[2]) if len(sys.argv) > 2 else 200,
+                                        max_steps=4000, check_every=50, use_graph=1)
+        wall = time.perf_counter() - t
+        tot += info["steps"]
+        r = {"round": rnd, "steps": info["steps"], "total_steps": tot, "wall_s": wall, "ms_per_step": info["device_ms"] / info["steps"],
+             "status": np.bincount(info["status"], minlength=6).tolist(), "newton_iters": [int(info["iterations"].min()), int(info["iterations"].max())],
+             "cg": info["cg_iterations"], "mean_log10_step": info["mean_log10_step"], "F": [float(F[0]), float(F[5]), float(F[10]), float(F[15])]}
+        out["tn100k_round%d" % rnd] = r
+        print(json.dumps(r), flush=True)
+        Xc = X
+        if (info["status"] > 0).all():
+            break
+    plp.close()
+
 if "ncubig" in what or "ncusmall" in what:
     import bench
     if "ncubig" in what:
@@ -140,7 +187,8 @@ if "ncubig" in what or "ncusmall" in what:
     plp.set_freeparams(P, False, fp)
     plp.batch_configure(B, lane_smoothing=np.full(B, 10.0))
     X0 = bench.make_vectors(flat, P, B, 7) if "ncubig" in what else np.repeat(cv.start_vector(flat, P, n - 1)[:, None], B, axis=1)
-    X, F, info = plp.optimize_batch(X0, lo, hi, date_scale=ds, history=8, max_steps=64, check_every=32, use_graph=0)
+    X, F, info = plp.optimize_batch(X0, lo, hi, date_scale=ds, history=8, max_steps=64 if "tnm" not in what else 200, check_every=32, use_graph=0,
+                                    method=1 if "tnm" in what else 0)
     print(info["steps"], info["device_ms"], F[:2])
 
 json.dump(out, open("gpurun_out/opt_bench_%s.json" % "_".join(what), "w"), indent=1, default=str)

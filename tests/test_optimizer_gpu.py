@@ -116,7 +116,7 @@ def test_loocv_m1155_chisq_table_matches_the_reference_run():
     gd = Golden("M1155")
     cals = [(t, lo, hi) for t, lo, hi in gd.meta["calibrations"]]
     ft = tf.flatten_newick(gd.meta["newick"], gd.meta["numsites"], cals, seed=1)
-    res = cv.loocv(dict(gd.flat), [1000.0, 100.0, 10.0, 1.0, 0.1], ft.tips_postorder, max_iter=6000, native=True)
+    res = cv.loocv(dict(gd.flat), [1000.0, 100.0, 10.0, 1.0, 0.1], ft.tips_postorder, max_iter=6000, native=True, method=0)
     ref = np.array([2730.97, 2365.8, 2130.28, 2178.18, 2187.12])
     assert res["cv_converged"] == res["n_vectors"]
     assert np.all(np.abs(np.array(res["chisq"]) - ref) <= 5e-5 * ref), res["chisq"]      # the reference prints 6 digits; at smoothing 0.1 chi-square moves by ~2e-5 between equally converged optima

@@ -33,7 +33,7 @@ def load_sim():
     lib.tn_sim_hessvec.restype = None
     lib.tn_sim_hessvec.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, ip, dp, dp, dp, dp, dp, up, dp, dp, C.c_double, dp, dp, dp, dp, dp]
     lib.tn_sim.restype = C.c_int
-    lib.tn_sim.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+    lib.tn_sim.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                            C.c_double, C.c_double, EVAL_FN, C.c_void_p, ip, ip, ip,
                            C.c_int, ip, ip, ip, ip, ip, dp, dp, dp, dp, dp, up, dp, C.c_double]
     return lib
@@ -185,7 +185,7 @@ def test_hessian_vector_product_matches_finite_differences(sim, name, lams, mask
         assert np.allclose(Wd[row], DG[row], rtol=1e-12, atol=1e-300), (row, Wd[row], DG[row])
 
 
-def fit(sim, name, lams, max_steps=20000, max_cg=100, masks=None, ftol=1e-13, patience=3):
+def fit(sim, name, lams, max_steps=20000, max_cg=100, masks=None, ftol=1e-13, patience=3, cg_per_step=4):
     flat = Golden(name).flat
     pr = Problem(flat, lams, masks)
     n = pr.n
@@ -196,7 +196,7 @@ def fit(sim, name, lams, max_steps=20000, max_cg=100, masks=None, ftol=1e-13, pa
     iters = np.zeros(pr.B, np.int32)
     ncg = np.zeros(pr.B, np.int32)
     cb = pr.callback()
-    steps = sim.tn_sim(pr.P, pr.B, pr.nr, _d(X), _d(F), _d(pr.lo), _d(pr.hi), _d(pr.sc), max_steps, max_cg, patience, 40, ftol, 1e-8, 1e-4, 0.9,
+    steps = sim.tn_sim(pr.P, pr.B, pr.nr, _d(X), _d(F), _d(pr.lo), _d(pr.hi), _d(pr.sc), max_steps, max_cg, cg_per_step, patience, 40, ftol, 1e-8, 1e-4, 0.9,
                        cb, None, _i(status), _i(iters), _i(ncg), *pr.tree_args(), _d(pr.lams), 0.0025)
     return pr, X, F, status, iters, ncg, steps
 
@@ -212,4 +212,4 @@ def test_tn_reproduces_reference_final_pl_values(sim):
     assert ((status >= 1) & (status <= 2)).all(), status
     want = [434.8684339, 337.8462252, 252.3558021, 223.2864918, 219.3542532]      # converged L-BFGS / reference final PL 252.3558
     assert np.allclose(F, want, rtol=2e-9), F
-    assert steps < 4000, steps          # far fewer evaluations than L-BFGS needs (3,000+ for smoothing 0.1 alone)
+    assert steps < 1500, steps          # far fewer evaluations than L-BFGS needs (3,000+ for smoothing 0.1 alone)

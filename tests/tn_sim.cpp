@@ -67,7 +67,7 @@ extern "C" void tn_sim_hessvec(int P, int B, int n, const int* parent, const int
 }
 
 extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const double* lo, const double* hi, const double* sc,
-                      int max_steps, int max_cg, int patience, int max_ls, double ftol, double gtol, double c1, double boundary_frac,
+                      int max_steps, int max_cg, int cg_per_step, int patience, int max_ls, double ftol, double gtol, double c1, double boundary_frac,
                       eval_fn ev, void* ctx, int* status, int* iters, int* ncg_out,
                       int n, const int* parent, const int* child_off, const int* children, const int* rslot, const int* dslot,
                       const double* c, const double* hfix, const double* rfix, const double* pmin, const double* pmax,
@@ -139,9 +139,10 @@ extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const doubl
             }
             if (phase_setup(lane(b), Ft[b], red, o)) ndone++;
         }
+        for (int sub = 0; sub < cg_per_step; sub++) {
         // tn_hv_kernel
         for (int b = 0; b < B; b++) {
-            if (st[b] != TS_CG) continue;
+            if (st[b] != TS_CG || (act[b] & ACT_FIN)) continue;
             HostView hv = {t, B, b, X, Pv.data(), Gx.data(), sc, Hp.data(), lam[b], pb};
             double red[2] = {0.0, 0.0};
             for (int i = 0; i < n; i++) {
@@ -175,6 +176,7 @@ extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const doubl
                 const size_t i = (size_t)p * B + b;
                 Pv[i] = fma(beta[b], Pv[i], ZZ[i]);
             }
+        }
         }
         // tn_gd_kernel + tn_stepmax_kernel
         for (int b = 0; b < B; b++) {

@@ -917,6 +917,9 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
     const int WY = tplopt::OPT_WY;
     const int max_steps = o.max_steps > 0 ? o.max_steps : 20000;
     const int check_every = o.check_every > 0 ? o.check_every : 32;
+    // CG iterations per evaluation: most vectors are inside a CG solve most of the time, and only the vectors in a
+    // line search need the objective; 4 CG iterations per step make the (then mostly idle) evaluation a ~5 % overhead
+    const int cg_per_step = o.cg_per_step > 0 ? std::min(o.cg_per_step, 64) : 4;
     const dim3 blk(32, WY);
     const dim3 rgrd(groups, a.row_chunks), ngrd(groups, a.node_chunks);
     cudaEvent_t ev0, ev1;
@@ -933,16 +936,18 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
         if (rc != TPL_OK) return rc;
         tn_diag_kernel<<<ngrd, blk, 0, s>>>(a);
         tn_setup_kernel<<<rgrd, blk, 0, s>>>(a);
-        tn_hv_kernel<<<ngrd, blk, 0, s>>>(a);
-        tn_update_kernel<<<rgrd, blk, 0, s>>>(a);
-        tn_dir_kernel<<<rgrd, blk, 0, s>>>(a);
+        for (int k = 0; k < cg_per_step; k++) {
+            tn_hv_kernel<<<ngrd, blk, 0, s>>>(a);
+            tn_update_kernel<<<rgrd, blk, 0, s>>>(a);
+            tn_dir_kernel<<<rgrd, blk, 0, s>>>(a);
+        }
         tn_gd_kernel<<<rgrd, blk, 0, s>>>(a);
         tn_stepmax_kernel<<<ngrd, blk, 0, s>>>(a);
         tn_trial_kernel<<<rgrd, blk, 0, s>>>(a);
         CK(cudaGetLastError());
         return TPL_OK;
     };
-    const int per_step = 10;
+    const int per_step = 7 + 3 * cg_per_step;
     int steps = 0;
     int rc = one_step();               // first step outside any capture: sizes the evaluation work space
     if (rc != TPL_OK) return rc;

@@ -1,8 +1,8 @@
 // Streaming kernels of the batched truncated-Newton optimiser (sm_100a).  Method, math and what it replaces in the
 // reference (TNC, src/tnc.c:483-827 behind src/optimize_tnc.cpp:107-172): tpl_tn_core.h.
 //
-// One optimiser step = one PL evaluation of the trial points (for the vectors in their line search) + one analytic
-// Hessian-vector product (for the vectors inside their CG solve) + the CG vector updates.  Vectors advance
+// One optimiser step = one PL evaluation of the trial points (for the vectors in their line search) + `cg_per_step`
+// CG iterations (analytic Hessian-vector product + vector updates, for the vectors inside their CG solve).  Vectors advance
 // independently; each kernel skips the 32-vector groups that have nothing to do in it.  Every per-vector reduction
 // (p.Hp, r.M^-1 r, gp.s, the ratio test) is finished by the LAST block of the vector group to arrive (fixed-order
 // sums over the chunk partials, so the result does not depend on which block that is), and that block also runs the
@@ -230,7 +230,8 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int b = blockIdx.x * 32 + tx;
     const int B = a.o.B;
-    const bool active = b < B && a.st[b] == TS_CG;
+    // a vector whose CG solve ended in an earlier sub-iteration of this step waits for the line-search set-up
+    const bool active = b < B && a.st[b] == TS_CG && !(a.act[b] & ACT_FIN);
     if (!__syncthreads_or(active)) return;
     double v[2] = {0.0, 0.0};
     if (active) {

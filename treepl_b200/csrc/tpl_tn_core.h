@@ -100,7 +100,7 @@ TPL_HD bool phase_setup(const Lane& L, double Ft, const double* red, const TnCon
 
 // after H p: red = {p.Hp, p.p}
 TPL_HD void phase_hv(const Lane& L, const double* red, const TnConst& o) {
-    if (*L.st != TS_CG) return;
+    if (*L.st != TS_CG || (*L.act & ACT_FIN)) return;
     const double pHp = red[0], pp = red[1];
     if (!(pHp > 1e-14 * pp)) {                 // negative / vanishing curvature (or NaN): truncate
         *L.act = ACT_FIN | (*L.cgit == 0 ? ACT_TAKEP : 0);

@@ -55,12 +55,15 @@ def loocv_chisq(flat, X, lane_tip, freeparams):
 
 
 def _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose, **opt):
-    """-> (X, F, info) with info keys iterations (max accepted steps), nfev (batched evaluations), converged [B]."""
+    """-> (X, F, info) with info keys iterations (max accepted steps), nfev (batched evaluations), converged [B].
+    method (option): 1 = batched truncated Newton (default; gradient-converged optima in far fewer evaluations),
+    0 = batched L-BFGS (also serves the log-penalty objective)."""
     P, B = X0.shape
     if native:
+        opt.setdefault("method", 1)
         # chi-square is far more sensitive to the last digits of the optimum than the objective is (at small
         # smoothing the pruned tip's prediction hangs on weakly determined rates): converge tightly
-        if opt.get("method", 0) == 0:
+        if opt["method"] == 0:
             opt.setdefault("ftol", 1e-15)
             opt.setdefault("patience", 40)
         X, F, info = plp.optimize_batch(X0, lo, hi, mode=eng.GRAD_AD, history=history, max_steps=20 * max_iter,
@@ -70,7 +73,7 @@ def _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose, *
             raise ValueError("start point infeasible for vectors %s" % bad.tolist()[:8])
         return X, F, {"iterations": int(info["iterations"].max()), "nfev": info["steps"],
                       "converged": (info["status"] >= 1) & (info["status"] <= 3), "device_ms": info["device_ms"],
-                      "launches": info["launches"]}
+                      "launches": info["launches"], "cg_iterations": info["cg_iterations"]}
     opt = batchopt.BatchedLBFGS(plp, P, B, nr, lo, hi, date_scale=dscale)
     return opt.minimize(X0, max_iter=max_iter, verbose=verbose)
 
@@ -131,6 +134,8 @@ def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_p
     n = len(flat["parents"])
     plp = eng.PLCalcParallel.from_flat(flat, device=device)
     plp.set_log_pen(log_pen)
+    if log_pen:
+        opt.setdefault("method", 0)              # the truncated-Newton kernels carry the plain-penalty Hessian only
     fp, P = eng.generate_param_order_vector(flat["free"], lf=False)
     plp.set_freeparams(P, False, fp)
     nr = n - 1
@@ -183,6 +188,7 @@ def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_p
             "cv_iterations": info2["iterations"], "cv_nfev": info2["nfev"], "cv_converged": int(info2["converged"][:B2].sum()),
             "full_device_ms": info1.get("device_ms"), "cv_device_ms": info2.get("device_ms"),
             "launches": (info1.get("launches") or 0) + (info2.get("launches") or 0),
+            "cg_iterations": (info1.get("cg_iterations") or 0) + (info2.get("cg_iterations") or 0),
             "n_vectors": n_items, "n_local_vectors": B2, "terms": terms}
 
 

@@ -35,7 +35,7 @@ _lib = None
 class OptOptions(C.Structure):
     """tpl_opt_options (include/treepl_b200.h); 0 = library default"""
     _fields_ = [("history", C.c_int), ("max_steps", C.c_int), ("patience", C.c_int), ("max_ls", C.c_int),
-                ("check_every", C.c_int), ("use_graph", C.c_int), ("method", C.c_int), ("max_cg", C.c_int), ("ftol", C.c_double), ("gtol", C.c_double),
+                ("check_every", C.c_int), ("use_graph", C.c_int), ("method", C.c_int), ("max_cg", C.c_int), ("cg_per_step", C.c_int), ("ftol", C.c_double), ("gtol", C.c_double),
                 ("armijo", C.c_double), ("date_scale", C.c_double), ("boundary_frac", C.c_double)]
 
 
