@@ -25,6 +25,9 @@ one step = the complete leave-one-out cross-validation of examples/M1155.cppr8s 
 tests/golden/M1155.npz) with the library's device-resident batched L-BFGS; the (smoothing, fold) vectors are
 dealt to the ranks and the chi-square terms all-gathered over NCCL (strong scaling).  The reference arm replays
 the reference's own CV loop around its optimize_full (annealer + TNC) on the host cores (oracle/_ref).
+    python bench.py --workload restarts [--gpus N]
+one step = 1,024 random-restart optimisations of the examples/big_test.cppr8s tree (BASELINE.json config 4), starts
+dealt to the ranks, best-of-restarts exchange over NCCL.
 """
 import argparse
 import json
@@ -320,6 +323,73 @@ def run_loocv(args):
         dist.destroy_process_group()
 
 
+def run_restarts(args):
+    """--workload restarts: BASELINE.json config 4 - 1,024 batched random-restart optimisations of examples/big_test.cppr8s
+    (N = 9,313 nodes, P = 13,967 parameters) sharded over the GPUs, best-of-restarts exchange over NCCL."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import Golden
+    flat = dict(Golden("big_test").flat)
+    n_starts = 1024
+    workload = "examples/big_test.cppr8s tree (N=9313, P=13967), smoothing 1: %d random-restart optimisations to |g| <= 1e-8 |f|" % n_starts
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "the reference has no batched multi-start driver; one big_test fit "
+                              "with its optimize_full takes minutes per start on one core (SURVEY.md 6)"}))
+        return
+    import torch
+    from treepl_b200 import cv
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the PL engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    times, res = [], None
+    for s in range(args.warmup + args.steps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        res = cv.multistart(flat, 1.0, n_starts, device=local, dist=dist, check_every=50)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        dt = time.perf_counter() - t
+        if dist is not None:
+            tt = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        if s >= args.warmup:
+            times.append(dt)
+    clocks = sampler.stop() if rank == 0 else None
+    conv = res["local_converged"]
+    if dist is not None:
+        tt = torch.tensor([conv], dtype=torch.int64, device=torch.device("cuda", local))
+        dist.all_reduce(tt)
+        conv = int(tt.item())
+    if rank == 0:
+        val = sum(times) / len(times)
+        print(json.dumps({"metric": "multistart_wall_seconds", "value": val, "unit": "s", "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * val, "higher_is_better": False, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "examples/big_test.tre (tests/golden/big_test.npz), synthetic random starts",
+                          "config": {"workload": workload, "optimizer": "tpl_optimize_batch method 1 (batched truncated Newton)",
+                                     "parallelism": "starts dealt to %d GPU(s); all-gather of best objectives + broadcast of the winner" % world},
+                          "optimisations_per_second": n_starts / val, "converged": conv, "best_objective": res["best"],
+                          "winner_rank": res["winner_rank"], "gpu_launches": int(res["launches"]) * world, "clocks": clocks,
+                          "batched_evaluations": res["nfev"], "hessian_vector_products_rank0": res["cg_iterations"],
+                          "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": int(13967 * 8 * res["n_local"]),
+                                  "d2h_bytes_per_step": int(13967 * 8 * res["n_local"])}}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -332,9 +402,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--min-warm-seconds", type=float, default=1.0)
-    ap.add_argument("--workload", default="evals", choices=["evals", "loocv"])
+    ap.add_argument("--workload", default="evals", choices=["evals", "loocv", "restarts"])
     ap.add_argument("--no-loocv", action="store_true", help="skip the LOO-CV summary attached to the default line")
     args = ap.parse_args()
+    if args.workload == "restarts":
+        if args.steps == 200:
+            args.steps = 2
+        if args.warmup == 3:
+            args.warmup = 1
+        run_restarts(args)
+        return
     if args.workload == "loocv":
         if args.steps == 200:
             args.steps = 1 if args.impl == "reference" else 5

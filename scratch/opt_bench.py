@@ -172,6 +172,33 @@ if "tn" in what:
             break
     plp.close()
 
+if "restarts" in what:
+    flat = dict(Golden("big_test").flat)
+    fp, P = tf.generate_param_order_vector(flat["free"], lf=False)
+    n = len(flat["parents"])
+    lo, hi = batchopt.reference_bounds(flat, fp, P)
+    par = flat["parents"]
+    ds = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
+    x0 = cv.start_vector(flat, P, n - 1)
+    for B in (64, 1024):
+        rng = np.random.RandomState(1)
+        X0 = np.repeat(x0[:, None], B, axis=1)
+        X0[: n - 1] *= np.exp(0.3 * rng.randn(n - 1, B))
+        plp = eng.PLCalcParallel.from_flat(flat, device=0)
+        plp.set_freeparams(P, False, fp)
+        plp.smoothing = 1.0
+        plp.batch_configure(B)
+        for method in (1,):
+            t = time.perf_counter()
+            X, F, info = plp.optimize_batch(X0, lo, hi, date_scale=ds, method=method, max_steps=20000, check_every=50, use_graph=1)
+            wall = time.perf_counter() - t
+            r = {"B": B, "method": method, "steps": info["steps"], "wall_s": wall, "device_ms": info["device_ms"], "status": np.bincount(info["status"], minlength=6).tolist(),
+                 "iters": [int(info["iterations"].min()), int(info["iterations"].max())], "cg": info["cg_iterations"], "Fmin": float(F.min()), "Fmax": float(F.max()),
+                 "Fspread_rel": float((F.max() - F.min()) / abs(F.min()))}
+            out["restarts_B%d_m%d" % (B, method)] = r
+            print(json.dumps(r), flush=True)
+        plp.close()
+
 if "ncubig" in what or "ncusmall" in what:
     import bench
     if "ncubig" in what:

@@ -111,3 +111,13 @@ def test_tn_loocv_m1155_chisq_table():
     assert res["cv_converged"] == res["n_vectors"]
     assert np.all(np.abs(np.array(res["chisq"]) - ref) <= 2e-5 * ref), res["chisq"]
     assert res["best"] == 10.0
+
+
+def test_multistart_finds_the_common_optimum():
+    """random restarts (treepl_b200/cv.py::multistart): every start of M1155 at smoothing 10 reaches the reference's
+    final PL 252.3558, and the exchanged best is the minimum over the starts"""
+    flat = dict(Golden("M1155").flat)
+    res = cv.multistart(flat, 10.0, 16, jitter=0.3, seed=3)
+    assert res["local_converged"] == 16
+    assert np.all(np.abs(res["local_objectives"] - 252.3558) <= 2e-6 * 252.3558), res["local_objectives"]
+    assert res["best"] == res["local_objectives"].min() and res["winner_rank"] == 0

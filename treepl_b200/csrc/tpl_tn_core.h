@@ -67,6 +67,16 @@ TPL_HD bool phase_setup(const Lane& L, double Ft, const double* red, const TnCon
     if (dec == DEC_REJECT) {
         const int ls = *L.ls + 1;
         if (ls < o.max_ls) { *L.ls = ls; *L.t *= 0.5; *L.act = ACT_TRIAL; return false; }
+        if (*L.cgit >= 0) {
+            // the truncated-Newton direction found no decrease: one more line search along the preconditioned
+            // steepest-descent direction (cgit = -1 marks the retry) before the vector is declared stalled
+            *L.cgit = -1;
+            *L.ls = 0;
+            *L.t = 1.0;
+            *L.gd = -*L.rz0;
+            *L.act = ACT_TRIAL | ACT_SD;
+            return false;
+        }
         *L.st = TS_DONE;
         *L.flag = FLAG_STALLED;
         return true;

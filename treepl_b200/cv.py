@@ -195,3 +195,48 @@ def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_p
 def loocv(flat, smoothing_grid, tips, **kw):
     """Leave-one-out CV: one fold per tip (tips in externalNodes order, main.cpp:603-608)."""
     return cross_validate(flat, smoothing_grid, [[int(t)] for t in tips], randomcv=False, **kw)
+
+
+def multistart(flat, smoothing, n_starts, jitter=0.3, seed=1, device=0, dist=None, **opt):
+    """n_starts independent optimisations from random starts (rates jittered log-normally around the clock-like
+    start, feasible start dates), sharded over the ranks; the global best is exchanged with
+    cvshard.best_of_restarts (all-gather of the best objectives, broadcast of the winner's vector).
+    Start k depends on (seed, k) only, so the set of starts is the same for every world size.
+    -> dict(best objective, best vector, per-start objectives of this rank, timings)."""
+    from . import cvshard
+
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    n = len(flat["parents"])
+    plp = eng.PLCalcParallel.from_flat(flat, device=device)
+    fp, P = eng.generate_param_order_vector(flat["free"], lf=False)
+    plp.set_freeparams(P, False, fp)
+    plp.smoothing = float(smoothing)
+    nr = n - 1
+    lo, hi = batchopt.reference_bounds(flat, fp, P)
+    mine = cvshard.shard_items(n_starts, rank, world)
+    B = max(2, len(mine) + (len(mine) % 2))
+    x0 = start_vector(flat, P, nr)
+    X0 = np.repeat(x0[:, None], B, axis=1)
+    for b in range(B):
+        k = mine[min(b, len(mine) - 1)] if mine else 0
+        X0[:nr, b] *= np.exp(jitter * np.random.RandomState(seed * 1000003 + k).randn(nr))
+    plp.batch_configure(B)
+    par = flat["parents"]
+    dscale = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
+    t0 = time.perf_counter()
+    X, F, info = _minimize(plp, X0, lo, hi, nr, dscale, 3000, True, 8, False, **opt)
+    t1 = time.perf_counter()
+    Fm = F[: len(mine)]
+    ok = info["converged"][: len(mine)]
+    kbest = int(np.argmin(np.where(ok, Fm, np.inf))) if len(mine) else 0
+    dev = None
+    if dist is not None and dist.get_backend() == "nccl":
+        import torch
+
+        dev = torch.device("cuda", device)
+    fbest, xbest, winner = cvshard.best_of_restarts(Fm[kbest] if len(mine) else np.inf, X[:, kbest], dist=dist, device=dev)
+    plp.close()
+    return {"best": fbest, "x": xbest, "winner_rank": winner, "local_objectives": Fm, "local_converged": int(ok.sum()),
+            "n_local": len(mine), "optimize_seconds": t1 - t0, "nfev": info["nfev"], "cg_iterations": info.get("cg_iterations"),
+            "launches": info.get("launches"), "device_ms": info.get("device_ms")}
