@@ -42,6 +42,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL_DEBUG=VERSION makes NCCL print its banner on stdout, in front of the one JSON line this script owes the driver
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "pl_obj_grad_evals_per_sec"
 UNIT = "evals/s"
