@@ -199,6 +199,24 @@ if "restarts" in what:
             print(json.dumps(r), flush=True)
         plp.close()
 
+if "cv100k" in what:
+    import bench
+    flat = bench.build_problem(100000)
+    n = flat["parents"].shape[0]
+    tips = np.flatnonzero(flat["child_counts"] == 0)
+    grid = list(10.0 ** np.linspace(3, -1, 16))
+    groups = cv.sample_random_groups(flat, tips, n_groups=10, frac=0.1, seed=1)
+    print("folds", len(groups), "tips per fold", len(groups[0]), flush=True)
+    t = time.perf_counter()
+    res = cv.cross_validate(flat, grid, groups, randomcv=True, max_iter=int(sys.argv[2]) if len(sys.argv) > 2 else 400, check_every=25)
+    wall = time.perf_counter() - t
+    r = {k: v for k, v in res.items() if k not in ("terms", "full_info")}
+    r["wall_s"] = wall
+    r["full_converged"] = int(np.sum(res["full_info"]["converged"]))
+    r["full_nfev"] = res["full_info"]["nfev"]
+    out["cv100k"] = r
+    print(json.dumps(r), flush=True)
+
 if "ncubig" in what or "ncusmall" in what:
     import bench
     if "ncubig" in what:

@@ -110,9 +110,30 @@ def sample_random_groups(flat, tips, n_groups, frac, seed=1):
 
 def group_chisq(flat, x, group, freeparams, randomcv):
     """chi-square contribution of one fold from its optimised vector x [P] (src/main.cpp:737-757 LOOCV,
-    :769-793 random-subsample: mean over the group's tips)."""
-    t = loocv_chisq(flat, np.repeat(x[:, None], len(group), axis=1), list(group), freeparams)
-    return float(np.sum(t)) / (len(group) if randomcv else 1.0)
+    :769-793 random-subsample: mean over the group's tips).  Vectorised over the fold's tips (a random fold of
+    the 100k-tip tree prunes 10,000 of them)."""
+    n = len(flat["parents"])
+    par = np.asarray(flat["parents"])
+    fp = np.asarray(freeparams)
+    tips = np.asarray(list(group), dtype=np.int64)
+    p = par[tips]
+    rslot = fp[np.maximum(p, 0)]
+    r = np.where(rslot >= 0, x[np.maximum(rslot, 0)], 0.0)
+    for k in np.flatnonzero(p == 0):                      # child of the root: the rate of its LAST sibling (main.cpp:741-746)
+        sib = [j for j in np.flatnonzero(par == 0) if j != tips[k]][-1]
+        r[k] = x[fp[sib]]
+    dslot = fp[n + p]
+    hp = np.where(dslot >= 0, x[np.maximum(dslot, 0)], flat["start_dates"][p])
+    d = hp - flat["start_dates"][tips]
+    d = np.where(d == 0, 2.2250738585072014e-308, d)
+    expe = r * d
+    c = flat["c"][tips]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        terms = np.where((d < 1e-100) | (expe < 1e-100), 0.0, (c - expe) ** 2 / expe)
+    total = 0.0
+    for v in terms:                                        # tip order, fixed
+        total += float(v)
+    return total / (len(tips) if randomcv else 1.0)
 
 
 def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_pen=False, max_iter=3000, verbose=False,
