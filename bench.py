@@ -28,6 +28,8 @@ the reference's own CV loop around its optimize_full (annealer + TNC) on the hos
     python bench.py --workload restarts [--gpus N]
 one step = 1,024 random-restart optimisations of the examples/big_test.cppr8s tree (BASELINE.json config 4), starts
 dealt to the ranks, best-of-restarts exchange over NCCL.
+    python bench.py --workload cv100k [--gpus N] [--cv-steps S]
+random-subsample CV over 16 smoothing values on the synthetic 100k-tip tree (BASELINE.json config 5), capped.
 """
 import argparse
 import json
@@ -393,6 +395,73 @@ def run_restarts(args):
         dist.destroy_process_group()
 
 
+def run_cv100k(args):
+    """--workload cv100k: BASELINE.json config 5 - random-subsample cross-validation (10 folds of 10 % of the tips,
+    src/main.cpp:609-656) over 16 smoothing values 10^3 ... 10^-1 on the synthetic 100,000-tip tree, (smoothing, fold)
+    vectors dealt to the GPUs.  Every optimisation is capped at `--cv-steps` batched evaluations (x 4 CG iterations):
+    with the Jacobi preconditioner the vectors with smoothing >= ~50 are NOT converged at the default cap and the line
+    says how many are."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "the reference needs ~11 min of O(N^2) set-up and ~14 ms per "
+                              "evaluation per thread on this tree (SURVEY.md 6): its CV over 176 optimisations is not runnable"}))
+        return
+    import torch
+    from treepl_b200 import cv
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the PL engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    flat = build_problem(args.tips)
+    tips = np.flatnonzero(flat["child_counts"] == 0)
+    grid = [float(v) for v in 10.0 ** np.linspace(3, -1, 16)]
+    groups = cv.sample_random_groups(flat, tips, n_groups=10, frac=0.1, seed=1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    res = cv.cross_validate(flat, grid, groups, randomcv=True, device=local, dist=dist, max_iter=max(1, args.cv_steps // 20), check_every=25)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    dt = time.perf_counter() - t
+    conv = res["cv_converged"]
+    if dist is not None:
+        tt = torch.tensor([dt, float(conv)], dtype=torch.float64, device=torch.device("cuda", local))
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt)
+        dt, conv = float(mx[0].item()), int(tt[1].item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        n = flat["parents"].shape[0]
+        print(json.dumps({"metric": "random_cv_wall_seconds", "value": dt, "unit": "s", "n_gpus": world, "steps": 1, "warmup": 0,
+                          "ms_per_step": 1e3 * dt, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic",
+                          "config": {"workload": "synthetic %d-tip Yule tree (N=%d): random-subsample CV, 10 folds x 10 %% of the tips, "
+                                                 "16 smoothing values 1e3..1e-1 = 16 full-data fits + 160 fold optimisations, each capped at "
+                                                 "%d batched evaluations" % (args.tips, n, args.cv_steps),
+                                     "optimizer": "tpl_optimize_batch method 1 (batched truncated Newton)",
+                                     "parallelism": "(smoothing, fold) vectors dealt to %d GPU(s), chi-square all-gather" % world},
+                          "chisq": res["chisq"], "best_smoothing": res["best"], "full_objective": res["full_objective"],
+                          "full_fits_converged": int(np.sum(res["full_info"]["converged"][:16])), "fold_vectors_converged": conv,
+                          "seconds": {"full_fits": res["full_seconds"], "folds": res["cv_seconds"], "scoring_and_gather": res["gather_seconds"]},
+                          "gpu_launches": int(res["launches"]) * world, "clocks": clocks,
+                          "e2e": {"value": dt, "unit": "s", "h2d_bytes_per_step": int(8 * 299996 * (16 + res["n_local_vectors"])),
+                                  "d2h_bytes_per_step": int(8 * 299996 * (16 + res["n_local_vectors"]))}}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -405,9 +474,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--min-warm-seconds", type=float, default=1.0)
-    ap.add_argument("--workload", default="evals", choices=["evals", "loocv", "restarts"])
+    ap.add_argument("--workload", default="evals", choices=["evals", "loocv", "restarts", "cv100k"])
+    ap.add_argument("--cv-steps", type=int, default=8000, help="cv100k: cap on batched evaluations per optimisation")
     ap.add_argument("--no-loocv", action="store_true", help="skip the LOO-CV summary attached to the default line")
     args = ap.parse_args()
+    if args.workload == "cv100k":
+        run_cv100k(args)
+        return
     if args.workload == "restarts":
         if args.steps == 200:
             args.steps = 2

@@ -121,3 +121,33 @@ def test_multistart_finds_the_common_optimum():
     assert res["local_converged"] == 16
     assert np.all(np.abs(res["local_objectives"] - 252.3558) <= 2e-6 * 252.3558), res["local_objectives"]
     assert res["best"] == res["local_objectives"].min() and res["winner_rank"] == 0
+
+
+def test_tn_refuses_what_it_does_not_support_loudly():
+    flat = dict(Golden("test").flat)
+    pr = TS.Problem(flat, [0.1, 0.1])
+    lower, upper = batchopt.reference_bounds(flat, pr.fp, pr.P)
+    x0 = cv.start_vector(flat, pr.P, pr.n - 1)
+    X0 = np.repeat(x0[:, None], 2, axis=1)
+    plp = _engine(pr, flat)
+    plp.set_log_pen(True)
+    with pytest.raises(eng.EngineError, match="log-penalty"):
+        plp.optimize_batch(X0, lower, upper, method=1)
+    plp.set_log_pen(False)
+    with pytest.raises(eng.EngineError, match="TPL_GRAD_AD"):
+        plp.optimize_batch(X0, lower, upper, method=1, mode=eng.GRAD_ANALYTIC)
+    with pytest.raises(eng.EngineError, match="method must be"):
+        plp.optimize_batch(X0, lower, upper, method=7)
+    cvm = np.zeros(pr.n, np.int32)
+    cvm[12] = 1
+    plp.set_cv_nodes(cvm)
+    with pytest.raises(eng.EngineError, match="per vector"):
+        plp.optimize_batch(X0, lower, upper, method=1)
+    plp.close()
+    # Langley-Fitch layout: one shared rate
+    plp = eng.PLCalcParallel.from_flat(flat, device=0)
+    fp, P = eng.generate_param_order_vector(flat["free"], lf=True)
+    x = plp.set_freeparams(P, True, fp)
+    with pytest.raises(eng.EngineError, match="PL layout"):
+        plp.optimize_batch(np.repeat(x[:, None], 2, axis=1), np.full(P, 1e-40), np.full(P, 1e15), method=1)
+    plp.close()
