@@ -453,7 +453,7 @@ def run_cv100k(args):
                                      "optimizer": "tpl_optimize_batch method 1 (batched truncated Newton)",
                                      "parallelism": "(smoothing, fold) vectors dealt to %d GPU(s), chi-square all-gather" % world},
                           "chisq": res["chisq"], "best_smoothing": res["best"], "full_objective": res["full_objective"],
-                          "full_fits_converged": int(np.sum(res["full_info"]["converged"][:16])), "fold_vectors_converged": conv,
+                          "full_fits_converged": res["full_converged"], "fold_vectors_converged": conv,
                           "seconds": {"full_fits": res["full_seconds"], "folds": res["cv_seconds"], "scoring_and_gather": res["gather_seconds"]},
                           "gpu_launches": int(res["launches"]) * world, "clocks": clocks,
                           "e2e": {"value": dt, "unit": "s", "h2d_bytes_per_step": int(8 * 299996 * (16 + res["n_local_vectors"])),

@@ -30,6 +30,9 @@ def _worker(rank, world, port, n_items, out):
         full, total = cvshard.gather_fold_scores(mine, n_items, dist=dist)
         # restarts: rank r's best objective / vector
         f, x, winner = cvshard.best_of_restarts(10.0 - rank, np.full(5, float(rank)), dist=dist)
+        vecs = {i: np.arange(7, dtype=np.float64) + 100 * i for i in cvshard.shard_items(n_items, rank, world)}
+        mat = cvshard.gather_vectors(vecs, n_items, 7, dist=dist)
+        assert np.array_equal(mat, np.arange(7)[:, None] + 100.0 * np.arange(n_items)[None, :])
         out.put((rank, full.tolist(), total, f, x.tolist(), winner))
     finally:
         dist.destroy_process_group()

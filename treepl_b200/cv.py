@@ -163,14 +163,23 @@ def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_p
     lo, hi = batchopt.reference_bounds(flat, fp, P)
     K, T = len(smoothing_grid), len(groups)
     t0 = time.perf_counter()
-    # ---- full-data fits: one vector per smoothing value (padded to an even batch), replicated on every rank ----
-    B1 = K + (K % 2)
-    lam1 = np.array(list(smoothing_grid) + [smoothing_grid[-1]] * (B1 - K), dtype=np.float64)
+    # ---- full-data fits: one vector per smoothing value, dealt to the ranks; the optima are all-gathered ----
+    dev = None
+    if dist is not None and dist.get_backend() == "nccl":
+        import torch
+
+        dev = torch.device("cuda", device)
+    mine_k = cvshard.shard_items(K, rank, world)
+    B1 = max(2, len(mine_k) + (len(mine_k) % 2))
+    lam1 = np.array([smoothing_grid[mine_k[min(b, len(mine_k) - 1)]] if mine_k else smoothing_grid[0] for b in range(B1)], dtype=np.float64)
     plp.batch_configure(B1, lane_smoothing=lam1)
     x0 = start_vector(flat, P, nr)
     par = flat["parents"]
     dscale = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
-    Xfull, Ffull, info1 = _minimize(plp, np.repeat(x0[:, None], B1, axis=1), lo, hi, nr, dscale, max_iter, native, history, verbose, **opt)
+    Xl, Fl, info1 = _minimize(plp, np.repeat(x0[:, None], B1, axis=1), lo, hi, nr, dscale, max_iter, native, history, verbose, **opt)
+    packed = {k: np.concatenate([Xl[:, b], [Fl[b], float(info1["converged"][b])]]) for b, k in enumerate(mine_k)}
+    allfull = cvshard.gather_vectors(packed, K, P + 2, dist=dist, device=dev)
+    Xfull, Ffull, full_conv = allfull[:P], allfull[P], allfull[P + 1]
     t1 = time.perf_counter()
     # ---- folds: one vector per (smoothing value, fold); this rank's share ----
     n_items = K * T
@@ -190,11 +199,6 @@ def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_p
     Xcv, Fcv, info2 = _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose, **opt)
     t2 = time.perf_counter()
     local = {item: group_chisq(flat, Xcv[:, b], groups[item % T], fp, randomcv) for b, item in enumerate(mine)}
-    dev = None
-    if dist is not None and dist.get_backend() == "nccl":
-        import torch
-
-        dev = torch.device("cuda", device)
     full, _ = cvshard.gather_fold_scores(local, n_items, dist=dist, device=dev)
     terms = full.reshape(K, T)
     chisq = np.zeros(K)
@@ -204,7 +208,7 @@ def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_p
     t3 = time.perf_counter()
     plp.close()
     return {"smoothing": list(smoothing_grid), "chisq": chisq.tolist(), "best": float(smoothing_grid[int(np.argmin(chisq))]),
-            "full_objective": Ffull[:K].tolist(), "full_seconds": t1 - t0, "cv_seconds": t2 - t1, "gather_seconds": t3 - t2,
+            "full_objective": Ffull[:K].tolist(), "full_converged": int(full_conv.sum()), "full_seconds": t1 - t0, "cv_seconds": t2 - t1, "gather_seconds": t3 - t2,
             "full_info": {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in info1.items()},
             "cv_iterations": info2["iterations"], "cv_nfev": info2["nfev"], "cv_converged": int(info2["converged"][:B2].sum()),
             "full_device_ms": info1.get("device_ms"), "cv_device_ms": info2.get("device_ms"),

@@ -50,6 +50,31 @@ def gather_fold_scores(local_scores, n_items, dist=None, device=None):
     return full, total
 
 
+def gather_vectors(local_vectors, n_items, length, dist=None, device=None):
+    """local_vectors: {item: 1-D array of `length` doubles} for this rank's items (shard_items order).
+    Returns the [length, n_items] matrix of all items on every rank (all-gather of length x per-rank-items doubles:
+    the full-data optima every fold of a smoothing value starts from)."""
+    import torch
+
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    per = (n_items + world - 1) // world
+    mine = torch.zeros((per, length), dtype=torch.float64, device=device)
+    for k, item in enumerate(shard_items(n_items, rank, world)):
+        mine[k] = torch.as_tensor(np.asarray(local_vectors[item], dtype=np.float64), device=device)
+    if dist is None:
+        parts = [mine]
+    else:
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+    out = np.zeros((length, n_items))
+    for r, part in enumerate(parts):
+        vals = part.cpu().numpy()
+        for k, item in enumerate(range(r, n_items, world)):
+            out[:, item] = vals[k]
+    return out
+
+
 def best_of_restarts(best_f, best_x, dist=None, device=None):
     """Each rank passes its best (objective, parameter vector); returns the global best on every rank.
     Ties go to the lowest rank."""
