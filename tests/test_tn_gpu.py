@@ -151,3 +151,26 @@ def test_tn_refuses_what_it_does_not_support_loudly():
     with pytest.raises(eng.EngineError, match="PL layout"):
         plp.optimize_batch(np.repeat(x[:, None], 2, axis=1), np.full(P, 1e-40), np.full(P, 1e15), method=1)
     plp.close()
+
+
+def test_end_to_end_dating_of_the_example_configs(tmp_path):
+    """treepl_b200/run.py::date_tree on examples/test.cppr8s (smooth = 0.1) and examples/M1155.cppr8s (cv): the reference's
+    dated tree (node heights within 2e-3), selected smoothing, final PL, cv.out lines"""
+    import test_output as TO
+    from treepl_b200 import output, run
+    gd = Golden("test")
+    r = run.date_tree(dict(gd.flat), gd.meta["names"], gd.meta["numsites"], smooth=0.1, outfile=str(tmp_path / "out_dates.tre"))
+    assert r["converged"] and abs(r["objective"] - 234.23049) <= 1e-4 * 234.23049
+    strip = lambda s: "".join(ch for ch in s if not (ch.isdigit() or ch == "."))
+    assert strip(r["dated_tree"]) == strip(TO.REF_DATED)
+    g = [float(t.split(")")[0].split(",")[0]) for t in r["dated_tree"].split(":")[1:]]
+    ref = [float(t.split(")")[0].split(",")[0]) for t in TO.REF_DATED.split(":")[1:]]
+    assert np.allclose(g, ref, rtol=0, atol=1.5e-2), np.abs(np.array(g) - np.array(ref)).max()     # the reference stops on the bound (DESIGN 8.3)
+    assert open(tmp_path / "out_dates.tre").read().strip() == r["dated_tree"]
+    assert open(str(tmp_path / "out_dates.tre") + ".r8s").read().strip() == r["rate_tree"]
+    gd = Golden("M1155")
+    r = run.date_tree(dict(gd.flat), gd.meta["names"], gd.meta["numsites"], do_cv=True, outfile=str(tmp_path / "m.tre"),
+                      cvoutfile=str(tmp_path / "cv.out"))
+    assert r["smoothing"] == 10.0 and abs(r["objective"] - 252.3558) <= 2e-6 * 252.3558
+    assert open(tmp_path / "cv.out").read().split("\n")[:5] == ["chisq: (1000) 2730.97", "chisq: (100) 2365.8", "chisq: (10) 2130.28",
+                                                              "chisq: (1) 2178.17", "chisq: (0.1) 2187.12"]
