@@ -457,7 +457,7 @@ tpl::DevTree dev_tree(tpl_engine* e) {
     return t;
 }
 
-constexpr int G4_NCW = 15;            // consumer warps of the generation-4 kernel
+constexpr int G4_NCW = tpl::DESC_NCW;  // consumer warps of the generation-4 kernel
 
 // cuTensorMapEncodeTiled through the runtime (no link against libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -601,12 +601,12 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
     if (gen == 4) {
         tile = tpl::TILE_NODES;
         ntiles = e->ntiles2;
-        nwarps = G4_NCW;
+        nwarps = 1;                    // the kernel reduces its consumer warps' partials itself: one row per CTA and slot
         c.grid = dim3(G);
         c.block = dim3((G4_NCW + 1) * 32);
         c.smem = tpl::desc_kernel_smem(e->tile_hrows, g4_stages);
         c.stages = g4_stages;
-        npart = (size_t)G * 2 * G4_NCW * tpl::TILE_LANES;
+        npart = (size_t)G * 2 * tpl::TILE_LANES;
     } else if (gen == 3) {
         tile = tpl::TILE_NODES;
         ntiles = e->ntiles2;
