@@ -736,501 +736,8 @@ double eval_point(tpl_engine* e, const double* x, double* g, int mode, bool keep
 }
 
 
-// ---- device-resident batched L-BFGS (tpl_lbfgs_core.h / tpl_lbfgs.cuh) --------------------------------------
+#include "tpl_optimize_host.inl"   // run_optimizer, tn_prepare, optimize_tn, tpl_optimize_batch, tpl_debug_hessvec
 
-template <int HM>
-int run_optimizer(tpl_engine* e, tplopt::OptArgs a, int B, int mode, int max_steps, int check_every, bool use_graph,
-                  tpl_opt_result* res) {
-    using namespace tplopt;
-    typedef Layout<HM> L;
-    cudaStream_t s = e->stream;
-    const dim3 blk(32, OPT_WY);
-    const dim3 grd((B + 31) / 32, a.nchunks);
-    const dim3 lblk(OPT_LX, OPT_NY);
-    const dim3 lgrd((B + OPT_LX - 1) / OPT_LX);
-    const size_t lsmem = (size_t)(L::NACC + L::NB * L::NB) * OPT_LX * sizeof(double);
-    CK(cudaFuncSetAttribute(opt_lane_kernel<HM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
-    int launches = 0;
-    const dim3 tgrd((B + 31) / 32, a.tchunks);
-    const dim3 fgrd((B + 31) / 32, a.light_chunks);
-    opt_init_kernel<<<fgrd, blk, 0, s>>>(a);
-    opt_trial_kernel<<<fgrd, blk, 0, s>>>(a);
-    launches += 2;
-    CK(cudaGetLastError());
-    auto one_step = [&]() -> int {
-        int rc = eval_device(e, B, a.X, const_cast<double*>(a.Ft), const_cast<double*>(a.Gx), mode, true, s);
-        if (rc != TPL_OK) return rc;
-        opt_update_kernel<HM><<<grd, dim3(32, HM), 0, s>>>(a);
-        if (a.lane_part == a.part_red) opt_reduce_kernel<HM><<<dim3((B + 31) / 32, L::NACC), blk, 0, s>>>(a);
-        opt_lane_kernel<HM><<<lgrd, lblk, lsmem, s>>>(a);
-        opt_direction_kernel<HM><<<dim3((B + 31) / 32, a.dir_chunks), blk, 0, s>>>(a);
-        if (a.boundary_frac > 0.0) opt_stepmax_kernel<<<tgrd, blk, 0, s>>>(a);
-        opt_trial_kernel<<<fgrd, blk, 0, s>>>(a);
-        CK(cudaGetLastError());
-        return TPL_OK;
-    };
-    const int per_step = (a.boundary_frac > 0.0 ? 7 : 6) + (a.lane_part == a.part_red ? 1 : 0);
-    int steps = 0;
-    int rc = one_step();               // first step outside any capture: sizes the evaluation work space
-    if (rc != TPL_OK) return rc;
-    steps++;
-    launches += per_step;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t gexec = nullptr;
-    const bool was_timing = e->timing;
-    e->timing = false;
-    if (use_graph) {
-        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        for (int k = 0; k < check_every && rc == TPL_OK; k++) rc = one_step();
-        cudaError_t ce = cudaStreamEndCapture(s, &graph);
-        if (rc != TPL_OK || ce != cudaSuccess) {
-            if (graph) cudaGraphDestroy(graph);
-            e->timing = was_timing;
-            return rc != TPL_OK ? rc : fail(TPL_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
-        }
-        CK(cudaGraphInstantiate(&gexec, graph, 0));
-    }
-    int ndone = 0;
-    while (steps < max_steps) {
-        if (use_graph) {
-            CK(cudaGraphLaunch(gexec, s));
-        } else {
-            for (int k = 0; k < check_every && rc == TPL_OK; k++) rc = one_step();
-            if (rc != TPL_OK) break;
-        }
-        steps += check_every;
-        launches += per_step * check_every;
-        CK(cudaMemcpyAsync(e->opt.h_done.p, a.ndone, sizeof(int), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        ndone = e->opt.h_done.p[0];
-        if (ndone >= B) break;
-    }
-    if (gexec) cudaGraphExecDestroy(gexec);
-    if (graph) cudaGraphDestroy(graph);
-    e->timing = was_timing;
-    if (rc != TPL_OK) return rc;
-    opt_final_kernel<<<fgrd, blk, 0, s>>>(a, e->opt.Fout.p);
-    launches++;
-    CK(cudaGetLastError());
-    res->steps = steps;
-    res->n_done = ndone;
-    res->launches = launches;
-    return TPL_OK;
-}
-
-// ---- batched truncated Newton (tpl_tn_core.h / tpl_tn.cuh) ---------------------------------------------------------
-
-// work space, tree operands and chunking of the truncated-Newton kernels; uploads lo / hi / sc and X
-int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>& lo, const std::vector<double>& hi,
-               const std::vector<double>& sc, int nr, const tpl_opt_options& o, tpltn::TnArgs& a) {
-    using namespace tpltn;
-    if (e->lf_mode) return fail(TPL_ERR_ARG, "truncated Newton needs the PL layout (one rate per branch)");
-    if (e->log_pen) return fail(TPL_ERR_ARG, "truncated Newton does not carry the log-penalty Hessian; use method 0");
-    if (e->cv_any) return fail(TPL_ERR_ARG, "truncated Newton takes CV masks per vector (tpl_batch_configure), not set_cv_nodes");
-    const int P = e->numparams, n = e->n;
-    const size_t PB = (size_t)P * B;
-    tpl_engine::OptWork& w = e->opt;
-    cudaStream_t s = e->stream;
-    const int groups = (B + 31) / 32;
-    const int WY = tplopt::OPT_WY;
-    auto one_wave = [&](int occ, int total, int align, int* nch, int* per) {
-        int c = std::max(1, (e->num_sms * std::max(occ, 1)) / groups);
-        c = std::min(c, (total + align - 1) / align);
-        int r = (total + c - 1) / c;
-        r = ((r + align - 1) / align) * align;
-        *per = r;
-        *nch = (total + r - 1) / r;
-    };
-    int occ_row = 1, occ_node = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_row, tn_update_kernel, 32 * WY, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_node, tn_hv_kernel, 32 * WY, 0);
-    one_wave(occ_row, P, WY, &a.row_chunks, &a.rows_per_chunk);
-    one_wave(occ_node, n, WY, &a.node_chunks, &a.nodes_per_chunk);
-    CK(w.Z.ensure(PB)); CK(w.Gz.ensure(PB)); CK(w.D.ensure(PB)); CK(w.X.ensure(PB)); CK(w.Gx.ensure(PB));
-    CK(w.R.ensure(PB)); CK(w.ZZ.ensure(PB)); CK(w.Pv.ensure(PB)); CK(w.Hp.ensure(PB)); CK(w.Minv.ensure(PB)); CK(w.DG.ensure(PB));
-    CK(w.lo.ensure(P)); CK(w.hi.ensure(P)); CK(w.sc.ensure(P)); CK(w.Ft.ensure(B)); CK(w.Fout.ensure(B)); CK(w.h_done.ensure(1));
-    const size_t npart = (size_t)(3 + 1 + 1) * a.row_chunks * B + (size_t)(2 + 1) * a.node_chunks * B;
-    CK(w.tn_part.ensure(npart));
-    CK(w.tn_lane_d.ensure((size_t)11 * B));
-    CK(w.tn_lane_i.ensure((size_t)8 * B + 1 + 5 * (size_t)groups));
-    CK(w.pmin_n.upload(e->pen_min, s));
-    CK(w.pmax_n.upload(e->pen_max, s));
-    CK(cudaMemcpyAsync(w.lo.p, lo.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(w.hi.p, hi.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(w.sc.p, sc.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(w.X.p, X, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(w.tn_lane_d.p, 0, sizeof(double) * 11 * B, s));
-    CK(cudaMemsetAsync(w.tn_lane_i.p, 0, sizeof(int) * (8 * (size_t)B + 1 + 5 * (size_t)groups), s));     // st = TS_INIT, t = 0
-    for (DevBuf<double>* buf : {&w.Gz, &w.D, &w.R, &w.ZZ, &w.Pv, &w.Hp, &w.Minv, &w.DG, &w.Gx})
-        CK(cudaMemsetAsync(buf->p, 0, sizeof(double) * PB, s));
-    CK(cudaStreamSynchronize(s));       // pen_min / pen_max uploads read host vectors of the engine; lo / hi / sc are the caller's
-    a.o.P = P; a.o.B = B; a.o.nr = nr;
-    a.o.max_ls = o.max_ls > 0 ? o.max_ls : 40;
-    a.o.max_cg = o.max_cg > 0 ? o.max_cg : 100;
-    a.o.patience = o.patience > 0 ? o.patience : 3;
-    a.o.c1 = o.armijo > 0 ? o.armijo : 1e-4;
-    a.o.ftol = o.ftol > 0 ? o.ftol : 1e-13;
-    a.o.gtol = o.gtol > 0 ? o.gtol : 1e-8;
-    a.o.boundary_frac = o.boundary_frac < 0 ? 0.0 : (o.boundary_frac > 0 ? std::min(o.boundary_frac, 0.999999) : 0.9);
-    a.t = dev_tree(e);
-    a.pmin_n = w.pmin_n.p; a.pmax_n = w.pmax_n.p;
-    const bool lanemask = e->cfg_mask && e->cfg_B == B;
-    a.lanemask = lanemask ? e->d_lanemask.p : nullptr;
-    a.mask_stride = e->ntiles2 * tpl::TILE_NODES;
-    a.lane_lambda = (e->cfg_lambda && e->cfg_B == B) ? e->d_lane_lambda.p : nullptr;
-    a.lambda = e->smoothing;
-    a.pb = e->pb;
-    a.sc = w.sc.p; a.lo = w.lo.p; a.hi = w.hi.p;
-    a.Z = w.Z.p; a.Gz = w.Gz.p; a.S = w.D.p; a.X = w.X.p; a.R = w.R.p; a.ZZ = w.ZZ.p; a.Pv = w.Pv.p; a.Hp = w.Hp.p;
-    a.Minv = w.Minv.p; a.DG = w.DG.p; a.Gx = w.Gx.p; a.Ft = w.Ft.p;
-    int* li = w.tn_lane_i.p;
-    const size_t Bs = (size_t)B;
-    a.st = li; a.ls = li + Bs; a.cgit = li + 2 * Bs; a.flag = li + 3 * Bs; a.stall = li + 4 * Bs; a.iters = li + 5 * Bs;
-    a.ncg = li + 6 * Bs; a.act = li + 7 * Bs; a.ndone = li + 8 * Bs;
-    int* cnt = li + 8 * Bs + 1;
-    a.cnt_setup = cnt; a.cnt_hv = cnt + groups; a.cnt_upd = cnt + 2 * groups; a.cnt_gd = cnt + 3 * groups; a.cnt_tm = cnt + 4 * groups;
-    double* ld = w.tn_lane_d.p;
-    a.F0 = ld; a.t_ = ld + Bs; a.gd = ld + 2 * Bs; a.rz = ld + 3 * Bs; a.rz0 = ld + 4 * Bs; a.tol2 = ld + 5 * Bs; a.alpha = ld + 6 * Bs;
-    a.beta = ld + 7 * Bs; a.gmax = ld + 8 * Bs; a.tlog = ld + 9 * Bs; a.gdtmp = ld + 10 * Bs;
-    double* pp = w.tn_part.p;
-    a.part_setup = pp; pp += (size_t)3 * a.row_chunks * B;
-    a.part_upd = pp; pp += (size_t)a.row_chunks * B;
-    a.part_gd = pp; pp += (size_t)a.row_chunks * B;
-    a.part_hv = pp; pp += (size_t)2 * a.node_chunks * B;
-    a.part_tm = pp;
-    return TPL_OK;
-}
-
-int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<double>& lo, const std::vector<double>& hi,
-                const std::vector<double>& sc, int nr, int mode, const tpl_opt_options& o, int* status, int* iters,
-                tpl_opt_result* result) {
-    using namespace tpltn;
-    if (mode != TPL_GRAD_AD) return fail(TPL_ERR_ARG, "truncated Newton differentiates the AD objective (TPL_GRAD_AD)");
-    TnArgs a;
-    int prc = tn_prepare(e, B, X, lo, hi, sc, nr, o, a);
-    if (prc != TPL_OK) return prc;
-    const int P = e->numparams;
-    const size_t PB = (size_t)P * B;
-    tpl_engine::OptWork& w = e->opt;
-    cudaStream_t s = e->stream;
-    const int groups = (B + 31) / 32;
-    const int WY = tplopt::OPT_WY;
-    const int max_steps = o.max_steps > 0 ? o.max_steps : 20000;
-    const int check_every = o.check_every > 0 ? o.check_every : 32;
-    // CG iterations per evaluation: most vectors are inside a CG solve most of the time, and only the vectors in a
-    // line search need the objective; 4 CG iterations per step make the (then mostly idle) evaluation a ~5 % overhead
-    const int cg_per_step = o.cg_per_step > 0 ? std::min(o.cg_per_step, 64) : 4;
-    const dim3 blk(32, WY);
-    const dim3 rgrd(groups, a.row_chunks), ngrd(groups, a.node_chunks);
-    cudaEvent_t ev0, ev1;
-    CK(cudaEventCreate(&ev0));
-    CK(cudaEventCreate(&ev1));
-    CK(cudaEventRecord(ev0, s));
-    int launches = 0;
-    tn_init_kernel<<<rgrd, blk, 0, s>>>(a);
-    tn_trial_kernel<<<rgrd, blk, 0, s>>>(a);
-    launches += 2;
-    CK(cudaGetLastError());
-    auto one_step = [&]() -> int {
-        int rc = eval_device(e, B, a.X, const_cast<double*>(a.Ft), const_cast<double*>(a.Gx), mode, true, s);
-        if (rc != TPL_OK) return rc;
-        tn_diag_kernel<<<ngrd, blk, 0, s>>>(a);
-        tn_setup_kernel<<<rgrd, blk, 0, s>>>(a);
-        for (int k = 0; k < cg_per_step; k++) {
-            tn_hv_kernel<<<ngrd, blk, 0, s>>>(a);
-            tn_update_kernel<<<rgrd, blk, 0, s>>>(a);
-            tn_dir_kernel<<<rgrd, blk, 0, s>>>(a);
-        }
-        tn_gd_kernel<<<rgrd, blk, 0, s>>>(a);
-        tn_stepmax_kernel<<<ngrd, blk, 0, s>>>(a);
-        tn_trial_kernel<<<rgrd, blk, 0, s>>>(a);
-        CK(cudaGetLastError());
-        return TPL_OK;
-    };
-    const int per_step = 7 + 3 * cg_per_step;
-    int steps = 0;
-    int rc = one_step();               // first step outside any capture: sizes the evaluation work space
-    if (rc != TPL_OK) return rc;
-    steps++;
-    launches += per_step;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t gexec = nullptr;
-    const bool was_timing = e->timing;
-    e->timing = false;
-    if (o.use_graph) {
-        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        for (int k = 0; k < check_every && rc == TPL_OK; k++) rc = one_step();
-        cudaError_t ce = cudaStreamEndCapture(s, &graph);
-        if (rc != TPL_OK || ce != cudaSuccess) {
-            if (graph) cudaGraphDestroy(graph);
-            e->timing = was_timing;
-            return rc != TPL_OK ? rc : fail(TPL_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
-        }
-        CK(cudaGraphInstantiate(&gexec, graph, 0));
-    }
-    int ndone = 0;
-    while (steps < max_steps) {
-        if (o.use_graph) {
-            CK(cudaGraphLaunch(gexec, s));
-        } else {
-            for (int k = 0; k < check_every && rc == TPL_OK; k++) rc = one_step();
-            if (rc != TPL_OK) break;
-        }
-        steps += check_every;
-        launches += per_step * check_every;
-        CK(cudaMemcpyAsync(w.h_done.p, a.ndone, sizeof(int), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        ndone = w.h_done.p[0];
-        if (ndone >= B) break;
-    }
-    if (gexec) cudaGraphExecDestroy(gexec);
-    if (graph) cudaGraphDestroy(graph);
-    e->timing = was_timing;
-    if (rc != TPL_OK) return rc;
-    tn_final_kernel<<<rgrd, blk, 0, s>>>(a, w.Fout.p);
-    launches++;
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(ev1, s));
-    CK(cudaMemcpyAsync(X, w.X.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(F, w.Fout.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
-    if (status) CK(cudaMemcpyAsync(status, a.flag, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
-    std::vector<double> tlog(B);
-    std::vector<int> nit(B), ncg(B);
-    CK(cudaMemcpyAsync(tlog.data(), a.tlog, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(nit.data(), a.iters, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(ncg.data(), a.ncg, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ev0, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
-    tpl_opt_result res;
-    memset(&res, 0, sizeof(res));
-    double ts = 0.0;
-    long long ni = 0, nc = 0;
-    for (int b = 0; b < B; b++) { ts += tlog[b]; ni += nit[b]; nc += ncg[b]; if (iters) iters[b] = nit[b]; }
-    res.steps = steps;
-    res.n_done = ndone;
-    res.launches = launches;
-    res.cg_iterations = (int)std::min<long long>(nc, 2147483647LL);
-    res.device_ms = ms;
-    res.mean_log10_step = ni > 0 ? ts / (double)ni : 0.0;
-    e->last_launches = launches;
-    if (result) *result = res;
-    return TPL_OK;
-}
-
-}  // namespace
-
-extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, const double* lower, const double* upper,
-                                  int mode, const tpl_opt_options* opts, int* status, int* iters, tpl_opt_result* result) {
-    using namespace tplopt;
-    if (!e || !X || !F || !lower || !upper || B < 1) return fail(TPL_ERR_ARG, "tpl_optimize_batch: null or B < 1");
-    if (!e->have_fp) return fail(TPL_ERR_STATE, "set_freeparams has not been called");
-    CK(cudaSetDevice(e->device));
-    int rc = sync_device_tree(e);
-    if (rc != TPL_OK) return rc;
-    if (e->static_bad) return fail(TPL_ERR_STATE, "a fixed date violates its own bounds: every point is infeasible");
-    tpl_opt_options o;
-    memset(&o, 0, sizeof(o));
-    if (opts) o = *opts;
-    const int HM = o.history ? o.history : 8;
-    if (HM != 4 && HM != 8 && HM != 16) return fail(TPL_ERR_ARG, "history must be 4, 8 or 16");
-    const int max_steps = o.max_steps > 0 ? o.max_steps : 20000;
-    const int check_every = o.check_every > 0 ? o.check_every : 32;
-    const int P = e->numparams, n = e->n;
-    int nr = 0;
-    for (int i = 0; i < n; i++) nr = std::max(nr, e->freeparams[i] + 1);
-    const double ds = o.date_scale > 0 ? o.date_scale : 1.0;
-    // bounds in the transformed variables.  Date bounds are kept OPEN by a relative margin: exactly ON a penalised
-    // bound the reference's objectives drop the infinite barrier term (calc_penalty resets, the AD paths skip it,
-    // SURVEY.md 8 a13), so a step clamped onto the bound would sit in a spurious discontinuous minimum.
-    std::vector<double> lo(P), hi(P), sc(P);
-    for (int p = 0; p < P; p++) {
-        sc[p] = p < nr ? 1.0 : ds;
-        if (p < nr) {
-            lo[p] = std::log(std::max(lower[p], 1e-300)) / sc[p];
-            hi[p] = std::log(upper[p]) / sc[p];
-        } else {
-            double dlo = lower[p], dhi = upper[p];
-            const double ref = dhi < 1e19 ? dhi : dlo;
-            const double margin = 1e-9 * std::max(1.0, std::fabs(ref));
-            dlo += margin;
-            if (dhi < 1e19) dhi -= margin;
-            lo[p] = dlo / sc[p];
-            hi[p] = dhi / sc[p];
-        }
-        if (!(lo[p] <= hi[p])) return fail(TPL_ERR_ARG, "empty bound interval");
-    }
-    if (o.method == 1) return optimize_tn(e, B, X, F, lo, hi, sc, nr, mode, o, status, iters, result);
-    if (o.method != 0) return fail(TPL_ERR_ARG, "method must be 0 (L-BFGS) or 1 (truncated Newton)");
-    const size_t PB = (size_t)P * B;
-    tpl_engine::OptWork& w = e->opt;
-    const int NB = 2 * HM + 1, NACC = 6 * HM + 2;
-    // Row chunking.  The two heavy kernels run as exactly ONE wave of equally loaded blocks (blocks = resident
-    // slots of the kernel's own occupancy): with a few hundred long blocks a partial second wave would cost up to
-    // half of the kernel's time (ncu: 1.14 waves -> 68 % of the HBM rate, profiles/r01j).
-    const int groups = (B + 31) / 32;
-    int occ_upd = 1, occ_dir = 1;
-    if (HM == 4) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_upd, tplopt::opt_update_kernel<4>, 32 * 4, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dir, tplopt::opt_direction_kernel<4>, 32 * OPT_WY, 0);
-    } else if (HM == 8) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_upd, tplopt::opt_update_kernel<8>, 32 * 8, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dir, tplopt::opt_direction_kernel<8>, 32 * OPT_WY, 0);
-    } else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_upd, tplopt::opt_update_kernel<16>, 32 * 16, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dir, tplopt::opt_direction_kernel<16>, 32 * OPT_WY, 0);
-    }
-    auto one_wave = [&](int occ, int align, int* nch, int* rws) {
-        int c = std::max(1, (e->num_sms * std::max(occ, 1)) / groups);
-        c = std::min(c, (P + align - 1) / align);
-        int r = (P + c - 1) / c;
-        r = ((r + align - 1) / align) * align;
-        *rws = r;
-        *nch = (P + r - 1) / r;
-    };
-    int nchunks, rows, dir_chunks, dir_rows;
-    one_wave(occ_upd, 16, &nchunks, &rows);          // whole row tiles of the update kernel for every history size
-    one_wave(occ_dir, 2 * OPT_WY, &dir_chunks, &dir_rows);
-    CK(w.Z.ensure(PB)); CK(w.Gz.ensure(PB)); CK(w.D.ensure(PB)); CK(w.X.ensure(PB)); CK(w.Gx.ensure(PB));
-    CK(w.S.ensure(PB * HM)); CK(w.Y.ensure(PB * HM));
-    CK(w.lo.ensure(P)); CK(w.hi.ensure(P)); CK(w.sc.ensure(P));
-    CK(w.lane_d.ensure((size_t)6 * B)); CK(w.lane_i.ensure((size_t)9 * B + 1 + groups));
-    CK(w.rho.ensure((size_t)HM * B)); CK(w.delta.ensure((size_t)NB * B)); CK(w.M.ensure((size_t)NB * NB * B));
-    CK(w.part.ensure((size_t)nchunks * NACC * B)); CK(w.Ft.ensure(B)); CK(w.Fout.ensure(B));
-    CK(w.h_done.ensure(1));
-    cudaStream_t s = e->stream;
-    CK(cudaMemcpyAsync(w.lo.p, lo.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(w.hi.p, hi.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(w.sc.p, sc.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(w.X.p, X, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(w.lane_d.p, 0, sizeof(double) * 6 * B, s));
-    CK(cudaMemsetAsync(w.lane_i.p, 0, sizeof(int) * (9 * (size_t)B + 1 + groups), s));      // st = ST_INIT = 0, t = 0
-    CK(cudaMemsetAsync(w.rho.p, 0, sizeof(double) * HM * B, s));
-    CK(cudaMemsetAsync(w.delta.p, 0, sizeof(double) * NB * B, s));
-    CK(cudaMemsetAsync(w.M.p, 0, sizeof(double) * NB * NB * B, s));
-    CK(cudaMemsetAsync(w.S.p, 0, sizeof(double) * PB * HM, s));
-    CK(cudaMemsetAsync(w.Y.p, 0, sizeof(double) * PB * HM, s));
-    CK(cudaMemsetAsync(w.Gz.p, 0, sizeof(double) * PB, s));
-    OptArgs a;
-    a.o.P = P; a.o.B = B; a.o.nr = nr;
-    a.o.max_ls = o.max_ls > 0 ? o.max_ls : 40;
-    a.o.patience = o.patience > 0 ? o.patience : 5;
-    a.o.c1 = o.armijo > 0 ? o.armijo : 1e-4;
-    a.o.ftol = o.ftol > 0 ? o.ftol : 1e-12;
-    a.o.gtol = o.gtol > 0 ? o.gtol : 1e-8;
-    a.Z = w.Z.p; a.Gz = w.Gz.p; a.D = w.D.p; a.X = w.X.p; a.Gx = w.Gx.p; a.S = w.S.p; a.Y = w.Y.p;
-    a.lo = w.lo.p; a.hi = w.hi.p; a.sc = w.sc.p;
-    int* li = w.lane_i.p;
-    a.st = li; a.ls = li + B; a.head = li + 2 * (size_t)B; a.stall = li + 3 * (size_t)B; a.flag = li + 4 * (size_t)B;
-    a.newdir = li + 5 * (size_t)B; a.iters = li + 6 * (size_t)B; a.nfail = li + 7 * (size_t)B;
-    a.valid = (unsigned*)(li + 8 * (size_t)B);
-    a.ndone = li + 9 * (size_t)B;
-    double* ld = w.lane_d.p;
-    a.F0 = ld; a.t = ld + B; a.gd = ld + 2 * (size_t)B; a.gamma = ld + 3 * (size_t)B; a.gmax = ld + 4 * (size_t)B; a.tlog = ld + 5 * (size_t)B;
-    a.Ft = w.Ft.p;
-    a.rho = w.rho.p; a.delta = w.delta.p; a.M = w.M.p; a.part = w.part.p;
-    a.nchunks = nchunks; a.rows_per_chunk = rows;
-    a.dir_chunks = dir_chunks; a.dir_rows = dir_rows;
-    CK(w.part_red.ensure((size_t)NACC * B));
-    a.part_red = w.part_red.p;
-    const bool two_level = nchunks > 32;            // many chunks: reduce them with a grid of blocks first
-    a.lane_part = two_level ? w.part_red.p : w.part.p;
-    a.lane_nchunks = two_level ? 1 : nchunks;
-    a.tcount = li + 9 * (size_t)B + 1;
-    a.n = n; a.parent = e->d_parent.p; a.dslot = e->d_dslot.p; a.hfix = e->d_hfix.p;
-    {   // light kernels carry ~40 registers: give the machine ~16 blocks per SM
-        int lc = (16 * e->num_sms + groups - 1) / groups;
-        lc = std::max(1, std::min(lc, (P + 4 * OPT_WY - 1) / (4 * OPT_WY)));
-        int lr = (P + lc - 1) / lc;
-        lr = ((lr + OPT_WY - 1) / OPT_WY) * OPT_WY;
-        a.light_rows = lr;
-        a.light_chunks = (P + lr - 1) / lr;
-    }
-    int tchunks = std::max(1, std::min(4 * nchunks, (n + 8 * OPT_WY - 1) / (8 * OPT_WY)));
-    int npc = (n + tchunks - 1) / tchunks;
-    npc = ((npc + OPT_WY - 1) / OPT_WY) * OPT_WY;
-    tchunks = (n + npc - 1) / npc;
-    a.tchunks = tchunks; a.nodes_per_chunk = npc;
-    CK(w.tpart.ensure((size_t)tchunks * B));
-    a.tpart = w.tpart.p;
-    a.boundary_frac = o.boundary_frac < 0 ? 0.0 : (o.boundary_frac > 0 ? std::min(o.boundary_frac, 0.999999) : 0.9);
-    tpl_opt_result res;
-    memset(&res, 0, sizeof(res));
-    cudaEvent_t ev0, ev1;
-    CK(cudaEventCreate(&ev0));
-    CK(cudaEventCreate(&ev1));
-    CK(cudaEventRecord(ev0, s));
-    const bool graph = o.use_graph != 0;
-    if (HM == 4) rc = run_optimizer<4>(e, a, B, mode, max_steps, check_every, graph, &res);
-    else if (HM == 8) rc = run_optimizer<8>(e, a, B, mode, max_steps, check_every, graph, &res);
-    else rc = run_optimizer<16>(e, a, B, mode, max_steps, check_every, graph, &res);
-    if (rc != TPL_OK) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc; }
-    CK(cudaEventRecord(ev1, s));
-    CK(cudaMemcpyAsync(X, w.X.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(F, w.Fout.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
-    if (status) CK(cudaMemcpyAsync(status, a.flag, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
-    if (iters) CK(cudaMemcpyAsync(iters, a.iters, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
-    std::vector<double> tlog(B);
-    std::vector<int> nit(B);
-    CK(cudaMemcpyAsync(tlog.data(), a.tlog, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(nit.data(), a.iters, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    {
-        double ts = 0.0;
-        long long ni = 0;
-        for (int b = 0; b < B; b++) { ts += tlog[b]; ni += nit[b]; }
-        res.mean_log10_step = ni > 0 ? ts / (double)ni : 0.0;
-    }
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ev0, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
-    res.device_ms = ms;
-    e->last_launches = res.launches;
-    if (result) *result = res;
-    return TPL_OK;
-}
-
-
-extern "C" int tpl_debug_hessvec(tpl_engine* e, int B, const double* X, const double* V, const double* sc_rows, double* W, double* DG) {
-    using namespace tpltn;
-    if (!e || !X || !V || !sc_rows || !W || !DG || B < 1) return fail(TPL_ERR_ARG, "null or B < 1");
-    if (!e->have_fp) return fail(TPL_ERR_STATE, "set_freeparams has not been called");
-    CK(cudaSetDevice(e->device));
-    int rc = sync_device_tree(e);
-    if (rc != TPL_OK) return rc;
-    const int P = e->numparams;
-    const size_t PB = (size_t)P * B;
-    int nr = 0;
-    for (int i = 0; i < e->n; i++) nr = std::max(nr, e->freeparams[i] + 1);
-    std::vector<double> lo(P, -1e300), hi(P, 1e300), sc(sc_rows, sc_rows + P);
-    tpl_opt_options o;
-    memset(&o, 0, sizeof(o));
-    TnArgs a;
-    rc = tn_prepare(e, B, X, lo, hi, sc, nr, o, a);
-    if (rc != TPL_OK) return rc;
-    cudaStream_t s = e->stream;
-    tpl_engine::OptWork& w = e->opt;
-    rc = eval_device(e, B, a.X, const_cast<double*>(a.Ft), const_cast<double*>(a.Gx), TPL_GRAD_AD, true, s);
-    if (rc != TPL_OK) return rc;
-    const dim3 blk(32, tplopt::OPT_WY);
-    const dim3 ngrd((B + 31) / 32, a.node_chunks);
-    CK(cudaMemcpyAsync(w.Pv.p, V, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
-    tn_diag_kernel<<<ngrd, blk, 0, s>>>(a);                     // st = TS_INIT and a finite objective: every vector "accepts"
-    std::vector<int> cg(B, TS_CG);
-    CK(cudaMemcpyAsync(a.st, cg.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
-    tn_hv_kernel<<<ngrd, blk, 0, s>>>(a);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(W, w.Hp.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(DG, w.DG.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    return TPL_OK;
-}
-
-namespace {
-}  // namespace
 
 extern "C" {
 
