@@ -371,7 +371,10 @@ pl_desc_kernel(const EvalArgs a, const TileArgs ta, const DescArgs da, const __g
             const unsigned long long* sMask = stage_mask(s);
             const int n0 = tile * T;
             const int tn = min(T, a.t.n - n0);
-            for (int j = w; j < tn; j += NCW) {
+            // 64 rows over 15 warps leave 4 warps with a fifth row; the extra rows rotate from tile to tile so that no warp
+            // is systematically the slowest (the ring releases a stage only when its slowest warp is done)
+            const int rot = (it * (T % NCW)) % NCW;
+            for (int j = (w + NCW - rot) % NCW; j < tn; j += NCW) {
                 const int4 q0 = sDesc[4 * j];
                 bool done = false;
                 if (FASTABLE && q0.z != -2) {
