@@ -239,7 +239,7 @@ __device__ __noinline__ RowAcc general_row_global(const EvalArgs& a, const TileA
 
 template <int MODE, bool LOGPEN, bool WANT_G, bool MASK, int S, int NCW>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1)
-pl_desc_kernel(const EvalArgs a, const TileArgs ta, const DescArgs da, const __grid_constant__ CUtensorMap tmapR,
+pl_desc_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ TileArgs ta, const __grid_constant__ DescArgs da, const __grid_constant__ CUtensorMap tmapR,
                const __grid_constant__ CUtensorMap tmapD) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int T = TILE_NODES, LW = TILE_LANES;

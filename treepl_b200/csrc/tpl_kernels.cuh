@@ -159,7 +159,7 @@ __device__ __forceinline__ double duration_rule(double hp, double h, int& bad, b
 }
 
 template <int MODE, bool LF, bool LOGPEN, bool WANT_G, int MASKMODE>
-__global__ void __launch_bounds__(256) pl_main_kernel(const EvalArgs a) {
+__global__ void __launch_bounds__(256) pl_main_kernel(const __grid_constant__ EvalArgs a) {
     __shared__ double2 s_tab[LOG_TABLE_N];
     __shared__ double s_red[3][256];
     __shared__ int s_bad[256];
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256) pl_main_kernel(const EvalArgs a) {
 // matching sparse gradient corrections to rows the main kernel has already written.
 constexpr int FIN_SEGS = 32;
 template <int MODE, bool LF, bool LOGPEN, bool WANT_G, int MASKMODE>
-__global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const EvalArgs a) {
+__global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const __grid_constant__ EvalArgs a) {
     __shared__ double s_sum[3][FIN_SEGS][32];
     __shared__ int s_bad[FIN_SEGS][32];
     const DevTree& t = a.t;

@@ -367,7 +367,7 @@ inline size_t tile_kernel_smem(int hrows) {
 // generation 2: one CTA (8 warps) per (tile, 64-vector chunk)
 // ---------------------------------------------------------------------------------------------
 template <int MODE, bool LOGPEN, bool WANT_G, bool MASK>
-__global__ void __launch_bounds__(256, 3) pl_tile_kernel(const EvalArgs a, const TileArgs ta) {
+__global__ void __launch_bounds__(256, 3) pl_tile_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ TileArgs ta) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int T = TILE_NODES, LW = TILE_LANES;
     double* sR = reinterpret_cast<double*>(smem_raw);                      // [T][LW]
@@ -474,7 +474,7 @@ inline size_t persist_kernel_smem(int hrows) {
 __host__ __device__ inline long long persist_lo(long long c, long long W, long long G) { return c * W / G; }
 
 template <int MODE, bool LOGPEN, bool WANT_G, bool MASK>
-__global__ void __launch_bounds__(P_THREADS, 1) pl_persist_kernel(const EvalArgs a, const TileArgs ta) {
+__global__ void __launch_bounds__(P_THREADS, 1) pl_persist_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ TileArgs ta) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int T = TILE_NODES, LW = TILE_LANES, S = P_STAGES, NCW = P_CONSUMER_WARPS;
     const size_t stage_bytes = persist_stage_bytes(ta.hrows);
