@@ -27,7 +27,9 @@ namespace tpl {
 constexpr int DESC_HALO = 24;                 // halo rows per tile (p94 of the 100k-tip Yule tree; overflow -> general rows)
 constexpr int DESC_INTS = 16;                 // 64-byte descriptor = 4 x int4
 constexpr int DESC_DBOX = 8;                  // rows per TMA box of the date range (rate range: one 64-row box)
-constexpr int DESC_NCW = 15;                  // consumer warps (110 registers x 512 threads fill the register file)
+// consumer warps: 15 + the producer = 16 warps = 4 per SM sub-partition, whose 16,384 registers then allow 128 per thread
+// (the kernel uses 118).  A 17th warp would put 5 on one sub-partition and cap every thread at 96 registers (spills).
+constexpr int DESC_NCW = 15;
 
 // descriptor words (int4 x 4):
 //   q0 = { idx_lo, idx_hi, rslot, dslot }   idx bytes: r_own h_own r_par h_par | r_c1 h_c1 r_c2 h_c2
