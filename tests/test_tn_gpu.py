@@ -174,3 +174,24 @@ def test_end_to_end_dating_of_the_example_configs(tmp_path):
     assert r["smoothing"] == 10.0 and abs(r["objective"] - 252.3558) <= 2e-6 * 252.3558
     assert open(tmp_path / "cv.out").read().split("\n")[:5] == ["chisq: (1000) 2730.97", "chisq: (100) 2365.8", "chisq: (10) 2130.28",
                                                               "chisq: (1) 2178.17", "chisq: (0.1) 2187.12"]
+
+
+def test_random_subsample_cv_end_to_end():
+    """examples/pl4203.cppr8s runs a random-subsample CV (cvstart 1e-4 ... cvstop 100, x 0.1 is its own grid; here the default
+    grid direction 1000 -> 0.1): folds are sister-free tip groups, every fold optimisation converges, and the final fit at the
+    selected smoothing is the optimum of the engine's own objective."""
+    from treepl_b200 import run
+    gd = Golden("pl4203")
+    flat = dict(gd.flat)
+    r = run.date_tree(flat, gd.meta["names"], gd.meta["numsites"], do_cv=True, randomcv=True, randomcviter=6, randomcvsamp=0.15, seed=2)
+    grid, chisq = r["cv"]
+    assert grid == [1000.0, 100.0, 10.0, 1.0, 0.1] and len(chisq) == 5 and np.all(np.isfinite(chisq)) and np.all(np.array(chisq) > 0)
+    assert r["smoothing"] == grid[int(np.argmin(chisq))] and r["converged"]
+    pr = TS.Problem(flat, [r["smoothing"], r["smoothing"]])
+    plp = _engine(pr, flat)
+    f, g = plp.calc_pl_grad_batch(np.repeat(r["x"][:, None], 2, axis=1), mode=eng.GRAD_AD)
+    assert abs(f[0] - r["objective"]) <= 1e-12 * abs(f[0])
+    gz = g[:, 0].copy()
+    gz[: pr.nr] *= r["x"][: pr.nr]
+    assert np.abs(gz).max() <= 1e-6 * abs(f[0])
+    plp.close()
