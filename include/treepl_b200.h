@@ -172,6 +172,26 @@ typedef struct tpl_opt_result {
 int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, const double* lower, const double* upper,
                        int mode, const tpl_opt_options* opts, int* status, int* iters, tpl_opt_result* result);
 
+/* ---- batched simulated annealing ------------------------------------------------------------------
+ * siman_calc_par::optimize (siman_calc_par.cpp:80-229) for B chains at once, one GPU thread per chain: the reference's
+ * proposal (one parameter scaled by 1 + u, rates and dates with probability 1/2 each), acceptance rule, cooling, step-size
+ * adaptation and stopping rules, with the objective updated by an O(degree) delta evaluation instead of a full calc_pl per
+ * proposal.  Objective = calc_pl (TPL_GRAD_ANALYTIC flavour), PL layout; per-vector smoothing and CV masks of the installed
+ * batch configuration apply.  The random stream is a per-chain xorshift generator, not libc rand(): trajectories are
+ * reproducible for a given seed but are not the reference's.
+ * X [P][B] host in/out, F [B] out; status [B] (may be NULL): 1 finished, 4 infeasible start; iterations [B] (may be NULL). */
+typedef struct tpl_anneal_options {
+    double temperature;        /* 0 = 50     (set_pl arguments of optimize_full, utils.cpp:689) */
+    double cool;               /* 0 = 0.999 */
+    double rate_step;          /* 0 = 0.07 */
+    double date_step;          /* 0 = 0.25 */
+    double stop_temperature;   /* 0 = 0.001 */
+    int max_iterations;        /* 0 = 15000 (lfsimaniter, optim_options.cpp) */
+    unsigned long long seed;   /* 0 = 1 */
+} tpl_anneal_options;
+
+int tpl_anneal_batch(tpl_engine* e, int B, double* X, double* F, const tpl_anneal_options* opts, int* status, int* iterations);
+
 /* number of kernels the last evaluation call launched (for bench accounting) */
 int tpl_last_launch_count(const tpl_engine* e);
 

@@ -19,6 +19,7 @@
 #include "tpl_desc_kernel.cuh"
 #include "tpl_lbfgs.cuh"
 #include "tpl_tn.cuh"
+#include "tpl_anneal.cuh"
 
 namespace {
 
@@ -175,6 +176,10 @@ struct tpl_engine {
         // truncated Newton
         DevBuf<double> R, ZZ, Pv, Hp, Minv, DG, pmin_n, pmax_n, tn_part, tn_lane_d;
         DevBuf<int> tn_lane_i;
+        // annealer
+        DevBuf<int> sa_date_node, sa_bar_node, sa_done;
+        DevBuf<double> sa_hmin, sa_hmax;
+        DevBuf<unsigned char> sa_chains;
     } opt;
     // optional per-launch device timing (bench.py roofline): events around the main kernel
     bool timing = false;

@@ -496,3 +496,92 @@ extern "C" int tpl_debug_hessvec(tpl_engine* e, int B, const double* X, const do
     return TPL_OK;
 }
 
+// ---- batched simulated annealing (tpl_anneal_core.h / tpl_anneal.cuh) -----------------------------------------------
+
+extern "C" int tpl_anneal_batch(tpl_engine* e, int B, double* X, double* F, const tpl_anneal_options* opts, int* status, int* iterations) {
+    using namespace tplsa;
+    if (!e || !X || !F || B < 1) return fail(TPL_ERR_ARG, "tpl_anneal_batch: null or B < 1");
+    if (!e->have_fp) return fail(TPL_ERR_STATE, "set_freeparams has not been called");
+    CK(cudaSetDevice(e->device));
+    int rc = sync_device_tree(e);
+    if (rc != TPL_OK) return rc;
+    if (e->lf_mode) return fail(TPL_ERR_ARG, "the batched annealer needs the PL layout (one rate per branch)");
+    if (e->cv_any) return fail(TPL_ERR_ARG, "the batched annealer takes CV masks per vector (tpl_batch_configure), not set_cv_nodes");
+    if (e->static_bad) return fail(TPL_ERR_STATE, "a fixed date violates its own bounds: every point is infeasible");
+    tpl_anneal_options o;
+    memset(&o, 0, sizeof(o));
+    if (opts) o = *opts;
+    const int P = e->numparams, n = e->n;
+    const size_t PB = (size_t)P * B;
+    int nr = 0;
+    for (int i = 0; i < n; i++) nr = std::max(nr, e->freeparams[i] + 1);
+    std::vector<int> date_node, bar_node;
+    for (int i = 0; i < n; i++) if (e->freeparams[n + i] != -1) date_node.push_back(i);
+    for (int i = 0; i < n; i++) if (e->pen_min[i] != -1 || e->pen_max[i] != -1) bar_node.push_back(i);
+    tpl_engine::OptWork& w = e->opt;
+    cudaStream_t s = e->stream;
+    CK(w.X.ensure(PB));
+    CK(w.sa_date_node.upload(date_node, s));
+    CK(w.sa_bar_node.upload(bar_node, s));
+    CK(w.sa_hmin.upload(e->hmin, s));
+    CK(w.sa_hmax.upload(e->hmax, s));
+    CK(w.sa_chains.ensure((size_t)B * sizeof(Chain)));
+    CK(w.sa_done.ensure((size_t)B + 1));
+    CK(w.h_done.ensure(1));
+    CK(cudaMemcpyAsync(w.X.p, X, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(w.sa_done.p, 0, sizeof(int) * ((size_t)B + 1), s));
+    CK(cudaStreamSynchronize(s));                   // the uploads above read temporaries
+    SaArgs a;
+    a.o.n = n; a.o.P = P; a.o.nr = nr; a.o.ndates = (int)date_node.size();
+    a.o.maxit = o.max_iterations > 0 ? o.max_iterations : 15000;            // lfsimaniter / plsimaniter (optim_options.cpp)
+    a.o.cool = o.cool > 0 ? o.cool : 0.999;                                  // utils.cpp:689
+    a.o.stop_temp = o.stop_temperature > 0 ? o.stop_temperature : 0.001;
+    a.o.pb = e->pb;
+    a.o.log_pen = e->log_pen ? 1 : 0;
+    a.t = dev_tree(e);
+    a.date_node = w.sa_date_node.p;
+    a.bar_node = w.sa_bar_node.p;
+    a.hmin = w.sa_hmin.p;
+    a.hmax = w.sa_hmax.p;
+    const bool lanemask = e->cfg_mask && e->cfg_B == B;
+    a.lanemask = lanemask ? e->d_lanemask.p : nullptr;
+    a.mask_stride = e->ntiles2 * tpl::TILE_NODES;
+    a.lane_lambda = (e->cfg_lambda && e->cfg_B == B) ? e->d_lane_lambda.p : nullptr;
+    a.lambda = e->smoothing;
+    a.X = w.X.p;
+    a.chains = reinterpret_cast<Chain*>(w.sa_chains.p);
+    a.done = w.sa_done.p;
+    a.ndone = w.sa_done.p + B;
+    a.B = B;
+    const int grid = (B + 31) / 32;
+    sa_init_kernel<<<grid, 32, 0, s>>>(a, o.temperature > 0 ? o.temperature : 50.0, o.rate_step > 0 ? o.rate_step : 0.07,
+                                       o.date_step > 0 ? o.date_step : 0.25, o.seed ? o.seed : 1ull);
+    CK(cudaGetLastError());
+    int launches = 1;
+    // a chain needs maxit counted iterations plus its discarded proposals; the cap only guards against a chain whose every
+    // proposal is infeasible
+    const long long cap = 40LL * a.o.maxit + 100000;
+    long long issued = 0;
+    int ndone = 0;
+    while (ndone < B && issued < cap) {
+        sa_run_kernel<<<grid, 32, 0, s>>>(a, 2048);
+        issued += 2048;
+        launches++;
+        CK(cudaMemcpyAsync(w.h_done.p, a.ndone, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        ndone = w.h_done.p[0];
+    }
+    std::vector<Chain> chains(B);
+    std::vector<int> done(B);
+    CK(cudaMemcpyAsync(chains.data(), a.chains, sizeof(Chain) * B, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(done.data(), a.done, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(X, w.X.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int b = 0; b < B; b++) {
+        F[b] = done[b] == 2 ? TPL_LARGE : chains[b].f;
+        if (status) status[b] = done[b] == 2 ? 4 : (done[b] == 1 ? 1 : 0);
+        if (iterations) iterations[b] = chains[b].iteration;
+    }
+    e->last_launches = launches;
+    return TPL_OK;
+}

@@ -39,6 +39,12 @@ class OptOptions(C.Structure):
                 ("armijo", C.c_double), ("date_scale", C.c_double), ("boundary_frac", C.c_double)]
 
 
+class AnnealOptions(C.Structure):
+    """tpl_anneal_options (include/treepl_b200.h); 0 = the reference's default"""
+    _fields_ = [("temperature", C.c_double), ("cool", C.c_double), ("rate_step", C.c_double), ("date_step", C.c_double),
+                ("stop_temperature", C.c_double), ("max_iterations", C.c_int), ("seed", C.c_ulonglong)]
+
+
 class OptResult(C.Structure):
     _fields_ = [("steps", C.c_int), ("n_done", C.c_int), ("launches", C.c_int), ("cg_iterations", C.c_int), ("device_ms", C.c_double),
                 ("mean_log10_step", C.c_double)]
@@ -92,6 +98,8 @@ def load_library():
         fn.argtypes = args
     L.tpl_optimize_batch.restype = ci
     L.tpl_optimize_batch.argtypes = [vp, ci, dp, dp, dp, dp, ci, C.POINTER(OptOptions), ip, ip, C.POINTER(OptResult)]
+    L.tpl_anneal_batch.restype = ci
+    L.tpl_anneal_batch.argtypes = [vp, ci, dp, dp, C.POINTER(AnnealOptions), ip, ip]
     L.tpl_debug_hessvec.restype = ci
     L.tpl_debug_hessvec.argtypes = [vp, ci, dp, dp, dp, dp, dp]
     L.tpl_host_alloc.restype = vp
@@ -109,7 +117,7 @@ EXPORTED_SYMBOLS = (
     "tpl_calc_function_gradient", "tpl_calc_pl_grad", "tpl_get_rates", "tpl_get_dates", "tpl_get_durations",
     "tpl_batch_configure", "tpl_calc_pl_grad_batch", "tpl_calc_pl_grad_batch_dev", "tpl_last_launch_count",
     "tpl_host_alloc", "tpl_host_free", "tpl_device_sm", "tpl_debug_math", "tpl_set_timing", "tpl_get_timing", "tpl_debug_force_kernel",
-    "tpl_last_kernel_generation", "tpl_optimize_batch", "tpl_debug_hessvec",
+    "tpl_last_kernel_generation", "tpl_optimize_batch", "tpl_debug_hessvec", "tpl_anneal_batch",
 )
 
 
@@ -370,6 +378,24 @@ class PLCalcParallel:
                                                _ip(status), _ip(iters), C.byref(res)))
         return X, F, {"steps": res.steps, "n_done": res.n_done, "launches": res.launches, "device_ms": res.device_ms,
                       "mean_log10_step": res.mean_log10_step, "cg_iterations": res.cg_iterations, "status": status, "iterations": iters}
+
+    def anneal_batch(self, X0, **options):
+        """Batched simulated annealing (tpl_anneal_batch): X0 [P, B] feasible starts -> (X, F, status, iterations).
+        options: fields of tpl_anneal_options."""
+        X = _f64(X0).copy()
+        P, B = X.shape
+        if P != self.numparams:
+            raise ValueError("X0 has %d rows, engine expects %d" % (P, self.numparams))
+        F = np.zeros(B)
+        status = np.zeros(B, dtype=np.int32)
+        iters = np.zeros(B, dtype=np.int32)
+        o = AnnealOptions()
+        for k, v in options.items():
+            if not hasattr(o, k):
+                raise TypeError("unknown annealer option %r" % k)
+            setattr(o, k, v)
+        self._check(self._L.tpl_anneal_batch(self._h, B, _dp(X), _dp(F), C.byref(o), _ip(status), _ip(iters)))
+        return X, F, status, iters
 
     def debug_hessvec(self, X, V, sc_rows):
         """-> (H_z V, diag H_z) at X through the truncated-Newton kernels (test hook)."""
