@@ -118,6 +118,13 @@ public:
         return res;
     }
 
+    // B annealing chains at once (siman_calc_par::optimize, siman_calc_par.cpp:80-229): X [P][B] in/out, F [B] out
+    void anneal_batch(int B, double* X, double* F, const tpl_anneal_options* opts = nullptr, int* status = nullptr,
+                      int* iterations = nullptr) {
+        ensure();
+        check(tpl_anneal_batch(e_, B, X, F, opts, status, iterations));
+    }
+
     void delete_ad_arrays() { if (e_) { tpl_destroy(e_); e_ = nullptr; } }     // main.cpp:798
     tpl_engine* handle() { ensure(); return e_; }
 

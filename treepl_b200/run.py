@@ -11,8 +11,9 @@ from . import batchopt, cv, output
 from . import engine as eng
 
 
-def fit(flat, smoothing, device=0, log_pen=False, **opt):
-    """One PL fit at `smoothing` -> (x [P], objective, freeparams, converged)."""
+def fit(flat, smoothing, device=0, log_pen=False, anneal=False, **opt):
+    """One PL fit at `smoothing` -> (x [P], objective, freeparams, converged).  anneal=True runs the reference's
+    annealing phase (optimize_full, utils.cpp:683-689) on the start vector first; the optimum does not depend on it."""
     n = len(flat["parents"])
     plp = eng.PLCalcParallel.from_flat(flat, device=device)
     plp.set_log_pen(log_pen)
@@ -25,7 +26,10 @@ def fit(flat, smoothing, device=0, log_pen=False, **opt):
     dscale = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
     if log_pen:
         opt.setdefault("method", 0)
-    X, F, info = cv._minimize(plp, np.repeat(x0[:, None], 2, axis=1), lo, hi, n - 1, dscale, 3000, True, 8, False, **opt)
+    X0 = np.repeat(x0[:, None], 2, axis=1)
+    if anneal:
+        X0, _, _, _ = plp.anneal_batch(X0)
+    X, F, info = cv._minimize(plp, X0, lo, hi, n - 1, dscale, 3000, True, 8, False, **opt)
     plp.close()
     return X[:, 0], float(F[0]), fp, bool(info["converged"][0])
 
