@@ -150,7 +150,7 @@ typedef struct tpl_opt_options {
     int method;         /* 0: L-BFGS (any layout); 1: truncated Newton, CG on the ANALYTIC Hessian-vector product with a
                          * Jacobi preconditioner — what the reference's TNC approximates with finite differences
                          * (tnc.c:483-827).  PL layout, AD gradient, no log penalty. */
-    int max_cg;         /* method 1: CG iterations per Newton step (0 = 100) */
+    int max_cg;         /* method 1: cap on CG iterations per Newton step (0 = 500; the forcing sequence usually stops far earlier) */
     int cg_per_step;    /* method 1: CG iterations run between two batched evaluations (0 = 4) */
     double ftol;        /* 0 = 1e-12 */
     double gtol;        /* 0 = 1e-8; on max |projected gradient| relative to max(|f|, 1) */

@@ -16,12 +16,13 @@ for name in ("clock",):
     x0 = cv.start_vector(flat, P, n - 1)
     par = flat["parents"]
     ds = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
-    for method in (1, 0):
+    for max_cg in (400, 1000):
+        method = 1
         X, F, info = plp.optimize_batch(np.repeat(x0[:, None], B, axis=1), lo, hi, method=method, date_scale=ds, max_steps=40000, use_graph=1,
-                                        **({"ftol": 1e-15, "patience": 40} if method == 0 else {}))
+                                        max_cg=max_cg)
         f, g = plp.calc_pl_grad_batch(X, mode=eng.GRAD_AD)
         gz = g.copy(); gz[: n - 1] *= X[: n - 1]; gz[n - 1:] *= ds
-        print("method", method, "steps", info["steps"], "mean_log10_step", info["mean_log10_step"])
+        print("max_cg", max_cg, "steps", info["steps"], "mean_log10_step", info["mean_log10_step"], "cg", info["cg_iterations"])
         for b in range(B):
             dur = []
             print("  lam %9.3g status %d iters %5d F %.10g |g|max %.3e  min rate %.3e max rate %.3e" % (lams[b], info["status"][b], info["iterations"][b], F[b], np.abs(gz[:, b]).max(), X[: n - 1, b].min(), X[: n - 1, b].max()))

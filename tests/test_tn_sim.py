@@ -185,7 +185,7 @@ def test_hessian_vector_product_matches_finite_differences(sim, name, lams, mask
         assert np.allclose(Wd[row], DG[row], rtol=1e-12, atol=1e-300), (row, Wd[row], DG[row])
 
 
-def fit(sim, name, lams, max_steps=20000, max_cg=100, masks=None, ftol=1e-13, patience=3, cg_per_step=4):
+def fit(sim, name, lams, max_steps=20000, max_cg=500, masks=None, ftol=1e-13, patience=3, cg_per_step=4):
     flat = Golden(name).flat
     pr = Problem(flat, lams, masks)
     n = pr.n

@@ -133,7 +133,7 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
     CK(cudaStreamSynchronize(s));       // pen_min / pen_max uploads read host vectors of the engine; lo / hi / sc are the caller's
     a.o.P = P; a.o.B = B; a.o.nr = nr;
     a.o.max_ls = o.max_ls > 0 ? o.max_ls : 40;
-    a.o.max_cg = o.max_cg > 0 ? o.max_cg : 100;
+    a.o.max_cg = o.max_cg > 0 ? o.max_cg : 500;     // a cap of 100 truncates stiff solves (large smoothing x large rates) into crawling
     a.o.patience = o.patience > 0 ? o.patience : 3;
     a.o.c1 = o.armijo > 0 ? o.armijo : 1e-4;
     a.o.ftol = o.ftol > 0 ? o.ftol : 1e-13;
