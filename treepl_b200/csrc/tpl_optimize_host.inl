@@ -3,6 +3,19 @@
 // eval_device, sync_device_tree, DevBuf, fail / CK); included there INSIDE the anonymous namespace, which this file closes before its extern "C" entry points.
 // Kernels: tpl_lbfgs.cuh (method 0), tpl_tn.cuh (method 1).
 #pragma once
+// start / stop events of one optimisation, released on every exit path
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaError_t create() {
+        cudaError_t e = cudaEventCreate(&a);
+        return e != cudaSuccess ? e : cudaEventCreate(&b);
+    }
+    ~EventPair() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+};
+
 // ---- device-resident batched L-BFGS (tpl_lbfgs_core.h / tpl_lbfgs.cuh) --------------------------------------
 
 template <int HM>
@@ -189,9 +202,9 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
     const int cg_per_step = o.cg_per_step > 0 ? std::min(o.cg_per_step, 64) : 4;
     const dim3 blk(32, WY);
     const dim3 rgrd(groups, a.row_chunks), ngrd(groups, a.node_chunks);
-    cudaEvent_t ev0, ev1;
-    CK(cudaEventCreate(&ev0));
-    CK(cudaEventCreate(&ev1));
+    EventPair evp;
+    CK(evp.create());
+    cudaEvent_t ev0 = evp.a, ev1 = evp.b;
     CK(cudaEventRecord(ev0, s));
     int launches = 0;
     tn_init_kernel<<<rgrd, blk, 0, s>>>(a);
@@ -269,8 +282,6 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
     CK(cudaStreamSynchronize(s));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
     tpl_opt_result res;
     memset(&res, 0, sizeof(res));
     double ts = 0.0;
@@ -425,15 +436,15 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
     a.boundary_frac = o.boundary_frac < 0 ? 0.0 : (o.boundary_frac > 0 ? std::min(o.boundary_frac, 0.999999) : 0.9);
     tpl_opt_result res;
     memset(&res, 0, sizeof(res));
-    cudaEvent_t ev0, ev1;
-    CK(cudaEventCreate(&ev0));
-    CK(cudaEventCreate(&ev1));
+    EventPair evp;
+    CK(evp.create());
+    cudaEvent_t ev0 = evp.a, ev1 = evp.b;
     CK(cudaEventRecord(ev0, s));
     const bool graph = o.use_graph != 0;
     if (HM == 4) rc = run_optimizer<4>(e, a, B, mode, max_steps, check_every, graph, &res);
     else if (HM == 8) rc = run_optimizer<8>(e, a, B, mode, max_steps, check_every, graph, &res);
     else rc = run_optimizer<16>(e, a, B, mode, max_steps, check_every, graph, &res);
-    if (rc != TPL_OK) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc; }
+    if (rc != TPL_OK) return rc;
     CK(cudaEventRecord(ev1, s));
     CK(cudaMemcpyAsync(X, w.X.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(F, w.Fout.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
@@ -452,8 +463,6 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
     }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
     res.device_ms = ms;
     e->last_launches = res.launches;
     if (result) *result = res;
