@@ -7,6 +7,7 @@ tree and per mode (LF / PL / CV-masked / log_pen; feasible, infeasible and edge 
 
     f_pl, g_an   calc_pl + calc_gradient            (pl_calc_parallel.cpp:73, :657)
     f_ad, g_ad   calc_function_gradient (RAD tape)  (pl_calc_parallel.cpp:132)
+    f_adolc, g_adolc   calc_pl_function_gradient_adolc / calc_lf_function_gradient_adolc (ADOL-C 2.6.3 tape, :622 / :224)
 
 together with the flat arrays produced by the reference's extract_tree_info.
 /root/reference does not exist on the GPU box, so these fixtures are what travels.
@@ -115,6 +116,13 @@ def run_case(name, newick, numsites, cals, smooth, rng, rad_ok=True, want_edge=T
                     rec["f_ad"] = repr(float(f_ad))
                     if not np.isnan(g_ad).all():
                         arrays["e%d_g_ad" % k] = g_ad
+                    # the ADOL-C twin: recorded only where it differs from the RAD tape
+                    f_dc, g_dc = p.calc_function_gradient_adolc(x)
+                    rec["f_adolc"] = repr(float(f_dc))
+                    same = np.array_equal(g_dc, g_ad, equal_nan=True)
+                    rec["g_adolc_equals_g_ad"] = bool(same)
+                    if not same and not np.isnan(g_dc).all():
+                        arrays["e%d_g_adolc" % k] = g_dc
                 meta["evals"].append(rec)
                 k += 1
         p.close()

@@ -17,9 +17,10 @@
  * golden vectors under tests/golden/, and (2) time the reference's CPU path on
  * the GPU box's host cores (bench.py cpu_baseline.kind == "reference").
  *
- * NLopt is a third-party consumer of the path that is not built here; the four
- * optimize_plcp_nlopt* symbols that utils.cpp references are defined below as
- * stubs that report failure.  Nothing in this harness calls them.
+ * NLopt 2.4.2 and ADOL-C 2.6.3 are built from the reference's own deps/ tarballs (oracle/build_deps.sh), so the
+ * reference's optimize_nlopt.cpp and its ADOL-C taping paths are the real ones:
+ *   pl_calc_parallel::calc_pl_function_gradient_adolc   (pl_calc_parallel.cpp:622)
+ *   pl_calc_parallel::calc_lf_function_gradient_adolc   (pl_calc_parallel.cpp:224)
  */
 #include <cmath>
 #include <cstdio>
@@ -34,6 +35,7 @@
 #include <vector>
 #include <chrono>
 #include <omp.h>
+#include <adolc/adolc_openmp.h>
 
 #include "node.h"
 #include "tree.h"
@@ -41,17 +43,10 @@
 #include "utils.h"
 #include "pl_calc_parallel.h"
 #include "optimize_nlopt.h"
+#include "optimize_tnc.h"
 #include "optim_options.h"
 
 using namespace std;
-
-/* ---- link-only stubs for the NLopt adapters (optimize_nlopt.cpp is not compiled) ---- */
-double function_plcp_nlopt_ad(unsigned, const double*, double*, void*) { return 1e15; }
-double function_plcp_nlopt(unsigned, const double*, double*, void*) { return 1e15; }
-double function_plcp_nlopt_nograd(unsigned, const double*, double*, void*) { return 1e15; }
-double function_plcp_nlopt_ad_parallel(unsigned, const double*, double*, void*) { return 1e15; }
-int optimize_plcp_nlopt(double*, pl_calc_parallel*, int, int, bool, bool, double, double) { return -1; }
-int optimize_plcp_nlopt_ad_parallel(double*, pl_calc_parallel*, int, int, bool, double, double) { return -1; }
 
 namespace {
 
@@ -305,6 +300,18 @@ double ref_calc_function_gradient(void* h, const double* x, double* g) {
     return f;
 }
 
+/* ADOL-C taped f and gradient: calc_pl_function_gradient_adolc (pl_calc_parallel.cpp:622-655) in PL mode,
+ * calc_lf_function_gradient_adolc (:224-333) in LF mode — what function_plcp_ad_parallel / function_plcp_nlopt_ad_parallel
+ * call (optimize_tnc.cpp:58-73, optimize_nlopt.cpp:88-105).  g pre-filled with NaN as above. */
+double ref_calc_function_gradient_adolc(void* h, const double* x, double* g) {
+    RefProblem* p = (RefProblem*)h;
+    CoutMute mute;
+    vector<double> v(x, x + p->numparams), gv(p->numparams, numeric_limits<double>::quiet_NaN());
+    double f = p->islf ? p->plp.calc_lf_function_gradient_adolc(&v, &gv) : p->plp.calc_pl_function_gradient_adolc(&v, &gv);
+    memcpy(g, gv.data(), gv.size() * sizeof(double));
+    return f;
+}
+
 /* Wall seconds for `reps` calls of calc_pl (+ calc_gradient if with_grad) per thread on
  * `nthreads` independent pl_calc_parallel instances (one per OpenMP thread, as the
  * reference's fold loop does, main.cpp:689-710).  Returns seconds; total evals = reps*nthreads. */
@@ -432,6 +439,44 @@ int ref_cv(void* h, int nlam, const double* lams, int ngroups, const int* goff, 
     seconds[1] = tfull;
     seconds[2] = tfold;
     return 0;
+}
+
+/* The reference's optimiser adapters on the reference's own class — the CPU side of the drop-in comparison
+ * (tests/test_dropin*.py; same `which` codes as tests/dropin/dropin_harness.cpp):
+ *   0 optimize_plcp_tnc(ad=false)  1 optimize_plcp_tnc(ad=true)  2 optimize_plcp_tnc_ad_parallel      (optimize_tnc.cpp:107-231)
+ *   10+k optimize_plcp_nlopt(whichone=k, ad=false)  20+k (ad=true)  30+k optimize_plcp_nlopt_ad_parallel (optimize_nlopt.cpp:116-341)
+ *   100 optimize_full(cv=false), default OptimOptions, srand(seed) first                               (utils.cpp:671-763)
+ * Starts from x (numparams doubles, in/out) after a calc_pl(x) as main() does; *f_out = calc_pl(final x).
+ * The adapters' chatter ("nfeval: N rc: ...") is returned in log. */
+int ref_optimize(void* h, int which, int numiter, double ftol, double xtol, int seed, double* x, double* f_out,
+                 char* log, int logcap) {
+    RefProblem* p = (RefProblem*)h;
+    ostringstream os;
+    streambuf* old = cout.rdbuf(os.rdbuf());
+    pl_calc_parallel& plp = p->plp;
+    vector<double> params(x, x + p->numparams);
+    plp.calc_pl(params);
+    int rc = 0;
+    if (which == 100) {
+        srand(seed);
+        OptimOptions oo;
+        optimize_full(plp, &params, &oo, false);
+    } else {
+        vector<double> x2(params);
+        if (which == 0) rc = optimize_plcp_tnc(x2.data(), &plp, numiter, false, ftol);
+        else if (which == 1) rc = optimize_plcp_tnc(x2.data(), &plp, numiter, true, ftol);
+        else if (which == 2) rc = optimize_plcp_tnc_ad_parallel(x2.data(), &plp, ftol);
+        else if (which >= 10 && which < 20) rc = optimize_plcp_nlopt(x2.data(), &plp, numiter, which - 10, false, false, ftol, xtol);
+        else if (which >= 20 && which < 30) rc = optimize_plcp_nlopt(x2.data(), &plp, numiter, which - 20, true, false, ftol, xtol);
+        else if (which >= 30 && which < 40) rc = optimize_plcp_nlopt_ad_parallel(x2.data(), &plp, numiter, which - 30, false, ftol, xtol);
+        else rc = -999;
+        params = x2;
+    }
+    *f_out = plp.calc_pl(params);
+    memcpy(x, params.data(), params.size() * sizeof(double));
+    cout.rdbuf(old);
+    if (log && logcap > 0) { strncpy(log, os.str().c_str(), logcap - 1); log[logcap - 1] = 0; }
+    return rc;
 }
 
 int ref_hw_threads(void) { return omp_get_num_procs(); }

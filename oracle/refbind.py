@@ -1,8 +1,8 @@
 """TEST INFRASTRUCTURE ONLY: ctypes binding of oracle/_ref/libtreepl_ref.so.
 
-The library is the UNMODIFIED reference hot path (pl_calc_parallel.cpp, utils.cpp, the
-tree classes and the RAD tape, compiled from /root/reference/src by oracle/Makefile)
-behind the thin harness oracle/ref_harness.cpp.  Only tests/, __graft_entry__.smoke()
+The library is the UNMODIFIED reference (every source of its Makefile.in except main.cpp,
+compiled from /root/reference/src by oracle/Makefile against NLopt 2.4.2 and ADOL-C 2.6.3
+built from the reference's own deps/ tarballs) behind the thin harness oracle/ref_harness.cpp.  Only tests/, __graft_entry__.smoke()
 and bench.py's cpu_baseline / --impl reference legs may import this module; the product
 package treepl_b200/ never does.
 """
@@ -48,11 +48,15 @@ def lib():
         L.ref_calc_pl_and_gradient.argtypes = [vp, dp, dp]
         L.ref_calc_function_gradient.restype = cd
         L.ref_calc_function_gradient.argtypes = [vp, dp, dp]
+        L.ref_calc_function_gradient_adolc.restype = cd
+        L.ref_calc_function_gradient_adolc.argtypes = [vp, dp, dp]
         L.ref_time_evals.restype = cd
         L.ref_time_evals.argtypes = [vp, dp, ci, ci, ci]
         L.ref_cv.restype = ci
         L.ref_cv.argtypes = [vp, ci, dp, ci, ip, ip, ci, ci, dp, dp, dp]
         L.ref_hw_threads.restype = ci
+        L.ref_optimize.restype = ci
+        L.ref_optimize.argtypes = [vp, ci, ci, cd, cd, ci, dp, dp, C.c_char_p, ci]
         _lib = L
     return _lib
 
@@ -190,6 +194,14 @@ class RefProblem:
         f = lib().ref_calc_function_gradient(self.h, _dp(x), _dp(g))
         return f, g
 
+    def calc_function_gradient_adolc(self, x):
+        """ADOL-C tape (calc_pl_function_gradient_adolc / calc_lf_function_gradient_adolc)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.size == self.numparams
+        g = np.zeros_like(x)
+        f = lib().ref_calc_function_gradient_adolc(self.h, _dp(x), _dp(g))
+        return f, g
+
     def cross_validate(self, smoothing_grid, groups, randomcv=False, nthreads=1):
         """The reference's Langley-Fitch fit + cross-validation loop (main.cpp:497-822) around its own
         optimize_full (annealer + TNC).  groups: list of lists of tip node numbers.  Call right after
@@ -207,6 +219,16 @@ class RefProblem:
         if rc != 0:
             raise RuntimeError("reference cross-validation failed to initialise (rc=%d)" % rc)
         return {"chisq": chisq, "full_pl": full, "seconds": {"lf": secs[0], "full": secs[1], "folds": secs[2]}}
+
+    def optimize(self, which, x0, numiter=10000, ftol=1e-7, xtol=1e-7, seed=1):
+        """The reference's own optimiser adapter `which` (codes: oracle/ref_harness.cpp::ref_optimize) from x0
+        -> (rc, x, f, log)."""
+        x = np.ascontiguousarray(x0, dtype=np.float64).copy()
+        assert x.size == self.numparams
+        f = C.c_double()
+        log = C.create_string_buffer(1 << 16)
+        rc = lib().ref_optimize(self.h, int(which), int(numiter), float(ftol), float(xtol), int(seed), _dp(x), C.byref(f), log, len(log))
+        return rc, x, f.value, log.value.decode(errors="replace")
 
     def time_evals(self, x, reps, nthreads, with_grad=True):
         x = np.ascontiguousarray(x, dtype=np.float64)
