@@ -108,8 +108,11 @@ int tpl_get_durations(tpl_engine* e, double* out);
 /* ---- batched evaluation: B independent parameter vectors per launch ---------------------------
  * The batch dimension is innermost: X[p*B + b] is parameter p of vector b, G likewise, F[b].
  * Vectors use the FULL parameter layout of the installed slot map (set_freeparams); vector b may
- * additionally carry its own smoothing value and its own CV mask (folds, main.cpp:693-696):
- * a masked node's rate row is ignored on input and its gradient row is written as 0.
+ * additionally carry its own smoothing value and its own CV mask (folds, main.cpp:693-696).  A masked node's
+ * rate row is not a variable (its gradient row is written as 0, optimisers and the annealer never move it); its
+ * VALUE is the rate the pruned branch keeps — what the reference's per-fold engine holds in its member `rates`
+ * (the full-data optimum, main.cpp:681,702-704), which still enters the root-children variance term when the
+ * pruned tip hangs off the root (pl_calc_parallel.cpp:866-878).
  * This is the data-parallel form of the fold loop (main.cpp:689), of the lambda grid
  * (main.cpp:668) and of multi-start optimisation (utils.cpp:475-553).                           */
 

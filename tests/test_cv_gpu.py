@@ -24,6 +24,13 @@ def _oracle_fit(flat, lam, tip, x0, lo, hi, nr):
         cvm[tip] = 1
         keep[tip - 1] = False
     o.set_smoothing(lam)
+    if tip is not None:
+        # the fold engine starts from, and a pruned tip keeps, the full-data optimum (cvstrates, main.cpp:681,702-704);
+        # x0 is that optimum in the full layout
+        fp_full, _ = tf.generate_param_order_vector(flat["free"], lf=False)
+        rates = np.array(flat["start_rates"], dtype=np.float64)
+        rates[1:] = x0[fp_full[1:n]]
+        o.set_state(rates, flat["start_dates"])
     o.set_cv(cvm if tip is not None else None)
     o.set_freeparams(False, use_cv=tip is not None)
     nrc = nr - (0 if tip is None else 1)
@@ -82,3 +89,30 @@ def test_batched_loocv_reaches_the_oracle_optimum(name, lams):
             f, x = _oracle_fit(flat, lam, int(tip), x_full, lo, hi, n - 1)
             chisq += cv.loocv_chisq(flat, x[:, None], [int(tip)], fp)[0]
         assert abs(res["chisq"][k] - chisq) <= 2e-3 * abs(chisq), (lam, res["chisq"][k], chisq)
+
+
+def test_pruned_tip_on_the_root_keeps_the_full_data_rate():
+    """examples/vib: node 174 is a tip that hangs off the root.  Pruned, its rate still enters the root-children
+    variance term (pl_calc_parallel.cpp:866-878) and must be the full-data optimum of that smoothing value, as in the
+    reference's fold engines (main.cpp:681,702-704) — not the engine's start rate."""
+    gd = Golden("vib")
+    flat = gd.flat
+    cals = [(t, lo, hi) for t, lo, hi in gd.meta["calibrations"]]
+    ft = tf.flatten_newick(gd.meta["newick"], gd.meta["numsites"], cals, seed=1)
+    n = len(flat["parents"])
+    root_tips = [int(t) for t in ft.tips_postorder if flat["parents"][t] == 0]
+    assert root_tips, "vib has a tip child of the root"
+    tips = root_tips + [int(t) for t in ft.tips_postorder if flat["parents"][t] != 0][:3]
+    lams = [1000.0, 10.0]
+    res = cv.loocv(flat, lams, tips, max_iter=6000)
+    fp, P = tf.generate_param_order_vector(flat["free"], lf=False)
+    lo, hi = batchopt.reference_bounds(flat, fp, P)
+    x0 = cv.start_vector(flat, P, n - 1)
+    for k, lam in enumerate(lams):
+        f_full, x_full = _oracle_fit(flat, lam, None, x0, lo, hi, n - 1)
+        assert abs(res["full_objective"][k] - f_full) <= 1e-7 * abs(f_full)
+        for g, tip in enumerate(tips):
+            f, x = _oracle_fit(flat, lam, tip, x_full, lo, hi, n - 1)
+            want = cv.loocv_chisq(flat, x[:, None], [tip], fp)[0]
+            got = res["terms"][k, g]
+            assert abs(got - want) <= 2e-3 * max(abs(want), 1e-3), (lam, tip, got, want)

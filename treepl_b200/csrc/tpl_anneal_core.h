@@ -72,7 +72,7 @@ TPL_HD double sa_duration(double hp, double h, bool& bad) {
 template <class View>
 TPL_HD double sa_rate(const View& V, int i) {
     const int rs = V.rslot(i);
-    return (rs >= 0 && !V.masked(i)) ? V.x(rs) : V.rfix(i);
+    return rs >= 0 ? V.x(rs) : V.rfix(i);     // a masked node keeps the rate of its X row (never proposed)
 }
 template <class View>
 TPL_HD double sa_date(const View& V, int i) {

@@ -113,11 +113,6 @@ __device__ __noinline__ RowAcc general_row_global(const EvalArgs& a, const TileA
             double r[2], h[2];
             rate_of(i, rec, r);
             date_of(i, rec, h);
-            if (MASK && mi && rec.y >= 0) {              // a masked vector ignores its rate row
-                const double rf = a.t.rfix[i];
-                if (mi & 1u) r[0] = rf;
-                if (mi & 2u) r[1] = rf;
-            }
             if (MODE == 0) {                             // calc_pl :74-78
 #pragma unroll
                 for (int l = 0; l < 2; l++) {
@@ -142,14 +137,6 @@ __device__ __noinline__ RowAcc general_row_global(const EvalArgs& a, const TileA
                 double rp[2] = {0.0, 0.0};
                 if (p != 0) {
                     rate_of(p, prec, rp);
-                    if (MASK) {
-                        const unsigned mp = mask_of(p);
-                        if (mp && prec.y >= 0) {
-                            const double rf = a.t.rfix[p];
-                            if (mp & 1u) rp[0] = rf;
-                            if (mp & 2u) rp[1] = rf;
-                        }
-                    }
                 }
 #pragma unroll
                 for (int l = 0; l < 2; l++) {

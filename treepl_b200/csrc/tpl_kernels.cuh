@@ -36,7 +36,7 @@ struct DevTree {
     const double* c;              // [n] char_durations
     const double* lf;             // [n] log_fact_char_durations
     const double* hfix;           // [n] member dates[]  (used when dslot < 0)
-    const double* rfix;           // [n] member rates[]  (used when rslot < 0 or masked)
+    const double* rfix;           // [n] member rates[]  (used when rslot < 0)
     // sparse date-bound rows (set_durations :887-896).  Only nodes whose [min,max] is NOT implied by
     // a neighbour are listed: h_i <= h_parent <= max_parent <= max_i makes an inherited max redundant
     // once every duration is checked to be >= 0, and likewise an inherited min through a child.
@@ -185,10 +185,11 @@ __global__ void __launch_bounds__(256) pl_main_kernel(const __grid_constant__ Ev
         for (int i = n0 + ty; i < n1; i += NY) {
             const int rs = t.rslot[i], ds = t.dslot[i];
             const bool mi = is_masked<MASKMODE>(a, i, lane);
-            // a per-vector mask ignores the rate row; with the engine-level mask the reference still
-            // scatters x into rates[i] when a slot exists (:82-89)
+            // calc_pl scatters x into rates[i] whenever a slot exists, masked or not (:82-89).  In the per-vector form a
+            // masked node's X row is the rate the node KEEPS (the member rate of the reference's fold engine, i.e. the
+            // full-data optimum, main.cpp:681,702-704): it is read like any other rate but it is not a variable.
             const bool rfree = (rs >= 0) && !(MASKMODE == 2 && mi);
-            const double r = rfree ? X[(size_t)rs * B + lane] : t.rfix[i];
+            const double r = (rs >= 0) ? X[(size_t)rs * B + lane] : t.rfix[i];
             const double h = (ds >= 0) ? X[(size_t)ds * B + lane] : t.hfix[i];
             if (MODE == 0) {                                             // calc_pl :74-78
                 if (rfree && r < 0.0) bad = 1;
@@ -217,8 +218,7 @@ __global__ void __launch_bounds__(256) pl_main_kernel(const __grid_constant__ Ev
                 }
                 if (!LF && !mi) {
                     if (p != 0) {
-                        const bool pm = is_masked<MASKMODE>(a, p, lane);
-                        const double rp = (prs >= 0 && !pm) ? X[(size_t)prs * B + lane] : t.rfix[p];
+                        const double rp = (prs >= 0) ? X[(size_t)prs * B + lane] : t.rfix[p];
                         const double q = r - rp;
                         acc_su = fma(q, q, acc_su);                      // :862-864
                         if (WANT_G) {
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const __grid
                 const int ch = t.children[t.child_off[0] + j];
                 const bool mc = is_masked<MASKMODE>(a, ch, lane);
                 const int crs = t.rslot[ch];
-                s_rc[j][tx] = (crs >= 0 && !(MASKMODE == 2 && mc)) ? X[(size_t)crs * B + lane] : t.rfix[ch];
+                s_rc[j][tx] = (crs >= 0) ? X[(size_t)crs * B + lane] : t.rfix[ch];
                 s_rcm[j][tx] = mc ? 1 : 0;
                 if (tx == 0) s_rcs[j] = crs;
             }
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const __grid
                     const int ch = t.children[j];
                     mc = is_masked<MASKMODE>(a, ch, lane);
                     const int crs = t.rslot[ch];
-                    rc = (crs >= 0 && !(MASKMODE == 2 && mc)) ? X[(size_t)crs * B + lane] : t.rfix[ch];
+                    rc = (crs >= 0) ? X[(size_t)crs * B + lane] : t.rfix[ch];
                 }
                 const double y = LOGPEN ? log(rc) : rc;
                 s += y;

@@ -158,7 +158,7 @@ template <class View>
 TPL_HD void node_values(const View& V, int i, bool& rfree, double& r, double& h, double& vr, double& vh) {
     const int rs = V.rslot(i), ds = V.dslot(i);
     rfree = rs >= 0 && !V.masked(i);
-    r = rfree ? V.x(rs) : V.rfix(i);
+    r = rs >= 0 ? V.x(rs) : V.rfix(i);        // a masked node keeps the rate of its X row (it is not a variable)
     h = ds >= 0 ? V.x(ds) : V.hfix(i);
     vr = rfree ? V.sc(rs) * r * V.v(rs) : 0.0;
     vh = ds >= 0 ? V.sc(ds) * V.v(ds) : 0.0;
