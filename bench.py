@@ -155,6 +155,25 @@ def measured_traffic(tips, batch, mode):
     return None
 
 
+def oracle_parity(flat, Xh, Fh, G, ad, lanes):
+    """CHECKER, never timed: vectors `lanes` of the bench batch against oracle/pl_oracle.c (the plain-C restatement of
+    pl_calc_parallel.cpp); -> max relative objective error and max gradient error (norm-wise floor of SURVEY 7)."""
+    from oracle import plo
+    o = plo.OracleProblem(flat)
+    o.set_smoothing(1.0)
+    o.set_freeparams(False)
+    f_rel = g_rel = 0.0
+    for b in lanes:
+        xb = np.ascontiguousarray(Xh[:, b])
+        f, g = o.calc_function_gradient(xb) if ad else o.calc_pl_and_gradient(xb)
+        gb = G[:, b].cpu().numpy()
+        f_rel = max(f_rel, abs(float(Fh[b]) - f) / max(abs(f), 1.0))
+        scale = np.maximum(np.abs(g), 1e-8 * np.max(np.abs(g)))
+        g_rel = max(g_rel, float(np.max(np.abs(gb - g) / scale)))
+    return {"f_rel": f_rel, "g_rel": g_rel, "vectors": list(lanes), "checker": "oracle/pl_oracle.c",
+            "gates": {"f_rel": 1e-10, "g_rel": 1e-8}}
+
+
 def cpu_reference_rate(flat, x, seconds=12.0, nthreads=None):
     """Reference calc_pl + calc_gradient on the host cores -> (evals/s, threads, sample description)."""
     from oracle import refbind as rb
@@ -558,6 +577,13 @@ def main():
     if not (np.isfinite(Fh).all() and (Fh < 1e15).all()):
         raise SystemExit("bench.py: engine returned infeasible/NaN objectives on the bench vectors")
 
+    # checker leg (outside the timed region, rank 0): two of the bench's own vectors against the CPU oracle
+    parity = None
+    if rank == 0:
+        parity = oracle_parity(flat, Xh, Fh, G, mode == eng.GRAD_AD, (0, B - 1))
+        if parity["f_rel"] > 1e-10 or parity["g_rel"] > 1e-8:
+            raise SystemExit("bench.py: the bench vectors fail the parity gate against the oracle: %r" % (parity,))
+
     plp.set_timing(True)
     if dist is not None:
         dist.barrier()
@@ -622,6 +648,7 @@ def main():
                                        "no flush needed)" % (args.tips, n, P, B, args.mode, 2 * P * B * 8 / 1e6),
                            "batch_per_gpu": B, "parallelism": "independent vectors sharded over %d GPU(s)" % world},
                 "gpu_launches": launches,
+                "parity": parity,
                 "clocks": clocks,
                 "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(P * B * 8),
                         "d2h_bytes_per_step": int(P * B * 8 + B * 8), "steps": e2e_steps},

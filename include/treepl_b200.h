@@ -54,7 +54,9 @@ int tpl_create(tpl_engine** out, int device, int numnodes,
 /* pl_calc_parallel::delete_ad_arrays + destructor (main.cpp:798) */
 void tpl_destroy(tpl_engine* e);
 
-/* message of the last failing call on this thread */
+/* message of the last failing call on this thread.  The evaluation entry points that return a double (tpl_calc_pl,
+ * tpl_calc_function_gradient, tpl_calc_pl_grad) clear it on entry: NaN with an EMPTY message is a NaN objective (the
+ * reference propagates NaN to its wrappers), NaN with a message is a failure. */
 const char* tpl_last_error(void);
 
 /* ---- configuration (public data members / setters of pl_calc_parallel) ---------------------- */

@@ -1,4 +1,4 @@
-"""Host logic of the batched optimiser (treepl_b200/batchopt.py) on CPU, with the ORACLE as the evaluator,
+"""Host logic of the batched optimiser (tests/torch_lbfgs_proto.py, an independent eager-torch L-BFGS) on CPU, with the ORACLE as the evaluator,
 against the reference's own END-TO-END results (`seed=1, nthreads=1` runs of the reference):
 the optimum it finds is the reference's final PL value and dated tree."""
 import numpy as np
@@ -7,6 +7,7 @@ import torch
 
 from golden_util import Golden
 from oracle import plo
+import torch_lbfgs_proto
 from treepl_b200 import batchopt, cv
 from treepl_b200 import treeflat as tf
 
@@ -36,7 +37,7 @@ def _fit(name, lams, max_iter):
     x0 = cv.start_vector(flat, P, n - 1)
     par = flat["parents"]
     ds = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
-    opt = batchopt.BatchedLBFGS(evaluator, P, B, n - 1, lo, hi, date_scale=ds)
+    opt = torch_lbfgs_proto.BatchedLBFGS(evaluator, P, B, n - 1, lo, hi, date_scale=ds)
     X, F, info = opt.minimize(np.repeat(x0[:, None], B, axis=1), max_iter=max_iter)
     return flat, fp, X, F, info
 

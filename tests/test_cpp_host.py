@@ -54,7 +54,7 @@ int main() {
 '''
 
 
-def test_cpp_host_mirror_compiles_links_and_fails_loudly_without_gpu():
+def _compile_and_run():
     lib = tbuild.build()
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     with tempfile.TemporaryDirectory() as td:
@@ -62,15 +62,42 @@ def test_cpp_host_mirror_compiles_links_and_fails_loudly_without_gpu():
         exe = os.path.join(td, "t")
         open(src, "w").write(SRC)
         subprocess.check_call([cxx, "-std=c++11", "-O1", "-I", ROOT, src, "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib)])
-        res = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+
+
+def _has_gpu():
     try:
         import torch
-        has_gpu = torch.cuda.is_available()
+        return torch.cuda.is_available()
     except Exception:
-        has_gpu = False
-    if has_gpu:
-        assert res.returncode == 0 and res.stdout.startswith("GPU f="), res.stdout
-        opt = [ln for ln in res.stdout.splitlines() if ln.startswith("OPT ")][0].split()
-        assert float(opt[1].split("=")[1]) < float(opt[2].split("=")[1]) and opt[3] in ("status=1", "status=2", "status=3"), res.stdout
-    else:
-        assert res.returncode == 3 and "EXCEPTION" in res.stdout and "no CUDA device" in res.stdout, res.stdout
+        return False
+
+
+def test_cpp_host_mirror_compiles_links_and_fails_loudly_without_gpu():
+    if _has_gpu():
+        pytest.skip("a CUDA device is present: covered by test_cpp_host_mirror_on_the_gpu")
+    res = _compile_and_run()
+    assert res.returncode == 3 and "EXCEPTION" in res.stdout and "no CUDA device" in res.stdout, res.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_on_the_gpu():
+    """the same program on the B200: single-point calls through the mirror == the oracle, and the device-resident
+    batched optimiser reached through the mirror improves the objective and reports a convergence status."""
+    res = _compile_and_run()
+    assert res.returncode == 0 and res.stdout.startswith("GPU f="), res.stdout
+    import numpy as np
+    from golden_util import Golden
+    from oracle import plo
+    flat = dict(Golden("test").flat)
+    flat["lf"] = np.ones(13)
+    flat["start_dates"] = np.array([10, 3.5, 0, 0, 6.7, 3.5, 0, 1.5, 0, 0, 3.7, 0, 0], dtype=np.float64)
+    flat["start_rates"] = np.full(13, 0.08)
+    flat["start_durations"] = np.ones(13)
+    o = plo.OracleProblem(flat)
+    x0 = o.set_freeparams(False)
+    f, g = o.calc_pl_and_gradient(x0)
+    first = res.stdout.splitlines()[0].split()
+    assert abs(float(first[1].split("=")[1]) - f) <= 1e-6 and abs(float(first[3].split("=")[1]) - g[0]) <= 1e-5 * abs(g[0]), (res.stdout, f, g[0])
+    opt = [ln for ln in res.stdout.splitlines() if ln.startswith("OPT ")][0].split()
+    assert float(opt[1].split("=")[1]) < float(opt[2].split("=")[1]) and opt[3] in ("status=1", "status=2", "status=3"), res.stdout

@@ -57,3 +57,34 @@ def test_chisq_terms_follow_the_reference_formula():
     grp = tips[:12]
     assert np.isclose(cv.group_chisq(flat, x, grp, fp, True), np.sum(want) / 12, rtol=1e-13)
     assert np.isclose(cv.group_chisq(flat, x, grp, fp, False), np.sum(want), rtol=1e-13)
+
+
+def test_smoothing_grid_follows_the_reference_fixups():
+    """main.cpp:275-284 (swap start/stop, invert a step > 1 in float) and :668,814 (while(curcv >= cvstop) curcv *= step)."""
+    import pytest
+    from treepl_b200 import config
+    g = config.smoothing_grid(1000.0, 0.1, 0.1)
+    cur, want = 1000.0, []
+    while cur >= 0.1:
+        want.append(cur)
+        cur *= 0.1
+    assert g == want and len(g) in (4, 5)
+    assert config.smoothing_grid(0.1, 1000.0, 0.1) == want                       # swapped
+    g10 = config.smoothing_grid(1000.0, 0.1, 10)                                 # inverted in float: terminates
+    assert 4 <= len(g10) <= 5 and abs(g10[1] - 100.0) < 1e-4 and g10[1] != 100.0
+    assert config.Config(cvstart=0.0001, cvstop=100.0, cvmultstep=0.1).smoothing_grid()[0] == 100.0   # examples/pl4203.cppr8s
+    for bad in (1.0, 0.0, -2.0):
+        with pytest.raises(ValueError):
+            config.smoothing_grid(1000.0, 0.1, bad)
+
+
+def test_control_file_tokens_like_the_reference():
+    """mrca / min / max values tokenise on commas and blanks (main.cpp:109-137); randomcv implies cv (:237-239);
+    atoi / atof tolerate trailing text."""
+    from treepl_b200 import config
+    cfg = config.parse_config_text("treefile = t.tre\nnumsites = 2744 sites\nmrca = A t1,t2  t3\nmin = A,10\nmax = A 20.5x\n"
+                                   "randomcv\n[cv]\n#thorough\ncvmultstep = 10\nsmooth = 1e-4\n")
+    assert cfg.mrcas == {"A": ["t1", "t2", "t3"]} and cfg.mins == {"A": 10.0} and cfg.maxs == {"A": 20.5}
+    assert cfg.randomcv and cfg.cv and not cfg.thorough
+    assert cfg.numsites == 2744 and cfg.smooth == 1e-4
+    assert len(cfg.smoothing_grid()) in (4, 5)

@@ -66,3 +66,35 @@ def test_shard_items_partition():
         assert seen == list(range(59))
         sizes = [len(cvshard.shard_items(59, r, world)) for r in range(world)]
         assert max(sizes) - min(sizes) <= 1
+
+
+def _raise_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        try:
+            cvshard.raise_together(ValueError("start point infeasible") if rank == 1 else None, dist=dist)
+            out.put((rank, "no error"))
+        except ValueError as ex:
+            out.put((rank, "ValueError"))
+        except RuntimeError as ex:
+            out.put((rank, str(ex)))
+        cvshard.raise_together(None, dist=dist)            # and the group is still usable afterwards
+    finally:
+        dist.destroy_process_group()
+
+
+def test_a_failure_on_one_rank_is_raised_on_every_rank():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_raise_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(out.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[1] == "ValueError" and "rank(s) [1]" in res[0]

@@ -205,6 +205,52 @@ def test_large_tree_properties_100k_nodes():
     plp.close()
 
 
+def test_headline_bench_configuration_against_the_oracle():
+    """The EXACT problem and vectors bench.py times (synthetic 100,000-tip tree, N = 199,999, P = 299,996, 16 bounded
+    calibrations, B = 256, descriptor ring kernel) against oracle/pl_oracle.c: both gradient flavours, three of the bench's
+    own vectors, one CV-masked vector with its own smoothing value and one infeasible vector."""
+    import bench
+    flat = bench.build_problem(100000)
+    n = flat["parents"].shape[0]
+    fp, P = eng.generate_param_order_vector(flat["free"], lf=False)
+    assert (n, P) == (199999, 299996)
+    B = 256
+    X = bench.make_vectors(flat, P, B, 1000)
+    tips = np.flatnonzero(flat["child_counts"] == 0)
+    rng = np.random.RandomState(3)
+    masked = np.sort(rng.choice(tips, 10000, replace=False))       # one random-subsample fold of BASELINE config 5
+    X[:, 9] = X[:, 8]
+    X[n - 1 + 12345, 200] = -1.0                                   # a negative date: infeasible
+    lam = np.ones(B)
+    lam[9] = 37.0
+    plp = eng.PLCalcParallel.from_flat(flat)
+    plp.set_freeparams(P, False, fp)
+    plp.smoothing = 1.0
+    plp.batch_configure(B, lane_smoothing=lam, masks=[masked if b == 9 else [] for b in range(B)])
+    o = plo.OracleProblem(flat)
+    for mode in (eng.GRAD_AD, eng.GRAD_ANALYTIC):
+        F, G = plp.calc_pl_grad_batch(X, mode=mode)
+        assert plp.last_kernel_generation() == 4
+        assert F[200] == 1e15
+        for b in (0, 101, 255, 9):
+            cv = np.zeros(n, np.int32)
+            keep = np.ones(P, dtype=bool)
+            if b == 9:
+                cv[masked] = 1
+                keep[masked - 1] = False
+            o.set_state(_fold_rates(flat, X[:, b], masked if b == 9 else []), flat["start_dates"])
+            o.set_smoothing(lam[b])
+            o.set_cv(cv)
+            o.set_freeparams(False, use_cv=True)
+            xb = np.ascontiguousarray(X[keep, b])
+            f, g = o.calc_function_gradient(xb) if mode == eng.GRAD_AD else o.calc_pl_and_gradient(xb)
+            assert close_f(F[b], f), (mode, b, F[b], f)
+            assert rel_err(G[keep, b], g) < G_TOL, (mode, b, rel_err(G[keep, b], g))
+            assert (G[~keep, b] == 0).all()
+        assert F[9] != F[8]
+    plp.close()
+
+
 def test_state_readback_and_freeparams_emission():
     """evaluate, then read back rates/dates/durations (main.cpp:865-878) and switch LF -> PL (main.cpp:828-833)."""
     gd = Golden("pl4203")

@@ -9,6 +9,7 @@ are kept verbatim in `.raw`.
 from __future__ import annotations
 
 import os
+import re
 from dataclasses import dataclass, field
 
 
@@ -53,18 +54,46 @@ class Config:
         return self.treefile if os.path.isabs(self.treefile) else os.path.join(self.basedir, self.treefile)
 
     def smoothing_grid(self):
-        """CV grid as the while-loop of main.cpp:668,814 walks it (after the swap/invert fix-ups of :275-284)."""
-        start, stop, mult = self.cvstart, self.cvstop, self.cvmultstep
-        if start < stop:
-            start, stop = stop, start
-        if mult > 1:
-            mult = 1.0 / mult
-        g = []
-        cur = start
-        while cur >= stop:
-            g.append(cur)
-            cur *= mult
-        return g
+        return smoothing_grid(self.cvstart, self.cvstop, self.cvmultstep)
+
+
+def smoothing_grid(cvstart, cvstop, cvmultstep):
+    """CV grid as the while-loop of main.cpp:668,814 walks it (`while(curcv >= cvstop) ... curcv *= cvmultstep`) after
+    the fix-ups of main.cpp:275-284: start/stop swapped when start < stop, a step > 1 inverted (in float, as the
+    reference's `1/(float)cvmultstep`).  A step of exactly 1 or <= 0 never terminates / never descends in the reference;
+    it is rejected here."""
+    import numpy as np
+    start, stop, mult = float(cvstart), float(cvstop), float(cvmultstep)
+    if start < stop:
+        start, stop = stop, start
+    if mult > 1:
+        mult = float(np.float32(1.0) / np.float32(mult))
+    if not (0.0 < mult < 1.0):
+        raise ValueError("cvmultstep = %r: the smoothing grid needs a step in (0, 1) (or > 1, which is inverted)" % cvmultstep)
+    if stop <= 0.0:
+        raise ValueError("cvstop = %r: the geometric smoothing grid needs a positive lower end" % cvstop)
+    g = []
+    cur = start
+    while cur >= stop:
+        g.append(cur)
+        cur *= mult
+    return g
+
+
+def _tokens(val):
+    """main.cpp tokenises mrca / min / max values on commas and blanks (Tokenize(..., ",     "))."""
+    return [t for t in re.split(r"[,\s]+", val or "") if t]
+
+
+def _atof(tok):
+    """atof: the longest numeric prefix, 0 when there is none"""
+    m = re.match(r"\s*[-+]?(\d+\.?\d*([eE][-+]?\d+)?|\.\d+([eE][-+]?\d+)?)", tok or "")
+    return float(m.group(0)) if m else 0.0
+
+
+def _atoi(tok):
+    m = re.match(r"\s*[-+]?\d+", tok or "")
+    return int(m.group(0)) if m else 0
 
 
 def parse_config_text(text, basedir="."):
@@ -81,28 +110,29 @@ def parse_config_text(text, basedir="."):
         if key == "treefile":
             cfg.treefile = val
         elif key == "numsites":
-            cfg.numsites = int(val)
+            cfg.numsites = _atoi(val)
         elif key == "smooth":
-            cfg.smooth = float(val)
+            cfg.smooth = _atof(val)
         elif key == "mrca":
-            parts = val.split()
+            parts = _tokens(val)
             cfg.mrcas[parts[0]] = parts[1:]
         elif key == "min":
-            parts = val.split()
-            cfg.mins[parts[0]] = float(parts[1])
+            parts = _tokens(val)
+            cfg.mins[parts[0]] = _atof(parts[1])
         elif key == "max":
-            parts = val.split()
-            cfg.maxs[parts[0]] = float(parts[1])
+            parts = _tokens(val)
+            cfg.maxs[parts[0]] = _atof(parts[1])
         elif key == "cv":
             cfg.cv = True
         elif key == "randomcv":
             cfg.randomcv = True
+            cfg.cv = True                        # main.cpp:237-239 sets both
         elif key == "cvstart":
-            cfg.cvstart = float(val)
+            cfg.cvstart = _atof(val)
         elif key == "cvstop":
-            cfg.cvstop = float(val)
+            cfg.cvstop = _atof(val)
         elif key == "cvmultstep":
-            cfg.cvmultstep = float(val)
+            cfg.cvmultstep = _atof(val)
         elif key == "log_pen":
             cfg.log_pen = True
         elif key == "thorough":
@@ -114,17 +144,17 @@ def parse_config_text(text, basedir="."):
         elif key == "set1":
             cfg.set1 = True
         elif key == "seed":
-            cfg.seed = int(val)
+            cfg.seed = _atoi(val)
         elif key == "nthreads":
-            cfg.nthreads = int(val)
+            cfg.nthreads = _atoi(val)
         elif key == "outfile":
             cfg.outfile = val
         elif key == "cvoutfile":
             cfg.cvoutfile = val
         elif key == "opt":
-            cfg.opt = int(val)
+            cfg.opt = _atoi(val)
         elif key == "optad":
-            cfg.optad = int(val)
+            cfg.optad = _atoi(val)
     return cfg
 
 

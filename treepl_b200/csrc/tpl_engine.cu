@@ -12,6 +12,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "tpl_kernels.cuh"
@@ -181,6 +182,15 @@ struct tpl_engine {
         DevBuf<double> sa_hmin, sa_hmax;
         DevBuf<unsigned char> sa_chains;
     } opt;
+    // generation-4 launch state that does not change between launches on the same buffers: the two tensor maps of X
+    // (keyed by pointer and shape) and the opt-in shared-memory size already granted to each kernel instantiation
+    struct MapCache {
+        const double* X = nullptr;
+        int P = 0, B = 0;
+        CUtensorMap mapR, mapD;
+    } maps[4];
+    int maps_next = 0;
+    std::vector<std::pair<const void*, size_t> > smem_granted;
     // optional per-launch device timing (bench.py roofline): events around the main kernel
     bool timing = false;
     std::vector<cudaEvent_t> ev;      // triples: before main, after main, after finalize
@@ -492,6 +502,7 @@ bool make_x_map(CUtensorMap* m, const double* X, int P, int B, int box_rows) {
 }
 
 struct LaunchCfg {
+    tpl_engine* eng;
     int gen;
     int stages = 3;
     tpl::DescArgs da;
@@ -506,6 +517,22 @@ struct LaunchCfg {
     cudaEvent_t* ev;
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (engine, kernel instantiation, size), not per launch
+template <class K>
+cudaError_t grant_smem(tpl_engine* e, K kern, size_t smem) {
+    const void* key = (const void*)kern;
+    for (auto& kv : e->smem_granted)
+        if (kv.first == key) {
+            if (kv.second >= smem) return cudaSuccess;
+            cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err == cudaSuccess) kv.second = smem;
+            return err;
+        }
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess) e->smem_granted.push_back(std::make_pair(key, smem));
+    return err;
+}
+
 template <int MODE, bool LF, bool LOGPEN, bool WANT_G, int MASKMODE>
 cudaError_t launch_pair(const tpl::EvalArgs& a, const LaunchCfg& c) {
     if (c.ev) cudaEventRecord(c.ev[0], c.s);
@@ -516,23 +543,23 @@ cudaError_t launch_pair(const tpl::EvalArgs& a, const LaunchCfg& c) {
                 cudaError_t e = cudaSuccess;
                 if (c.stages == 3) {
                     auto kern = tpl::pl_desc_kernel<MODE, false, WANT_G, MASKMODE == 2, 3, G4_NCW>;
-                    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+                    e = grant_smem(c.eng, kern, c.smem);
                     if (e != cudaSuccess) return e;
                     kern<<<c.grid, c.block, c.smem, c.s>>>(a, c.ta, c.da, c.tmapR, c.tmapD);
                 } else {
                     auto kern = tpl::pl_desc_kernel<MODE, false, WANT_G, MASKMODE == 2, 2, G4_NCW>;
-                    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+                    e = grant_smem(c.eng, kern, c.smem);
                     if (e != cudaSuccess) return e;
                     kern<<<c.grid, c.block, c.smem, c.s>>>(a, c.ta, c.da, c.tmapR, c.tmapD);
                 }
             } else if (c.gen == 3) {
                 auto kern = tpl::pl_persist_kernel<MODE, LOGPEN, WANT_G, MASKMODE == 2>;
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+                cudaError_t e = grant_smem(c.eng, kern, c.smem);
                 if (e != cudaSuccess) return e;
                 kern<<<c.grid, c.block, c.smem, c.s>>>(a, c.ta);
             } else {
                 auto kern = tpl::pl_tile_kernel<MODE, LOGPEN, WANT_G, MASKMODE == 2>;
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+                cudaError_t e = grant_smem(c.eng, kern, c.smem);
                 if (e != cudaSuccess) return e;
                 kern<<<c.grid, c.block, c.smem, c.s>>>(a, c.ta);
             }
@@ -599,6 +626,7 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
     if (e->force_gen == 4 && desc_legal) gen = 4;
     const bool gen2 = gen >= 2;
     LaunchCfg c;
+    c.eng = e;
     c.gen = gen;
     int ntiles, tile;
     size_t npart;
@@ -687,9 +715,20 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
     c.da.nchunks = nchunks2;
     c.da.ncta = G;
     if (gen == 4) {
-        if (!make_x_map(&c.tmapR, dX, e->numparams, B, tpl::TILE_NODES) ||
-            !make_x_map(&c.tmapD, dX, e->numparams, B, tpl::DESC_DBOX))
-            return fail(TPL_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+        tpl_engine::MapCache* mc = nullptr;
+        for (auto& m : e->maps)
+            if (m.X == dX && m.P == e->numparams && m.B == B) mc = &m;
+        if (!mc) {
+            mc = &e->maps[e->maps_next];
+            e->maps_next = (e->maps_next + 1) % 4;
+            mc->X = nullptr;
+            if (!make_x_map(&mc->mapR, dX, e->numparams, B, tpl::TILE_NODES) ||
+                !make_x_map(&mc->mapD, dX, e->numparams, B, tpl::DESC_DBOX))
+                return fail(TPL_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+            mc->X = dX; mc->P = e->numparams; mc->B = B;
+        }
+        c.tmapR = mc->mapR;
+        c.tmapD = mc->mapD;
     }
     c.s = s;
     c.ev = nullptr;
@@ -703,6 +742,7 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
 // single point: host x -> device, evaluate, bring f (and g) back
 double eval_point(tpl_engine* e, const double* x, double* g, int mode, bool keep_state) {
     const double nan = std::numeric_limits<double>::quiet_NaN();
+    g_err.clear();      // a NaN RESULT is legal (the reference propagates NaN); callers tell it from a failure by tpl_last_error()
     if (!e || !x) { fail(TPL_ERR_ARG, "null argument"); return nan; }
     if (!e->have_fp) { fail(TPL_ERR_STATE, "set_freeparams has not been called"); return nan; }
     if (cudaSetDevice(e->device) != cudaSuccess) { fail(TPL_ERR_CUDA, "cudaSetDevice failed"); return nan; }
@@ -917,30 +957,36 @@ int tpl_get_durations(tpl_engine* e, double* out) {
 
 int tpl_batch_configure(tpl_engine* e, int B, const double* lane_smoothing, const int* mask_off, const int* mask_nodes) {
     if (!e || B < 1) return fail(TPL_ERR_ARG, "null or B < 1");
+    // validate everything first: a failed call leaves the previous configuration intact
+    if (mask_off) {
+        if (mask_off[0] != 0) return fail(TPL_ERR_ARG, "mask_off[0] != 0");
+        for (int b = 0; b < B; b++)
+            if (mask_off[b + 1] < mask_off[b]) return fail(TPL_ERR_ARG, "mask_off is not non-decreasing");
+        if (!mask_nodes && mask_off[B] > 0) return fail(TPL_ERR_ARG, "mask_nodes is null");
+        for (int k = 0; k < mask_off[B]; k++)
+            if (mask_nodes[k] < 0 || mask_nodes[k] >= e->n) return fail(TPL_ERR_ARG, "mask node out of range");
+    }
     CK(cudaSetDevice(e->device));
-    e->cfg_B = B;
-    e->cfg_lambda = lane_smoothing != nullptr;
-    e->cfg_mask = mask_off != nullptr;
-    if (e->cfg_lambda) {
+    if (lane_smoothing) {
         std::vector<double> v(lane_smoothing, lane_smoothing + B);
         CK(e->d_lane_lambda.upload(v, e->stream));
         CK(cudaStreamSynchronize(e->stream));
     }
-    if (e->cfg_mask) {
-        if (!mask_nodes && mask_off[B] > 0) return fail(TPL_ERR_ARG, "mask_nodes is null");
-        const int nch = (B + 63) / 64;
+    int nch = e->cfg_nchunks;
+    if (mask_off) {
+        nch = (B + 63) / 64;
         const size_t npad = (size_t)((e->n + tpl::TILE_NODES - 1) / tpl::TILE_NODES) * tpl::TILE_NODES;
         std::vector<unsigned long long> bits(npad * nch, 0ull);
         for (int b = 0; b < B; b++)
-            for (int k = mask_off[b]; k < mask_off[b + 1]; k++) {
-                int node = mask_nodes[k];
-                if (node < 0 || node >= e->n) return fail(TPL_ERR_ARG, "mask node out of range");
-                bits[(size_t)(b >> 6) * npad + node] |= 1ull << (b & 63);
-            }
-        e->cfg_nchunks = nch;
+            for (int k = mask_off[b]; k < mask_off[b + 1]; k++)
+                bits[(size_t)(b >> 6) * npad + mask_nodes[k]] |= 1ull << (b & 63);
         CK(e->d_lanemask.upload(bits, e->stream));
         CK(cudaStreamSynchronize(e->stream));
     }
+    e->cfg_B = B;
+    e->cfg_lambda = lane_smoothing != nullptr;
+    e->cfg_mask = mask_off != nullptr;
+    e->cfg_nchunks = nch;
     return TPL_OK;
 }
 
@@ -961,14 +1007,10 @@ int tpl_calc_pl_grad_batch(tpl_engine* e, int B, const double* X, double* F, dou
         // of sub-batch k and the download of sub-batch k-1 overlap (PCIe is full duplex; a single H2D -> kernel
         // -> D2H sequence leaves each direction idle half of the time).  X and G are [P][B] on the host, so a
         // sub-batch is a 2-D copy: P rows of 512 bytes with pitch 8 B.
-        static int sb_env = -1;                        // tuning hook: TPL_PIPE_SB = 32, 64 or 128
-        if (sb_env < 0) { const char* v = getenv("TPL_PIPE_SB"); sb_env = v ? atoi(v) : 0; if (sb_env != 32 && sb_env != 64 && sb_env != 128) sb_env = 0; }
         // 64-vector sub-batches (512-byte rows of the 2-D copies) measured best: 32 shortens the pipeline's fill and
         // drain but its 256-byte rows copy slower (14.4 k vs 16.5 k evals/s), 128 lengthens fill and drain (14.2 k).
         // Per-vector CV masks are addressed in 64-vector words, so masked batches never go below 64.
-        const bool masked_cfg = e->cfg_mask && e->cfg_B == B;
-        int SB = sb_env ? sb_env : 64;
-        if (masked_cfg && SB < 64) SB = 64;
+        const int SB = 64;
         const int nsub = (B + SB - 1) / SB;
         for (int k = 0; k < 3; k++) {
             if (!e->pstream[k]) CK(cudaStreamCreateWithFlags(&e->pstream[k], cudaStreamNonBlocking));

@@ -16,6 +16,21 @@ struct EventPair {
     }
 };
 
+// the replayed step graph and the engine's timing flag (no event records inside a capture): released / restored on
+// every exit path, CK early returns included
+struct GraphGuard {
+    tpl_engine* e;
+    bool was_timing;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    explicit GraphGuard(tpl_engine* eng) : e(eng), was_timing(eng->timing) { e->timing = false; }
+    ~GraphGuard() {
+        if (gexec) cudaGraphExecDestroy(gexec);
+        if (graph) cudaGraphDestroy(graph);
+        e->timing = was_timing;
+    }
+};
+
 // ---- device-resident batched L-BFGS (tpl_lbfgs_core.h / tpl_lbfgs.cuh) --------------------------------------
 
 template <int HM>
@@ -55,40 +70,32 @@ int run_optimizer(tpl_engine* e, tplopt::OptArgs a, int B, int mode, int max_ste
     if (rc != TPL_OK) return rc;
     steps++;
     launches += per_step;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t gexec = nullptr;
-    const bool was_timing = e->timing;
-    e->timing = false;
+    GraphGuard gg(e);
     if (use_graph) {
         CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         for (int k = 0; k < check_every && rc == TPL_OK; k++) rc = one_step();
-        cudaError_t ce = cudaStreamEndCapture(s, &graph);
-        if (rc != TPL_OK || ce != cudaSuccess) {
-            if (graph) cudaGraphDestroy(graph);
-            e->timing = was_timing;
+        cudaError_t ce = cudaStreamEndCapture(s, &gg.graph);
+        if (rc != TPL_OK || ce != cudaSuccess)
             return rc != TPL_OK ? rc : fail(TPL_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
-        }
-        CK(cudaGraphInstantiate(&gexec, graph, 0));
+        CK(cudaGraphInstantiate(&gg.gexec, gg.graph, 0));
     }
     int ndone = 0;
     while (steps < max_steps) {
-        if (use_graph) {
-            CK(cudaGraphLaunch(gexec, s));
+        // the last chunk is clamped to max_steps (plain launches; a graph replays whole chunks only)
+        const int chunk = std::min(check_every, max_steps - steps);
+        if (use_graph && chunk == check_every) {
+            CK(cudaGraphLaunch(gg.gexec, s));
         } else {
-            for (int k = 0; k < check_every && rc == TPL_OK; k++) rc = one_step();
-            if (rc != TPL_OK) break;
+            for (int k = 0; k < chunk && rc == TPL_OK; k++) rc = one_step();
+            if (rc != TPL_OK) return rc;
         }
-        steps += check_every;
-        launches += per_step * check_every;
+        steps += chunk;
+        launches += per_step * chunk;
         CK(cudaMemcpyAsync(e->opt.h_done.p, a.ndone, sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         ndone = e->opt.h_done.p[0];
         if (ndone >= B) break;
     }
-    if (gexec) cudaGraphExecDestroy(gexec);
-    if (graph) cudaGraphDestroy(graph);
-    e->timing = was_timing;
-    if (rc != TPL_OK) return rc;
     opt_final_kernel<<<fgrd, blk, 0, s>>>(a, e->opt.Fout.p);
     launches++;
     CK(cudaGetLastError());
@@ -233,40 +240,32 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
     if (rc != TPL_OK) return rc;
     steps++;
     launches += per_step;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t gexec = nullptr;
-    const bool was_timing = e->timing;
-    e->timing = false;
+    GraphGuard gg(e);
     if (o.use_graph) {
         CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         for (int k = 0; k < check_every && rc == TPL_OK; k++) rc = one_step();
-        cudaError_t ce = cudaStreamEndCapture(s, &graph);
-        if (rc != TPL_OK || ce != cudaSuccess) {
-            if (graph) cudaGraphDestroy(graph);
-            e->timing = was_timing;
+        cudaError_t ce = cudaStreamEndCapture(s, &gg.graph);
+        if (rc != TPL_OK || ce != cudaSuccess)
             return rc != TPL_OK ? rc : fail(TPL_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
-        }
-        CK(cudaGraphInstantiate(&gexec, graph, 0));
+        CK(cudaGraphInstantiate(&gg.gexec, gg.graph, 0));
     }
     int ndone = 0;
     while (steps < max_steps) {
-        if (o.use_graph) {
-            CK(cudaGraphLaunch(gexec, s));
+        // the last chunk is clamped to max_steps (plain launches; a graph replays whole chunks only)
+        const int chunk = std::min(check_every, max_steps - steps);
+        if (o.use_graph && chunk == check_every) {
+            CK(cudaGraphLaunch(gg.gexec, s));
         } else {
-            for (int k = 0; k < check_every && rc == TPL_OK; k++) rc = one_step();
-            if (rc != TPL_OK) break;
+            for (int k = 0; k < chunk && rc == TPL_OK; k++) rc = one_step();
+            if (rc != TPL_OK) return rc;
         }
-        steps += check_every;
-        launches += per_step * check_every;
+        steps += chunk;
+        launches += per_step * chunk;
         CK(cudaMemcpyAsync(w.h_done.p, a.ndone, sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         ndone = w.h_done.p[0];
         if (ndone >= B) break;
     }
-    if (gexec) cudaGraphExecDestroy(gexec);
-    if (graph) cudaGraphDestroy(graph);
-    e->timing = was_timing;
-    if (rc != TPL_OK) return rc;
     tn_final_kernel<<<rgrd, blk, 0, s>>>(a, w.Fout.p);
     launches++;
     CK(cudaGetLastError());

@@ -54,28 +54,39 @@ def loocv_chisq(flat, X, lane_tip, freeparams):
     return out
 
 
-def _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose, **opt):
+def _minimize(plp, X0, lo, hi, nr, dscale, max_iter, history, verbose, **opt):
     """-> (X, F, info) with info keys iterations (max accepted steps), nfev (batched evaluations), converged [B].
     method (option): 1 = batched truncated Newton (default; gradient-converged optima in far fewer evaluations),
     0 = batched L-BFGS (also serves the log-penalty objective)."""
     P, B = X0.shape
-    if native:
-        opt.setdefault("method", 1)
-        # chi-square is far more sensitive to the last digits of the optimum than the objective is (at small
-        # smoothing the pruned tip's prediction hangs on weakly determined rates): converge tightly
-        if opt["method"] == 0:
-            opt.setdefault("ftol", 1e-15)
-            opt.setdefault("patience", 40)
-        X, F, info = plp.optimize_batch(X0, lo, hi, mode=eng.GRAD_AD, history=history, max_steps=20 * max_iter,
-                                        date_scale=dscale, use_graph=1, **opt)
-        bad = np.nonzero(info["status"] == 4)[0]
-        if bad.size:
-            raise ValueError("start point infeasible for vectors %s" % bad.tolist()[:8])
-        return X, F, {"iterations": int(info["iterations"].max()), "nfev": info["steps"],
-                      "converged": (info["status"] >= 1) & (info["status"] <= 3), "device_ms": info["device_ms"],
-                      "launches": info["launches"], "cg_iterations": info["cg_iterations"]}
-    opt = batchopt.BatchedLBFGS(plp, P, B, nr, lo, hi, date_scale=dscale)
-    return opt.minimize(X0, max_iter=max_iter, verbose=verbose)
+    opt.setdefault("method", 1)
+    # chi-square is far more sensitive to the last digits of the optimum than the objective is (at small
+    # smoothing the pruned tip's prediction hangs on weakly determined rates): converge tightly
+    if opt["method"] == 0:
+        opt.setdefault("ftol", 1e-15)
+        opt.setdefault("patience", 40)
+    X, F, info = plp.optimize_batch(X0, lo, hi, mode=eng.GRAD_AD, history=history, max_steps=20 * max_iter,
+                                    date_scale=dscale, use_graph=1, **opt)
+    bad = np.nonzero(info["status"] == 4)[0]
+    if bad.size:
+        raise ValueError("start point infeasible for vectors %s" % bad.tolist()[:8])
+    return X, F, {"iterations": int(info["iterations"].max()), "nfev": info["steps"],
+                  "converged": (info["status"] >= 1) & (info["status"] <= 3), "device_ms": info["device_ms"],
+                  "launches": info["launches"], "cg_iterations": info["cg_iterations"]}
+
+
+def _minimize_together(dist, dev, plp, *args, **opt):
+    """_minimize on every rank; a failure on one rank (e.g. an infeasible start) is raised on all of them instead of
+    leaving the others blocked in the next collective."""
+    from . import cvshard
+
+    err, res = None, None
+    try:
+        res = _minimize(plp, *args, **opt)
+    except (ValueError, eng.EngineError) as ex:
+        err = ex
+    cvshard.raise_together(err, dist=dist, device=dev)
+    return res
 
 
 def sample_random_groups(flat, tips, n_groups, frac, seed=1):
@@ -137,19 +148,15 @@ def group_chisq(flat, x, group, freeparams, randomcv):
 
 
 def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_pen=False, max_iter=3000, verbose=False,
-                   native=True, history=8, dist=None, **opt):
+                   history=8, dist=None, **opt):
     """-> dict(chisq per smoothing value, best smoothing, timings).  groups: list of folds, each a list of tip node
     numbers (LOOCV: one tip per fold in externalNodes order, main.cpp:603-608).
     Every (smoothing value, fold) pair is one work item.  With `dist` (torch.distributed, one process per GPU) the
     items are dealt block-cyclically to the ranks (cvshard.shard_items), each rank optimises its share as one batch,
     and the per-item chi-square terms are all-gathered and summed in item order (deterministic for every world size).
-    native=True: the library's own device-resident L-BFGS (tpl_optimize_batch); False: the torch prototype."""
+    The optimiser is the library's own device-resident one (tpl_optimize_batch)."""
     from . import cvshard
 
-    if not native:
-        import torch
-
-        torch.cuda.set_device(device)
     world = dist.get_world_size() if dist is not None else 1
     rank = dist.get_rank() if dist is not None else 0
     n = len(flat["parents"])
@@ -176,7 +183,7 @@ def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_p
     x0 = start_vector(flat, P, nr)
     par = flat["parents"]
     dscale = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
-    Xl, Fl, info1 = _minimize(plp, np.repeat(x0[:, None], B1, axis=1), lo, hi, nr, dscale, max_iter, native, history, verbose, **opt)
+    Xl, Fl, info1 = _minimize_together(dist, dev, plp, np.repeat(x0[:, None], B1, axis=1), lo, hi, nr, dscale, max_iter, history, verbose, **opt)
     packed = {k: np.concatenate([Xl[:, b], [Fl[b], float(info1["converged"][b])]]) for b, k in enumerate(mine_k)}
     allfull = cvshard.gather_vectors(packed, K, P + 2, dist=dist, device=dev)
     Xfull, Ffull, full_conv = allfull[:P], allfull[P], allfull[P + 1]
@@ -196,7 +203,7 @@ def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_p
         masks.append([int(t) for t in groups[g]])
         X0[:, b] = Xfull[:, k]
     plp.batch_configure(B2p, lane_smoothing=lam2, masks=masks)
-    Xcv, Fcv, info2 = _minimize(plp, X0, lo, hi, nr, dscale, max_iter, native, history, verbose, **opt)
+    Xcv, Fcv, info2 = _minimize_together(dist, dev, plp, X0, lo, hi, nr, dscale, max_iter, history, verbose, **opt)
     t2 = time.perf_counter()
     local = {item: group_chisq(flat, Xcv[:, b], groups[item % T], fp, randomcv) for b, item in enumerate(mine)}
     full, _ = cvshard.gather_fold_scores(local, n_items, dist=dist, device=dev)
@@ -250,17 +257,18 @@ def multistart(flat, smoothing, n_starts, jitter=0.3, seed=1, device=0, dist=Non
     par = flat["parents"]
     dscale = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
     t0 = time.perf_counter()
-    X, F, info = _minimize(plp, X0, lo, hi, nr, dscale, 3000, True, 8, False, **opt)
-    t1 = time.perf_counter()
-    Fm = F[: len(mine)]
-    ok = info["converged"][: len(mine)]
-    kbest = int(np.argmin(np.where(ok, Fm, np.inf))) if len(mine) else 0
     dev = None
     if dist is not None and dist.get_backend() == "nccl":
         import torch
 
         dev = torch.device("cuda", device)
-    fbest, xbest, winner = cvshard.best_of_restarts(Fm[kbest] if len(mine) else np.inf, X[:, kbest], dist=dist, device=dev)
+    X, F, info = _minimize_together(dist, dev, plp, X0, lo, hi, nr, dscale, 3000, 8, False, **opt)
+    t1 = time.perf_counter()
+    Fm = F[: len(mine)]
+    ok = info["converged"][: len(mine)]
+    have = bool(len(mine)) and bool(ok.any())         # a rank whose starts all failed submits +inf, not an unconverged value
+    kbest = int(np.argmin(np.where(ok, Fm, np.inf))) if have else 0
+    fbest, xbest, winner = cvshard.best_of_restarts(Fm[kbest] if have else np.inf, X[:, kbest], dist=dist, device=dev)
     plp.close()
     return {"best": fbest, "x": xbest, "winner_rank": winner, "local_objectives": Fm, "local_converged": int(ok.sum()),
             "n_local": len(mine), "optimize_seconds": t1 - t0, "nfev": info["nfev"], "cg_iterations": info.get("cg_iterations"),

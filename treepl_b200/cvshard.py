@@ -92,3 +92,22 @@ def best_of_restarts(best_f, best_x, dist=None, device=None):
     x = torch.as_tensor(np.asarray(best_x, dtype=np.float64), device=device).clone()
     dist.broadcast(x, src=winner)
     return float(fs[winner]), x.cpu().numpy(), winner
+
+
+def raise_together(error, dist=None, device=None):
+    """Collective error agreement: every rank passes its local exception (or None); if ANY rank failed, every rank
+    raises, so no rank is left blocked in the next all-gather / broadcast."""
+    if dist is None:
+        if error is not None:
+            raise error
+        return
+    import torch
+
+    flag = torch.tensor([0.0 if error is None else 1.0], dtype=torch.float64, device=device)
+    flags = [torch.empty_like(flag) for _ in range(dist.get_world_size())]
+    dist.all_gather(flags, flag)
+    failed = [r for r, t in enumerate(flags) if t.item() != 0.0]
+    if error is not None:
+        raise error
+    if failed:
+        raise RuntimeError("optimisation failed on rank(s) %s" % failed)

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import batchopt, cv, output
+from . import batchopt, config, cv, output
 from . import engine as eng
 
 
@@ -29,22 +29,18 @@ def fit(flat, smoothing, device=0, log_pen=False, anneal=False, **opt):
     X0 = np.repeat(x0[:, None], 2, axis=1)
     if anneal:
         X0, _, _, _ = plp.anneal_batch(X0)
-    X, F, info = cv._minimize(plp, X0, lo, hi, n - 1, dscale, 3000, True, 8, False, **opt)
+    X, F, info = cv._minimize(plp, X0, lo, hi, n - 1, dscale, 3000, 8, False, **opt)
     plp.close()
     return X[:, 0], float(F[0]), fp, bool(info["converged"][0])
 
 
-def date_tree(flat, names, numsites, smooth=1.0, do_cv=False, randomcv=False, cvstart=1000.0, cvstop=0.1, cvmultstep=0.1,
+def date_tree(flat, names, numsites, smooth=10.0, do_cv=False, randomcv=False, cvstart=1000.0, cvstop=0.1, cvmultstep=0.1,
               randomcviter=10, randomcvsamp=0.1, outfile=None, cvoutfile="cv.out", device=0, log_pen=False, seed=1, **opt):
     """-> dict(smoothing, objective, dated_tree, rate_tree, cv).  Option names and defaults are the reference's control-file
-    keys (src/main.cpp:71-73, 100-270)."""
+    keys (src/main.cpp:62, 71-73, 100-270)."""
     table = None
     if do_cv:
-        grid = []
-        lam = cvstart
-        while lam >= cvstop * (1 - 1e-12):                      # main.cpp:667 `while(curcv >= cvstop)`
-            grid.append(lam)
-            lam *= cvmultstep
+        grid = config.smoothing_grid(cvstart, cvstop, cvmultstep)     # main.cpp:275-284,668,814
         tips = np.flatnonzero(np.asarray(flat["child_counts"]) == 0)
         if randomcv:
             groups = cv.sample_random_groups(flat, tips, randomcviter, randomcvsamp, seed=seed)
