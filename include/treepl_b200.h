@@ -152,11 +152,14 @@ typedef struct tpl_opt_options {
     int max_ls;         /* halvings per line search (0 = 40) */
     int check_every;    /* host polls the device-side done counter every this many steps (0 = 32) */
     int use_graph;      /* 1: replay `check_every` steps as one CUDA graph launch */
-    int method;         /* 0: L-BFGS (any layout); 1: truncated Newton, CG on the ANALYTIC Hessian-vector product with a
-                         * Jacobi preconditioner — what the reference's TNC approximates with finite differences
-                         * (tnc.c:483-827).  PL layout, AD gradient, no log penalty. */
+    int method;         /* 0: L-BFGS (any layout); 1: truncated Newton, CG on the ANALYTIC Hessian-vector product — what the
+                         * reference's TNC approximates with finite differences (tnc.c:483-827).  PL layout, AD gradient,
+                         * plain or log penalty. */
     int max_cg;         /* method 1: cap on CG iterations per Newton step (0 = 500; the forcing sequence usually stops far earlier) */
-    int cg_per_step;    /* method 1: CG iterations run between two batched evaluations (0 = 4) */
+    int cg_per_step;    /* method 1: CG iterations run between two batched evaluations (0 = 2 with the tree preconditioner, 4 with Jacobi) */
+    int precond;        /* method 1: preconditioner of the CG solve.  0 / 2: exact block-tree factorisation of the Hessian
+                         * (children eliminated before parents, 2x2 pivots; a handful of CG iterations per Newton step for
+                         * every smoothing value); 1: Jacobi (round-1 behaviour; TNC itself uses a diagonal, tnc.c:829-905) */
     double ftol;        /* 0 = 1e-12 */
     double gtol;        /* 0 = 1e-8; on max |projected gradient| relative to max(|f|, 1) */
     double armijo;      /* 0 = 1e-4 */
@@ -219,6 +222,11 @@ int tpl_last_kernel_generation(const tpl_engine* e);
 /* test hook: W = H_z V and DG = diag(H_z) at X through the truncated-Newton kernels (z = w / sc_rows[p], w = ln r | h);
  * X, V, W, DG: host [P][B].  Uses the installed batch configuration (per-vector smoothing and masks) when made for B. */
 int tpl_debug_hessvec(tpl_engine* e, int B, const double* X, const double* V, const double* sc_rows, double* W, double* DG);
+
+/* test hook: Out = M^-1 Rhs, M = the truncated-Newton method's block-tree factorisation of H_z at X (tpl_opt_options.precond);
+ * rows with Free > 0 are the variables of the solve, the others come out as 0.  X, Free, Rhs, Out: host [P][B]. */
+int tpl_debug_treesolve(tpl_engine* e, int B, const double* X, const double* Free, const double* Rhs, const double* sc_rows,
+                        double* Out);
 
 /* test hook: evaluates the kernels' log and reciprocal on n host values (tests only) */
 int tpl_debug_math(int n, const double* x, double* log_out, double* rcp_out);

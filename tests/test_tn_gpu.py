@@ -48,7 +48,7 @@ def test_hessvec_kernel_equals_cpu_emulation(name, lams, masked):
     W, DG = plp.debug_hessvec(X, V, pr.sc)
     Ws, DGs = np.zeros((P, B)), np.zeros((P, B))
     Xc, Gc, Vc = np.ascontiguousarray(X), np.ascontiguousarray(G), np.ascontiguousarray(V)
-    sim.tn_sim_hessvec(P, B, *pr.tree_args(), TS._d(pr.sc), TS._d(pr.lams), 0.0025, TS._d(Xc), TS._d(Gc), TS._d(Vc), TS._d(Ws), TS._d(DGs))
+    sim.tn_sim_hessvec(P, B, *pr.tree_args(), TS._d(pr.sc), TS._d(pr.lams), 0.0025, TS._d(Xc), TS._d(Gc), TS._d(Vc), TS._d(Ws), TS._d(DGs), 0)
     scale = np.abs(Ws).max(axis=0)
     assert np.all(np.abs(W - Ws).max(axis=0) <= 1e-11 * scale), np.abs(W - Ws).max(axis=0) / scale
     assert np.allclose(DG, DGs, rtol=1e-11, atol=0)
@@ -66,19 +66,110 @@ def _run(name, lams, masks=None, **opt):
     return pr, plp, X, F, info
 
 
-def test_tn_reproduces_reference_final_pl_and_cpu_emulation():
+@pytest.mark.parametrize("name,lams,masked,log_pen", [("test", [0.1, 100.0], False, False), ("M1155", [10.0, 0.1, 1000.0, 1.0], True, False),
+                                                      ("vib", [1e4, 1.0], True, True), ("big_test", [1e-4] * 17 + [100.0] * 17, True, False)])
+def test_tree_preconditioner_kernels_equal_cpu_emulation(name, lams, masked, log_pen):
+    """zz = M^-1 r through the level-sweep kernels (tn_tree_up / top / down) == the same node functions run in
+    elimination order on the CPU (tests/tn_sim.cpp::tree_solve), which tests/test_tn_sim.py pins against a dense solve."""
+    sim = TS.load_sim()
+    flat = Golden(name).flat
+    n = len(flat["parents"])
+    tips = np.flatnonzero(flat["child_counts"] == 0)
+    masks = None
+    if masked:
+        masks = [[int(tips[(3 + 2 * b) % len(tips)])] for b in range(len(lams))]
+        masks[0] = []
+    pr = TS.Problem(flat, lams, masks, log_pen=log_pen)
+    P, B = pr.P, pr.B
+    rng = np.random.RandomState(12)
+    x0 = cv.start_vector(flat, P, n - 1)
+    X = np.repeat(x0[:, None], B, axis=1)
+    X[: n - 1] *= np.exp(0.1 * rng.randn(n - 1, B))
+    rhs = rng.randn(P, B)
+    free = (rng.rand(P, B) > 0.02).astype(np.float64)            # a few frozen rows per vector
+    plp = _engine(pr, flat)
+    plp.set_log_pen(log_pen)
+    F, G = plp.calc_pl_grad_batch(X, mode=eng.GRAD_AD)
+    out = plp.debug_treesolve(X, free, rhs, pr.sc)
+    want = np.zeros((P, B))
+    Xc, Gc, Fc, Rc = (np.ascontiguousarray(v) for v in (X, G, free, rhs))
+    sim.tn_sim_treesolve(P, B, *pr.tree_args(), TS._d(pr.sc), TS._d(pr.lams), 0.0025, TS._d(Xc), TS._d(Gc), TS._d(Fc), TS._d(Rc), TS._d(want),
+                         int(log_pen))
+    scale = np.abs(want).max(axis=0)
+    assert np.all(np.isfinite(out))
+    # elimination amplifies the rounding differences between host and device arithmetic (FMA contraction) by the condition of
+    # the pivots: 1e-11 typical; up to 1e-5 on the 9,313-node tree at this random, non-optimal point
+    tol = 1e-4 if name == "big_test" else 1e-7
+    err = np.abs(out - want).max(axis=0) / scale
+    assert np.all(err <= tol) and np.median(err) <= 1e-7, err
+    assert np.all(out[free == 0] == 0.0)
+    plp.close()
+
+
+@pytest.mark.parametrize("precond", [1, 2])
+def test_tn_reproduces_reference_final_pl_and_cpu_emulation(precond):
+    """precond 1: Jacobi (round 1); 2: block-tree factorisation (default).  Same optima, the reference's final PL values."""
     sim = TS.load_sim()
     for name, lams, ref in (("test", [0.1, 0.1], 234.23049), ("pl4203", [100.0, 1.0], 390.04656), ("M1155", [10.0, 1000.0, 0.1, 1.0], 252.3558)):
-        pr, plp, X, F, info = _run(name, lams, max_steps=20000)
+        pr, plp, X, F, info = _run(name, lams, max_steps=20000, precond=precond)
         assert ((info["status"] >= 1) & (info["status"] <= 2)).all(), info
         assert abs(F[0] - ref) <= (1e-4 if name == "test" else 2e-6) * ref and F[0] <= ref + 1e-6 * ref, (name, F)
-        _, Xs, Fs, ss, its, ncg, steps = TS.fit(sim, name, lams)
+        _, Xs, Fs, ss, its, ncg, steps = TS.fit(sim, name, lams, precond=precond - 1, cg_per_step=4 if precond == 1 else 2)
         assert np.all(np.abs(F - Fs) <= 1e-9 * np.abs(Fs)), (name, F, Fs)
         assert 0.5 * steps <= info["steps"] <= 2.0 * steps + 64, (info["steps"], steps)
+        if precond == 2:
+            assert info["cg_iterations"] <= 4 * int(info["iterations"].sum()) + 8, info      # a handful of CG iterations per Newton step
         # a stationary point of the engine's own objective
         f, g = plp.calc_pl_grad_batch(X, mode=eng.GRAD_AD)
         assert np.all(np.abs(f - F) <= 1e-12 * np.abs(F))
         plp.close()
+
+
+def test_tn_log_penalty_objective_reaches_the_lbfgs_optimum():
+    """examples/big_test.cppr8s sets log_pen (pl_calc_parallel.cpp:866-879: the root-children variance term on ln r);
+    truncated Newton carries that Hessian block: same optimum as the L-BFGS path and as the CPU emulation."""
+    sim = TS.load_sim()
+    for name, lams in (("vib", [1000.0, 10.0]), ("test", [0.1, 100.0])):
+        flat = Golden(name).flat
+        pr = TS.Problem(flat, lams, log_pen=True)
+        plp = _engine(pr, flat)
+        plp.set_log_pen(True)
+        lower, upper = batchopt.reference_bounds(flat, pr.fp, pr.P)
+        x0 = cv.start_vector(flat, pr.P, pr.n - 1)
+        X0 = np.repeat(x0[:, None], pr.B, axis=1)
+        X, F, info = plp.optimize_batch(X0, lower, upper, method=1, date_scale=float(pr.sc[-1]), max_steps=20000)
+        Xl, Fl, il = plp.optimize_batch(X0, lower, upper, method=0, date_scale=float(pr.sc[-1]), max_steps=40000, ftol=1e-15, patience=40)
+        plp.close()
+        assert ((info["status"] >= 1) & (info["status"] <= 2)).all(), info
+        assert np.all(np.abs(F - Fl) <= 1e-7 * np.abs(Fl)) and np.all(F <= Fl + 1e-9 * np.abs(Fl)), (name, F, Fl)
+        _, Xs, Fs, ss, its, ncg, steps = TS.fit(sim, name, lams, precond=1, cg_per_step=2, log_pen=True)
+        assert np.all(np.abs(F - Fs) <= 1e-9 * np.abs(Fs)), (name, F, Fs)
+
+
+def test_tn_converges_for_every_smoothing_value_on_a_large_tree():
+    """the regime round 1 left open: large tree x large smoothing.  20,000-tip synthetic tree, smoothing
+    1e4 ... 1e-2: every vector gradient-converged, a few CG iterations per Newton step."""
+    ft, _, _ = tf.synth_problem(20000, seed=3, ncal=8)
+    flat = ft.as_dict()
+    lams = [1e4, 1e3, 300.0, 100.0, 10.0, 1.0, 0.1, 0.01]
+    fp, P = tf.generate_param_order_vector(flat["free"], lf=False)
+    n = len(flat["parents"])
+    plp = eng.PLCalcParallel.from_flat(flat, device=0)
+    plp.set_freeparams(P, False, fp)
+    plp.batch_configure(len(lams), lane_smoothing=np.array(lams))
+    lower, upper = batchopt.reference_bounds(flat, fp, P)
+    x0 = cv.start_vector(flat, P, n - 1)
+    par = flat["parents"]
+    ds = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
+    X, F, info = plp.optimize_batch(np.repeat(x0[:, None], len(lams), axis=1), lower, upper, method=1, date_scale=ds, max_steps=6000, use_graph=1)
+    assert (info["status"] == 1).all(), info
+    assert np.all(np.diff(F) < 0)                     # less smoothing, lower objective
+    f, g = plp.calc_pl_grad_batch(X, mode=eng.GRAD_AD)
+    gz = g.copy()
+    gz[: n - 1] *= X[: n - 1]
+    gz[n - 1:] *= ds
+    assert np.all(np.abs(gz).max(axis=0) <= 1e-8 * np.abs(f) * 1.0001), np.abs(gz).max(axis=0) / np.abs(f)
+    plp.close()
 
 
 def test_tn_graph_replay_is_bitwise_and_uses_fewer_evaluations_than_lbfgs():
@@ -130,10 +221,6 @@ def test_tn_refuses_what_it_does_not_support_loudly():
     x0 = cv.start_vector(flat, pr.P, pr.n - 1)
     X0 = np.repeat(x0[:, None], 2, axis=1)
     plp = _engine(pr, flat)
-    plp.set_log_pen(True)
-    with pytest.raises(eng.EngineError, match="log-penalty"):
-        plp.optimize_batch(X0, lower, upper, method=1)
-    plp.set_log_pen(False)
     with pytest.raises(eng.EngineError, match="TPL_GRAD_AD"):
         plp.optimize_batch(X0, lower, upper, method=1, mode=eng.GRAD_ANALYTIC)
     with pytest.raises(eng.EngineError, match="method must be"):

@@ -4,6 +4,8 @@
 // tests/test_tn_sim.py).  Also exports the Hessian-vector product alone so that it can be checked against finite
 // differences of the oracle's gradient.  Not part of the product.
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -31,6 +33,16 @@ struct HostView {
     const double *X, *Vv, *Gx, *sc_;
     double* W;
     double lam, pb;
+    bool log_pen = false;
+    // tree preconditioner (tpl_tn_core.h::tree_*_node)
+    const double* Minv_ = nullptr;
+    const double* Rhs = nullptr;
+    double* TW = nullptr;
+    bool fr(int row) const { return Minv_[(size_t)row * B + b] > 0.0; }
+    double rhs(int row) const { return Rhs[(size_t)row * B + b]; }
+    double outv(int row) const { return W[(size_t)row * B + b]; }
+    double tw(int q, int i) const { return TW[((size_t)q * t.n + i) * B + b]; }
+    void tw_put(int q, int i, double v) { TW[((size_t)q * t.n + i) * B + b] = v; }
     int parent(int i) const { return t.parent[i]; }
     int child_begin(int i) const { return t.child_off[i]; }
     int child_end(int i) const { return t.child_off[i + 1]; }
@@ -53,11 +65,11 @@ struct HostView {
 extern "C" void tn_sim_hessvec(int P, int B, int n, const int* parent, const int* child_off, const int* children, const int* rslot,
                                const int* dslot, const double* c, const double* hfix, const double* rfix, const double* pmin,
                                const double* pmax, const unsigned char* mask, const double* sc, const double* lam, double pb,
-                               const double* X, const double* Gx, const double* V, double* W, double* DG) {
+                               const double* X, const double* Gx, const double* V, double* W, double* DG, int log_pen) {
     Tree t = {n, parent, child_off, children, rslot, dslot, c, hfix, rfix, pmin, pmax, mask};
     for (int b = 0; b < B; b++) {
-        HostView hv = {t, B, b, X, V, Gx, sc, W, lam[b], pb};
-        HostView dv = {t, B, b, X, V, Gx, sc, DG, lam[b], pb};
+        HostView hv = {t, B, b, X, V, Gx, sc, W, lam[b], pb, log_pen != 0};
+        HostView dv = {t, B, b, X, V, Gx, sc, DG, lam[b], pb, log_pen != 0};
         for (int i = 0; i < n; i++) {
             double vw, vv;
             hess_node(hv, i, vw, vv);
@@ -66,14 +78,38 @@ extern "C" void tn_sim_hessvec(int P, int B, int n, const int* parent, const int
     }
 }
 
+// M^-1 rhs for vector b: factorise (when `factor`), forward and back substitution.  Children have larger preorder
+// numbers than their parents, so descending node order is a valid elimination order (the kernels go by height levels).
+static void tree_solve(const Tree& t, int B, int b, const double* X, const double* Gx, const double* sc, double lam, double pb,
+                       bool log_pen, const double* Minv, const double* Rhs, double* Out, double* TW, bool factor) {
+    HostView v = {t, B, b, X, nullptr, Gx, sc, Out, lam, pb, log_pen, Minv, Rhs, TW};
+    for (int i = t.n - 1; i >= 0; i--) {
+        if (factor) tree_factor_node(v, i);
+        tree_up_node(v, i);
+    }
+    for (int i = 0; i < t.n; i++) tree_down_node(v, i);
+}
+
+// test entry: Out = M^-1 Rhs with every row whose Free flag is > 0 a variable
+extern "C" void tn_sim_treesolve(int P, int B, int n, const int* parent, const int* child_off, const int* children, const int* rslot,
+                                 const int* dslot, const double* c, const double* hfix, const double* rfix, const double* pmin,
+                                 const double* pmax, const unsigned char* mask, const double* sc, const double* lam, double pb,
+                                 const double* X, const double* Gx, const double* Free, const double* Rhs, double* Out, int log_pen) {
+    Tree t = {n, parent, child_off, children, rslot, dslot, c, hfix, rfix, pmin, pmax, mask};
+    std::vector<double> TW((size_t)TW_PLANES * n * B, 0.0);
+    for (int b = 0; b < B; b++) tree_solve(t, B, b, X, Gx, sc, lam[b], pb, log_pen != 0, Free, Rhs, Out, TW.data(), true);
+}
+
 extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const double* lo, const double* hi, const double* sc,
                       int max_steps, int max_cg, int cg_per_step, int patience, int max_ls, double ftol, double gtol, double c1, double boundary_frac,
                       eval_fn ev, void* ctx, int* status, int* iters, int* ncg_out,
                       int n, const int* parent, const int* child_off, const int* children, const int* rslot, const int* dslot,
                       const double* c, const double* hfix, const double* rfix, const double* pmin, const double* pmax,
-                      const unsigned char* mask, const double* lam, double pb) {
+                      const unsigned char* mask, const double* lam, double pb, int precond, int log_pen) {
     Tree t = {n, parent, child_off, children, rslot, dslot, c, hfix, rfix, pmin, pmax, mask};
     const size_t PB = (size_t)P * B;
+    const bool lp = log_pen != 0;
+    std::vector<double> TW(precond ? (size_t)TW_PLANES * n * B : 0, 0.0);
     TnConst o;
     o.P = P; o.B = B; o.nr = nr; o.max_ls = max_ls; o.max_cg = max_cg; o.patience = patience; o.c1 = c1; o.ftol = ftol; o.gtol = gtol;
     o.boundary_frac = boundary_frac;
@@ -114,7 +150,7 @@ extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const doubl
             double red[3] = {0.0, 0.0, 0.0};
             if (dec == DEC_ACCEPT || dec == DEC_INIT) {
                 // tn_diag_kernel
-                HostView dv = {t, B, b, X, Pv.data(), Gx.data(), sc, DG.data(), lam[b], pb};
+                HostView dv = {t, B, b, X, Pv.data(), Gx.data(), sc, DG.data(), lam[b], pb, lp};
                 for (int i = 0; i < n; i++) diag_node(dv, i);
                 // tn_setup_kernel
                 for (int p = 0; p < P; p++) {
@@ -136,14 +172,25 @@ extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const doubl
                     red[1] = fmax(red[1], fabs(gp));
                     red[2] = fma(gp, gp, red[2]);
                 }
+                if (precond) {           // tn_tree_factor / up / down kernels: zz = M^-1 r, p = zz, rz0 = r.zz
+                    tree_solve(t, B, b, X, Gx.data(), sc, lam[b], pb, lp, Minv.data(), R.data(), ZZ.data(), TW.data(), true);
+                    red[0] = 0.0;
+                    for (int p = 0; p < P; p++) {
+                        const size_t i = (size_t)p * B + b;
+                        Pv[i] = ZZ[i];
+                        red[0] = fma(R[i], ZZ[i], red[0]);
+                    }
+                }
             }
+            if (getenv("TN_SIM_VERBOSE") && dec != DEC_SKIP)
+                fprintf(stderr, "step %d lane %d dec %d Ft %.10g F0 %.10g t %.3g ls %d cgit %d gd %.3g rz0 %.3g gmax %.3g\n", steps, b, dec, Ft[b], F0[b], tt[b], ls[b], cgit[b], gd[b], red[0], red[1]);
             if (phase_setup(lane(b), Ft[b], red, o)) ndone++;
         }
         for (int sub = 0; sub < cg_per_step; sub++) {
         // tn_hv_kernel
         for (int b = 0; b < B; b++) {
             if (st[b] != TS_CG || (act[b] & ACT_FIN)) continue;
-            HostView hv = {t, B, b, X, Pv.data(), Gx.data(), sc, Hp.data(), lam[b], pb};
+            HostView hv = {t, B, b, X, Pv.data(), Gx.data(), sc, Hp.data(), lam[b], pb, lp};
             double red[2] = {0.0, 0.0};
             for (int i = 0; i < n; i++) {
                 double vw, vv;
@@ -166,6 +213,11 @@ extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const doubl
                 const double zz = r * Minv[i];
                 ZZ[i] = zz;
                 red[0] = fma(r, zz, red[0]);
+            }
+            if (precond) {
+                tree_solve(t, B, b, X, Gx.data(), sc, lam[b], pb, lp, Minv.data(), R.data(), ZZ.data(), TW.data(), false);
+                red[0] = 0.0;
+                for (int p = 0; p < P; p++) red[0] = fma(R[(size_t)p * B + b], ZZ[(size_t)p * B + b], red[0]);
             }
             phase_update(lane(b), red, o);
         }
@@ -195,6 +247,10 @@ extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const doubl
                 const double zp = rp >= 0 ? Z[(size_t)rp * B + b] * sc[rp] : hfix[pa];
                 const double dp = rp >= 0 ? S[(size_t)rp * B + b] * sc[rp] : 0.0;
                 tmin = fmin(tmin, branch_step_limit(zi, di, zp, dp));
+            }
+            for (int i = 0; i < n; i++) {
+                const int ri = dslot[i];
+                if (ri >= 0) tmin = fmin(tmin, tplopt::bound_step_limit(Z[(size_t)ri * B + b], S[(size_t)ri * B + b], lo[ri], hi[ri]));
             }
             phase_finish(lane(b), g, tmin, o);
         }

@@ -176,7 +176,9 @@ struct tpl_engine {
         PinBuf<int> h_done;
         // truncated Newton
         DevBuf<double> R, ZZ, Pv, Hp, Minv, DG, pmin_n, pmax_n, tn_part, tn_lane_d;
-        DevBuf<int> tn_lane_i;
+        DevBuf<int> tn_lane_i, tn_lev_nodes, tn_lev_off;
+        DevBuf<double> tn_tw;
+        std::vector<int> tn_lev_off_host;
         // annealer
         DevBuf<int> sa_date_node, sa_bar_node, sa_done;
         DevBuf<double> sa_hmin, sa_hmax;

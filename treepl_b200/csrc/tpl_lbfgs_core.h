@@ -89,6 +89,17 @@ TPL_HD double branch_step_limit(double zi, double di, double zp, double dp) {
     return shrink > 0.0 ? (zp - zi) / shrink : 1e300;
 }
 
+// fraction-to-the-boundary rule for the box: the step length at which z + t d reaches its bound (1e300: never).  A
+// variable already ON the bound is left to the clamp of trial_point.  Date bounds are never active at an optimum (a
+// calibrated node carries the barrier term, every other node's bound is implied by its neighbours' durations), and a
+// step clamped onto them can close a chain of durations to exactly zero, where the objective is finite (d == 0 ->
+// DBL_MIN, pl_calc_parallel.cpp:905) and the iteration stays trapped.
+TPL_HD double bound_step_limit(double z, double d, double lo, double hi) {
+    if (d < 0.0 && z > lo) return (z - lo) / (-d);
+    if (d > 0.0 && z < hi) return (hi - z) / d;
+    return 1e300;
+}
+
 struct LaneIO {
     // scalars of this vector
     int *st, *ls, *head, *stall, *flag, *newdir, *iters, *nfail;

@@ -112,7 +112,6 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
                const std::vector<double>& sc, int nr, const tpl_opt_options& o, tpltn::TnArgs& a) {
     using namespace tpltn;
     if (e->lf_mode) return fail(TPL_ERR_ARG, "truncated Newton needs the PL layout (one rate per branch)");
-    if (e->log_pen) return fail(TPL_ERR_ARG, "truncated Newton does not carry the log-penalty Hessian; use method 0");
     if (e->cv_any) return fail(TPL_ERR_ARG, "truncated Newton takes CV masks per vector (tpl_batch_configure), not set_cv_nodes");
     const int P = e->numparams, n = e->n;
     const size_t PB = (size_t)P * B;
@@ -136,18 +135,18 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
     CK(w.Z.ensure(PB)); CK(w.Gz.ensure(PB)); CK(w.D.ensure(PB)); CK(w.X.ensure(PB)); CK(w.Gx.ensure(PB));
     CK(w.R.ensure(PB)); CK(w.ZZ.ensure(PB)); CK(w.Pv.ensure(PB)); CK(w.Hp.ensure(PB)); CK(w.Minv.ensure(PB)); CK(w.DG.ensure(PB));
     CK(w.lo.ensure(P)); CK(w.hi.ensure(P)); CK(w.sc.ensure(P)); CK(w.Ft.ensure(B)); CK(w.Fout.ensure(B)); CK(w.h_done.ensure(1));
-    const size_t npart = (size_t)(3 + 1 + 1) * a.row_chunks * B + (size_t)(2 + 1) * a.node_chunks * B;
+    const size_t npart = (size_t)(3 + 1 + 1 + 1) * a.row_chunks * B + (size_t)(2 + 1) * a.node_chunks * B;
     CK(w.tn_part.ensure(npart));
-    CK(w.tn_lane_d.ensure((size_t)11 * B));
-    CK(w.tn_lane_i.ensure((size_t)8 * B + 1 + 5 * (size_t)groups));
+    CK(w.tn_lane_d.ensure((size_t)13 * B));
+    CK(w.tn_lane_i.ensure((size_t)8 * B + 1 + 6 * (size_t)groups));
     CK(w.pmin_n.upload(e->pen_min, s));
     CK(w.pmax_n.upload(e->pen_max, s));
     CK(cudaMemcpyAsync(w.lo.p, lo.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(w.hi.p, hi.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(w.sc.p, sc.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(w.X.p, X, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(w.tn_lane_d.p, 0, sizeof(double) * 11 * B, s));
-    CK(cudaMemsetAsync(w.tn_lane_i.p, 0, sizeof(int) * (8 * (size_t)B + 1 + 5 * (size_t)groups), s));     // st = TS_INIT, t = 0
+    CK(cudaMemsetAsync(w.tn_lane_d.p, 0, sizeof(double) * 13 * B, s));
+    CK(cudaMemsetAsync(w.tn_lane_i.p, 0, sizeof(int) * (8 * (size_t)B + 1 + 6 * (size_t)groups), s));     // st = TS_INIT, t = 0
     for (DevBuf<double>* buf : {&w.Gz, &w.D, &w.R, &w.ZZ, &w.Pv, &w.Hp, &w.Minv, &w.DG, &w.Gx})
         CK(cudaMemsetAsync(buf->p, 0, sizeof(double) * PB, s));
     CK(cudaStreamSynchronize(s));       // pen_min / pen_max uploads read host vectors of the engine; lo / hi / sc are the caller's
@@ -176,16 +175,69 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
     a.ncg = li + 6 * Bs; a.act = li + 7 * Bs; a.ndone = li + 8 * Bs;
     int* cnt = li + 8 * Bs + 1;
     a.cnt_setup = cnt; a.cnt_hv = cnt + groups; a.cnt_upd = cnt + 2 * groups; a.cnt_gd = cnt + 3 * groups; a.cnt_tm = cnt + 4 * groups;
+    a.cnt_pc = cnt + 5 * groups;
     double* ld = w.tn_lane_d.p;
     a.F0 = ld; a.t_ = ld + Bs; a.gd = ld + 2 * Bs; a.rz = ld + 3 * Bs; a.rz0 = ld + 4 * Bs; a.tol2 = ld + 5 * Bs; a.alpha = ld + 6 * Bs;
     a.beta = ld + 7 * Bs; a.gmax = ld + 8 * Bs; a.tlog = ld + 9 * Bs; a.gdtmp = ld + 10 * Bs;
+    a.gmax_tmp = ld + 11 * Bs; a.gg_tmp = ld + 12 * Bs;
     double* pp = w.tn_part.p;
     a.part_setup = pp; pp += (size_t)3 * a.row_chunks * B;
     a.part_upd = pp; pp += (size_t)a.row_chunks * B;
     a.part_gd = pp; pp += (size_t)a.row_chunks * B;
     a.part_hv = pp; pp += (size_t)2 * a.node_chunks * B;
-    a.part_tm = pp;
+    a.part_tm = pp; pp += (size_t)a.node_chunks * B;
+    a.part_pc = pp;
+    // ---- tree preconditioner: height levels (children before parents), node lists per level, work planes ----
+    a.precond = o.precond == 1 ? 0 : 1;
+    a.log_pen = e->log_pen ? 1 : 0;
+    a.TW = nullptr; a.lev_nodes = nullptr; a.lev_off = nullptr; a.nlev = a.nlev_wide = 0;
+    if (a.precond) {
+        std::vector<int> height(n, 0);
+        int hmax = 0;
+        for (int i = n - 1; i >= 0; i--) {              // preorder numbering: a child's number exceeds its parent's
+            int h = 0;
+            for (int j = e->child_off[i]; j < e->child_off[i + 1]; j++) h = std::max(h, height[e->children[j]] + 1);
+            height[i] = h;
+            hmax = std::max(hmax, h);
+        }
+        std::vector<int> off(hmax + 2, 0), nodes(n);
+        for (int i = 0; i < n; i++) off[height[i] + 1]++;
+        for (int l = 0; l <= hmax; l++) off[l + 1] += off[l];
+        std::vector<int> fill(off.begin(), off.end() - 1);
+        for (int i = 0; i < n; i++) nodes[fill[height[i]]++] = i;
+        a.nlev = hmax + 1;
+        a.nlev_wide = 0;
+        while (a.nlev_wide < a.nlev && off[a.nlev_wide + 1] - off[a.nlev_wide] >= 4 * tpltn::TREE_TOP_WY) a.nlev_wide++;
+        if (a.nlev - a.nlev_wide > 4096) return fail(TPL_ERR_ARG, "tree preconditioner: more than 4096 narrow levels (ladder-like tree); use precond = 1");
+        CK(w.tn_lev_nodes.upload(nodes, s));
+        CK(w.tn_lev_off.upload(off, s));
+        CK(w.tn_tw.ensure((size_t)tpltn::TW_PLANES * n * B));
+        CK(cudaStreamSynchronize(s));
+        w.tn_lev_off_host = off;
+        a.TW = w.tn_tw.p; a.lev_nodes = w.tn_lev_nodes.p; a.lev_off = w.tn_lev_off.p;
+    }
     return TPL_OK;
+}
+
+// zz = M^-1 r through the block-tree factorisation: wide levels one launch each, the narrow top in one block per group
+void tn_launch_tree_solve(const tpltn::TnArgs& a, const std::vector<int>& loff, int groups, cudaStream_t s, bool factor, bool finish) {
+    using namespace tpltn;
+    const dim3 blk(32, tplopt::OPT_WY), tblk(32, TREE_TOP_WY);
+    for (int l = 0; l < a.nlev_wide; l++) {
+        const dim3 g(groups, (loff[l + 1] - loff[l] + TREE_NODES_PER_BLOCK - 1) / TREE_NODES_PER_BLOCK);
+        if (factor) tn_tree_up_kernel<true><<<g, blk, 0, s>>>(a, l); else tn_tree_up_kernel<false><<<g, blk, 0, s>>>(a, l);
+    }
+    if (a.nlev > a.nlev_wide) {
+        if (factor) tn_tree_top_kernel<true><<<groups, tblk, 0, s>>>(a); else tn_tree_top_kernel<false><<<groups, tblk, 0, s>>>(a);
+    }
+    for (int l = a.nlev_wide - 1; l >= 0; l--) {
+        const dim3 g(groups, (loff[l + 1] - loff[l] + TREE_NODES_PER_BLOCK - 1) / TREE_NODES_PER_BLOCK);
+        if (factor) tn_tree_down_kernel<true><<<g, blk, 0, s>>>(a, l); else tn_tree_down_kernel<false><<<g, blk, 0, s>>>(a, l);
+    }
+    if (finish) {
+        const dim3 rgrd(groups, a.row_chunks);
+        if (factor) tn_pc_finish_kernel<true><<<rgrd, blk, 0, s>>>(a); else tn_pc_finish_kernel<false><<<rgrd, blk, 0, s>>>(a);
+    }
 }
 
 int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<double>& lo, const std::vector<double>& hi,
@@ -206,7 +258,8 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
     const int check_every = o.check_every > 0 ? o.check_every : 32;
     // CG iterations per evaluation: most vectors are inside a CG solve most of the time, and only the vectors in a
     // line search need the objective; 4 CG iterations per step make the (then mostly idle) evaluation a ~5 % overhead
-    const int cg_per_step = o.cg_per_step > 0 ? std::min(o.cg_per_step, 64) : 4;
+    // (with the tree preconditioner a solve takes one to three iterations: 2 per step)
+    const int cg_per_step = o.cg_per_step > 0 ? std::min(o.cg_per_step, 64) : (a.precond ? 2 : 4);
     const dim3 blk(32, WY);
     const dim3 rgrd(groups, a.row_chunks), ngrd(groups, a.node_chunks);
     EventPair evp;
@@ -218,14 +271,18 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
     tn_trial_kernel<<<rgrd, blk, 0, s>>>(a);
     launches += 2;
     CK(cudaGetLastError());
+    const int tree_launches = a.precond ? 2 * a.nlev_wide + (a.nlev > a.nlev_wide ? 1 : 0) + 1 : 0;
+    auto tree_solve = [&](bool factor) { tn_launch_tree_solve(a, w.tn_lev_off_host, groups, s, factor, true); };
     auto one_step = [&]() -> int {
         int rc = eval_device(e, B, a.X, const_cast<double*>(a.Ft), const_cast<double*>(a.Gx), mode, true, s);
         if (rc != TPL_OK) return rc;
         tn_diag_kernel<<<ngrd, blk, 0, s>>>(a);
         tn_setup_kernel<<<rgrd, blk, 0, s>>>(a);
+        if (a.precond) tree_solve(true);
         for (int k = 0; k < cg_per_step; k++) {
             tn_hv_kernel<<<ngrd, blk, 0, s>>>(a);
             tn_update_kernel<<<rgrd, blk, 0, s>>>(a);
+            if (a.precond) tree_solve(false);
             tn_dir_kernel<<<rgrd, blk, 0, s>>>(a);
         }
         tn_gd_kernel<<<rgrd, blk, 0, s>>>(a);
@@ -234,7 +291,7 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
         CK(cudaGetLastError());
         return TPL_OK;
     };
-    const int per_step = 7 + 3 * cg_per_step;
+    const int per_step = 7 + 3 * cg_per_step + (1 + cg_per_step) * tree_launches;
     int steps = 0;
     int rc = one_step();               // first step outside any capture: sizes the evaluation work space
     if (rc != TPL_OK) return rc;
@@ -483,6 +540,7 @@ extern "C" int tpl_debug_hessvec(tpl_engine* e, int B, const double* X, const do
     std::vector<double> lo(P, -1e300), hi(P, 1e300), sc(sc_rows, sc_rows + P);
     tpl_opt_options o;
     memset(&o, 0, sizeof(o));
+    o.precond = 1;                      // no tree work space for a single product
     TnArgs a;
     rc = tn_prepare(e, B, X, lo, hi, sc, nr, o, a);
     if (rc != TPL_OK) return rc;
@@ -500,6 +558,38 @@ extern "C" int tpl_debug_hessvec(tpl_engine* e, int B, const double* X, const do
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(W, w.Hp.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(DG, w.DG.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return TPL_OK;
+}
+
+// test hook: Out = M^-1 Rhs with the block-tree factorisation of the Hessian at X; rows with Free > 0 are the variables
+extern "C" int tpl_debug_treesolve(tpl_engine* e, int B, const double* X, const double* Free, const double* Rhs, const double* sc_rows,
+                                   double* Out) {
+    using namespace tpltn;
+    if (!e || !X || !Free || !Rhs || !sc_rows || !Out || B < 1) return fail(TPL_ERR_ARG, "null or B < 1");
+    if (!e->have_fp) return fail(TPL_ERR_STATE, "set_freeparams has not been called");
+    CK(cudaSetDevice(e->device));
+    int rc = sync_device_tree(e);
+    if (rc != TPL_OK) return rc;
+    const int P = e->numparams;
+    const size_t PB = (size_t)P * B;
+    int nr = 0;
+    for (int i = 0; i < e->n; i++) nr = std::max(nr, e->freeparams[i] + 1);
+    std::vector<double> lo(P, -1e300), hi(P, 1e300), sc(sc_rows, sc_rows + P);
+    tpl_opt_options o;
+    memset(&o, 0, sizeof(o));
+    TnArgs a;
+    rc = tn_prepare(e, B, X, lo, hi, sc, nr, o, a);
+    if (rc != TPL_OK) return rc;
+    cudaStream_t s = e->stream;
+    tpl_engine::OptWork& w = e->opt;
+    rc = eval_device(e, B, a.X, const_cast<double*>(a.Ft), const_cast<double*>(a.Gx), TPL_GRAD_AD, true, s);
+    if (rc != TPL_OK) return rc;
+    CK(cudaMemcpyAsync(w.Minv.p, Free, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w.R.p, Rhs, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
+    tn_launch_tree_solve(a, w.tn_lev_off_host, (B + 31) / 32, s, true, false);   // st = TS_INIT, finite objective: every vector active
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(Out, w.ZZ.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return TPL_OK;
 }

@@ -16,6 +16,13 @@
 //   tn_gd_kernel      row-indexed    gd = Gz.s  (s = p when CG stopped at its first iteration)
 //   tn_stepmax_kernel node-indexed   largest step keeping all durations positive                             -> phase_finish
 //   tn_trial_kernel   row-indexed    X = to_param(z + t s)
+// Tree preconditioner (tpl_tn_core.h::tree_*_node; TnArgs::precond): zz = M^-1 r by one leaf-to-root and one root-to-leaf
+// sweep over HEIGHT levels (a node's children sit on lower levels; level sizes never increase): one launch per wide
+// level, and ONE block per 32-vector group for all the narrow top levels (block-level barriers between levels):
+//   tn_tree_up_kernel<FACTOR>    one wide level: [factorise S_i, K_i, T_i] + forward substitution
+//   tn_tree_top_kernel<FACTOR>   narrow levels: up to the root, then back down
+//   tn_tree_down_kernel<FACTOR>  one wide level: back substitution -> ZZ rows
+//   tn_pc_finish_kernel<FACTOR>  row-indexed    [p = zz] and r.zz                                        -> phase_setup / phase_update
 #pragma once
 #include "tpl_kernels.cuh"
 #include "tpl_lbfgs.cuh"
@@ -44,6 +51,16 @@ struct TnArgs {
     double *part_setup, *part_hv, *part_upd, *part_gd, *part_tm;
     int *cnt_setup, *cnt_hv, *cnt_upd, *cnt_gd, *cnt_tm;      // [groups] arrival counters, zero between launches
     int* ndone;
+    // tree preconditioner
+    int precond;                             // 0 Jacobi, 1 block-tree factorisation
+    int log_pen;
+    double* TW;                              // [TW_PLANES][n][B] node-indexed factors and sweep scratch
+    const int* lev_nodes;                    // [n] node numbers grouped by height level (tips first)
+    const int* lev_off;                      // [nlev + 1]
+    int nlev, nlev_wide;                     // levels [0, nlev_wide): one launch each; [nlev_wide, nlev): tn_tree_top_kernel
+    double *gmax_tmp, *gg_tmp;               // [B] reductions of the set-up pass kept until the solve has produced r.zz
+    double* part_pc;
+    int* cnt_pc;
 };
 
 __device__ __forceinline__ Lane lane_of(const TnArgs& a, int b) {
@@ -112,6 +129,12 @@ struct DevView {
     const double* Vv;
     double* W;
     double lam, pb;
+    bool log_pen;
+    __device__ bool fr(int row) const { return a.Minv[(size_t)row * B + b] > 0.0; }       // free variable of this solve
+    __device__ double rhs(int row) const { return a.R[(size_t)row * B + b]; }
+    __device__ double outv(int row) const { return W[(size_t)row * B + b]; }
+    __device__ double tw(int q, int i) const { return a.TW[((size_t)q * a.t.n + i) * B + b]; }
+    __device__ void tw_put(int q, int i, double val) { a.TW[((size_t)q * a.t.n + i) * B + b] = val; }
     __device__ int parent(int i) const { return a.t.parent[i]; }
     __device__ int child_begin(int i) const { return a.t.child_off[i]; }
     __device__ int child_end(int i) const { return a.t.child_off[i + 1]; }
@@ -181,7 +204,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_diag_kernel(TnArgs a) {
     if (b >= B) return;
     const int dec = lane_decision(a, b);
     if (dec != DEC_ACCEPT && dec != DEC_INIT) return;
-    DevView V = {a, B, b, a.Pv, a.DG, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb};
+    DevView V = {a, B, b, a.Pv, a.DG, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0};
     const int i0 = blockIdx.y * a.nodes_per_chunk, i1 = min(a.t.n, i0 + a.nodes_per_chunk);
     for (int i = i0 + threadIdx.y; i < i1; i += OPT_WY) diag_node(V, i);
 }
@@ -222,8 +245,15 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_setup_kernel(TnArgs a) {
         }
     }
     if (!group_reduce<3, 2u, 0u>(v, a.part_setup, a.cnt_setup, B, b)) return;
-    if (ty == 0 && b < B)
-        if (phase_setup(lane_of(a, b), a.Ft[b], v, a.o)) atomicAdd(a.ndone, 1);
+    if (ty == 0 && b < B) {
+        if (a.precond && (dec == DEC_ACCEPT || dec == DEC_INIT)) {
+            // r.M^-1 r comes from the tree solve (tn_pc_finish_kernel runs phase_setup); the decision inputs stay untouched
+            a.gmax_tmp[b] = v[1];
+            a.gg_tmp[b] = v[2];
+        } else if (phase_setup(lane_of(a, b), a.Ft[b], v, a.o)) {
+            atomicAdd(a.ndone, 1);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
@@ -235,7 +265,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
     if (!__syncthreads_or(active)) return;
     double v[2] = {0.0, 0.0};
     if (active) {
-        DevView V = {a, B, b, a.Pv, a.Hp, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb};
+        DevView V = {a, B, b, a.Pv, a.Hp, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0};
         const int i0 = blockIdx.y * a.nodes_per_chunk, i1 = min(a.t.n, i0 + a.nodes_per_chunk);
         for (int i = i0 + ty; i < i1; i += OPT_WY) {
             double vw, vv;
@@ -269,8 +299,101 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_update_kernel(TnArgs a) {
             v[0] = fma(r, zz, v[0]);
         }
     }
+    if (a.precond) return;                       // zz = M^-1 r and r.zz follow from the tree sweeps
     if (!group_reduce<1, 0u, 0u>(v, a.part_upd, a.cnt_upd, B, b)) return;
     if (ty == 0 && active) phase_update(lane_of(a, b), v, a.o);
+}
+
+// ---- tree preconditioner sweeps ------------------------------------------------------------------------------------------
+constexpr int TREE_TOP_WY = 16;              // warps of the block that walks the narrow top levels
+constexpr int TREE_NODES_PER_BLOCK = 4 * OPT_WY;
+
+// FACTOR: the sweep that follows an accepted step (factorise at the new point, solve for the gradient);
+// otherwise the solve inside a CG iteration (same vectors as tn_update_kernel)
+template <bool FACTOR>
+__device__ __forceinline__ bool tree_lane_active(const TnArgs& a, int b) {
+    if (b >= a.o.B) return false;
+    if (FACTOR) {
+        const int dec = lane_decision(a, b);
+        return dec == DEC_ACCEPT || dec == DEC_INIT;
+    }
+    return a.st[b] == TS_CG && (a.act[b] & ACT_CG);
+}
+
+template <bool FACTOR>
+__global__ void __launch_bounds__(32 * OPT_WY) tn_tree_up_kernel(TnArgs a, int level) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    if (!tree_lane_active<FACTOR>(a, b)) return;
+    DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0};
+    const int k0 = a.lev_off[level] + blockIdx.y * TREE_NODES_PER_BLOCK;
+    const int k1 = min(a.lev_off[level + 1], k0 + TREE_NODES_PER_BLOCK);
+    for (int k = k0 + threadIdx.y; k < k1; k += OPT_WY) {
+        const int i = a.lev_nodes[k];
+        if (FACTOR) tree_factor_node(V, i);
+        tree_up_node(V, i);
+    }
+}
+
+template <bool FACTOR>
+__global__ void __launch_bounds__(32 * OPT_WY) tn_tree_down_kernel(TnArgs a, int level) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    if (!tree_lane_active<FACTOR>(a, b)) return;
+    DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0};
+    const int k0 = a.lev_off[level] + blockIdx.y * TREE_NODES_PER_BLOCK;
+    const int k1 = min(a.lev_off[level + 1], k0 + TREE_NODES_PER_BLOCK);
+    for (int k = k0 + threadIdx.y; k < k1; k += OPT_WY) tree_down_node(V, a.lev_nodes[k]);
+}
+
+// the narrow levels [nlev_wide, nlev): up to the root and back down inside one block per vector group
+template <bool FACTOR>
+__global__ void __launch_bounds__(32 * TREE_TOP_WY) tn_tree_top_kernel(TnArgs a) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    const bool active = tree_lane_active<FACTOR>(a, b);
+    if (!__syncthreads_or(active)) return;
+    DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[min(b, a.o.B - 1)] : a.lambda, a.pb, a.log_pen != 0};
+    for (int level = a.nlev_wide; level < a.nlev; level++) {
+        if (active)
+            for (int k = a.lev_off[level] + threadIdx.y; k < a.lev_off[level + 1]; k += TREE_TOP_WY) {
+                const int i = a.lev_nodes[k];
+                if (FACTOR) tree_factor_node(V, i);
+                tree_up_node(V, i);
+            }
+        __syncthreads();
+    }
+    for (int level = a.nlev - 1; level >= a.nlev_wide; level--) {
+        if (active)
+            for (int k = a.lev_off[level] + threadIdx.y; k < a.lev_off[level + 1]; k += TREE_TOP_WY) tree_down_node(V, a.lev_nodes[k]);
+        __syncthreads();
+    }
+}
+
+// after the sweeps: [p = zz,] r.zz -> the state machine that the Jacobi path runs inside tn_setup / tn_update
+template <bool FACTOR>
+__global__ void __launch_bounds__(32 * OPT_WY) tn_pc_finish_kernel(TnArgs a) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int b = blockIdx.x * 32 + tx;
+    const int B = a.o.B, P = a.o.P;
+    const bool active = tree_lane_active<FACTOR>(a, b);
+    if (!__syncthreads_or(active)) return;
+    double v[1] = {0.0};
+    if (active) {
+        const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
+        for (int p = p0 + ty; p < p1; p += OPT_WY) {
+            const size_t i = (size_t)p * B + b;
+            const double zz = a.ZZ[i];
+            if (FACTOR) a.Pv[i] = zz;
+            v[0] = fma(a.R[i], zz, v[0]);
+        }
+    }
+    if (!group_reduce<1, 0u, 0u>(v, a.part_pc, a.cnt_pc, B, b)) return;
+    if (ty == 0 && active) {
+        if (FACTOR) {
+            const double red[3] = {v[0], a.gmax_tmp[b], a.gg_tmp[b]};
+            if (phase_setup(lane_of(a, b), a.Ft[b], red, a.o)) atomicAdd(a.ndone, 1);
+        } else {
+            phase_update(lane_of(a, b), v, a.o);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_dir_kernel(TnArgs a) {
@@ -330,6 +453,11 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_stepmax_kernel(TnArgs a) {
             if (ri >= 0) { const double sc = a.sc[ri]; zi = a.Z[(size_t)ri * B + b] * sc; di = a.S[(size_t)ri * B + b] * sc; } else zi = a.t.hfix[i];
             if (rp >= 0) { const double sc = a.sc[rp]; zp = a.Z[(size_t)rp * B + b] * sc; dp = a.S[(size_t)rp * B + b] * sc; } else zp = a.t.hfix[pa];
             v[0] = fmin(v[0], tplopt::branch_step_limit(zi, di, zp, dp));
+            if (ri >= 0) v[0] = fmin(v[0], tplopt::bound_step_limit(a.Z[(size_t)ri * B + b], a.S[(size_t)ri * B + b], a.lo[ri], a.hi[ri]));
+        }
+        if (blockIdx.y == 0 && ty == 0) {            // the root's own date (no branch above it)
+            const int r0 = a.t.dslot[0];
+            if (r0 >= 0) v[0] = fmin(v[0], tplopt::bound_step_limit(a.Z[(size_t)r0 * B + b], a.S[(size_t)r0 * B + b], a.lo[r0], a.hi[r0]));
         }
     }
     if (!group_reduce<1, 0u, 1u>(v, a.part_tm, a.cnt_tm, B, b)) return;

@@ -151,7 +151,7 @@ TPL_HD void phase_finish(const Lane& L, double gd, double tmin, const TnConst& o
 // ---- node-level Hessian --------------------------------------------------------------------------------------------
 // View: accessor of ONE vector's operands (device: strided global arrays; host: plain arrays).  Required members:
 //   int n; int parent(i), child_begin(i), child_end(i), child(j), rslot(i), dslot(i);
-//   double c(i), hfix(i), rfix(i), pmin(i), pmax(i), sc(row), x(row), v(row), gx(row), lam, pb; bool masked(i);
+//   double c(i), hfix(i), rfix(i), pmin(i), pmax(i), sc(row), x(row), v(row), gx(row), lam, pb; bool masked(i), log_pen;
 // Writes W(row) through view.put(row, value).
 
 template <class View>
@@ -189,15 +189,19 @@ TPL_HD void hess_node(View& V, int i, double& vw, double& vv) {
         if (p != 0) {
             w_r += lam2 * (vr - vrp);
         } else {                                             // child of the root: variance term over ALL root children
-            double sum = 0.0, m = 0.0;
+            double sum = 0.0, m = 0.0, sy = 0.0;
             for (int j = V.child_begin(0); j < V.child_end(0); j++) {
                 bool f2;
                 double r2, h2, vr2, vh2;
                 node_values(V, V.child(j), f2, r2, h2, vr2, vh2);
-                sum += vr2;
+                if (V.log_pen) { sum += vr2 / r2; sy += log(r2); }      // y = ln r: dy = dr / r
+                else sum += vr2;
                 m += 1.0;
             }
-            w_r += (lam2 / m) * (vr - sum / m);
+            if (V.log_pen)                                    // pl_calc_parallel.cpp:866-879 with y = ln r
+                w_r += (lam2 / m) * ((vr / r - sum / m) / r - (log(r) - sy / m) * vr / (r * r));
+            else
+                w_r += (lam2 / m) * (vr - sum / m);
         }
     }
     for (int j = V.child_begin(i); j < V.child_end(i); j++) {
@@ -240,6 +244,9 @@ TPL_HD void hess_node(View& V, int i, double& vw, double& vv) {
     }
 }
 
+template <class View>
+TPL_HD double root_child_curvature(const View& V, int i, double r);
+
 // diagonal of H_z for the rows of node i
 template <class View>
 TPL_HD void diag_node(View& V, int i) {
@@ -259,10 +266,7 @@ TPL_HD void diag_node(View& V, int i) {
         H_r = c / (r * r);
         H_h = c / (d * d);
         if (p != 0) H_r += lam2;
-        else {
-            const double m = (double)(V.child_end(0) - V.child_begin(0));
-            H_r += (lam2 / m) * (1.0 - 1.0 / m);
-        }
+        else H_r += root_child_curvature(V, i, r);
     }
     for (int j = V.child_begin(i); j < V.child_end(i); j++) {
         const int ch = V.child(j);
@@ -292,6 +296,190 @@ TPL_HD void diag_node(View& V, int i) {
         const double sc = V.sc(ds);
         V.put(ds, sc * sc * H_h);
     }
+}
+
+// ---- tree-structured preconditioner -----------------------------------------------------------------------------------
+// With one 2x2 block (z_u, z_h) per node, H_z is BLOCK-TREE structured: every term of the objective couples a node with
+// its parent only (branch likelihood: r_i, h_i, h_p; roughness: r_i, r_p), except the variance term over the children of
+// the root, which couples siblings.  M = H_z without those sibling couplings is therefore factorised EXACTLY, without
+// fill-in, by eliminating children before parents (block LDL^T over the tree, 2x2 pivots):
+//     S_i = A_i - sum_ch C_ch^T S_ch^-1 C_ch          (A_i diagonal block, C_i coupling of node i with its parent)
+//     up:   y_i = rhs_i - sum_ch K_ch^T y_ch,  K_i = S_i^-1 C_i
+//     down: x_i = S_i^-1 y_i - K_i x_parent
+// A pivot that is not safely positive definite (far from the optimum H_z can be indefinite) falls back to the absolute
+// diagonal for that variable, so M is SPD by construction and CG stays valid; near the optimum M = H_z up to the sibling
+// couplings of the root's children (a rank-2 perturbation for a binary root), and CG needs a handful of iterations
+// whatever the smoothing value.  The reference's TNC preconditions with a diagonal BFGS update (src/tnc.c:829-905), which
+// is what makes its solves at large smoothing x large trees slow; this replaces the Jacobi preconditioner of round 1.
+// Node-indexed work planes TW[q][node] per vector:
+enum { TW_S = 0 /* s11 s12 s22: inverse pivot */, TW_K = 3 /* k11 k12 k21 k22: S^-1 C */, TW_T = 7 /* t11 t12 t22: C^T K */,
+       TW_Y = 10 /* y_u y_h */, TW_PLANES = 12 };
+// Additional View members: bool fr(row) (row is a free variable of this solve), double rhs(row), double outv(row),
+// double tw(q, i), void tw_put(q, i, value), bool log_pen.
+
+template <class View>
+TPL_HD void node_rh(const View& V, int i, double& r, double& h) {
+    const int rs = V.rslot(i), ds = V.dslot(i);
+    r = rs >= 0 ? V.x(rs) : V.rfix(i);
+    h = ds >= 0 ? V.x(ds) : V.hfix(i);
+}
+
+// second derivative of the root-children variance term with respect to the rate of root child i (x space), and its
+// sibling part; plain penalty: (lam2/m)(1 - 1/m).  Log penalty (pl_calc_parallel.cpp:866-879, y = ln r):
+// d2/dr_i2 = (lam2/m)[(1 - 1/m) - (y_i - ybar)] / r_i^2
+template <class View>
+TPL_HD double root_child_curvature(const View& V, int i, double r) {
+    const int j0 = V.child_begin(0), j1 = V.child_end(0);
+    const double m = (double)(j1 - j0);
+    const double lam2 = 2.0 * V.lam;
+    if (!V.log_pen) return (lam2 / m) * (1.0 - 1.0 / m);
+    double sy = 0.0;
+    for (int j = j0; j < j1; j++) {
+        double r2, h2;
+        node_rh(V, V.child(j), r2, h2);
+        sy += log(r2);
+    }
+    return (lam2 / m) * ((1.0 - 1.0 / m) - (log(r) - sy / m)) / (r * r);
+}
+
+// factorisation step of node i (its children are done): writes TW_S, TW_K, TW_T
+template <class View>
+TPL_HD void tree_factor_node(View& V, int i) {
+    const int rs = V.rslot(i), ds = V.dslot(i);
+    const bool mi = V.masked(i);
+    const bool fu = rs >= 0 && !mi && V.fr(rs);
+    const bool fh = ds >= 0 && V.fr(ds);
+    const double lam2 = 2.0 * V.lam;
+    double r, h;
+    node_rh(V, i, r, h);
+    double Hrr = 0.0, Hhh = 0.0, Hrh = 0.0;
+    double cuu = 0.0, cuh = 0.0, chh = 0.0;                   // z-space coupling with the parent's (u, h)
+    const double su = rs >= 0 ? V.sc(rs) * r : 0.0, sh = ds >= 0 ? V.sc(ds) : 0.0;
+    if (i != 0 && !mi) {
+        const int p = V.parent(i);
+        double rp, hp;
+        node_rh(V, p, rp, hp);
+        const double d = safe_duration(hp - h);
+        const double c = V.c(i);
+        const double cdd = c / (d * d);
+        Hrr = c / (r * r);
+        Hhh = cdd;
+        Hrh = -1.0;
+        if (p != 0) Hrr += lam2;
+        else Hrr += root_child_curvature(V, i, r);
+        const int prs = V.rslot(p), pds = V.dslot(p);
+        const bool pu = prs >= 0 && !V.masked(p) && V.fr(prs);
+        const bool ph = pds >= 0 && V.fr(pds);
+        if (fu && pu && p != 0) cuu = -lam2 * su * (V.sc(prs) * rp);
+        if (fu && ph) cuh = su * V.sc(pds);
+        if (fh && ph) chh = -cdd * sh * V.sc(pds);
+    }
+    double a = 0.0, b = 0.0, dd = 0.0;
+    for (int j = V.child_begin(i); j < V.child_end(i); j++) {
+        const int ch = V.child(j);
+        a -= V.tw(TW_T + 0, ch);
+        b -= V.tw(TW_T + 1, ch);
+        dd -= V.tw(TW_T + 2, ch);
+        if (V.masked(ch)) continue;
+        if (ds >= 0) {
+            double rc, hc;
+            node_rh(V, ch, rc, hc);
+            const double dc = safe_duration(h - hc);
+            Hhh += V.c(ch) / (dc * dc);
+        }
+        if (rs >= 0 && i != 0 && !mi) Hrr += lam2;
+    }
+    if (ds >= 0) {
+        const double pmn = V.pmin(i), pmx = V.pmax(i);
+        if (pmn != -1.0) { const double q = h - pmn; if (q > 0.0) Hhh += V.pb * 2.0 / (q * q * q); }
+        if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) Hhh += V.pb * 2.0 / (q * q * q); }
+    }
+    double a0 = 1.0, d0 = 1.0;                                 // the node's own diagonal (what Jacobi would use)
+    if (fu) { a0 = su * su * Hrr + V.gx(rs) * V.sc(rs) * su; a += a0; a0 = fabs(a0); } else { a = 1.0; b = 0.0; }
+    if (fh) { d0 = sh * sh * Hhh; dd += d0; d0 = fabs(d0); } else { dd = 1.0; b = 0.0; }
+    if (fu && fh) b += su * sh * Hrh;
+    // safeguards: every pivot positive definite (M is SPD whatever H_z is).  An indefinite pivot is replaced by its
+    // absolute value |S| = Q |L| Q^T (eigenvalues mirrored, floored relative to the node's own diagonal): the curvature
+    // MAGNITUDE along a negative-curvature direction still sets the step length there, and M = H_z wherever H_z is
+    // positive definite.
+    double s11 = 0.0, s12 = 0.0, s22 = 0.0;
+    if (fu && fh) {
+        const double mean = 0.5 * (a + dd), dif = 0.5 * (a - dd);
+        const double rad = sqrt(dif * dif + b * b);
+        double l1 = mean + rad, l2 = mean - rad;                 // l1 >= l2
+        const double fl = 1e-10 * fmax(a0, d0);
+        if (!(l2 > fl) || !opt_finite(l1)) {
+            if (!opt_finite(l1) || !opt_finite(l2)) {            // NaN / inf: Jacobi for this node
+                a = a0 > 1e-300 ? a0 : 1.0; dd = d0 > 1e-300 ? d0 : 1.0; b = 0.0;
+            } else {
+                const double m1 = fmax(fabs(l1), fl), m2 = fmax(fabs(l2), fl);
+                // eigenvector of l1: (b, l1 - a) or (l1 - dd, b); pick the better conditioned one
+                double vx, vy;
+                if (fabs(l1 - a) > fabs(l1 - dd)) { vx = b; vy = l1 - a; } else { vx = l1 - dd; vy = b; }
+                const double nrm = sqrt(vx * vx + vy * vy);
+                if (nrm > 0.0) { vx /= nrm; vy /= nrm; } else { vx = 1.0; vy = 0.0; }
+                a = m1 * vx * vx + m2 * vy * vy;
+                dd = m1 * vy * vy + m2 * vx * vx;
+                b = (m1 - m2) * vx * vy;
+            }
+        }
+        const double det = a * dd - b * b;
+        s11 = dd / det; s12 = -b / det; s22 = a / det;
+    } else if (fu) {
+        if (!(a > 1e-10 * a0)) a = fmax(fabs(a), a0 > 1e-300 ? 1e-10 * a0 : 1.0);
+        if (!opt_finite(a)) a = a0 > 1e-300 && opt_finite(a0) ? a0 : 1.0;
+        s11 = 1.0 / a;
+    } else if (fh) {
+        if (!(dd > 1e-10 * d0)) dd = fmax(fabs(dd), d0 > 1e-300 ? 1e-10 * d0 : 1.0);
+        if (!opt_finite(dd)) dd = d0 > 1e-300 && opt_finite(d0) ? d0 : 1.0;
+        s22 = 1.0 / dd;
+    }
+    V.tw_put(TW_S + 0, i, s11);
+    V.tw_put(TW_S + 1, i, s12);
+    V.tw_put(TW_S + 2, i, s22);
+    const double k11 = s11 * cuu, k12 = s11 * cuh + s12 * chh, k21 = s12 * cuu, k22 = s12 * cuh + s22 * chh;
+    V.tw_put(TW_K + 0, i, k11);
+    V.tw_put(TW_K + 1, i, k12);
+    V.tw_put(TW_K + 2, i, k21);
+    V.tw_put(TW_K + 3, i, k22);
+    V.tw_put(TW_T + 0, i, cuu * k11);
+    V.tw_put(TW_T + 1, i, cuu * k12);
+    V.tw_put(TW_T + 2, i, cuh * k12 + chh * k22);
+}
+
+// forward substitution at node i (children done): y_i = rhs_i - sum_ch K_ch^T y_ch
+template <class View>
+TPL_HD void tree_up_node(View& V, int i) {
+    const int rs = V.rslot(i), ds = V.dslot(i);
+    double yu = (rs >= 0 && V.fr(rs) && !V.masked(i)) ? V.rhs(rs) : 0.0;
+    double yh = (ds >= 0 && V.fr(ds)) ? V.rhs(ds) : 0.0;
+    for (int j = V.child_begin(i); j < V.child_end(i); j++) {
+        const int ch = V.child(j);
+        const double cu = V.tw(TW_Y + 0, ch), chh = V.tw(TW_Y + 1, ch);
+        yu -= V.tw(TW_K + 0, ch) * cu + V.tw(TW_K + 2, ch) * chh;
+        yh -= V.tw(TW_K + 1, ch) * cu + V.tw(TW_K + 3, ch) * chh;
+    }
+    V.tw_put(TW_Y + 0, i, yu);
+    V.tw_put(TW_Y + 1, i, yh);
+}
+
+// back substitution at node i (parent done): x_i = S_i^-1 y_i - K_i x_parent, written to the rows of node i
+template <class View>
+TPL_HD void tree_down_node(View& V, int i) {
+    const int rs = V.rslot(i), ds = V.dslot(i);
+    const double yu = V.tw(TW_Y + 0, i), yh = V.tw(TW_Y + 1, i);
+    const double s12 = V.tw(TW_S + 1, i);
+    double xu = V.tw(TW_S + 0, i) * yu + s12 * yh;
+    double xh = s12 * yu + V.tw(TW_S + 2, i) * yh;
+    if (i != 0) {
+        const int p = V.parent(i);
+        const int prs = V.rslot(p), pds = V.dslot(p);
+        const double pu = prs >= 0 ? V.outv(prs) : 0.0, ph = pds >= 0 ? V.outv(pds) : 0.0;
+        xu -= V.tw(TW_K + 0, i) * pu + V.tw(TW_K + 1, i) * ph;
+        xh -= V.tw(TW_K + 2, i) * pu + V.tw(TW_K + 3, i) * ph;
+    }
+    if (rs >= 0) V.put(rs, xu);
+    if (ds >= 0) V.put(ds, xh);
 }
 
 // inverse of the (absolute) diagonal; 0 freezes the variable (on a bound with the gradient pushing outward,

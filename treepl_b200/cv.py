@@ -162,8 +162,6 @@ def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_p
     n = len(flat["parents"])
     plp = eng.PLCalcParallel.from_flat(flat, device=device)
     plp.set_log_pen(log_pen)
-    if log_pen:
-        opt.setdefault("method", 0)              # the truncated-Newton kernels carry the plain-penalty Hessian only
     fp, P = eng.generate_param_order_vector(flat["free"], lf=False)
     plp.set_freeparams(P, False, fp)
     nr = n - 1

@@ -35,7 +35,7 @@ _lib = None
 class OptOptions(C.Structure):
     """tpl_opt_options (include/treepl_b200.h); 0 = library default"""
     _fields_ = [("history", C.c_int), ("max_steps", C.c_int), ("patience", C.c_int), ("max_ls", C.c_int),
-                ("check_every", C.c_int), ("use_graph", C.c_int), ("method", C.c_int), ("max_cg", C.c_int), ("cg_per_step", C.c_int), ("ftol", C.c_double), ("gtol", C.c_double),
+                ("check_every", C.c_int), ("use_graph", C.c_int), ("method", C.c_int), ("max_cg", C.c_int), ("cg_per_step", C.c_int), ("precond", C.c_int), ("ftol", C.c_double), ("gtol", C.c_double),
                 ("armijo", C.c_double), ("date_scale", C.c_double), ("boundary_frac", C.c_double)]
 
 
@@ -102,6 +102,8 @@ def load_library():
     L.tpl_anneal_batch.argtypes = [vp, ci, dp, dp, C.POINTER(AnnealOptions), ip, ip]
     L.tpl_debug_hessvec.restype = ci
     L.tpl_debug_hessvec.argtypes = [vp, ci, dp, dp, dp, dp, dp]
+    L.tpl_debug_treesolve.restype = ci
+    L.tpl_debug_treesolve.argtypes = [vp, ci, dp, dp, dp, dp, dp]
     L.tpl_host_alloc.restype = vp
     L.tpl_host_alloc.argtypes = [C.c_ulonglong]
     L.tpl_host_free.restype = None
@@ -117,7 +119,7 @@ EXPORTED_SYMBOLS = (
     "tpl_calc_function_gradient", "tpl_calc_pl_grad", "tpl_get_rates", "tpl_get_dates", "tpl_get_durations",
     "tpl_batch_configure", "tpl_calc_pl_grad_batch", "tpl_calc_pl_grad_batch_dev", "tpl_last_launch_count",
     "tpl_host_alloc", "tpl_host_free", "tpl_device_sm", "tpl_debug_math", "tpl_set_timing", "tpl_get_timing", "tpl_debug_force_kernel",
-    "tpl_last_kernel_generation", "tpl_optimize_batch", "tpl_debug_hessvec", "tpl_anneal_batch",
+    "tpl_last_kernel_generation", "tpl_optimize_batch", "tpl_debug_hessvec", "tpl_debug_treesolve", "tpl_anneal_batch",
 )
 
 
@@ -358,7 +360,7 @@ class PLCalcParallel:
     def optimize_batch(self, X0, lower, upper, mode=GRAD_AD, **options):
         """Device-resident batched L-BFGS (tpl_optimize_batch): X0 [P, B] feasible start vectors ->
         (X [P, B], F [B], info).  options: fields of tpl_opt_options (history, max_steps, patience, max_ls,
-        check_every, use_graph, method (0 L-BFGS, 1 truncated Newton), max_cg, ftol, gtol, armijo, date_scale, boundary_frac)."""
+        check_every, use_graph, method (0 L-BFGS, 1 truncated Newton), max_cg, cg_per_step, precond, ftol, gtol, armijo, date_scale, boundary_frac)."""
         X = _f64(X0).copy()
         P, B = X.shape
         if P != self.numparams:
@@ -396,6 +398,14 @@ class PLCalcParallel:
             setattr(o, k, v)
         self._check(self._L.tpl_anneal_batch(self._h, B, _dp(X), _dp(F), C.byref(o), _ip(status), _ip(iters)))
         return X, F, status, iters
+
+    def debug_treesolve(self, X, free, rhs, sc_rows):
+        """-> M^-1 rhs through the block-tree factorisation kernels of the truncated-Newton method (test hook)."""
+        X, Fr, R, sc = _f64(X), _f64(free), _f64(rhs), _f64(sc_rows)
+        P, B = X.shape
+        out = np.zeros((P, B))
+        self._check(self._L.tpl_debug_treesolve(self._h, B, _dp(X), _dp(Fr), _dp(R), _dp(sc), _dp(out)))
+        return out
 
     def debug_hessvec(self, X, V, sc_rows):
         """-> (H_z V, diag H_z) at X through the truncated-Newton kernels (test hook)."""

@@ -24,8 +24,6 @@ def fit(flat, smoothing, device=0, log_pen=False, anneal=False, **opt):
     x0 = cv.start_vector(flat, P, n - 1)
     par = flat["parents"]
     dscale = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
-    if log_pen:
-        opt.setdefault("method", 0)
     X0 = np.repeat(x0[:, None], 2, axis=1)
     if anneal:
         X0, _, _, _ = plp.anneal_batch(X0)
