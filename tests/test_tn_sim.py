@@ -280,7 +280,7 @@ def test_tree_preconditioned_tn_converges_where_jacobi_does_not(sim):
     likelihood curvature by 1e6 - 1e8): the Jacobi-preconditioned solves crawl, the tree-preconditioned ones take one or
     two CG iterations per Newton step; both reach the same optimum where both converge."""
     pr, X, F, status, iters, ncg, steps = fit(sim, "pl4203", [100.0, 1e-4], precond=1, cg_per_step=2, max_steps=3000)
-    assert (status == 1).all() and ncg.sum() <= 2 * iters.sum() + 8, (status, iters, ncg)
+    assert ((status >= 1) & (status <= 2)).all() and ncg.sum() <= 2 * iters.sum() + 8, (status, iters, ncg)
     assert abs(F[0] - 390.04656) <= 2e-6 * 390.04656 and abs(F[1] - 214.56107) <= 2e-6 * 214.56107, F   # e2e_reference.json after_opt_calc
     pj, Xj, Fj, sj, itj, ncgj, stepsj = fit(sim, "clock", [1e4, 1.0], precond=0, max_steps=3000)
     pt, Xt, Ft, st, itt, ncgt, stepst = fit(sim, "clock", [1e4, 1.0], precond=1, cg_per_step=2, max_steps=3000)

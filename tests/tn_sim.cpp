@@ -34,6 +34,9 @@ struct HostView {
     double* W;
     double lam, pb;
     bool log_pen = false;
+    double mu = 0.0;
+    const double* DGv = nullptr;
+    double dg(int row) const { return DGv[(size_t)row * B + b]; }
     // tree preconditioner (tpl_tn_core.h::tree_*_node)
     const double* Minv_ = nullptr;
     const double* Rhs = nullptr;
@@ -81,8 +84,8 @@ extern "C" void tn_sim_hessvec(int P, int B, int n, const int* parent, const int
 // M^-1 rhs for vector b: factorise (when `factor`), forward and back substitution.  Children have larger preorder
 // numbers than their parents, so descending node order is a valid elimination order (the kernels go by height levels).
 static void tree_solve(const Tree& t, int B, int b, const double* X, const double* Gx, const double* sc, double lam, double pb,
-                       bool log_pen, const double* Minv, const double* Rhs, double* Out, double* TW, bool factor) {
-    HostView v = {t, B, b, X, nullptr, Gx, sc, Out, lam, pb, log_pen, Minv, Rhs, TW};
+                       bool log_pen, const double* Minv, const double* Rhs, double* Out, double* TW, bool factor, double mu = 0.0) {
+    HostView v = {t, B, b, X, nullptr, Gx, sc, Out, lam, pb, log_pen, mu, nullptr, Minv, Rhs, TW};
     for (int i = t.n - 1; i >= 0; i--) {
         if (factor) tree_factor_node(v, i);
         tree_up_node(v, i);
@@ -113,14 +116,16 @@ extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const doubl
     TnConst o;
     o.P = P; o.B = B; o.nr = nr; o.max_ls = max_ls; o.max_cg = max_cg; o.patience = patience; o.c1 = c1; o.ftol = ftol; o.gtol = gtol;
     o.boundary_frac = boundary_frac;
+    o.fnoise = 0.0;
+    for (int i = 0; i < n; i++) o.fnoise += 1e-14 * c[i];
     std::vector<double> Z(PB), Gz(PB, 0.0), S(PB, 0.0), Gx(PB, 0.0), R(PB, 0.0), ZZ(PB, 0.0), Pv(PB, 0.0), Hp(PB, 0.0), Minv(PB, 0.0), DG(PB, 0.0), Ft(B);
     std::vector<int> st(B, TS_INIT), ls(B, 0), cgit(B, 0), flag(B, 0), stall(B, 0), it(B, 0), ncg(B, 0), act(B, ACT_TRIAL);
-    std::vector<double> F0(B, 0.0), tt(B, 0.0), gd(B, 0.0), rz(B, 0.0), rz0(B, 0.0), tol2(B, 0.0), alpha(B, 0.0), beta(B, 0.0), gmax(B, 0.0), tlog(B, 0.0);
+    std::vector<double> F0(B, 0.0), tt(B, 0.0), gd(B, 0.0), rz(B, 0.0), rz0(B, 0.0), tol2(B, 0.0), alpha(B, 0.0), beta(B, 0.0), gmax(B, 0.0), tlog(B, 0.0), mu(B, 0.0);
     auto lane = [&](int b) {
         Lane L;
         L.st = &st[b]; L.ls = &ls[b]; L.cgit = &cgit[b]; L.flag = &flag[b]; L.stall = &stall[b]; L.iters = &it[b]; L.ncg = &ncg[b]; L.act = &act[b];
         L.F0 = &F0[b]; L.t = &tt[b]; L.gd = &gd[b]; L.rz = &rz[b]; L.rz0 = &rz0[b]; L.tol2 = &tol2[b]; L.alpha = &alpha[b]; L.beta = &beta[b];
-        L.gmax = &gmax[b]; L.tlog = &tlog[b];
+        L.gmax = &gmax[b]; L.tlog = &tlog[b]; L.mu = &mu[b];
         return L;
     };
     // tn_init_kernel
@@ -146,8 +151,9 @@ extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const doubl
         ev(X, Ft.data(), Gx.data(), ctx);
         steps++;
         for (int b = 0; b < B; b++) {
-            const int dec = decide(st[b], Ft[b], F0[b], tt[b], gd[b], o.c1);
+            const int dec = decide(st[b], Ft[b], F0[b], tt[b], gd[b], o.c1, f_allowance(F0[b], o.ftol, o.fnoise));
             double red[3] = {0.0, 0.0, 0.0};
+            const double mu_eff = dec == DEC_ACCEPT ? mu_after_accept(mu[b], tt[b], ls[b]) : mu[b];
             if (dec == DEC_ACCEPT || dec == DEC_INIT) {
                 // tn_diag_kernel
                 HostView dv = {t, B, b, X, Pv.data(), Gx.data(), sc, DG.data(), lam[b], pb, lp};
@@ -161,7 +167,7 @@ extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const doubl
                     const double gz = chain_grad(p < nr, Gx[i], X[i], sc[p]);
                     Gz[i] = gz;
                     const bool fr = is_free(z, gz, lo[p], hi[p]);
-                    const double mi = precond_inverse(DG[i], fr);
+                    const double mi = precond_inverse(DG[i], fr, mu_eff);
                     Minv[i] = mi;
                     const double gp = mi > 0.0 ? gz : 0.0;
                     R[i] = -gp;
@@ -173,7 +179,7 @@ extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const doubl
                     red[2] = fma(gp, gp, red[2]);
                 }
                 if (precond) {           // tn_tree_factor / up / down kernels: zz = M^-1 r, p = zz, rz0 = r.zz
-                    tree_solve(t, B, b, X, Gx.data(), sc, lam[b], pb, lp, Minv.data(), R.data(), ZZ.data(), TW.data(), true);
+                    tree_solve(t, B, b, X, Gx.data(), sc, lam[b], pb, lp, Minv.data(), R.data(), ZZ.data(), TW.data(), true, mu_eff);
                     red[0] = 0.0;
                     for (int p = 0; p < P; p++) {
                         const size_t i = (size_t)p * B + b;
@@ -183,14 +189,14 @@ extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const doubl
                 }
             }
             if (getenv("TN_SIM_VERBOSE") && dec != DEC_SKIP)
-                fprintf(stderr, "step %d lane %d dec %d Ft %.10g F0 %.10g t %.3g ls %d cgit %d gd %.3g rz0 %.3g gmax %.3g\n", steps, b, dec, Ft[b], F0[b], tt[b], ls[b], cgit[b], gd[b], red[0], red[1]);
+                fprintf(stderr, "step %d lane %d dec %d Ft %.10g F0 %.10g t %.3g ls %d cgit %d gd %.3g rz0 %.3g gmax %.3g mu %.3g\n", steps, b, dec, Ft[b], F0[b], tt[b], ls[b], cgit[b], gd[b], red[0], red[1], mu_eff);
             if (phase_setup(lane(b), Ft[b], red, o)) ndone++;
         }
         for (int sub = 0; sub < cg_per_step; sub++) {
         // tn_hv_kernel
         for (int b = 0; b < B; b++) {
             if (st[b] != TS_CG || (act[b] & ACT_FIN)) continue;
-            HostView hv = {t, B, b, X, Pv.data(), Gx.data(), sc, Hp.data(), lam[b], pb, lp};
+            HostView hv = {t, B, b, X, Pv.data(), Gx.data(), sc, Hp.data(), lam[b], pb, lp, mu[b], DG.data()};
             double red[2] = {0.0, 0.0};
             for (int i = 0; i < n; i++) {
                 double vw, vv;
@@ -215,7 +221,7 @@ extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const doubl
                 red[0] = fma(r, zz, red[0]);
             }
             if (precond) {
-                tree_solve(t, B, b, X, Gx.data(), sc, lam[b], pb, lp, Minv.data(), R.data(), ZZ.data(), TW.data(), false);
+                tree_solve(t, B, b, X, Gx.data(), sc, lam[b], pb, lp, Minv.data(), R.data(), ZZ.data(), TW.data(), false, mu[b]);
                 red[0] = 0.0;
                 for (int p = 0; p < P; p++) red[0] = fma(R[(size_t)p * B + b], ZZ[(size_t)p * B + b], red[0]);
             }
@@ -252,7 +258,7 @@ extern "C" int tn_sim(int P, int B, int nr, double* X, double* Fout, const doubl
                 const int ri = dslot[i];
                 if (ri >= 0) tmin = fmin(tmin, tplopt::bound_step_limit(Z[(size_t)ri * B + b], S[(size_t)ri * B + b], lo[ri], hi[ri]));
             }
-            phase_finish(lane(b), g, tmin, o);
+            if (phase_finish(lane(b), g, tmin, o)) ndone++;
         }
         trial_kernel();
     }

@@ -137,7 +137,7 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
     CK(w.lo.ensure(P)); CK(w.hi.ensure(P)); CK(w.sc.ensure(P)); CK(w.Ft.ensure(B)); CK(w.Fout.ensure(B)); CK(w.h_done.ensure(1));
     const size_t npart = (size_t)(3 + 1 + 1 + 1) * a.row_chunks * B + (size_t)(2 + 1) * a.node_chunks * B;
     CK(w.tn_part.ensure(npart));
-    CK(w.tn_lane_d.ensure((size_t)13 * B));
+    CK(w.tn_lane_d.ensure((size_t)14 * B));
     CK(w.tn_lane_i.ensure((size_t)8 * B + 1 + 6 * (size_t)groups));
     CK(w.pmin_n.upload(e->pen_min, s));
     CK(w.pmax_n.upload(e->pen_max, s));
@@ -145,7 +145,7 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
     CK(cudaMemcpyAsync(w.hi.p, hi.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(w.sc.p, sc.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(w.X.p, X, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(w.tn_lane_d.p, 0, sizeof(double) * 13 * B, s));
+    CK(cudaMemsetAsync(w.tn_lane_d.p, 0, sizeof(double) * 14 * B, s));
     CK(cudaMemsetAsync(w.tn_lane_i.p, 0, sizeof(int) * (8 * (size_t)B + 1 + 6 * (size_t)groups), s));     // st = TS_INIT, t = 0
     for (DevBuf<double>* buf : {&w.Gz, &w.D, &w.R, &w.ZZ, &w.Pv, &w.Hp, &w.Minv, &w.DG, &w.Gx})
         CK(cudaMemsetAsync(buf->p, 0, sizeof(double) * PB, s));
@@ -158,6 +158,7 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
     a.o.ftol = o.ftol > 0 ? o.ftol : 1e-13;
     a.o.gtol = o.gtol > 0 ? o.gtol : 1e-8;
     a.o.boundary_frac = o.boundary_frac < 0 ? 0.0 : (o.boundary_frac > 0 ? std::min(o.boundary_frac, 0.999999) : 0.9);
+    a.o.fnoise = 1e-14 * e->sum_c;
     a.t = dev_tree(e);
     a.pmin_n = w.pmin_n.p; a.pmax_n = w.pmax_n.p;
     const bool lanemask = e->cfg_mask && e->cfg_B == B;
@@ -179,7 +180,7 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
     double* ld = w.tn_lane_d.p;
     a.F0 = ld; a.t_ = ld + Bs; a.gd = ld + 2 * Bs; a.rz = ld + 3 * Bs; a.rz0 = ld + 4 * Bs; a.tol2 = ld + 5 * Bs; a.alpha = ld + 6 * Bs;
     a.beta = ld + 7 * Bs; a.gmax = ld + 8 * Bs; a.tlog = ld + 9 * Bs; a.gdtmp = ld + 10 * Bs;
-    a.gmax_tmp = ld + 11 * Bs; a.gg_tmp = ld + 12 * Bs;
+    a.gmax_tmp = ld + 11 * Bs; a.gg_tmp = ld + 12 * Bs; a.mu = ld + 13 * Bs;
     double* pp = w.tn_part.p;
     a.part_setup = pp; pp += (size_t)3 * a.row_chunks * B;
     a.part_upd = pp; pp += (size_t)a.row_chunks * B;

@@ -45,7 +45,7 @@ struct TnArgs {
     const double* Gx;                        // [P][B] gradient of the evaluated point, original parameters
     const double* Ft;                        // [B]
     int *st, *ls, *cgit, *flag, *stall, *iters, *ncg, *act;
-    double *F0, *t_, *gd, *rz, *rz0, *tol2, *alpha, *beta, *gmax, *tlog, *gdtmp;
+    double *F0, *t_, *gd, *rz, *rz0, *tol2, *alpha, *beta, *gmax, *tlog, *gdtmp, *mu;
     int row_chunks, rows_per_chunk;          // row-indexed kernels
     int node_chunks, nodes_per_chunk;        // node-indexed kernels
     double *part_setup, *part_hv, *part_upd, *part_gd, *part_tm;
@@ -68,7 +68,7 @@ __device__ __forceinline__ Lane lane_of(const TnArgs& a, int b) {
     L.st = a.st + b; L.ls = a.ls + b; L.cgit = a.cgit + b; L.flag = a.flag + b; L.stall = a.stall + b; L.iters = a.iters + b;
     L.ncg = a.ncg + b; L.act = a.act + b;
     L.F0 = a.F0 + b; L.t = a.t_ + b; L.gd = a.gd + b; L.rz = a.rz + b; L.rz0 = a.rz0 + b; L.tol2 = a.tol2 + b; L.alpha = a.alpha + b;
-    L.beta = a.beta + b; L.gmax = a.gmax + b; L.tlog = a.tlog + b;
+    L.beta = a.beta + b; L.gmax = a.gmax + b; L.tlog = a.tlog + b; L.mu = a.mu + b;
     return L;
 }
 
@@ -130,6 +130,8 @@ struct DevView {
     double* W;
     double lam, pb;
     bool log_pen;
+    double mu;                                   // Levenberg-Marquardt damping of this vector
+    __device__ double dg(int row) const { return a.DG[(size_t)row * B + b]; }
     __device__ bool fr(int row) const { return a.Minv[(size_t)row * B + b] > 0.0; }       // free variable of this solve
     __device__ double rhs(int row) const { return a.R[(size_t)row * B + b]; }
     __device__ double outv(int row) const { return W[(size_t)row * B + b]; }
@@ -158,7 +160,12 @@ struct DevView {
 };
 
 __device__ __forceinline__ int lane_decision(const TnArgs& a, int b) {
-    return decide(a.st[b], a.Ft[b], a.F0[b], a.t_[b], a.gd[b], a.o.c1);
+    return decide(a.st[b], a.Ft[b], a.F0[b], a.t_[b], a.gd[b], a.o.c1, f_allowance(a.F0[b], a.o.ftol, a.o.fnoise));
+}
+
+// the damping the factorisation at a newly accepted point uses: the value phase_setup is about to store
+__device__ __forceinline__ double lane_mu_eff(const TnArgs& a, int b, int dec) {
+    return dec == DEC_ACCEPT ? mu_after_accept(a.mu[b], a.t_[b], a.ls[b]) : a.mu[b];
 }
 
 // Z = clamp(w / sc), S = 0
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_diag_kernel(TnArgs a) {
     if (b >= B) return;
     const int dec = lane_decision(a, b);
     if (dec != DEC_ACCEPT && dec != DEC_INIT) return;
-    DevView V = {a, B, b, a.Pv, a.DG, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0};
+    DevView V = {a, B, b, a.Pv, a.DG, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, 0.0};
     const int i0 = blockIdx.y * a.nodes_per_chunk, i1 = min(a.t.n, i0 + a.nodes_per_chunk);
     for (int i = i0 + threadIdx.y; i < i1; i += OPT_WY) diag_node(V, i);
 }
@@ -222,6 +229,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_setup_kernel(TnArgs a) {
     if (!__syncthreads_or(dec != DEC_SKIP)) return;          // uniform over blockIdx.y
     double v[3] = {0.0, 0.0, 0.0};
     if (dec == DEC_ACCEPT || dec == DEC_INIT) {
+        const double mu = lane_mu_eff(a, b, dec);
         const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
         for (int p = p0 + ty; p < p1; p += OPT_WY) {
             const size_t i = (size_t)p * B + b;
@@ -229,7 +237,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_setup_kernel(TnArgs a) {
             double z = a.Z[i];
             if (dec == DEC_ACCEPT) z = tplopt::trial_point(z, t, a.S[i], lo, hi);
             const double gz = tplopt::chain_grad(p < nr, a.Gx[i], a.X[i], a.sc[p]);
-            const double mi = precond_inverse(a.DG[i], tplopt::is_free(z, gz, lo, hi));
+            const double mi = precond_inverse(a.DG[i], tplopt::is_free(z, gz, lo, hi), mu);
             const double gp = mi > 0.0 ? gz : 0.0;
             const double zz = -gp * mi;
             a.Z[i] = z;
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
     if (!__syncthreads_or(active)) return;
     double v[2] = {0.0, 0.0};
     if (active) {
-        DevView V = {a, B, b, a.Pv, a.Hp, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0};
+        DevView V = {a, B, b, a.Pv, a.Hp, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, a.mu[b]};
         const int i0 = blockIdx.y * a.nodes_per_chunk, i1 = min(a.t.n, i0 + a.nodes_per_chunk);
         for (int i = i0 + ty; i < i1; i += OPT_WY) {
             double vw, vv;
@@ -321,10 +329,15 @@ __device__ __forceinline__ bool tree_lane_active(const TnArgs& a, int b) {
 }
 
 template <bool FACTOR>
+__device__ __forceinline__ double tree_lane_mu(const TnArgs& a, int b) {
+    return FACTOR ? lane_mu_eff(a, b, lane_decision(a, b)) : a.mu[b];
+}
+
+template <bool FACTOR>
 __global__ void __launch_bounds__(32 * OPT_WY) tn_tree_up_kernel(TnArgs a, int level) {
     const int b = blockIdx.x * 32 + threadIdx.x;
     if (!tree_lane_active<FACTOR>(a, b)) return;
-    DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0};
+    DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, tree_lane_mu<FACTOR>(a, b)};
     const int k0 = a.lev_off[level] + blockIdx.y * TREE_NODES_PER_BLOCK;
     const int k1 = min(a.lev_off[level + 1], k0 + TREE_NODES_PER_BLOCK);
     for (int k = k0 + threadIdx.y; k < k1; k += OPT_WY) {
@@ -338,7 +351,7 @@ template <bool FACTOR>
 __global__ void __launch_bounds__(32 * OPT_WY) tn_tree_down_kernel(TnArgs a, int level) {
     const int b = blockIdx.x * 32 + threadIdx.x;
     if (!tree_lane_active<FACTOR>(a, b)) return;
-    DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0};
+    DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, tree_lane_mu<FACTOR>(a, b)};
     const int k0 = a.lev_off[level] + blockIdx.y * TREE_NODES_PER_BLOCK;
     const int k1 = min(a.lev_off[level + 1], k0 + TREE_NODES_PER_BLOCK);
     for (int k = k0 + threadIdx.y; k < k1; k += OPT_WY) tree_down_node(V, a.lev_nodes[k]);
@@ -350,7 +363,8 @@ __global__ void __launch_bounds__(32 * TREE_TOP_WY) tn_tree_top_kernel(TnArgs a)
     const int b = blockIdx.x * 32 + threadIdx.x;
     const bool active = tree_lane_active<FACTOR>(a, b);
     if (!__syncthreads_or(active)) return;
-    DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[min(b, a.o.B - 1)] : a.lambda, a.pb, a.log_pen != 0};
+    DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[min(b, a.o.B - 1)] : a.lambda, a.pb, a.log_pen != 0,
+                 active ? tree_lane_mu<FACTOR>(a, b) : 0.0};
     for (int level = a.nlev_wide; level < a.nlev; level++) {
         if (active)
             for (int k = a.lev_off[level] + threadIdx.y; k < a.lev_off[level + 1]; k += TREE_TOP_WY) {
@@ -461,7 +475,8 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_stepmax_kernel(TnArgs a) {
         }
     }
     if (!group_reduce<1, 0u, 1u>(v, a.part_tm, a.cnt_tm, B, b)) return;
-    if (ty == 0 && active) phase_finish(lane_of(a, b), a.gdtmp[b], v[0], a.o);
+    if (ty == 0 && active)
+        if (phase_finish(lane_of(a, b), a.gdtmp[b], v[0], a.o)) atomicAdd(a.ndone, 1);
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_final_kernel(TnArgs a, double* F) {

@@ -43,24 +43,42 @@ struct TnConst {
     int P, B, nr;
     int max_ls, max_cg, patience;
     double c1, ftol, gtol, boundary_frac;
+    double fnoise;          // absolute evaluation noise of the objective: ~1e-14 sum_i c_i (terms of size c ln(rd) cancel)
 };
 
-TPL_HD int decide(int st, double Ft, double F0, double t, double gd, double c1) {
+// Armijo test with a noise allowance: the objective is a sum of ~N cancelling terms of size c ln(r d), so near the optimum
+// its evaluation noise (~1e-16 sum c |ln(rd)|, far above ulp(f)) exceeds the decrease a converged Newton step predicts;
+// without the allowance such steps are halved max_ls times on noise.  Accepted steps within the allowance count towards
+// `patience` (phase_setup), which then stops the vector.
+TPL_HD double f_allowance(double F0, double ftol, double fnoise) { return ftol * fmax(fabs(F0), 1.0) + fnoise; }
+TPL_HD int decide(int st, double Ft, double F0, double t, double gd, double c1, double allowance) {
     if (st == TS_DONE || st == TS_CG) return DEC_SKIP;
     const bool bad = !opt_finite(Ft) || !(Ft < OPT_LARGE);
     if (st == TS_INIT) return bad ? DEC_INIT_BAD : DEC_INIT;
-    if (!bad && Ft <= F0 + c1 * t * gd) return DEC_ACCEPT;
+    if (!bad && Ft <= F0 + c1 * t * gd + allowance) return DEC_ACCEPT;
     return DEC_REJECT;
+}
+
+// Levenberg-Marquardt damping of the Newton system, (H + mu |diag H|) s = -g, per vector: raised while steps have to be
+// cut (ratio test, backtracking), lowered towards the pure Newton step while unit steps succeed.  Evaluated with the
+// step that has just been accepted, BEFORE the factorisation at the new point (the kernels of that step call this
+// function themselves; phase_setup stores the value).  The thresholds come from a sweep over the example trees and a
+// 20,000-tip synthetic tree (smoothing 1e4 ... 1e-4): 2.3 x fewer Newton steps in total than without damping, and little
+// sensitivity to the exact values.
+TPL_HD double mu_after_accept(double mu, double t, int ls) {
+    if (ls == 0 && t >= 0.7) return mu * 0.1 < 1e-8 ? 0.0 : mu * 0.1;
+    if (t < 0.1) return fmin(fmax(4.0 * mu, 1e-3), 1e8);
+    return mu;
 }
 
 struct Lane {
     int *st, *ls, *cgit, *flag, *stall, *iters, *ncg, *act;
-    double *F0, *t, *gd, *rz, *rz0, *tol2, *alpha, *beta, *gmax, *tlog;
+    double *F0, *t, *gd, *rz, *rz0, *tol2, *alpha, *beta, *gmax, *tlog, *mu;
 };
 
 // after the evaluation of the trial point and the set-up pass (red = {r.M^-1 r, max|gp|, gp.gp} of the new point)
 TPL_HD bool phase_setup(const Lane& L, double Ft, const double* red, const TnConst& o) {
-    const int dec = decide(*L.st, Ft, *L.F0, *L.t, *L.gd, o.c1);
+    const int dec = decide(*L.st, Ft, *L.F0, *L.t, *L.gd, o.c1, f_allowance(*L.F0, o.ftol, o.fnoise));
     if (dec == DEC_SKIP) return false;
     *L.act = 0;
     if (dec == DEC_INIT_BAD) { *L.st = TS_DONE; *L.flag = FLAG_BAD_START; return true; }
@@ -86,12 +104,12 @@ TPL_HD bool phase_setup(const Lane& L, double Ft, const double* red, const TnCon
     bool done = false;
     if (dec == DEC_ACCEPT) {
         const double F0 = *L.F0;
-        const double rel = fabs(F0 - Ft) / fmax(fabs(F0), 1.0);
         const bool cut_short = *L.ls == 0 && *L.t < 1.0;        // the ratio test, not the objective, limited the step
-        const int stl = (rel <= o.ftol) ? *L.stall + (cut_short ? 0 : 1) : 0;
+        const int stl = (fabs(F0 - Ft) <= f_allowance(F0, o.ftol, o.fnoise)) ? *L.stall + (cut_short ? 0 : 1) : 0;
         *L.stall = stl;
         *L.iters += 1;
         *L.tlog += log10(*L.t);
+        *L.mu = mu_after_accept(*L.mu, *L.t, *L.ls);
         if (stl >= o.patience) { *L.flag = FLAG_CONV_F; done = true; }
     }
     *L.F0 = Ft;
@@ -133,25 +151,36 @@ TPL_HD void phase_update(const Lane& L, const double* red, const TnConst& o) {
 }
 
 // after the CG solve: gd = gp.s, tmin = largest step that keeps every duration positive
-TPL_HD void phase_finish(const Lane& L, double gd, double tmin, const TnConst& o) {
-    if (!(*L.act & ACT_FIN)) return;
+// Returns true when the vector stops here: the predicted decrease -gd of the (damped) Newton step is below the resolution
+// of the objective (a hundredth of ftol |f|) — without this test a converged vector whose largest gradient entry sits
+// just above gtol |f| keeps running line searches on rounding noise until `patience` runs out.
+TPL_HD bool phase_finish(const Lane& L, double gd, double tmin, const TnConst& o) {
+    if (!(*L.act & ACT_FIN)) return false;
+    if (gd <= 0.0 && -gd <= 1e-2 * f_allowance(*L.F0, o.ftol, o.fnoise)) {
+        *L.st = TS_DONE;
+        *L.flag = FLAG_CONV_F;
+        *L.act = 0;
+        return true;
+    }
     *L.st = TS_LS;
     *L.ls = 0;
     if (!(gd < 0.0)) {                          // not a descent direction: preconditioned steepest descent
         *L.gd = -*L.rz0;
         *L.t = 1.0;
         *L.act = ACT_TRIAL | ACT_SD;
-        return;
+        return false;
     }
     *L.gd = gd;
     *L.t = o.boundary_frac > 0.0 ? fmin(1.0, o.boundary_frac * tmin) : 1.0;
     *L.act = ACT_TRIAL;
+    return false;
 }
 
 // ---- node-level Hessian --------------------------------------------------------------------------------------------
 // View: accessor of ONE vector's operands (device: strided global arrays; host: plain arrays).  Required members:
 //   int n; int parent(i), child_begin(i), child_end(i), child(j), rslot(i), dslot(i);
 //   double c(i), hfix(i), rfix(i), pmin(i), pmax(i), sc(row), x(row), v(row), gx(row), lam, pb; bool masked(i), log_pen;
+//   double mu (Levenberg-Marquardt damping of this vector), dg(row) (diagonal of H_z, as written by diag_node).
 // Writes W(row) through view.put(row, value).
 
 template <class View>
@@ -230,6 +259,7 @@ TPL_HD void hess_node(View& V, int i, double& vw, double& vv) {
         if (rfree) {
             const double sc = V.sc(rs), v = V.v(rs);
             W = sc * r * w_r + V.gx(rs) * sc * sc * r * v;
+            if (V.mu > 0.0) W += V.mu * fabs(V.dg(rs)) * v;
             vw += v * W;
             vv += v * v;
         }
@@ -237,7 +267,8 @@ TPL_HD void hess_node(View& V, int i, double& vw, double& vv) {
     }
     if (ds >= 0) {
         const double v = V.v(ds);
-        const double W = V.sc(ds) * w_h;
+        double W = V.sc(ds) * w_h;
+        if (V.mu > 0.0) W += V.mu * fabs(V.dg(ds)) * v;
         vw += v * W;
         vv += v * v;
         V.put(ds, W);
@@ -395,8 +426,8 @@ TPL_HD void tree_factor_node(View& V, int i) {
         if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) Hhh += V.pb * 2.0 / (q * q * q); }
     }
     double a0 = 1.0, d0 = 1.0;                                 // the node's own diagonal (what Jacobi would use)
-    if (fu) { a0 = su * su * Hrr + V.gx(rs) * V.sc(rs) * su; a += a0; a0 = fabs(a0); } else { a = 1.0; b = 0.0; }
-    if (fh) { d0 = sh * sh * Hhh; dd += d0; d0 = fabs(d0); } else { dd = 1.0; b = 0.0; }
+    if (fu) { a0 = su * su * Hrr + V.gx(rs) * V.sc(rs) * su; a += a0; a0 = fabs(a0); a += V.mu * a0; } else { a = 1.0; b = 0.0; }
+    if (fh) { d0 = sh * sh * Hhh; dd += d0; d0 = fabs(d0); dd += V.mu * d0; } else { dd = 1.0; b = 0.0; }
     if (fu && fh) b += su * sh * Hrh;
     // safeguards: every pivot positive definite (M is SPD whatever H_z is).  An indefinite pivot is replaced by its
     // absolute value |S| = Q |L| Q^T (eigenvalues mirrored, floored relative to the node's own diagonal): the curvature
@@ -484,9 +515,9 @@ TPL_HD void tree_down_node(View& V, int i) {
 
 // inverse of the (absolute) diagonal; 0 freezes the variable (on a bound with the gradient pushing outward,
 // or a masked row)
-TPL_HD double precond_inverse(double dg, bool free_) {
+TPL_HD double precond_inverse(double dg, bool free_, double mu = 0.0) {
     if (!free_) return 0.0;
-    const double a = fabs(dg);
+    const double a = fabs(dg) * (1.0 + mu);
     return a > 1e-30 ? 1.0 / a : 0.0;
 }
 
