@@ -19,17 +19,27 @@ N > 1 (torchrun): one process per GPU, every rank evaluates its own B vectors of
 (CV folds / restarts are independent: weak scaling, no data-path collective); barrier + device
 timing, max over ranks.  `--impl reference` times the reference CPU path alone (rank 0 only).
 
-Second workload (BASELINE.json: "LOO-CV wall time at 1/8 B200"), not the driver's default:
+The default line also carries, at EVERY N, `sharded`: the optimiser-level jobs north_star shards over the GPUs (M1155 LOOCV,
+1,024 restarts of big_test, LOOCV of the big_test tree = 23,285 optimisations, random-subsample CV of the 100k-tip tree), each
+as wall seconds of the same job on N GPUs (strong scaling) with converged counts and chi-square tables; `--impl reference`
+carries the reference's own optimiser stack on the host cores for them (whole job for M1155, bounded + extrapolated samples
+for the big_test jobs).
+
+Each of these jobs can also be the measured workload (BASELINE.json: "LOO-CV wall time at 1/8 B200"):
     python bench.py --workload loocv [--gpus N] [--steps K] [--impl reference]
 one step = the complete leave-one-out cross-validation of examples/M1155.cppr8s (59 folds x 5 smoothing values,
-tests/golden/M1155.npz) with the library's device-resident batched L-BFGS; the (smoothing, fold) vectors are
+tests/golden/M1155.npz) with the library's device-resident batched truncated Newton; the (smoothing, fold) vectors are
 dealt to the ranks and the chi-square terms all-gathered over NCCL (strong scaling).  The reference arm replays
-the reference's own CV loop around its optimize_full (annealer + TNC) on the host cores (oracle/_ref).
-    python bench.py --workload restarts [--gpus N]
+the reference's own CV loop around its optimize_full (annealer + TNC / NLopt) on the host cores (oracle/_ref).
+    python bench.py --workload loocv_big [--gpus N]
+the same for the 4,657-tip examples/big_test.cppr8s tree (23,285 optimisations of 13,967 parameters).
+    python bench.py --workload restarts | restarts_cfg4 [--gpus N]
 one step = 1,024 random-restart optimisations of the examples/big_test.cppr8s tree (BASELINE.json config 4), starts
-dealt to the ranks, best-of-restarts exchange over NCCL.
+dealt to the ranks, best-of-restarts exchange over NCCL (restarts_cfg4: the control file's smooth = 0.0001 + log_pen).
     python bench.py --workload cv100k [--gpus N] [--cv-steps S]
-random-subsample CV over 16 smoothing values on the synthetic 100k-tip tree (BASELINE.json config 5), capped.
+random-subsample CV over 16 smoothing values on the synthetic 100k-tip tree (BASELINE.json config 5).
+    python bench.py --workload sweep
+B sweep of the evaluation path and the B = 1 callback latency next to the reference's per-evaluation time.
 """
 import argparse
 import json
@@ -227,20 +237,16 @@ def run_reference_arm(args, flat, P):
                                    % (args.tips, n, P)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    if not args.no_loocv:
-        # second half of BASELINE.json's metric: LOO-CV wall time (one run of the reference's CV loop, all host threads)
-        try:
-            gd, cals, tips = load_m1155()
-            p = rb.RefProblem.from_newick(gd.meta["newick"], gd.meta["numsites"], cals, seed=1)
-            t = time.perf_counter()
-            r = p.cross_validate(M1155_GRID, [[t_] for t_ in tips], nthreads=nthreads)
-            line["loocv"] = {"workload": "examples/M1155.cppr8s LOOCV (59 folds x 5 smoothing values)",
-                             "wall_s": time.perf_counter() - t, "cores": nthreads,
-                             "kind": "reference CV loop replayed around the reference's optimize_full (annealer + TNC)",
-                             "full_objective": r["full_pl"].tolist()}
-            p.close()
-        except Exception as ex:
-            line["loocv"] = {"error": repr(ex)}
+    if not args.no_sharded:
+        # the sharded optimiser-level jobs of the b200 arm's `sharded` key: the reference's own optimiser stack on all host
+        # threads - the whole M1155 LOOCV, and BOUNDED SAMPLES (extrapolated, labelled) of the two big_test jobs
+        sh = {}
+        for name, fn in (("loocv_M1155", ref_loocv_m1155), ("restarts", ref_sample_restarts), ("loocv_big_test", ref_sample_loocv_big)):
+            try:
+                sh[name] = fn(nthreads)
+            except Exception as ex:
+                sh[name] = {"error": repr(ex)}
+        line["sharded"] = sh
     print(json.dumps(line))
 
 
@@ -258,14 +264,228 @@ def load_m1155():
     return gd, cals, [int(t) for t in ft.tips_postorder]
 
 
-def run_loocv(args):
-    """--workload loocv: wall time of the complete M1155 leave-one-out cross-validation."""
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+BIG_GRID = [1000.0, 100.0, 10.0, 1.0, 0.1]          # the reference's default CV grid (cvstart 1000, cvstop 0.1, cvmultstep 0.1)
+N_STARTS = 1024
+
+
+def load_big_test():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import Golden
+    return dict(Golden("big_test").flat)
+
+
+def restart_vectors(flat, P, ks, jitter=0.3, seed=1):
+    """the start vectors of cv.multistart, [len(ks), P] (start k depends on (seed, k) only)"""
+    from treepl_b200 import cv
+    nr = len(flat["parents"]) - 1
+    x0 = cv.start_vector(flat, P, nr)
+    X0 = np.repeat(x0[None, :], len(ks), axis=0)
+    for j, k in enumerate(ks):
+        X0[j, :nr] *= np.exp(jitter * np.random.RandomState(seed * 1000003 + k).randn(nr))
+    return X0
+
+
+class Ranks:
+    """torch.distributed plumbing shared by the sharded jobs: barrier + device sync around a wall-clock region,
+    max over ranks."""
+
+    def __init__(self, dist, local):
+        import torch
+        self.torch, self.dist, self.local = torch, dist, local
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.dev = torch.device("cuda", local)
+
+    def fence(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn):
+        self.fence()
+        t = time.perf_counter()
+        res = fn()
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        dt = time.perf_counter() - t
+        return res, self.vmax(dt)
+
+    def vmax(self, v):
+        if self.dist is None:
+            return float(v)
+        tt = self.torch.tensor([float(v)], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(tt, op=self.dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def vsum(self, v):
+        if self.dist is None:
+            return v
+        tt = self.torch.tensor([float(v)], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(tt)
+        return float(tt.item())
+
+
+def job_loocv(rk, which, runs=1, warm=0):
+    """Complete leave-one-out cross-validation (main.cpp:588-822) of `which` = "M1155" (examples/M1155.cppr8s: 59 folds x
+    5 smoothing values, P = 170) or "big_test" (the examples/big_test.cppr8s tree: 4,657 folds x 5 smoothing values =
+    23,285 optimisations of P = 13,967); (smoothing, fold) vectors dealt to the ranks, chi-square terms all-gathered."""
+    from treepl_b200 import cv
+    if which == "M1155":
+        gd, cals, tips = load_m1155()
+        flat, grid = dict(gd.flat), M1155_GRID
+    else:
+        flat, grid = load_big_test(), BIG_GRID
+        tips = [int(t) for t in np.flatnonzero(flat["child_counts"] == 0)]
+    P = int((flat["free"] == 1).sum()) + len(flat["parents"]) - 1
+    times, res = [], None
+    for s in range(warm + runs):
+        res, dt = rk.timed(lambda: cv.loocv(dict(flat), grid, tips, device=rk.local, max_iter=6000, dist=rk.dist))
+        if s >= warm:
+            times.append(dt)
+    val = sum(times) / len(times)
+    out = {"workload": "LOOCV of the %s tree: %d folds x %d smoothing values = %d optimisations of P=%d parameters" % (
+               "examples/M1155.cppr8s" if which == "M1155" else "examples/big_test.cppr8s (comm_mol_rr.tre, N=9313)",
+               len(tips), len(grid), len(tips) * len(grid), P),
+           "wall_s": val, "runs": len(times), "n_gpus": rk.world, "chisq": res["chisq"], "best_smoothing": res["best"],
+           "full_objective": res["full_objective"], "full_fits_converged": res["full_converged"],
+           "fold_vectors_converged": int(rk.vsum(res["cv_converged"])), "fold_vectors": len(tips) * len(grid),
+           "seconds": {"full_fits": res["full_seconds"], "folds": res["cv_seconds"], "scoring_and_gather": res["gather_seconds"]},
+           "device_ms": {"full_fits": res["full_device_ms"], "folds": res["cv_device_ms"]},
+           "batched_evaluations": {"full_fits": res["full_info"]["nfev"], "folds": res["cv_nfev"]},
+           "hessian_vector_products_rank0": res["cg_iterations"], "gpu_launches": int(res["launches"]) * rk.world,
+           "n_local_vectors": res["n_local_vectors"], "P": P}
+    if which == "M1155":
+        out["chisq_reference_run"] = M1155_REF_CHISQ
+        out["chisq_max_rel_diff"] = max(abs(a - b) / b for a, b in zip(res["chisq"], M1155_REF_CHISQ))
+    return out
+
+
+def job_restarts(rk, runs=1, warm=0, config4=False):
+    """BASELINE.json config 4: 1,024 batched random-restart optimisations of the examples/big_test.cppr8s tree
+    (N = 9,313, P = 13,967), starts dealt to the ranks, best-of-restarts exchange.  config4: the control file's own
+    objective (smooth = 0.0001, log_pen; big_test.cppr8s:6,14) instead of smoothing 1."""
+    from treepl_b200 import cv
+    flat = load_big_test()
+    lam, lp = (0.0001, True) if config4 else (1.0, False)
+    times, res = [], None
+    for s in range(warm + runs):
+        res, dt = rk.timed(lambda: cv.multistart(flat, lam, N_STARTS, device=rk.local, dist=rk.dist, check_every=50, log_pen=lp))
+        if s >= warm:
+            times.append(dt)
+    val = sum(times) / len(times)
+    return {"workload": "examples/big_test.cppr8s tree (N=9313, P=13967), smoothing %g%s: %d random-restart optimisations to |g| <= 1e-8 |f|"
+                        % (lam, ", log_pen" if lp else "", N_STARTS),
+            "wall_s": val, "runs": len(times), "n_gpus": rk.world, "optimisations_per_second": N_STARTS / val,
+            "converged": int(rk.vsum(res["local_converged"])), "best_objective": res["best"], "winner_rank": res["winner_rank"],
+            "objective_spread_rank0": [float(np.min(res["local_objectives"])), float(np.max(res["local_objectives"]))],
+            "gpu_launches": int(res["launches"]) * rk.world, "batched_evaluations": res["nfev"],
+            "hessian_vector_products_rank0": res["cg_iterations"], "n_local": res["n_local"]}
+
+
+def job_cv100k(rk, tips_n, cv_steps):
+    """BASELINE.json config 5: random-subsample cross-validation (10 folds of 10 % of the tips, main.cpp:609-656) over 16
+    smoothing values 10^3 ... 10^-1 on the synthetic 100,000-tip tree, (smoothing, fold) vectors dealt to the ranks."""
+    from treepl_b200 import cv
+    flat = build_problem(tips_n)
+    tips = np.flatnonzero(flat["child_counts"] == 0)
+    grid = [float(v) for v in 10.0 ** np.linspace(3, -1, 16)]
+    groups = cv.sample_random_groups(flat, tips, n_groups=10, frac=0.1, seed=1)
+    res, dt = rk.timed(lambda: cv.cross_validate(flat, grid, groups, randomcv=True, device=rk.local, dist=rk.dist,
+                                                 max_iter=max(1, cv_steps // 20), check_every=25))
+    n = flat["parents"].shape[0]
+    return {"workload": "synthetic %d-tip Yule tree (N=%d): random-subsample CV, 10 folds x 10 %% of the tips, 16 smoothing values "
+                        "1e3..1e-1 = 16 full-data fits + 160 fold optimisations, each capped at %d batched evaluations" % (tips_n, n, cv_steps),
+            "wall_s": dt, "runs": 1, "n_gpus": rk.world, "chisq": res["chisq"], "best_smoothing": res["best"],
+            "full_objective": res["full_objective"], "full_fits_converged": res["full_converged"],
+            "fold_vectors_converged": int(rk.vsum(res["cv_converged"])), "fold_vectors": 160,
+            "seconds": {"full_fits": res["full_seconds"], "folds": res["cv_seconds"], "scoring_and_gather": res["gather_seconds"]},
+            "gpu_launches": int(res["launches"]) * rk.world, "n_local_vectors": res["n_local_vectors"]}
+
+
+# ---- reference arms of the sharded jobs: BOUNDED SAMPLES of the reference's own optimiser stack on the host cores ----
+def ref_sample_restarts(nthreads, budget_starts=None):
+    """One optimize_full (utils.cpp:671-763: annealer + TNC rounds, default OptimOptions) per host thread on the first
+    `nthreads` of the 1,024 starts; the 1,024-start wall time is extrapolated (starts are independent)."""
+    from oracle import refbind as rb
+    from treepl_b200 import treeflat as tf
+    flat = load_big_test()
+    fp, P = tf.generate_param_order_vector(flat["free"], lf=False)
+    k = budget_starts or nthreads
+    X0 = restart_vectors(flat, P, list(range(k)))
+    rp = rb.RefProblem.from_flat(flat)
+    rp.set_smoothing(1.0)
+    rp.set_freeparams(False)
+    f, secs = rp.multistart(X0, nthreads=nthreads)
+    rp.close()
+    return {"workload": "examples/big_test.cppr8s tree, smoothing 1: %d of the %d random starts, reference optimize_full, one per host thread" % (k, N_STARTS),
+            "sample_wall_s": secs, "sample_starts": k, "cores": nthreads,
+            "wall_s_extrapolated": secs * N_STARTS / k, "extrapolation": "sample_wall_s x %d / %d (independent starts, all cores busy)" % (N_STARTS, k),
+            "objectives": f.tolist(),
+            "note": "the reference's optimisers stop far above the optimum on this tree from these starts (b200 arm: 291875.3)"}
+
+
+def ref_sample_loocv_big(nthreads):
+    """Reference CV loop (oracle/ref_harness.cpp::ref_cv = main.cpp:497-822 replayed around the reference's optimize_full) on the
+    big_test tree: Langley-Fitch fit + ONE smoothing value's full fit + `nthreads` folds; the 5 x 4,657-fold wall time is extrapolated."""
+    from oracle import refbind as rb
+    flat = load_big_test()
+    tips = [int(t) for t in np.flatnonzero(flat["child_counts"] == 0)]
+    rp = rb.RefProblem.from_flat(flat)
+    r = rp.cross_validate([10.0], [[t] for t in tips[:nthreads]], nthreads=nthreads)
+    rp.close()
+    sec = {k: float(v) for k, v in r["seconds"].items()}
+    nl, nf = len(BIG_GRID), len(tips)
+    extr = sec["lf"] + nl * sec["full"] + nl * sec["folds"] * nf / nthreads
+    return {"workload": "LOOCV of the examples/big_test.cppr8s tree: Langley-Fitch fit, 1 of %d smoothing values, %d of %d folds, %d host threads" % (nl, nthreads, nf, nthreads),
+            "sample_seconds": sec, "cores": nthreads, "wall_s_extrapolated": extr,
+            "extrapolation": "lf + %d x full + %d x folds x %d / %d" % (nl, nl, nf, nthreads),
+            "full_objective_sample": r["full_pl"].tolist()}
+
+
+def ref_loocv_m1155(nthreads):
+    from oracle import refbind as rb
     gd, cals, tips = load_m1155()
-    workload = "examples/M1155.cppr8s: LOOCV, %d folds x %d smoothing values = %d optimisations of P=170 parameters" % (
-        len(tips), len(M1155_GRID), len(tips) * len(M1155_GRID))
+    p = rb.RefProblem.from_newick(gd.meta["newick"], gd.meta["numsites"], cals, seed=1)
+    t = time.perf_counter()
+    r = p.cross_validate(M1155_GRID, [[t_] for t_ in tips], nthreads=nthreads)
+    dt = time.perf_counter() - t
+    p.close()
+    return {"workload": "examples/M1155.cppr8s LOOCV (59 folds x 5 smoothing values): the whole job", "wall_s": dt, "cores": nthreads,
+            "kind": "reference CV loop replayed around the reference's optimize_full (annealer + TNC / NLopt)",
+            "chisq": r["chisq"].tolist(), "full_objective": r["full_pl"].tolist()}
+
+
+def reference_line(args, metric, value, unit, workload, sample, nthreads, hib=False, scaling="strong", data="synthetic", extra=None):
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * value if unit == "s" else None, "higher_is_better": hib, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f64", "data": data, "config": {"workload": workload},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": nthreads, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line.update(extra or {})
+    return line
+
+
+def init_ranks():
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the PL engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return Ranks(dist, local)
+
+
+def run_job_workload(args):
+    """--workload loocv | loocv_big | restarts | restarts_cfg4 | cv100k: the sharded job is the measured workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    w = args.workload
+    metric = {"loocv": "loocv_wall_seconds", "loocv_big": "loocv_wall_seconds", "restarts": "multistart_wall_seconds",
+              "restarts_cfg4": "multistart_wall_seconds", "cv100k": "random_cv_wall_seconds"}[w]
     if args.impl == "reference":
         if rank != 0:
             return
@@ -274,211 +494,142 @@ def run_loocv(args):
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libtreepl_ref.so is not built"}))
             return
         nthreads = max(1, os.cpu_count() or 1)
-        times, last = [], None
-        for s in range(args.warmup + args.steps):
-            p = rb.RefProblem.from_newick(gd.meta["newick"], gd.meta["numsites"], cals, seed=1)
-            t = time.perf_counter()
-            last = p.cross_validate(M1155_GRID, [[t_] for t_ in tips], nthreads=nthreads)
-            dt = time.perf_counter() - t
-            p.close()
-            if s >= args.warmup:
-                times.append(dt)
-        val = sum(times) / len(times)
-        sample = ("the whole workload: reference Langley-Fitch fit + CV loop (main.cpp:497-822 replayed) around the "
-                  "reference's optimize_full (annealer + TNC; NLopt not built), %d OpenMP threads over folds" % nthreads)
-        print(json.dumps({"impl": "reference", "metric": "loocv_wall_seconds", "value": val, "unit": "s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * val, "higher_is_better": False,
-                          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "examples/M1155.tre",
-                          "config": {"workload": workload},
-                          "chisq": last["chisq"].tolist(), "full_objective": last["full_pl"].tolist(),
-                          "note": "TNC-only replay: its optimiser stops short of the optimum (compare full_objective with the "
-                                  "b200 arm's), so its chi-square table is NOT the parity reference; SURVEY.md 8c's is",
-                          "cpu_baseline": {"value": val, "unit": "s", "cores": nthreads, "kind": "reference", "sample": sample},
-                          "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        if w == "loocv":
+            r = ref_loocv_m1155(nthreads)
+            print(json.dumps(reference_line(args, metric, r["wall_s"], "s", r["workload"], "the whole workload, %d OpenMP threads over folds" % nthreads,
+                                            nthreads, data="examples/M1155.tre", extra={"loocv": r})))
+        elif w == "loocv_big":
+            r = ref_sample_loocv_big(nthreads)
+            print(json.dumps(reference_line(args, metric, r["wall_s_extrapolated"], "s", r["workload"], r["extrapolation"] + " (EXTRAPOLATED from a bounded sample)",
+                                            nthreads, data="examples/comm_mol_rr.tre", extra={"loocv_big": r})))
+        elif w == "restarts":
+            r = ref_sample_restarts(nthreads)
+            print(json.dumps(reference_line(args, metric, r["wall_s_extrapolated"], "s", r["workload"], r["extrapolation"] + " (EXTRAPOLATED from a bounded sample)",
+                                            nthreads, data="examples/comm_mol_rr.tre", extra={"restarts": r})))
+        else:
+            print(json.dumps({"impl": "reference", "unavailable": "cv100k: the reference needs ~11 min of O(N^2) set-up and ~14 ms per evaluation per thread "
+                              "on this tree (SURVEY.md 6); restarts_cfg4: its optimize_full does not move from these starts under log_pen"}))
         return
-    import torch
-    from treepl_b200 import cv
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the PL engine has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    sampler = ClockSampler(local)
-    if rank == 0:
+    rk = init_ranks()
+    sampler = ClockSampler(rk.local)
+    if rk.rank == 0:
         sampler.start()
-    times, res = [], None
-    for s in range(args.warmup + args.steps):
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t = time.perf_counter()
-        res = cv.loocv(dict(gd.flat), M1155_GRID, tips, device=local, max_iter=6000, dist=dist)
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        dt = time.perf_counter() - t
-        if dist is not None:
-            tt = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        if s >= args.warmup:
-            times.append(dt)
-    clocks = sampler.stop() if rank == 0 else None
-    if rank == 0:
-        val = sum(times) / len(times)
-        chisq = res["chisq"]
-        rel = [abs(a - b) / b for a, b in zip(chisq, M1155_REF_CHISQ)]
-        print(json.dumps({"metric": "loocv_wall_seconds", "value": val, "unit": "s", "n_gpus": world, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": 1e3 * val, "higher_is_better": False, "scaling": "strong",
-                          "vs_baseline": None, "dtype": "f64", "data": "examples/M1155.tre (tests/golden/M1155.npz)",
-                          "config": {"workload": workload, "optimizer": "tpl_optimize_batch method 1 (batched truncated Newton, analytic Hessian-vector kernel, CUDA graph)",
-                                     "parallelism": "(smoothing, fold) vectors dealt to %d GPU(s), chi-square all-gather" % world},
-                          "gpu_launches": int(res["launches"]) * world, "clocks": clocks,
-                          "chisq": chisq, "chisq_reference_run": M1155_REF_CHISQ, "chisq_max_rel_diff": max(rel),
-                          "best_smoothing": res["best"], "full_objective": res["full_objective"],
-                          "device_ms": {"full_fits": res["full_device_ms"], "folds": res["cv_device_ms"]},
-                          "batched_evaluations": {"full_fits": res["full_info"]["nfev"], "folds": res["cv_nfev"]},
-                          "hessian_vector_products": res["cg_iterations"],
-                          "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": int(2 * 170 * 8 * (6 + res["n_local_vectors"])),
-                                  "d2h_bytes_per_step": int(2 * 170 * 8 * (6 + res["n_local_vectors"]))}}))
-    if dist is not None:
-        dist.destroy_process_group()
+    if w == "loocv":
+        r = job_loocv(rk, "M1155", runs=args.steps, warm=args.warmup)
+        data = "examples/M1155.tre (tests/golden/M1155.npz)"
+    elif w == "loocv_big":
+        r = job_loocv(rk, "big_test", runs=args.steps, warm=args.warmup)
+        data = "examples/comm_mol_rr.tre (tests/golden/big_test.npz)"
+    elif w in ("restarts", "restarts_cfg4"):
+        r = job_restarts(rk, runs=args.steps, warm=args.warmup, config4=(w == "restarts_cfg4"))
+        data = "examples/comm_mol_rr.tre (tests/golden/big_test.npz), synthetic random starts"
+    else:
+        r = job_cv100k(rk, args.tips, args.cv_steps)
+        data = "synthetic"
+    clocks = sampler.stop() if rk.rank == 0 else None
+    if rk.rank == 0:
+        P = r.get("P", 13967 if w.startswith("restarts") else 299996)
+        nloc = r.get("n_local_vectors", r.get("n_local", 0))
+        line = {"metric": metric, "value": r["wall_s"], "unit": "s", "n_gpus": rk.world, "steps": r["runs"], "warmup": args.warmup if w != "cv100k" else 0,
+                "ms_per_step": 1e3 * r["wall_s"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": data,
+                "config": {"workload": r["workload"], "optimizer": "tpl_optimize_batch method 1 (batched truncated Newton, analytic Hessian-vector kernel, "
+                           "block-tree preconditioner, CUDA graph)", "parallelism": "independent optimisations dealt to %d GPU(s); all-gather of chi-square terms / "
+                           "best objectives" % rk.world},
+                "gpu_launches": r["gpu_launches"], "clocks": clocks,
+                "e2e": {"value": r["wall_s"], "unit": "s", "h2d_bytes_per_step": int(8 * P * nloc), "d2h_bytes_per_step": int(8 * P * nloc)}}
+        line.update({k: v for k, v in r.items() if k not in ("workload", "wall_s", "runs", "gpu_launches")})
+        print(json.dumps(line))
+    if rk.dist is not None:
+        rk.dist.destroy_process_group()
 
 
-def run_restarts(args):
-    """--workload restarts: BASELINE.json config 4 - 1,024 batched random-restart optimisations of examples/big_test.cppr8s
-    (N = 9,313 nodes, P = 13,967 parameters) sharded over the GPUs, best-of-restarts exchange over NCCL."""
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+def run_sweep(args):
+    """--workload sweep: (1) evaluations/s and roofline fraction of the batched device-resident
+    entry at B in {1, 2, 16, 32, 64, 256, 1024} on the 100k-tip tree; (2) the B = 1 CALLBACK cost the reference's optimisers
+    pay (tpl_calc_pl_grad with host buffers: H2D of x, the kernels, D2H of f and g, one call per trial point - src/tnc.c:328)
+    on M1155 / big_test / the 100k-tip tree next to the reference's own calc_pl + calc_gradient on one host thread."""
+    import torch
+    from treepl_b200 import engine as eng
+    from treepl_b200 import treeflat as tf
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from golden_util import Golden
-    flat = dict(Golden("big_test").flat)
-    n_starts = 1024
-    workload = "examples/big_test.cppr8s tree (N=9313, P=13967), smoothing 1: %d random-restart optimisations to |g| <= 1e-8 |f|" % n_starts
-    if args.impl == "reference":
-        if rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "the reference has no batched multi-start driver; one big_test fit "
-                              "with its optimize_full takes minutes per start on one core (SURVEY.md 6)"}))
-        return
-    import torch
-    from treepl_b200 import cv
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the PL engine has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    times, res = [], None
-    for s in range(args.warmup + args.steps):
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t = time.perf_counter()
-        res = cv.multistart(flat, 1.0, n_starts, device=local, dist=dist, check_every=50)
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        dt = time.perf_counter() - t
-        if dist is not None:
-            tt = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        if s >= args.warmup:
-            times.append(dt)
-    clocks = sampler.stop() if rank == 0 else None
-    conv = res["local_converged"]
-    if dist is not None:
-        tt = torch.tensor([conv], dtype=torch.int64, device=torch.device("cuda", local))
-        dist.all_reduce(tt)
-        conv = int(tt.item())
-    if rank == 0:
-        val = sum(times) / len(times)
-        print(json.dumps({"metric": "multistart_wall_seconds", "value": val, "unit": "s", "n_gpus": world, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": 1e3 * val, "higher_is_better": False, "scaling": "strong",
-                          "vs_baseline": None, "dtype": "f64", "data": "examples/big_test.tre (tests/golden/big_test.npz), synthetic random starts",
-                          "config": {"workload": workload, "optimizer": "tpl_optimize_batch method 1 (batched truncated Newton)",
-                                     "parallelism": "starts dealt to %d GPU(s); all-gather of best objectives + broadcast of the winner" % world},
-                          "optimisations_per_second": n_starts / val, "converged": conv, "best_objective": res["best"],
-                          "winner_rank": res["winner_rank"], "gpu_launches": int(res["launches"]) * world, "clocks": clocks,
-                          "batched_evaluations": res["nfev"], "hessian_vector_products_rank0": res["cg_iterations"],
-                          "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": int(13967 * 8 * res["n_local"]),
-                                  "d2h_bytes_per_step": int(13967 * 8 * res["n_local"])}}))
-    if dist is not None:
-        dist.destroy_process_group()
-
-
-def run_cv100k(args):
-    """--workload cv100k: BASELINE.json config 5 - random-subsample cross-validation (10 folds of 10 % of the tips,
-    src/main.cpp:609-656) over 16 smoothing values 10^3 ... 10^-1 on the synthetic 100,000-tip tree, (smoothing, fold)
-    vectors dealt to the GPUs.  Every optimisation is capped at `--cv-steps` batched evaluations (x 4 CG iterations):
-    with the Jacobi preconditioner the vectors with smoothing >= ~50 are NOT converged at the default cap and the line
-    says how many are."""
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        if rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "the reference needs ~11 min of O(N^2) set-up and ~14 ms per "
-                              "evaluation per thread on this tree (SURVEY.md 6): its CV over 176 optimisations is not runnable"}))
-        return
-    import torch
-    from treepl_b200 import cv
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the PL engine has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    peak, peak_src = measured_peaks()
     flat = build_problem(args.tips)
-    tips = np.flatnonzero(flat["child_counts"] == 0)
-    grid = [float(v) for v in 10.0 ** np.linspace(3, -1, 16)]
-    groups = cv.sample_random_groups(flat, tips, n_groups=10, frac=0.1, seed=1)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t = time.perf_counter()
-    res = cv.cross_validate(flat, grid, groups, randomcv=True, device=local, dist=dist, max_iter=max(1, args.cv_steps // 20), check_every=25)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    dt = time.perf_counter() - t
-    conv = res["cv_converged"]
-    if dist is not None:
-        tt = torch.tensor([dt, float(conv)], dtype=torch.float64, device=torch.device("cuda", local))
-        mx = tt.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tt)
-        dt, conv = float(mx[0].item()), int(tt[1].item())
-    clocks = sampler.stop() if rank == 0 else None
-    if rank == 0:
-        n = flat["parents"].shape[0]
-        print(json.dumps({"metric": "random_cv_wall_seconds", "value": dt, "unit": "s", "n_gpus": world, "steps": 1, "warmup": 0,
-                          "ms_per_step": 1e3 * dt, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                          "data": "synthetic",
-                          "config": {"workload": "synthetic %d-tip Yule tree (N=%d): random-subsample CV, 10 folds x 10 %% of the tips, "
-                                                 "16 smoothing values 1e3..1e-1 = 16 full-data fits + 160 fold optimisations, each capped at "
-                                                 "%d batched evaluations" % (args.tips, n, args.cv_steps),
-                                     "optimizer": "tpl_optimize_batch method 1 (batched truncated Newton)",
-                                     "parallelism": "(smoothing, fold) vectors dealt to %d GPU(s), chi-square all-gather" % world},
-                          "chisq": res["chisq"], "best_smoothing": res["best"], "full_objective": res["full_objective"],
-                          "full_fits_converged": res["full_converged"], "fold_vectors_converged": conv,
-                          "seconds": {"full_fits": res["full_seconds"], "folds": res["cv_seconds"], "scoring_and_gather": res["gather_seconds"]},
-                          "gpu_launches": int(res["launches"]) * world, "clocks": clocks,
-                          "e2e": {"value": dt, "unit": "s", "h2d_bytes_per_step": int(8 * 299996 * (16 + res["n_local_vectors"])),
-                                  "d2h_bytes_per_step": int(8 * 299996 * (16 + res["n_local_vectors"]))}}))
-    if dist is not None:
-        dist.destroy_process_group()
+    n = flat["parents"].shape[0]
+    fp, P = tf.generate_param_order_vector(flat["free"], lf=False)
+    plp = eng.PLCalcParallel.from_flat(flat, device=0)
+    plp.set_freeparams(P, False, fp)
+    plp.smoothing = 1.0
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    rows = []
+    for B in (1, 2, 16, 32, 64, 256, 1024):
+        plp.batch_configure(B)
+        X = torch.from_numpy(make_vectors(flat, P, B, 1000)).to(dev)
+        F = torch.empty(B, dtype=torch.float64, device=dev)
+        G = torch.empty((P, B), dtype=torch.float64, device=dev)
+        step = lambda: plp.calc_pl_grad_batch_dev(B, X.data_ptr(), F.data_ptr(), G.data_ptr(), eng.GRAD_AD, tstream.cuda_stream)
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+        steps = 50 if B >= 64 else 200
+        plp.set_timing(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        cnt, main_ms, fin_ms = plp.get_timing()
+        plp.set_timing(False)
+        bytes_per_launch = (16.0 * P + 25.0 * n / B) * B
+        rows.append({"B": B, "ms_per_step": ms, "evals_per_s": B / (ms * 1e-3), "kernel_generation": plp.last_kernel_generation(),
+                     "launches_per_step": plp.last_launch_count(), "main_kernel_ms": main_ms / max(cnt, 1),
+                     "roofline_frac_step": bytes_per_launch / (ms * 1e-3) / 1e9 / peak,
+                     "roofline_frac_main_kernel": bytes_per_launch / (main_ms / max(cnt, 1) * 1e-3) / 1e9 / peak})
+        del X, F, G
+    plp.close()
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
+    # ---- B = 1 callback latency through the host-buffer single-point entry ----
+    from oracle import refbind as rb
+    cb = []
+    for name, fl in (("M1155", dict(Golden("M1155").flat)), ("big_test", dict(Golden("big_test").flat)), ("synthetic %d tips" % args.tips, flat)):
+        fpk, Pk = tf.generate_param_order_vector(fl["free"], lf=False)
+        q = eng.PLCalcParallel.from_flat(fl, device=0)
+        q.set_freeparams(Pk, False, fpk)
+        q.smoothing = 1.0
+        x = np.ascontiguousarray(make_vectors(fl, Pk, 1, 7)[:, 0]) if name.startswith("synthetic") else None
+        if x is None:
+            from treepl_b200 import cv
+            x = cv.start_vector(fl, Pk, len(fl["parents"]) - 1)
+        for _ in range(20):
+            q.calc_pl_grad(x, eng.GRAD_ANALYTIC)
+        reps = 300
+        t = time.perf_counter()
+        for _ in range(reps):
+            q.calc_pl_grad(x, eng.GRAD_ANALYTIC)
+        us = 1e6 * (time.perf_counter() - t) / reps
+        row = {"tree": name, "N": int(len(fl["parents"])), "P": int(Pk), "b200_callback_us": us,
+               "kernel_generation": q.last_kernel_generation(), "launches_per_call": q.last_launch_count()}
+        q.close()
+        if rb.available():
+            rp = rb.RefProblem.from_flat(fl)
+            rp.set_smoothing(1.0)
+            rp.set_freeparams(False)
+            t1 = rp.time_evals(x, 1, 1, True)
+            r = int(max(3, min(20000, 1.0 / max(t1, 1e-6))))
+            row["reference_one_thread_us"] = 1e6 * rp.time_evals(x, r, 1, True) / r
+            rp.close()
+        cb.append(row)
+    print(json.dumps({"metric": "pl_obj_grad_evals_per_sec_vs_B", "unit": "evals/s", "n_gpus": 1, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "B sweep on the synthetic %d-tip tree (N=%d, P=%d), AD gradient, operands resident in HBM; "
+                                             "B=1 callback latency through tpl_calc_pl_grad (host buffers)" % (args.tips, n, P)},
+                      "peak_gbs": peak, "peak_source": peak_src, "sweep": rows, "callback": cb}))
 
 
 def main():
@@ -493,26 +644,21 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--min-warm-seconds", type=float, default=1.0)
-    ap.add_argument("--workload", default="evals", choices=["evals", "loocv", "restarts", "cv100k"])
+    ap.add_argument("--workload", default="evals", choices=["evals", "loocv", "loocv_big", "restarts", "restarts_cfg4", "cv100k", "sweep"])
     ap.add_argument("--cv-steps", type=int, default=8000, help="cv100k: cap on batched evaluations per optimisation")
-    ap.add_argument("--no-loocv", action="store_true", help="skip the LOO-CV summary attached to the default line")
+    ap.add_argument("--no-sharded", "--no-loocv", dest="no_sharded", action="store_true",
+                    help="skip the sharded optimiser-level jobs attached to the default line")
     args = ap.parse_args()
-    if args.workload == "cv100k":
-        run_cv100k(args)
+    if args.workload == "sweep":
+        run_sweep(args)
         return
-    if args.workload == "restarts":
+    if args.workload != "evals":
+        big = args.workload != "loocv"
         if args.steps == 200:
-            args.steps = 2
+            args.steps = 1 if (big or args.impl == "reference") else 5
         if args.warmup == 3:
-            args.warmup = 1
-        run_restarts(args)
-        return
-    if args.workload == "loocv":
-        if args.steps == 200:
-            args.steps = 1 if args.impl == "reference" else 5
-        if args.impl == "reference" and args.warmup == 3:
-            args.warmup = 0
-        run_loocv(args)
+            args.warmup = 0 if (args.impl == "reference" or args.workload in ("cv100k", "loocv_big")) else (1 if big else 3)
+        run_job_workload(args)
         return
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -665,23 +811,28 @@ def main():
                     line["cpu_baseline"] = {"value": r[0], "unit": UNIT, "cores": r[1], "kind": "reference", "sample": r[2]}
             except Exception as ex:      # the baseline must never take the GPU number down with it
                 line["cpu_baseline"] = {"error": repr(ex)}
-        if world == 1 and not args.no_loocv:
-            try:
-                from treepl_b200 import cv
-                gd, cals, tips = load_m1155()
-                cv.loocv(dict(gd.flat), M1155_GRID, tips, device=local, max_iter=6000)        # warm (allocations, graphs)
-                t = time.perf_counter()
-                r = cv.loocv(dict(gd.flat), M1155_GRID, tips, device=local, max_iter=6000)
-                wall = time.perf_counter() - t
-                line["loocv"] = {"workload": "examples/M1155.cppr8s LOOCV (59 folds x 5 smoothing values), device-resident batched truncated Newton",
-                                 "wall_s": wall, "chisq": r["chisq"], "chisq_reference_run": M1155_REF_CHISQ,
-                                 "chisq_max_rel_diff": max(abs(a - b) / b for a, b in zip(r["chisq"], M1155_REF_CHISQ)),
-                                 "best_smoothing": r["best"], "full_objective": r["full_objective"],
-                                 "gpu_launches": int(r["launches"]), "batched_evaluations": r["full_info"]["nfev"] + r["cv_nfev"]}
-            except Exception as ex:
-                line["loocv"] = {"error": repr(ex)}
-        print(json.dumps(line))
     plp.close()
+    del X, G, F, Xp, Gp, Fp
+    torch.cuda.empty_cache()
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
+    # ---- the workloads north_star shards over the GPUs, at EVERY N: optimiser-level jobs through the device-resident
+    # batched optimiser (strong scaling: the same job on N GPUs), wall seconds incl. all host work of the job ----
+    if not args.no_sharded:
+        rk = Ranks(dist, local)
+        sh = {}
+        for name, fn in (("loocv_M1155", lambda: job_loocv(rk, "M1155", runs=1, warm=1)),
+                         ("restarts", lambda: job_restarts(rk, runs=1, warm=0)),
+                         ("loocv_big_test", lambda: job_loocv(rk, "big_test", runs=1, warm=0)),
+                         ("cv100k", lambda: job_cv100k(rk, args.tips, args.cv_steps))):
+            try:
+                sh[name] = fn()
+            except Exception as ex:                  # collective error agreement happens inside cv.*: every rank raises
+                sh[name] = {"error": repr(ex)}
+        if rank == 0:
+            line["sharded"] = sh
+            line["loocv"] = sh["loocv_M1155"]
+    if rank == 0:
+        print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -391,7 +391,7 @@ int ref_cv(void* h, int nlam, const double* lams, int ngroups, const int* goff, 
         auto b = now();
         tfull += secs(a, b);
         double chisq = 0.0;
-#pragma omp parallel for reduction(+ : chisq) num_threads(oopt.nthreads)
+#pragma omp parallel for ADOLC_OPENMP_NC reduction(+ : chisq) num_threads(oopt.nthreads)
         for (int g = 0; g < ngroups; g++) {
             vector<int> cvnodes(n, 0);
             for (int j = goff[g]; j < goff[g + 1]; j++) cvnodes[gnodes[j]] = 1;
@@ -477,6 +477,31 @@ int ref_optimize(void* h, int which, int numiter, double ftol, double xtol, int 
     cout.rdbuf(old);
     if (log && logcap > 0) { strncpy(log, os.str().c_str(), logcap - 1); log[logcap - 1] = 0; }
     return rc;
+}
+
+/* Multi-start on the host cores: nstarts independent optimisations with the reference's optimize_full (utils.cpp:671-763,
+ * default OptimOptions), one pl_calc_parallel per OpenMP thread exactly as the reference runs its CV folds
+ * (main.cpp:689-710, same ADOLC_OPENMP_NC clause).  Start k = X0[k*numparams ...].  -> f_out[k] = calc_pl(final x of start k); returns seconds. */
+double ref_multistart(void* h, int nstarts, const double* X0, int nthreads, int seed, double* f_out) {
+    RefProblem* p = (RefProblem*)h;
+    CoutMute mute;
+    srand(seed);
+    const int np = p->numparams;
+    auto t0 = chrono::steady_clock::now();
+#pragma omp parallel for ADOLC_OPENMP_NC schedule(dynamic, 1) num_threads(nthreads < 1 ? 1 : nthreads)
+    for (int k = 0; k < nstarts; k++) {
+        pl_calc_parallel q;
+        wire_clone(p, q);
+        vector<double> x(X0 + (size_t)k * np, X0 + (size_t)(k + 1) * np);
+        q.calc_pl(x);
+        OptimOptions oo;
+        /* cv = true selects the thread-parallel ADOL-C adapters (optimize_best_parallel), the only gradient path the
+         * reference itself runs inside an OpenMP region (main.cpp:689-722); the RAD tape of cv = false is global state */
+        optimize_full(q, &x, &oo, true);
+        f_out[k] = q.calc_pl(x);
+        q.delete_ad_arrays();
+    }
+    return chrono::duration<double>(chrono::steady_clock::now() - t0).count();
 }
 
 int ref_hw_threads(void) { return omp_get_num_procs(); }

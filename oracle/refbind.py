@@ -55,6 +55,8 @@ def lib():
         L.ref_cv.restype = ci
         L.ref_cv.argtypes = [vp, ci, dp, ci, ip, ip, ci, ci, dp, dp, dp]
         L.ref_hw_threads.restype = ci
+        L.ref_multistart.restype = cd
+        L.ref_multistart.argtypes = [vp, ci, dp, ci, ci, dp]
         L.ref_optimize.restype = ci
         L.ref_optimize.argtypes = [vp, ci, ci, cd, cd, ci, dp, dp, C.c_char_p, ci]
         _lib = L
@@ -229,6 +231,15 @@ class RefProblem:
         log = C.create_string_buffer(1 << 16)
         rc = lib().ref_optimize(self.h, int(which), int(numiter), float(ftol), float(xtol), int(seed), _dp(x), C.byref(f), log, len(log))
         return rc, x, f.value, log.value.decode(errors="replace")
+
+    def multistart(self, X0, nthreads=1, seed=1):
+        """X0 [nstarts, numparams]: the reference's optimize_full from every start, one engine per OpenMP thread
+        -> (objectives [nstarts], seconds)."""
+        X0 = np.ascontiguousarray(X0, dtype=np.float64)
+        assert X0.ndim == 2 and X0.shape[1] == self.numparams
+        f = np.zeros(X0.shape[0])
+        secs = lib().ref_multistart(self.h, X0.shape[0], _dp(X0), int(nthreads), int(seed), _dp(f))
+        return f, secs
 
     def time_evals(self, x, reps, nthreads, with_grad=True):
         x = np.ascontiguousarray(x, dtype=np.float64)

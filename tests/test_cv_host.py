@@ -59,6 +59,21 @@ def test_chisq_terms_follow_the_reference_formula():
     assert np.isclose(cv.group_chisq(flat, x, grp, fp, False), np.sum(want), rtol=1e-13)
 
 
+def test_single_tip_scoring_of_all_lanes_equals_the_per_fold_formula():
+    """cv.single_tip_chisq (LOOCV, every lane at once) == cv.group_chisq lane by lane, bit for bit, incl. a tip that is a
+    child of the root."""
+    flat, tips = _m1155()
+    n = len(flat["parents"])
+    fp, P = tf.generate_param_order_vector(flat["free"], lf=False)
+    rng = np.random.RandomState(1)
+    x = cv.start_vector(flat, P, n - 1)
+    lane_tips = [int(t) for t in tips] + [int(t) for t in tips[:7]]
+    X = x[:, None] * np.exp(0.1 * rng.randn(P, len(lane_tips)))
+    got = cv.single_tip_chisq(flat, X, lane_tips, fp)
+    want = np.array([cv.group_chisq(flat, X[:, b], [t], fp, False) for b, t in enumerate(lane_tips)])
+    assert np.array_equal(got, want)
+
+
 def test_smoothing_grid_follows_the_reference_fixups():
     """main.cpp:275-284 (swap start/stop, invert a step > 1 in float) and :668,814 (while(curcv >= cvstop) curcv *= step)."""
     import pytest

@@ -147,6 +147,31 @@ def group_chisq(flat, x, group, freeparams, randomcv):
     return total / (len(tips) if randomcv else 1.0)
 
 
+def single_tip_chisq(flat, X, tips, freeparams):
+    """group_chisq for one-tip folds, all lanes at once: X [P, B], tips[b] = the tip pruned in lane b
+    (src/main.cpp:737-757; same arithmetic per lane as group_chisq)."""
+    n = len(flat["parents"])
+    par = np.asarray(flat["parents"])
+    fp = np.asarray(freeparams)
+    tips = np.asarray(tips, dtype=np.int64)
+    lanes = np.arange(tips.shape[0])
+    p = par[tips]
+    rnode = p.copy()
+    root_kids = np.flatnonzero(par == 0)
+    for k in np.flatnonzero(p == 0):                      # child of the root: the rate of its LAST sibling (main.cpp:741-746)
+        rnode[k] = [j for j in root_kids if j != tips[k]][-1]
+    rslot = fp[rnode]
+    r = np.where(rslot >= 0, X[np.maximum(rslot, 0), lanes], 0.0)
+    dslot = fp[n + p]
+    hp = np.where(dslot >= 0, X[np.maximum(dslot, 0), lanes], flat["start_dates"][p])
+    d = hp - flat["start_dates"][tips]
+    d = np.where(d == 0, 2.2250738585072014e-308, d)
+    expe = r * d
+    c = flat["c"][tips]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where((d < 1e-100) | (expe < 1e-100), 0.0, (c - expe) ** 2 / expe)
+
+
 def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_pen=False, max_iter=3000, verbose=False,
                    history=8, dist=None, **opt):
     """-> dict(chisq per smoothing value, best smoothing, timings).  groups: list of folds, each a list of tip node
@@ -188,22 +213,21 @@ def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_p
     t1 = time.perf_counter()
     # ---- folds: one vector per (smoothing value, fold); this rank's share ----
     n_items = K * T
-    mine = cvshard.shard_items(n_items, rank, world)
+    mine = np.asarray(cvshard.shard_items(n_items, rank, world), dtype=np.int64)
     B2 = len(mine)
     B2p = max(2, B2 + (B2 % 2))
-    lam2 = np.empty(B2p)
-    masks = []
-    X0 = np.empty((P, B2p))
-    for b in range(B2p):
-        item = mine[min(b, B2 - 1)] if B2 else 0           # padding repeats the last item
-        k, g = divmod(item, T)
-        lam2[b] = smoothing_grid[k]
-        masks.append([int(t) for t in groups[g]])
-        X0[:, b] = Xfull[:, k]
+    lane_item = mine[np.minimum(np.arange(B2p), max(B2 - 1, 0))] if B2 else np.zeros(B2p, dtype=np.int64)   # padding repeats the last item
+    lane_k, lane_g = lane_item // T, lane_item % T
+    lam2 = np.asarray(smoothing_grid, dtype=np.float64)[lane_k]
+    masks = [groups[g] for g in lane_g]
+    X0 = np.ascontiguousarray(Xfull[:, lane_k])
     plp.batch_configure(B2p, lane_smoothing=lam2, masks=masks)
     Xcv, Fcv, info2 = _minimize_together(dist, dev, plp, X0, lo, hi, nr, dscale, max_iter, history, verbose, **opt)
     t2 = time.perf_counter()
-    local = {item: group_chisq(flat, Xcv[:, b], groups[item % T], fp, randomcv) for b, item in enumerate(mine)}
+    if all(len(g) == 1 for g in groups):
+        local = single_tip_chisq(flat, Xcv[:, :B2], np.array([groups[g][0] for g in lane_g[:B2]], dtype=np.int64), fp)
+    else:
+        local = np.array([group_chisq(flat, Xcv[:, b], groups[lane_g[b]], fp, randomcv) for b in range(B2)])
     full, _ = cvshard.gather_fold_scores(local, n_items, dist=dist, device=dev)
     terms = full.reshape(K, T)
     chisq = np.zeros(K)
@@ -227,7 +251,7 @@ def loocv(flat, smoothing_grid, tips, **kw):
     return cross_validate(flat, smoothing_grid, [[int(t)] for t in tips], randomcv=False, **kw)
 
 
-def multistart(flat, smoothing, n_starts, jitter=0.3, seed=1, device=0, dist=None, **opt):
+def multistart(flat, smoothing, n_starts, jitter=0.3, seed=1, device=0, dist=None, log_pen=False, **opt):
     """n_starts independent optimisations from random starts (rates jittered log-normally around the clock-like
     start, feasible start dates), sharded over the ranks; the global best is exchanged with
     cvshard.best_of_restarts (all-gather of the best objectives, broadcast of the winner's vector).
@@ -239,6 +263,7 @@ def multistart(flat, smoothing, n_starts, jitter=0.3, seed=1, device=0, dist=Non
     rank = dist.get_rank() if dist is not None else 0
     n = len(flat["parents"])
     plp = eng.PLCalcParallel.from_flat(flat, device=device)
+    plp.set_log_pen(log_pen)
     fp, P = eng.generate_param_order_vector(flat["free"], lf=False)
     plp.set_freeparams(P, False, fp)
     plp.smoothing = float(smoothing)

@@ -24,26 +24,31 @@ def owner_of(item, world):
 
 
 def gather_fold_scores(local_scores, n_items, dist=None, device=None):
-    """local_scores: {item: chi-square term}.  Returns the full vector (item order) on every rank and its
-    fixed-order sum.  With dist=None (single process) no collective is issued."""
+    """local_scores: {item: chi-square term}, or an array of this rank's terms in shard_items order.  Returns the
+    full vector (item order) on every rank and its fixed-order sum.  With dist=None (single process) no collective
+    is issued."""
     import torch
 
     world = dist.get_world_size() if dist is not None else 1
     rank = dist.get_rank() if dist is not None else 0
     per = (n_items + world - 1) // world
-    mine = torch.full((per,), float("nan"), dtype=torch.float64, device=device)
-    for k, item in enumerate(shard_items(n_items, rank, world)):
-        mine[k] = float(local_scores[item])
-    if dist is None:
-        parts = [mine]
+    if isinstance(local_scores, dict):
+        vals = np.array([float(local_scores[item]) for item in shard_items(n_items, rank, world)], dtype=np.float64)
     else:
-        parts = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(parts, mine)
+        vals = np.asarray(local_scores, dtype=np.float64)
+    host = np.full(per, np.nan)
+    host[: vals.shape[0]] = vals
+    if dist is None:
+        parts = [host]
+    else:
+        mine = torch.as_tensor(host, device=device)
+        got = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(got, mine)
+        parts = [t.cpu().numpy() for t in got]
     full = np.full(n_items, np.nan)
     for r, part in enumerate(parts):
-        vals = part.cpu().numpy()
-        for k, item in enumerate(range(r, n_items, world)):
-            full[item] = vals[k]
+        cnt = len(range(r, n_items, world))
+        full[r::world] = part[:cnt]
     total = 0.0
     for v in full:                    # fixed item order -> identical on every rank and for every world size
         total += v
@@ -59,19 +64,20 @@ def gather_vectors(local_vectors, n_items, length, dist=None, device=None):
     world = dist.get_world_size() if dist is not None else 1
     rank = dist.get_rank() if dist is not None else 0
     per = (n_items + world - 1) // world
-    mine = torch.zeros((per, length), dtype=torch.float64, device=device)
+    host = np.zeros((per, length))
     for k, item in enumerate(shard_items(n_items, rank, world)):
-        mine[k] = torch.as_tensor(np.asarray(local_vectors[item], dtype=np.float64), device=device)
+        host[k] = np.asarray(local_vectors[item], dtype=np.float64)
     if dist is None:
-        parts = [mine]
+        parts = [host]
     else:
-        parts = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(parts, mine)
+        mine = torch.as_tensor(host, device=device)
+        got = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(got, mine)
+        parts = [t.cpu().numpy() for t in got]
     out = np.zeros((length, n_items))
     for r, part in enumerate(parts):
-        vals = part.cpu().numpy()
-        for k, item in enumerate(range(r, n_items, world)):
-            out[:, item] = vals[k]
+        cnt = len(range(r, n_items, world))
+        out[:, r::world] = part[:cnt].T
     return out
 
 
