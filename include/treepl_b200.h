@@ -166,6 +166,9 @@ typedef struct tpl_opt_options {
     double date_scale;  /* 0 = 1 */
     double boundary_frac; /* a new direction's first step covers at most this fraction of the distance to the
                            * nearest zero-duration boundary (ratio test over the branches); 0 = 0.9, < 0 = off */
+    int tree_wide_min;  /* method 1, tree preconditioner: a height level with at least this many nodes gets its own launch per
+                         * sweep; the narrower levels above are walked inside one block per 32-vector group (0 = 64) */
+    int reserved;
 } tpl_opt_options;
 
 typedef struct tpl_opt_result {
@@ -224,9 +227,11 @@ int tpl_last_kernel_generation(const tpl_engine* e);
 int tpl_debug_hessvec(tpl_engine* e, int B, const double* X, const double* V, const double* sc_rows, double* W, double* DG);
 
 /* test hook: Out = M^-1 Rhs, M = the truncated-Newton method's block-tree factorisation of H_z at X (tpl_opt_options.precond);
- * rows with Free > 0 are the variables of the solve, the others come out as 0.  X, Free, Rhs, Out: host [P][B]. */
+ * rows with Free > 0 are the variables of the solve, the others come out as 0.  X, Free, Rhs, Out: host [P][B].
+ * Rhs2 / Out2 (both or neither, may be NULL): a second right-hand side solved with the SAME factors through the
+ * solve-only sweeps a CG iteration runs. */
 int tpl_debug_treesolve(tpl_engine* e, int B, const double* X, const double* Free, const double* Rhs, const double* sc_rows,
-                        double* Out);
+                        double* Out, const double* Rhs2, double* Out2);
 
 /* test hook: evaluates the kernels' log and reciprocal on n host values (tests only) */
 int tpl_debug_math(int n, const double* x, double* log_out, double* rcp_out);

@@ -69,8 +69,8 @@ def _run(name, lams, masks=None, **opt):
 @pytest.mark.parametrize("name,lams,masked,log_pen", [("test", [0.1, 100.0], False, False), ("M1155", [10.0, 0.1, 1000.0, 1.0], True, False),
                                                       ("vib", [1e4, 1.0], True, True), ("big_test", [1e-4] * 17 + [100.0] * 17, True, False)])
 def test_tree_preconditioner_kernels_equal_cpu_emulation(name, lams, masked, log_pen):
-    """zz = M^-1 r through the level-sweep kernels (tn_tree_up / top / down) == the same node functions run in
-    elimination order on the CPU (tests/tn_sim.cpp::tree_solve), which tests/test_tn_sim.py pins against a dense solve."""
+    """zz = M^-1 r through the sweep kernels (tn_tree_up / down per wide level, heavy paths in tn_tree_top_kernel) == the same
+    node functions run in elimination order on the CPU (tests/tn_sim.cpp::tree_solve), which tests/test_tn_sim.py pins against a dense solve."""
     sim = TS.load_sim()
     flat = Golden(name).flat
     n = len(flat["parents"])
@@ -90,19 +90,27 @@ def test_tree_preconditioner_kernels_equal_cpu_emulation(name, lams, masked, log
     plp = _engine(pr, flat)
     plp.set_log_pen(log_pen)
     F, G = plp.calc_pl_grad_batch(X, mode=eng.GRAD_AD)
-    out = plp.debug_treesolve(X, free, rhs, pr.sc)
-    want = np.zeros((P, B))
-    Xc, Gc, Fc, Rc = (np.ascontiguousarray(v) for v in (X, G, free, rhs))
-    sim.tn_sim_treesolve(P, B, *pr.tree_args(), TS._d(pr.sc), TS._d(pr.lams), 0.0025, TS._d(Xc), TS._d(Gc), TS._d(Fc), TS._d(Rc), TS._d(want),
-                         int(log_pen))
-    scale = np.abs(want).max(axis=0)
-    assert np.all(np.isfinite(out))
+    rhs2 = rng.randn(P, B)
+    # out: factorise + solve (the sweep after an accepted step); out2: the solve-only sweeps of a CG iteration, same factors
+    out, out2 = plp.debug_treesolve(X, free, rhs, pr.sc, rhs2=rhs2)
+    Xc, Gc, Fc = (np.ascontiguousarray(v) for v in (X, G, free))
     # elimination amplifies the rounding differences between host and device arithmetic (FMA contraction) by the condition of
     # the pivots: 1e-11 typical; up to 1e-5 on the 9,313-node tree at this random, non-optimal point
     tol = 1e-4 if name == "big_test" else 1e-7
-    err = np.abs(out - want).max(axis=0) / scale
-    assert np.all(err <= tol) and np.median(err) <= 1e-7, err
-    assert np.all(out[free == 0] == 0.0)
+    for got, r in ((out, rhs), (out2, rhs2)):
+        want = np.zeros((P, B))
+        Rc = np.ascontiguousarray(r)
+        sim.tn_sim_treesolve(P, B, *pr.tree_args(), TS._d(pr.sc), TS._d(pr.lams), 0.0025, TS._d(Xc), TS._d(Gc), TS._d(Fc), TS._d(Rc), TS._d(want),
+                             int(log_pen))
+        scale = np.abs(want).max(axis=0)
+        assert np.all(np.isfinite(got))
+        err = np.abs(got - want).max(axis=0) / scale
+        assert np.all(err <= tol) and np.median(err) <= 1e-7, err
+        assert np.all(got[free == 0] == 0.0)
+    # linearity in the right-hand side with fixed factors: M^-1 (rhs + rhs2) through the solve-only sweeps
+    _, out12 = plp.debug_treesolve(X, free, rhs, pr.sc, rhs2=rhs + rhs2)
+    s12 = np.abs(out + out2).max(axis=0)
+    assert np.all(np.abs(out12 - (out + out2)).max(axis=0) <= 1e-8 * s12)
     plp.close()
 
 

@@ -191,7 +191,7 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
     // ---- tree preconditioner: height levels (children before parents), node lists per level, work planes ----
     a.precond = o.precond == 1 ? 0 : 1;
     a.log_pen = e->log_pen ? 1 : 0;
-    a.TW = nullptr; a.lev_nodes = nullptr; a.lev_off = nullptr; a.nlev = a.nlev_wide = 0;
+    a.TW = nullptr; a.lev_nodes = nullptr; a.lev_off = nullptr; a.lev_rec = nullptr; a.nlev = a.nlev_wide = 0;
     if (a.precond) {
         std::vector<int> height(n, 0);
         int hmax = 0;
@@ -208,14 +208,26 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
         for (int i = 0; i < n; i++) nodes[fill[height[i]]++] = i;
         a.nlev = hmax + 1;
         a.nlev_wide = 0;
-        while (a.nlev_wide < a.nlev && off[a.nlev_wide + 1] - off[a.nlev_wide] >= 4 * tpltn::TREE_TOP_WY) a.nlev_wide++;
-        if (a.nlev - a.nlev_wide > 4096) return fail(TPL_ERR_ARG, "tree preconditioner: more than 4096 narrow levels (ladder-like tree); use precond = 1");
+        const int wide_min = o.tree_wide_min > 0 ? o.tree_wide_min : 4 * tpltn::TREE_TOP_WY;
+        while (a.nlev_wide < a.nlev && off[a.nlev_wide + 1] - off[a.nlev_wide] >= wide_min) a.nlev_wide++;
+        // one index record per node, in level order: what the sweeps' record views load first (tpl_tn.cuh)
+        std::vector<int> recs((size_t)n * tpltn::TREE_REC_INTS, -1);
+        for (int k = 0; k < n; k++) {
+            const int i = nodes[k];
+            int* r = recs.data() + (size_t)k * tpltn::TREE_REC_INTS;
+            const int pa = i == 0 ? -1 : e->parent[i];
+            const int c0 = e->child_off[i], nc = e->child_off[i + 1] - c0;
+            r[0] = i; r[1] = e->freeparams[i]; r[2] = e->freeparams[n + i]; r[3] = pa;
+            r[4] = pa >= 0 ? e->freeparams[pa] : -1; r[5] = pa >= 0 ? e->freeparams[n + pa] : -1; r[6] = c0; r[7] = nc;
+            for (int j = 0; j < 2 && j < nc; j++) { r[8 + j] = e->children[c0 + j]; r[10 + j] = e->freeparams[n + e->children[c0 + j]]; }
+        }
         CK(w.tn_lev_nodes.upload(nodes, s));
         CK(w.tn_lev_off.upload(off, s));
+        CK(w.tn_lev_rec.upload(recs, s));
         CK(w.tn_tw.ensure((size_t)tpltn::TW_PLANES * n * B));
         CK(cudaStreamSynchronize(s));
         w.tn_lev_off_host = off;
-        a.TW = w.tn_tw.p; a.lev_nodes = w.tn_lev_nodes.p; a.lev_off = w.tn_lev_off.p;
+        a.TW = w.tn_tw.p; a.lev_nodes = w.tn_lev_nodes.p; a.lev_off = w.tn_lev_off.p; a.lev_rec = w.tn_lev_rec.p;
     }
     return TPL_OK;
 }
@@ -565,7 +577,7 @@ extern "C" int tpl_debug_hessvec(tpl_engine* e, int B, const double* X, const do
 
 // test hook: Out = M^-1 Rhs with the block-tree factorisation of the Hessian at X; rows with Free > 0 are the variables
 extern "C" int tpl_debug_treesolve(tpl_engine* e, int B, const double* X, const double* Free, const double* Rhs, const double* sc_rows,
-                                   double* Out) {
+                                   double* Out, const double* Rhs2, double* Out2) {
     using namespace tpltn;
     if (!e || !X || !Free || !Rhs || !sc_rows || !Out || B < 1) return fail(TPL_ERR_ARG, "null or B < 1");
     if (!e->have_fp) return fail(TPL_ERR_STATE, "set_freeparams has not been called");
@@ -591,6 +603,16 @@ extern "C" int tpl_debug_treesolve(tpl_engine* e, int B, const double* X, const 
     tn_launch_tree_solve(a, w.tn_lev_off_host, (B + 31) / 32, s, true, false);   // st = TS_INIT, finite objective: every vector active
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(Out, w.ZZ.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
+    if (Rhs2 && Out2) {
+        // the solve-only sweeps of a CG iteration (FACTOR = false) with the factors just computed: every vector in TS_CG / ACT_CG
+        std::vector<int> st(B, TS_CG), act(B, ACT_CG);
+        CK(cudaMemcpyAsync(a.st, st.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(a.act, act.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w.R.p, Rhs2, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
+        tn_launch_tree_solve(a, w.tn_lev_off_host, (B + 31) / 32, s, false, false);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(Out2, w.ZZ.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaStreamSynchronize(s));
     return TPL_OK;
 }

@@ -57,6 +57,7 @@ struct TnArgs {
     double* TW;                              // [TW_PLANES][n][B] node-indexed factors and sweep scratch
     const int* lev_nodes;                    // [n] node numbers grouped by height level (tips first)
     const int* lev_off;                      // [nlev + 1]
+    const int* lev_rec;                      // [n][TREE_REC_INTS] index record of node lev_nodes[k] (tpl_tn.cuh: record views)
     int nlev, nlev_wide;                     // levels [0, nlev_wide): one launch each; [nlev_wide, nlev): tn_tree_top_kernel
     double *gmax_tmp, *gg_tmp;               // [B] reductions of the set-up pass kept until the solve has produced r.zz
     double* part_pc;
@@ -333,6 +334,203 @@ __device__ __forceinline__ double tree_lane_mu(const TnArgs& a, int b) {
     return FACTOR ? lane_mu_eff(a, b, lane_decision(a, b)) : a.mu[b];
 }
 
+// ---- record views: the sweeps are LATENCY bound (one warp = one node x 32 vectors, a chain of dependent loads
+// node -> slots -> parent -> parent's slots -> rows -> children -> children's factors: ~12 round trips to L2 / HBM, ~10 us per
+// node at batch sizes whose work planes exceed L2).  The host therefore flattens everything index-like into one 48-byte
+// record per node, stored in level order (tn_prepare), and a view loads the record (round trip 1), then ALL operands the
+// node function will ask for, unconditionally and side by side (round trip 2); the node functions of tpl_tn_core.h run
+// unchanged on top and find their operands in registers.  Nodes with more than two children fall through to the generic
+// accessors for the extra children.
+constexpr int TREE_REC_INTS = 12;            // i rs ds p | prs pds coff nch | ch0 ch1 cds0 cds1
+
+struct TreeRec {
+    int i, rs, ds, p, prs, pds, coff, nch, ch0, ch1, cds0, cds1;
+};
+__device__ __forceinline__ TreeRec tree_rec_load(const TnArgs& a, int k) {
+    const int4* r = reinterpret_cast<const int4*>(a.lev_rec + (size_t)k * TREE_REC_INTS);
+    const int4 q0 = __ldg(r), q1 = __ldg(r + 1), q2 = __ldg(r + 2);
+    TreeRec t = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+    return t;
+}
+
+struct RecBase : DevView {
+    TreeRec t;
+    __device__ RecBase(const DevView& v, const TreeRec& rec) : DevView(v), t(rec) {}
+    __device__ int parent(int n) const { return n == t.i ? t.p : DevView::parent(n); }
+    __device__ int child_begin(int n) const { return n == t.i ? t.coff : DevView::child_begin(n); }
+    __device__ int child_end(int n) const { return n == t.i ? t.coff + t.nch : DevView::child_end(n); }
+    __device__ int child(int j) const {
+        const int q = j - t.coff;
+        return (q == 0 && t.nch > 0) ? t.ch0 : ((q == 1 && t.nch > 1) ? t.ch1 : DevView::child(j));
+    }
+    __device__ int rslot(int n) const { return n == t.i ? t.rs : (n == t.p ? t.prs : DevView::rslot(n)); }
+    __device__ int dslot(int n) const {
+        return n == t.i ? t.ds : (n == t.p ? t.pds : (n == t.ch0 ? t.cds0 : (n == t.ch1 ? t.cds1 : DevView::dslot(n))));
+    }
+    __device__ unsigned long long mask_word(int n) const { return a.lanemask[(size_t)(b >> 6) * a.mask_stride + n]; }
+};
+
+// factorisation (+ the forward substitution that follows it in the same sweep)
+struct FactorView : RecBase {
+    bool m_i, m_p, m_c0, m_c1;
+    double r_i, h_i, x_prs, h_p, h_c0, h_c1;
+    double f_rs, f_ds, f_prs, f_pds, sc_rs, sc_ds, sc_prs, sc_pds, gx_rs, c_i, c_c0, c_c1, pmn, pmx, rhs_rs, rhs_ds;
+    double t0[3], t1[3];
+    __device__ FactorView(const DevView& v, const TreeRec& rec) : RecBase(v, rec) {
+        const size_t Bs = (size_t)B;
+        const bool hp = t.p >= 0, h0 = t.nch > 0, h1 = t.nch > 1;
+        m_i = m_p = m_c0 = m_c1 = false;
+        if (a.lanemask) {
+            const unsigned long long w_i = mask_word(t.i), w_p = hp ? mask_word(t.p) : 0ull;
+            const unsigned long long w_0 = h0 ? mask_word(t.ch0) : 0ull, w_1 = h1 ? mask_word(t.ch1) : 0ull;
+            m_i = (w_i >> (b & 63)) & 1ull; m_p = (w_p >> (b & 63)) & 1ull; m_c0 = (w_0 >> (b & 63)) & 1ull; m_c1 = (w_1 >> (b & 63)) & 1ull;
+        }
+        r_i = t.rs >= 0 ? a.X[(size_t)t.rs * Bs + b] : a.t.rfix[t.i];
+        h_i = t.ds >= 0 ? a.X[(size_t)t.ds * Bs + b] : a.t.hfix[t.i];
+        x_prs = t.prs >= 0 ? a.X[(size_t)t.prs * Bs + b] : 0.0;
+        h_p = t.pds >= 0 ? a.X[(size_t)t.pds * Bs + b] : (hp ? a.t.hfix[t.p] : 0.0);
+        h_c0 = t.cds0 >= 0 ? a.X[(size_t)t.cds0 * Bs + b] : (h0 ? a.t.hfix[t.ch0] : 0.0);
+        h_c1 = t.cds1 >= 0 ? a.X[(size_t)t.cds1 * Bs + b] : (h1 ? a.t.hfix[t.ch1] : 0.0);
+        f_rs = t.rs >= 0 ? a.Minv[(size_t)t.rs * Bs + b] : 0.0;
+        f_ds = t.ds >= 0 ? a.Minv[(size_t)t.ds * Bs + b] : 0.0;
+        f_prs = t.prs >= 0 ? a.Minv[(size_t)t.prs * Bs + b] : 0.0;
+        f_pds = t.pds >= 0 ? a.Minv[(size_t)t.pds * Bs + b] : 0.0;
+        rhs_rs = t.rs >= 0 ? a.R[(size_t)t.rs * Bs + b] : 0.0;
+        rhs_ds = t.ds >= 0 ? a.R[(size_t)t.ds * Bs + b] : 0.0;
+        gx_rs = t.rs >= 0 ? a.Gx[(size_t)t.rs * Bs + b] : 0.0;
+        sc_rs = t.rs >= 0 ? a.sc[t.rs] : 0.0;
+        sc_ds = t.ds >= 0 ? a.sc[t.ds] : 0.0;
+        sc_prs = t.prs >= 0 ? a.sc[t.prs] : 0.0;
+        sc_pds = t.pds >= 0 ? a.sc[t.pds] : 0.0;
+        c_i = a.t.c[t.i];
+        c_c0 = h0 ? a.t.c[t.ch0] : 0.0;
+        c_c1 = h1 ? a.t.c[t.ch1] : 0.0;
+        pmn = a.pmin_n[t.i];
+        pmx = a.pmax_n[t.i];
+        const size_t n = (size_t)a.t.n;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            t0[q] = h0 ? a.TW[((size_t)(TW_T + q) * n + t.ch0) * Bs + b] : 0.0;
+            t1[q] = h1 ? a.TW[((size_t)(TW_T + q) * n + t.ch1) * Bs + b] : 0.0;
+        }
+    }
+    __device__ bool masked(int n) const {
+        if (!a.lanemask) return false;
+        return n == t.i ? m_i : (n == t.p ? m_p : (n == t.ch0 ? m_c0 : (n == t.ch1 ? m_c1 : DevView::masked(n))));
+    }
+    __device__ double x(int row) const {
+        return row == t.rs ? r_i : (row == t.ds ? h_i : (row == t.prs ? x_prs : (row == t.pds ? h_p : (row == t.cds0 ? h_c0 : (row == t.cds1 ? h_c1 : DevView::x(row))))));
+    }
+    __device__ double rfix(int n) const { return (n == t.i && t.rs < 0) ? r_i : DevView::rfix(n); }
+    __device__ double hfix(int n) const {
+        if (n == t.i && t.ds < 0) return h_i;
+        if (n == t.p && t.pds < 0) return h_p;
+        if (n == t.ch0 && t.cds0 < 0) return h_c0;
+        if (n == t.ch1 && t.cds1 < 0) return h_c1;
+        return DevView::hfix(n);
+    }
+    __device__ bool fr(int row) const {
+        return (row == t.rs ? f_rs : (row == t.ds ? f_ds : (row == t.prs ? f_prs : (row == t.pds ? f_pds : a.Minv[(size_t)row * B + b])))) > 0.0;
+    }
+    __device__ double sc(int row) const {
+        return row == t.rs ? sc_rs : (row == t.ds ? sc_ds : (row == t.prs ? sc_prs : (row == t.pds ? sc_pds : DevView::sc(row))));
+    }
+    __device__ double gx(int row) const { return row == t.rs ? gx_rs : DevView::gx(row); }
+    __device__ double rhs(int row) const { return row == t.rs ? rhs_rs : (row == t.ds ? rhs_ds : DevView::rhs(row)); }
+    __device__ double c(int n) const { return n == t.i ? c_i : (n == t.ch0 ? c_c0 : (n == t.ch1 ? c_c1 : DevView::c(n))); }
+    __device__ double pmin(int n) const { return n == t.i ? pmn : DevView::pmin(n); }
+    __device__ double pmax(int n) const { return n == t.i ? pmx : DevView::pmax(n); }
+    __device__ double tw(int q, int n) const {
+        if (q >= TW_T && q < TW_Y) {
+            if (n == t.ch0) return t0[q - TW_T];
+            if (n == t.ch1) return t1[q - TW_T];
+        }
+        return DevView::tw(q, n);
+    }
+};
+
+// forward substitution alone (the solve inside a CG iteration)
+struct UpView : RecBase {
+    bool m_i;
+    double f_rs, f_ds, rhs_rs, rhs_ds, k0[4], k1[4], y0[2], y1[2];
+    __device__ UpView(const DevView& v, const TreeRec& rec) : RecBase(v, rec) {
+        const size_t Bs = (size_t)B, n = (size_t)a.t.n;
+        const bool h0 = t.nch > 0, h1 = t.nch > 1;
+        m_i = a.lanemask ? ((mask_word(t.i) >> (b & 63)) & 1ull) : false;
+        f_rs = t.rs >= 0 ? a.Minv[(size_t)t.rs * Bs + b] : 0.0;
+        f_ds = t.ds >= 0 ? a.Minv[(size_t)t.ds * Bs + b] : 0.0;
+        rhs_rs = t.rs >= 0 ? a.R[(size_t)t.rs * Bs + b] : 0.0;
+        rhs_ds = t.ds >= 0 ? a.R[(size_t)t.ds * Bs + b] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            k0[q] = h0 ? a.TW[((size_t)(TW_K + q) * n + t.ch0) * Bs + b] : 0.0;
+            k1[q] = h1 ? a.TW[((size_t)(TW_K + q) * n + t.ch1) * Bs + b] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            y0[q] = h0 ? a.TW[((size_t)(TW_Y + q) * n + t.ch0) * Bs + b] : 0.0;
+            y1[q] = h1 ? a.TW[((size_t)(TW_Y + q) * n + t.ch1) * Bs + b] : 0.0;
+        }
+    }
+    __device__ bool masked(int n) const { return n == t.i ? m_i : DevView::masked(n); }
+    __device__ bool fr(int row) const { return (row == t.rs ? f_rs : (row == t.ds ? f_ds : a.Minv[(size_t)row * B + b])) > 0.0; }
+    __device__ double rhs(int row) const { return row == t.rs ? rhs_rs : (row == t.ds ? rhs_ds : DevView::rhs(row)); }
+    __device__ double tw(int q, int n) const {
+        if (q >= TW_K && q < TW_T) {
+            if (n == t.ch0) return k0[q - TW_K];
+            if (n == t.ch1) return k1[q - TW_K];
+        }
+        if (q >= TW_Y) {
+            if (n == t.ch0) return y0[q - TW_Y];
+            if (n == t.ch1) return y1[q - TW_Y];
+        }
+        return DevView::tw(q, n);
+    }
+};
+
+// back substitution
+struct DownView : RecBase {
+    double sS[3], sK[4], sY[2], o_prs, o_pds;
+    __device__ DownView(const DevView& v, const TreeRec& rec) : RecBase(v, rec) {
+        const size_t Bs = (size_t)B, n = (size_t)a.t.n;
+#pragma unroll
+        for (int q = 0; q < 3; q++) sS[q] = a.TW[((size_t)(TW_S + q) * n + t.i) * Bs + b];
+#pragma unroll
+        for (int q = 0; q < 4; q++) sK[q] = a.TW[((size_t)(TW_K + q) * n + t.i) * Bs + b];
+#pragma unroll
+        for (int q = 0; q < 2; q++) sY[q] = a.TW[((size_t)(TW_Y + q) * n + t.i) * Bs + b];
+        o_prs = t.prs >= 0 ? W[(size_t)t.prs * Bs + b] : 0.0;
+        o_pds = t.pds >= 0 ? W[(size_t)t.pds * Bs + b] : 0.0;
+    }
+    __device__ double outv(int row) const { return row == t.prs ? o_prs : (row == t.pds ? o_pds : DevView::outv(row)); }
+    __device__ double tw(int q, int n) const {
+        if (n == t.i) {
+            if (q < TW_K) return sS[q - TW_S];
+            if (q < TW_T) return sK[q - TW_K];
+            if (q >= TW_Y) return sY[q - TW_Y];
+        }
+        return DevView::tw(q, n);
+    }
+};
+
+template <bool FACTOR>
+__device__ __forceinline__ void tree_up_at(const TnArgs& a, const DevView& V, int k) {
+    const TreeRec rec = tree_rec_load(a, k);
+    if (FACTOR) {
+        FactorView F(V, rec);
+        tree_factor_node(F, rec.i);
+        tree_up_node(F, rec.i);
+    } else {
+        UpView U(V, rec);
+        tree_up_node(U, rec.i);
+    }
+}
+__device__ __forceinline__ void tree_down_at(const TnArgs& a, const DevView& V, int k) {
+    const TreeRec rec = tree_rec_load(a, k);
+    DownView D(V, rec);
+    tree_down_node(D, rec.i);
+}
+
 template <bool FACTOR>
 __global__ void __launch_bounds__(32 * OPT_WY) tn_tree_up_kernel(TnArgs a, int level) {
     const int b = blockIdx.x * 32 + threadIdx.x;
@@ -340,11 +538,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_tree_up_kernel(TnArgs a, int l
     DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, tree_lane_mu<FACTOR>(a, b)};
     const int k0 = a.lev_off[level] + blockIdx.y * TREE_NODES_PER_BLOCK;
     const int k1 = min(a.lev_off[level + 1], k0 + TREE_NODES_PER_BLOCK);
-    for (int k = k0 + threadIdx.y; k < k1; k += OPT_WY) {
-        const int i = a.lev_nodes[k];
-        if (FACTOR) tree_factor_node(V, i);
-        tree_up_node(V, i);
-    }
+    for (int k = k0 + threadIdx.y; k < k1; k += OPT_WY) tree_up_at<FACTOR>(a, V, k);
 }
 
 template <bool FACTOR>
@@ -354,7 +548,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_tree_down_kernel(TnArgs a, int
     DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, tree_lane_mu<FACTOR>(a, b)};
     const int k0 = a.lev_off[level] + blockIdx.y * TREE_NODES_PER_BLOCK;
     const int k1 = min(a.lev_off[level + 1], k0 + TREE_NODES_PER_BLOCK);
-    for (int k = k0 + threadIdx.y; k < k1; k += OPT_WY) tree_down_node(V, a.lev_nodes[k]);
+    for (int k = k0 + threadIdx.y; k < k1; k += OPT_WY) tree_down_at(a, V, k);
 }
 
 // the narrow levels [nlev_wide, nlev): up to the root and back down inside one block per vector group
@@ -367,16 +561,12 @@ __global__ void __launch_bounds__(32 * TREE_TOP_WY) tn_tree_top_kernel(TnArgs a)
                  active ? tree_lane_mu<FACTOR>(a, b) : 0.0};
     for (int level = a.nlev_wide; level < a.nlev; level++) {
         if (active)
-            for (int k = a.lev_off[level] + threadIdx.y; k < a.lev_off[level + 1]; k += TREE_TOP_WY) {
-                const int i = a.lev_nodes[k];
-                if (FACTOR) tree_factor_node(V, i);
-                tree_up_node(V, i);
-            }
+            for (int k = a.lev_off[level] + threadIdx.y; k < a.lev_off[level + 1]; k += TREE_TOP_WY) tree_up_at<FACTOR>(a, V, k);
         __syncthreads();
     }
     for (int level = a.nlev - 1; level >= a.nlev_wide; level--) {
         if (active)
-            for (int k = a.lev_off[level] + threadIdx.y; k < a.lev_off[level + 1]; k += TREE_TOP_WY) tree_down_node(V, a.lev_nodes[k]);
+            for (int k = a.lev_off[level] + threadIdx.y; k < a.lev_off[level + 1]; k += TREE_TOP_WY) tree_down_at(a, V, k);
         __syncthreads();
     }
 }

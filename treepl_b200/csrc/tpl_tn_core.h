@@ -195,6 +195,16 @@ TPL_HD void node_values(const View& V, int i, bool& rfree, double& r, double& h,
 
 TPL_HD double safe_duration(double d) { return d > 2.2250738585072014e-308 ? d : 2.2250738585072014e-308; }
 
+// correctly rounded reciprocal: one MUFU seed + Newton on the device (about half the dependent chain of a division),
+// 1.0 / x on the host - the same value, so the CPU emulation stays bit-compatible with the kernels
+TPL_HD double tn_rcp(double x) {
+#ifdef __CUDA_ARCH__
+    return __drcp_rn(x);
+#else
+    return 1.0 / x;
+#endif
+}
+
 // W = H_z v restricted to the rows of node i; returns v.W over those rows in vw and v.v in vv
 template <class View>
 TPL_HD void hess_node(View& V, int i, double& vw, double& vv) {
@@ -373,7 +383,11 @@ TPL_HD double root_child_curvature(const View& V, int i, double r) {
     return (lam2 / m) * ((1.0 - 1.0 / m) - (log(r) - sy / m)) / (r * r);
 }
 
-// factorisation step of node i (its children are done): writes TW_S, TW_K, TW_T
+// factorisation step of node i (its children are done): writes TW_S, TW_K, TW_T.
+// The sweep kernels are bound by the LATENCY of this function's dependent chain (one warp = one node x 32 vectors), so
+// it is written for a short chain: reciprocals instead of divisions, nothing computed that the node's kind does not need
+// (a tip has no date variable: no duration, no date curvature), one reciprocal of the determinant, and the eigenvalue
+// safeguard decided without a square root in the positive-definite case.
 template <class View>
 TPL_HD void tree_factor_node(View& V, int i) {
     const int rs = V.rslot(i), ds = V.dslot(i);
@@ -388,22 +402,24 @@ TPL_HD void tree_factor_node(View& V, int i) {
     const double su = rs >= 0 ? V.sc(rs) * r : 0.0, sh = ds >= 0 ? V.sc(ds) : 0.0;
     if (i != 0 && !mi) {
         const int p = V.parent(i);
-        double rp, hp;
-        node_rh(V, p, rp, hp);
-        const double d = safe_duration(hp - h);
         const double c = V.c(i);
-        const double cdd = c / (d * d);
-        Hrr = c / (r * r);
-        Hhh = cdd;
+        Hrr = c * tn_rcp(r * r);
         Hrh = -1.0;
+        const int prs = V.rslot(p), pds = V.dslot(p);
+        const bool pm = V.masked(p);
         if (p != 0) Hrr += lam2;
         else Hrr += root_child_curvature(V, i, r);
-        const int prs = V.rslot(p), pds = V.dslot(p);
-        const bool pu = prs >= 0 && !V.masked(p) && V.fr(prs);
+        const bool pu = prs >= 0 && !pm && V.fr(prs);
         const bool ph = pds >= 0 && V.fr(pds);
-        if (fu && pu && p != 0) cuu = -lam2 * su * (V.sc(prs) * rp);
+        if (fu && pu && p != 0) cuu = -lam2 * su * (V.sc(prs) * V.x(prs));
         if (fu && ph) cuh = su * V.sc(pds);
-        if (fh && ph) chh = -cdd * sh * V.sc(pds);
+        if (ds >= 0) {                                         // only a node with a date variable needs its own duration
+            const double hp = pds >= 0 ? V.x(pds) : V.hfix(p);
+            const double d = safe_duration(hp - h);
+            const double cdd = c * tn_rcp(d * d);
+            Hhh = cdd;
+            if (fh && ph) chh = -cdd * sh * V.sc(pds);
+        }
     }
     double a = 0.0, b = 0.0, dd = 0.0;
     for (int j = V.child_begin(i); j < V.child_end(i); j++) {
@@ -413,17 +429,17 @@ TPL_HD void tree_factor_node(View& V, int i) {
         dd -= V.tw(TW_T + 2, ch);
         if (V.masked(ch)) continue;
         if (ds >= 0) {
-            double rc, hc;
-            node_rh(V, ch, rc, hc);
+            const int cds = V.dslot(ch);
+            const double hc = cds >= 0 ? V.x(cds) : V.hfix(ch);
             const double dc = safe_duration(h - hc);
-            Hhh += V.c(ch) / (dc * dc);
+            Hhh += V.c(ch) * tn_rcp(dc * dc);
         }
         if (rs >= 0 && i != 0 && !mi) Hrr += lam2;
     }
     if (ds >= 0) {
         const double pmn = V.pmin(i), pmx = V.pmax(i);
-        if (pmn != -1.0) { const double q = h - pmn; if (q > 0.0) Hhh += V.pb * 2.0 / (q * q * q); }
-        if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) Hhh += V.pb * 2.0 / (q * q * q); }
+        if (pmn != -1.0) { const double q = h - pmn; if (q > 0.0) Hhh += V.pb * 2.0 * tn_rcp(q * q * q); }
+        if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) Hhh += V.pb * 2.0 * tn_rcp(q * q * q); }
     }
     double a0 = 1.0, d0 = 1.0;                                 // the node's own diagonal (what Jacobi would use)
     if (fu) { a0 = su * su * Hrr + V.gx(rs) * V.sc(rs) * su; a += a0; a0 = fabs(a0); a += V.mu * a0; } else { a = 1.0; b = 0.0; }
@@ -436,13 +452,17 @@ TPL_HD void tree_factor_node(View& V, int i) {
     double s11 = 0.0, s12 = 0.0, s22 = 0.0;
     if (fu && fh) {
         const double mean = 0.5 * (a + dd), dif = 0.5 * (a - dd);
-        const double rad = sqrt(dif * dif + b * b);
-        double l1 = mean + rad, l2 = mean - rad;                 // l1 >= l2
+        const double q2 = dif * dif + b * b;                     // (l1 - l2)^2 / 4
         const double fl = 1e-10 * fmax(a0, d0);
-        if (!(l2 > fl) || !opt_finite(l1)) {
+        // smaller eigenvalue l2 = mean - sqrt(q2) > fl  <=>  mean - fl > 0 and (mean - fl)^2 > q2: no square root here
+        const double mf = mean - fl;
+        const bool pd = mf > 0.0 && mf * mf > q2 && opt_finite(mean) && opt_finite(q2);
+        if (!pd) {
+            const double rad = sqrt(q2);
+            const double l1 = mean + rad, l2 = mean - rad;       // l1 >= l2
             if (!opt_finite(l1) || !opt_finite(l2)) {            // NaN / inf: Jacobi for this node
                 a = a0 > 1e-300 ? a0 : 1.0; dd = d0 > 1e-300 ? d0 : 1.0; b = 0.0;
-            } else {
+            } else if (!(l2 > fl)) {
                 const double m1 = fmax(fabs(l1), fl), m2 = fmax(fabs(l2), fl);
                 // eigenvector of l1: (b, l1 - a) or (l1 - dd, b); pick the better conditioned one
                 double vx, vy;
@@ -454,16 +474,16 @@ TPL_HD void tree_factor_node(View& V, int i) {
                 b = (m1 - m2) * vx * vy;
             }
         }
-        const double det = a * dd - b * b;
-        s11 = dd / det; s12 = -b / det; s22 = a / det;
+        const double idet = tn_rcp(a * dd - b * b);
+        s11 = dd * idet; s12 = -b * idet; s22 = a * idet;
     } else if (fu) {
         if (!(a > 1e-10 * a0)) a = fmax(fabs(a), a0 > 1e-300 ? 1e-10 * a0 : 1.0);
         if (!opt_finite(a)) a = a0 > 1e-300 && opt_finite(a0) ? a0 : 1.0;
-        s11 = 1.0 / a;
+        s11 = tn_rcp(a);
     } else if (fh) {
         if (!(dd > 1e-10 * d0)) dd = fmax(fabs(dd), d0 > 1e-300 ? 1e-10 * d0 : 1.0);
         if (!opt_finite(dd)) dd = d0 > 1e-300 && opt_finite(d0) ? d0 : 1.0;
-        s22 = 1.0 / dd;
+        s22 = tn_rcp(dd);
     }
     V.tw_put(TW_S + 0, i, s11);
     V.tw_put(TW_S + 1, i, s12);

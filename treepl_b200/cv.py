@@ -272,10 +272,10 @@ def multistart(flat, smoothing, n_starts, jitter=0.3, seed=1, device=0, dist=Non
     mine = cvshard.shard_items(n_starts, rank, world)
     B = max(2, len(mine) + (len(mine) % 2))
     x0 = start_vector(flat, P, nr)
+    ks = [mine[min(b, len(mine) - 1)] if mine else 0 for b in range(B)]
+    J = np.stack([np.random.RandomState(seed * 1000003 + k).randn(nr) for k in ks])          # [B, nr], one stream per start
     X0 = np.repeat(x0[:, None], B, axis=1)
-    for b in range(B):
-        k = mine[min(b, len(mine) - 1)] if mine else 0
-        X0[:nr, b] *= np.exp(jitter * np.random.RandomState(seed * 1000003 + k).randn(nr))
+    X0[:nr] *= np.exp(jitter * J).T
     plp.batch_configure(B)
     par = flat["parents"]
     dscale = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))

@@ -36,7 +36,7 @@ class OptOptions(C.Structure):
     """tpl_opt_options (include/treepl_b200.h); 0 = library default"""
     _fields_ = [("history", C.c_int), ("max_steps", C.c_int), ("patience", C.c_int), ("max_ls", C.c_int),
                 ("check_every", C.c_int), ("use_graph", C.c_int), ("method", C.c_int), ("max_cg", C.c_int), ("cg_per_step", C.c_int), ("precond", C.c_int), ("ftol", C.c_double), ("gtol", C.c_double),
-                ("armijo", C.c_double), ("date_scale", C.c_double), ("boundary_frac", C.c_double)]
+                ("armijo", C.c_double), ("date_scale", C.c_double), ("boundary_frac", C.c_double), ("tree_wide_min", C.c_int), ("reserved", C.c_int)]
 
 
 class AnnealOptions(C.Structure):
@@ -103,7 +103,7 @@ def load_library():
     L.tpl_debug_hessvec.restype = ci
     L.tpl_debug_hessvec.argtypes = [vp, ci, dp, dp, dp, dp, dp]
     L.tpl_debug_treesolve.restype = ci
-    L.tpl_debug_treesolve.argtypes = [vp, ci, dp, dp, dp, dp, dp]
+    L.tpl_debug_treesolve.argtypes = [vp, ci, dp, dp, dp, dp, dp, dp, dp]
     L.tpl_host_alloc.restype = vp
     L.tpl_host_alloc.argtypes = [C.c_ulonglong]
     L.tpl_host_free.restype = None
@@ -360,7 +360,8 @@ class PLCalcParallel:
     def optimize_batch(self, X0, lower, upper, mode=GRAD_AD, **options):
         """Device-resident batched L-BFGS (tpl_optimize_batch): X0 [P, B] feasible start vectors ->
         (X [P, B], F [B], info).  options: fields of tpl_opt_options (history, max_steps, patience, max_ls,
-        check_every, use_graph, method (0 L-BFGS, 1 truncated Newton), max_cg, cg_per_step, precond, ftol, gtol, armijo, date_scale, boundary_frac)."""
+        check_every, use_graph, method (0 L-BFGS, 1 truncated Newton), max_cg, cg_per_step, precond, ftol, gtol, armijo, date_scale, boundary_frac,
+        tree_wide_min)."""
         X = _f64(X0).copy()
         P, B = X.shape
         if P != self.numparams:
@@ -399,13 +400,19 @@ class PLCalcParallel:
         self._check(self._L.tpl_anneal_batch(self._h, B, _dp(X), _dp(F), C.byref(o), _ip(status), _ip(iters)))
         return X, F, status, iters
 
-    def debug_treesolve(self, X, free, rhs, sc_rows):
-        """-> M^-1 rhs through the block-tree factorisation kernels of the truncated-Newton method (test hook)."""
+    def debug_treesolve(self, X, free, rhs, sc_rows, rhs2=None):
+        """-> M^-1 rhs through the block-tree factorisation kernels of the truncated-Newton method (test hook);
+        with rhs2 also M^-1 rhs2 through the solve-only sweeps (same factors): -> (out, out2)."""
         X, Fr, R, sc = _f64(X), _f64(free), _f64(rhs), _f64(sc_rows)
         P, B = X.shape
         out = np.zeros((P, B))
-        self._check(self._L.tpl_debug_treesolve(self._h, B, _dp(X), _dp(Fr), _dp(R), _dp(sc), _dp(out)))
-        return out
+        if rhs2 is None:
+            self._check(self._L.tpl_debug_treesolve(self._h, B, _dp(X), _dp(Fr), _dp(R), _dp(sc), _dp(out), None, None))
+            return out
+        R2 = _f64(rhs2)
+        out2 = np.zeros((P, B))
+        self._check(self._L.tpl_debug_treesolve(self._h, B, _dp(X), _dp(Fr), _dp(R), _dp(sc), _dp(out), _dp(R2), _dp(out2)))
+        return out, out2
 
     def debug_hessvec(self, X, V, sc_rows):
         """-> (H_z V, diag H_z) at X through the truncated-Newton kernels (test hook)."""
