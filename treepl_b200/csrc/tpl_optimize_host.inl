@@ -236,6 +236,7 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
 void tn_launch_tree_solve(const tpltn::TnArgs& a, const std::vector<int>& loff, int groups, cudaStream_t s, bool factor, bool finish) {
     using namespace tpltn;
     const dim3 blk(32, tplopt::OPT_WY), tblk(32, TREE_TOP_WY);
+    if (factor) tn_tree_local_kernel<<<dim3(groups, (a.t.n + TREE_NODES_PER_BLOCK - 1) / TREE_NODES_PER_BLOCK), blk, 0, s>>>(a);
     for (int l = 0; l < a.nlev_wide; l++) {
         const dim3 g(groups, (loff[l + 1] - loff[l] + TREE_NODES_PER_BLOCK - 1) / TREE_NODES_PER_BLOCK);
         if (factor) tn_tree_up_kernel<true><<<g, blk, 0, s>>>(a, l); else tn_tree_up_kernel<false><<<g, blk, 0, s>>>(a, l);
@@ -284,7 +285,7 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
     tn_trial_kernel<<<rgrd, blk, 0, s>>>(a);
     launches += 2;
     CK(cudaGetLastError());
-    const int tree_launches = a.precond ? 2 * a.nlev_wide + (a.nlev > a.nlev_wide ? 1 : 0) + 1 : 0;
+    const int tree_launches = a.precond ? 2 * a.nlev_wide + (a.nlev > a.nlev_wide ? 1 : 0) + 1 : 0;     // + 1 more (local blocks) when factorising
     auto tree_solve = [&](bool factor) { tn_launch_tree_solve(a, w.tn_lev_off_host, groups, s, factor, true); };
     auto one_step = [&]() -> int {
         int rc = eval_device(e, B, a.X, const_cast<double*>(a.Ft), const_cast<double*>(a.Gx), mode, true, s);
@@ -304,7 +305,7 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
         CK(cudaGetLastError());
         return TPL_OK;
     };
-    const int per_step = 7 + 3 * cg_per_step + (1 + cg_per_step) * tree_launches;
+    const int per_step = 7 + 3 * cg_per_step + (1 + cg_per_step) * tree_launches + (a.precond ? 1 : 0);
     int steps = 0;
     int rc = one_step();               // first step outside any capture: sizes the evaluation work space
     if (rc != TPL_OK) return rc;

@@ -19,7 +19,8 @@
 // Tree preconditioner (tpl_tn_core.h::tree_*_node; TnArgs::precond): zz = M^-1 r by one leaf-to-root and one root-to-leaf
 // sweep over HEIGHT levels (a node's children sit on lower levels; level sizes never increase): one launch per wide
 // level, and ONE block per 32-vector group for all the narrow top levels (block-level barriers between levels):
-//   tn_tree_up_kernel<FACTOR>    one wide level: [factorise S_i, K_i, T_i] + forward substitution
+//   tn_tree_local_kernel         FACTOR only, all nodes at once: the node's own block of H_z and its coupling with the parent
+//   tn_tree_up_kernel<FACTOR>    one wide level: [pivot step: S_i, K_i, T_i] + forward substitution
 //   tn_tree_top_kernel<FACTOR>   narrow levels: up to the root, then back down
 //   tn_tree_down_kernel<FACTOR>  one wide level: back substitution -> ZZ rows
 //   tn_pc_finish_kernel<FACTOR>  row-indexed    [p = zz] and r.zz                                        -> phase_setup / phase_update
@@ -370,13 +371,12 @@ struct RecBase : DevView {
     __device__ unsigned long long mask_word(int n) const { return a.lanemask[(size_t)(b >> 6) * a.mask_stride + n]; }
 };
 
-// factorisation (+ the forward substitution that follows it in the same sweep)
-struct FactorView : RecBase {
+// the point-only part of the factorisation (tree_local_node): every node independently
+struct LocalView : RecBase {
     bool m_i, m_p, m_c0, m_c1;
     double r_i, h_i, x_prs, h_p, h_c0, h_c1;
-    double f_rs, f_ds, f_prs, f_pds, sc_rs, sc_ds, sc_prs, sc_pds, gx_rs, c_i, c_c0, c_c1, pmn, pmx, rhs_rs, rhs_ds;
-    double t0[3], t1[3];
-    __device__ FactorView(const DevView& v, const TreeRec& rec) : RecBase(v, rec) {
+    double f_rs, f_ds, f_prs, f_pds, sc_rs, sc_ds, sc_prs, sc_pds, gx_rs, c_i, c_c0, c_c1, pmn, pmx;
+    __device__ LocalView(const DevView& v, const TreeRec& rec) : RecBase(v, rec) {
         const size_t Bs = (size_t)B;
         const bool hp = t.p >= 0, h0 = t.nch > 0, h1 = t.nch > 1;
         m_i = m_p = m_c0 = m_c1 = false;
@@ -395,8 +395,6 @@ struct FactorView : RecBase {
         f_ds = t.ds >= 0 ? a.Minv[(size_t)t.ds * Bs + b] : 0.0;
         f_prs = t.prs >= 0 ? a.Minv[(size_t)t.prs * Bs + b] : 0.0;
         f_pds = t.pds >= 0 ? a.Minv[(size_t)t.pds * Bs + b] : 0.0;
-        rhs_rs = t.rs >= 0 ? a.R[(size_t)t.rs * Bs + b] : 0.0;
-        rhs_ds = t.ds >= 0 ? a.R[(size_t)t.ds * Bs + b] : 0.0;
         gx_rs = t.rs >= 0 ? a.Gx[(size_t)t.rs * Bs + b] : 0.0;
         sc_rs = t.rs >= 0 ? a.sc[t.rs] : 0.0;
         sc_ds = t.ds >= 0 ? a.sc[t.ds] : 0.0;
@@ -407,12 +405,6 @@ struct FactorView : RecBase {
         c_c1 = h1 ? a.t.c[t.ch1] : 0.0;
         pmn = a.pmin_n[t.i];
         pmx = a.pmax_n[t.i];
-        const size_t n = (size_t)a.t.n;
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            t0[q] = h0 ? a.TW[((size_t)(TW_T + q) * n + t.ch0) * Bs + b] : 0.0;
-            t1[q] = h1 ? a.TW[((size_t)(TW_T + q) * n + t.ch1) * Bs + b] : 0.0;
-        }
     }
     __device__ bool masked(int n) const {
         if (!a.lanemask) return false;
@@ -436,23 +428,18 @@ struct FactorView : RecBase {
         return row == t.rs ? sc_rs : (row == t.ds ? sc_ds : (row == t.prs ? sc_prs : (row == t.pds ? sc_pds : DevView::sc(row))));
     }
     __device__ double gx(int row) const { return row == t.rs ? gx_rs : DevView::gx(row); }
-    __device__ double rhs(int row) const { return row == t.rs ? rhs_rs : (row == t.ds ? rhs_ds : DevView::rhs(row)); }
     __device__ double c(int n) const { return n == t.i ? c_i : (n == t.ch0 ? c_c0 : (n == t.ch1 ? c_c1 : DevView::c(n))); }
     __device__ double pmin(int n) const { return n == t.i ? pmn : DevView::pmin(n); }
     __device__ double pmax(int n) const { return n == t.i ? pmx : DevView::pmax(n); }
-    __device__ double tw(int q, int n) const {
-        if (q >= TW_T && q < TW_Y) {
-            if (n == t.ch0) return t0[q - TW_T];
-            if (n == t.ch1) return t1[q - TW_T];
-        }
-        return DevView::tw(q, n);
-    }
 };
 
-// forward substitution alone (the solve inside a CG iteration)
+// forward substitution (the solve inside a CG iteration), optionally preceded by the pivot step of the factorisation
+// (PIVOT: the node's own local block and the children's T are loaded with everything else)
+template <bool PIVOT>
 struct UpView : RecBase {
     bool m_i;
     double f_rs, f_ds, rhs_rs, rhs_ds, k0[4], k1[4], y0[2], y1[2];
+    double loc[PIVOT ? 7 : 1], t0[PIVOT ? 3 : 1], t1[PIVOT ? 3 : 1];
     __device__ UpView(const DevView& v, const TreeRec& rec) : RecBase(v, rec) {
         const size_t Bs = (size_t)B, n = (size_t)a.t.n;
         const bool h0 = t.nch > 0, h1 = t.nch > 1;
@@ -471,14 +458,28 @@ struct UpView : RecBase {
             y0[q] = h0 ? a.TW[((size_t)(TW_Y + q) * n + t.ch0) * Bs + b] : 0.0;
             y1[q] = h1 ? a.TW[((size_t)(TW_Y + q) * n + t.ch1) * Bs + b] : 0.0;
         }
+        if (PIVOT) {
+#pragma unroll
+            for (int q = 0; q < 7; q++) loc[q] = a.TW[((size_t)(TW_L + q) * n + t.i) * Bs + b];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                t0[q] = h0 ? a.TW[((size_t)(TW_T + q) * n + t.ch0) * Bs + b] : 0.0;
+                t1[q] = h1 ? a.TW[((size_t)(TW_T + q) * n + t.ch1) * Bs + b] : 0.0;
+            }
+        }
     }
     __device__ bool masked(int n) const { return n == t.i ? m_i : DevView::masked(n); }
     __device__ bool fr(int row) const { return (row == t.rs ? f_rs : (row == t.ds ? f_ds : a.Minv[(size_t)row * B + b])) > 0.0; }
     __device__ double rhs(int row) const { return row == t.rs ? rhs_rs : (row == t.ds ? rhs_ds : DevView::rhs(row)); }
     __device__ double tw(int q, int n) const {
+        if (PIVOT && n == t.i && q < TW_L + 7) return loc[q - TW_L];          // tree_pivot_node reads its local block first
         if (q >= TW_K && q < TW_T) {
             if (n == t.ch0) return k0[q - TW_K];
             if (n == t.ch1) return k1[q - TW_K];
+        }
+        if (PIVOT && q >= TW_T && q < TW_Y) {
+            if (n == t.ch0) return t0[q - TW_T];
+            if (n == t.ch1) return t1[q - TW_T];
         }
         if (q >= TW_Y) {
             if (n == t.ch0) return y0[q - TW_Y];
@@ -516,19 +517,27 @@ struct DownView : RecBase {
 template <bool FACTOR>
 __device__ __forceinline__ void tree_up_at(const TnArgs& a, const DevView& V, int k) {
     const TreeRec rec = tree_rec_load(a, k);
-    if (FACTOR) {
-        FactorView F(V, rec);
-        tree_factor_node(F, rec.i);
-        tree_up_node(F, rec.i);
-    } else {
-        UpView U(V, rec);
-        tree_up_node(U, rec.i);
-    }
+    UpView<FACTOR> U(V, rec);
+    if (FACTOR) tree_pivot_node(U, rec.i);
+    tree_up_node(U, rec.i);
 }
 __device__ __forceinline__ void tree_down_at(const TnArgs& a, const DevView& V, int k) {
     const TreeRec rec = tree_rec_load(a, k);
     DownView D(V, rec);
     tree_down_node(D, rec.i);
+}
+
+// the point-only part of the factorisation for every node (no dependence between nodes): one launch before the sweeps
+__global__ void __launch_bounds__(32 * OPT_WY) tn_tree_local_kernel(TnArgs a) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    if (!tree_lane_active<true>(a, b)) return;
+    DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, tree_lane_mu<true>(a, b)};
+    const int k0 = blockIdx.y * TREE_NODES_PER_BLOCK, k1 = min(a.t.n, k0 + TREE_NODES_PER_BLOCK);
+    for (int k = k0 + threadIdx.y; k < k1; k += OPT_WY) {
+        const TreeRec rec = tree_rec_load(a, k);
+        LocalView L(V, rec);
+        tree_local_node(L, rec.i);
+    }
 }
 
 template <bool FACTOR>

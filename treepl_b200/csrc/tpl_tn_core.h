@@ -383,13 +383,19 @@ TPL_HD double root_child_curvature(const View& V, int i, double r) {
     return (lam2 / m) * ((1.0 - 1.0 / m) - (log(r) - sy / m)) / (r * r);
 }
 
-// factorisation step of node i (its children are done): writes TW_S, TW_K, TW_T.
-// The sweep kernels are bound by the LATENCY of this function's dependent chain (one warp = one node x 32 vectors), so
-// it is written for a short chain: reciprocals instead of divisions, nothing computed that the node's kind does not need
-// (a tip has no date variable: no duration, no date curvature), one reciprocal of the determinant, and the eigenvalue
-// safeguard decided without a square root in the positive-definite case.
+// Factorisation of node i in two parts.
+//   tree_local_node: everything that depends on the point X only - the node's own diagonal block of H_z (branch
+//     likelihood, roughness, root-children variance, barrier) and its coupling with the parent's (u, h), in z space.
+//     No dependence on other nodes' factors: the kernels run it for ALL nodes in one parallel launch.  Results go to
+//     the node's own S / K planes (the pivot step overwrites them):
+//       TW_L + 0..6 = a0 (signed), d0 (signed), b0, cuu, cuh, chh, flags (1: rate variable free, 2: date variable free)
+//   tree_pivot_node: the elimination step proper (children done): Schur complement from the children's T, pivot
+//     safeguards, inverse pivot S, K = S^-1 C, T = C^T K.  This is the part on the leaf-to-root critical path, and it is
+//     short: ~100 arithmetic instructions, one reciprocal, no square root on the positive-definite path.
+enum { TW_L = 0 };
+
 template <class View>
-TPL_HD void tree_factor_node(View& V, int i) {
+TPL_HD void tree_local_node(View& V, int i) {
     const int rs = V.rslot(i), ds = V.dslot(i);
     const bool mi = V.masked(i);
     const bool fu = rs >= 0 && !mi && V.fr(rs);
@@ -421,12 +427,8 @@ TPL_HD void tree_factor_node(View& V, int i) {
             if (fh && ph) chh = -cdd * sh * V.sc(pds);
         }
     }
-    double a = 0.0, b = 0.0, dd = 0.0;
     for (int j = V.child_begin(i); j < V.child_end(i); j++) {
         const int ch = V.child(j);
-        a -= V.tw(TW_T + 0, ch);
-        b -= V.tw(TW_T + 1, ch);
-        dd -= V.tw(TW_T + 2, ch);
         if (V.masked(ch)) continue;
         if (ds >= 0) {
             const int cds = V.dslot(ch);
@@ -441,10 +443,32 @@ TPL_HD void tree_factor_node(View& V, int i) {
         if (pmn != -1.0) { const double q = h - pmn; if (q > 0.0) Hhh += V.pb * 2.0 * tn_rcp(q * q * q); }
         if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) Hhh += V.pb * 2.0 * tn_rcp(q * q * q); }
     }
+    V.tw_put(TW_L + 0, i, fu ? su * su * Hrr + V.gx(rs) * V.sc(rs) * su : 0.0);
+    V.tw_put(TW_L + 1, i, fh ? sh * sh * Hhh : 0.0);
+    V.tw_put(TW_L + 2, i, (fu && fh) ? su * sh * Hrh : 0.0);
+    V.tw_put(TW_L + 3, i, cuu);
+    V.tw_put(TW_L + 4, i, cuh);
+    V.tw_put(TW_L + 5, i, chh);
+    V.tw_put(TW_L + 6, i, (fu ? 1.0 : 0.0) + (fh ? 2.0 : 0.0));
+}
+
+template <class View>
+TPL_HD void tree_pivot_node(View& V, int i) {
+    const double a0s = V.tw(TW_L + 0, i), d0s = V.tw(TW_L + 1, i), b0 = V.tw(TW_L + 2, i);
+    const double cuu = V.tw(TW_L + 3, i), cuh = V.tw(TW_L + 4, i), chh = V.tw(TW_L + 5, i);
+    const double flags = V.tw(TW_L + 6, i);
+    const bool fu = flags == 1.0 || flags == 3.0, fh = flags >= 2.0;
+    double a = 0.0, b = 0.0, dd = 0.0;
+    for (int j = V.child_begin(i); j < V.child_end(i); j++) {
+        const int ch = V.child(j);
+        a -= V.tw(TW_T + 0, ch);
+        b -= V.tw(TW_T + 1, ch);
+        dd -= V.tw(TW_T + 2, ch);
+    }
     double a0 = 1.0, d0 = 1.0;                                 // the node's own diagonal (what Jacobi would use)
-    if (fu) { a0 = su * su * Hrr + V.gx(rs) * V.sc(rs) * su; a += a0; a0 = fabs(a0); a += V.mu * a0; } else { a = 1.0; b = 0.0; }
-    if (fh) { d0 = sh * sh * Hhh; dd += d0; d0 = fabs(d0); dd += V.mu * d0; } else { dd = 1.0; b = 0.0; }
-    if (fu && fh) b += su * sh * Hrh;
+    if (fu) { a0 = a0s; a += a0; a0 = fabs(a0); a += V.mu * a0; } else { a = 1.0; b = 0.0; }
+    if (fh) { d0 = d0s; dd += d0; d0 = fabs(d0); dd += V.mu * d0; } else { dd = 1.0; b = 0.0; }
+    if (fu && fh) b += b0;
     // safeguards: every pivot positive definite (M is SPD whatever H_z is).  An indefinite pivot is replaced by its
     // absolute value |S| = Q |L| Q^T (eigenvalues mirrored, floored relative to the node's own diagonal): the curvature
     // MAGNITUDE along a negative-curvature direction still sets the step length there, and M = H_z wherever H_z is
@@ -496,6 +520,13 @@ TPL_HD void tree_factor_node(View& V, int i) {
     V.tw_put(TW_T + 0, i, cuu * k11);
     V.tw_put(TW_T + 1, i, cuu * k12);
     V.tw_put(TW_T + 2, i, cuh * k12 + chh * k22);
+}
+
+// both parts in one call (the CPU emulation and small tests)
+template <class View>
+TPL_HD void tree_factor_node(View& V, int i) {
+    tree_local_node(V, i);
+    tree_pivot_node(V, i);
 }
 
 // forward substitution at node i (children done): y_i = rhs_i - sum_ch K_ch^T y_ch
