@@ -107,6 +107,19 @@ int run_optimizer(tpl_engine* e, tplopt::OptArgs a, int B, int mode, int max_ste
 
 // ---- batched truncated Newton (tpl_tn_core.h / tpl_tn.cuh) ---------------------------------------------------------
 
+// index record of node i for the kernels' record views (tpl_tn.cuh::TreeRec)
+static void tn_fill_record(const tpl_engine* e, int i, int* r) {
+    const int n = e->n;
+    const int pa = i == 0 ? -1 : e->parent[i];
+    const int c0 = e->child_off[i], nc = e->child_off[i + 1] - c0;
+    r[0] = i; r[1] = e->freeparams[i]; r[2] = e->freeparams[n + i]; r[3] = pa;
+    r[4] = pa >= 0 ? e->freeparams[pa] : -1; r[5] = pa >= 0 ? e->freeparams[n + pa] : -1; r[6] = c0; r[7] = nc;
+    for (int j = 0; j < 2 && j < nc; j++) {
+        const int ch = e->children[c0 + j];
+        r[8 + j] = ch; r[10 + j] = e->freeparams[n + ch];
+    }
+}
+
 // work space, tree operands and chunking of the truncated-Newton kernels; uploads lo / hi / sc and X
 int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>& lo, const std::vector<double>& hi,
                const std::vector<double>& sc, int nr, const tpl_opt_options& o, tpltn::TnArgs& a) {
@@ -188,6 +201,27 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
     a.part_hv = pp; pp += (size_t)2 * a.node_chunks * B;
     a.part_tm = pp; pp += (size_t)a.node_chunks * B;
     a.part_pc = pp;
+    {   // index records (node order) of the Hessian-vector kernel's fast path: every non-root node whose parent is not the root,
+        // with no or exactly two children (rates exist for all of them in the PL layout)
+        std::vector<int> hrec((size_t)n * tpltn::HV_REC_INTS, -1);
+        for (int i = 0; i < n; i++) {
+            int* r = hrec.data() + (size_t)i * tpltn::HV_REC_INTS;
+            const int pa = i == 0 ? -1 : e->parent[i];
+            const int c0 = e->child_off[i], nc = e->child_off[i + 1] - c0;
+            r[0] = i; r[1] = e->freeparams[i]; r[2] = e->freeparams[n + i]; r[3] = pa;
+            r[4] = pa >= 0 ? e->freeparams[pa] : -1; r[5] = pa >= 0 ? e->freeparams[n + pa] : -1; r[6] = nc;
+            bool fast = i != 0 && pa != 0 && (nc == 0 || nc == 2) && r[1] >= 0 && r[4] >= 0;
+            for (int j = 0; j < 2 && j < nc; j++) {
+                const int ch = e->children[c0 + j];
+                r[8 + j] = ch; r[10 + j] = e->freeparams[n + ch]; r[12 + j] = e->freeparams[ch];
+                if (e->freeparams[ch] < 0) fast = false;
+            }
+            r[7] = fast ? 1 : 0;
+        }
+        CK(w.tn_hv_rec.upload(hrec, s));
+        CK(cudaStreamSynchronize(s));
+        a.hv_rec = w.tn_hv_rec.p;
+    }
     // ---- tree preconditioner: height levels (children before parents), node lists per level, work planes ----
     a.precond = o.precond == 1 ? 0 : 1;
     a.log_pen = e->log_pen ? 1 : 0;
@@ -212,15 +246,7 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
         while (a.nlev_wide < a.nlev && off[a.nlev_wide + 1] - off[a.nlev_wide] >= wide_min) a.nlev_wide++;
         // one index record per node, in level order: what the sweeps' record views load first (tpl_tn.cuh)
         std::vector<int> recs((size_t)n * tpltn::TREE_REC_INTS, -1);
-        for (int k = 0; k < n; k++) {
-            const int i = nodes[k];
-            int* r = recs.data() + (size_t)k * tpltn::TREE_REC_INTS;
-            const int pa = i == 0 ? -1 : e->parent[i];
-            const int c0 = e->child_off[i], nc = e->child_off[i + 1] - c0;
-            r[0] = i; r[1] = e->freeparams[i]; r[2] = e->freeparams[n + i]; r[3] = pa;
-            r[4] = pa >= 0 ? e->freeparams[pa] : -1; r[5] = pa >= 0 ? e->freeparams[n + pa] : -1; r[6] = c0; r[7] = nc;
-            for (int j = 0; j < 2 && j < nc; j++) { r[8 + j] = e->children[c0 + j]; r[10 + j] = e->freeparams[n + e->children[c0 + j]]; }
-        }
+        for (int k = 0; k < n; k++) tn_fill_record(e, nodes[k], recs.data() + (size_t)k * tpltn::TREE_REC_INTS);
         CK(w.tn_lev_nodes.upload(nodes, s));
         CK(w.tn_lev_off.upload(off, s));
         CK(w.tn_lev_rec.upload(recs, s));
@@ -236,7 +262,10 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
 void tn_launch_tree_solve(const tpltn::TnArgs& a, const std::vector<int>& loff, int groups, cudaStream_t s, bool factor, bool finish) {
     using namespace tpltn;
     const dim3 blk(32, tplopt::OPT_WY), tblk(32, TREE_TOP_WY);
-    if (factor) tn_tree_local_kernel<<<dim3(groups, (a.t.n + TREE_NODES_PER_BLOCK - 1) / TREE_NODES_PER_BLOCK), blk, 0, s>>>(a);
+    if (factor) {
+        const dim3 lg(groups, (a.t.n + TREE_NODES_PER_BLOCK - 1) / TREE_NODES_PER_BLOCK);
+        if (groups < 32) tn_tree_local_kernel<true><<<lg, blk, 0, s>>>(a); else tn_tree_local_kernel<false><<<lg, blk, 0, s>>>(a);
+    }
     for (int l = 0; l < a.nlev_wide; l++) {
         const dim3 g(groups, (loff[l + 1] - loff[l] + TREE_NODES_PER_BLOCK - 1) / TREE_NODES_PER_BLOCK);
         if (factor) tn_tree_up_kernel<true><<<g, blk, 0, s>>>(a, l); else tn_tree_up_kernel<false><<<g, blk, 0, s>>>(a, l);

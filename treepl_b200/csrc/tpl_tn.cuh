@@ -59,6 +59,7 @@ struct TnArgs {
     const int* lev_nodes;                    // [n] node numbers grouped by height level (tips first)
     const int* lev_off;                      // [nlev + 1]
     const int* lev_rec;                      // [n][TREE_REC_INTS] index record of node lev_nodes[k] (tpl_tn.cuh: record views)
+    const int* hv_rec;                       // [n][HV_REC_INTS] index record of node i for hess_node_fast
     int nlev, nlev_wide;                     // levels [0, nlev_wide): one launch each; [nlev_wide, nlev): tn_tree_top_kernel
     double *gmax_tmp, *gg_tmp;               // [B] reductions of the set-up pass kept until the solve has produced r.zz
     double* part_pc;
@@ -207,6 +208,43 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_trial_kernel(TnArgs a) {
     }
 }
 
+// ---- record views: the tree sweeps are LATENCY bound (one warp = one node x 32 vectors, a chain of dependent loads
+// node -> slots -> parent -> parent's slots -> rows -> children -> children's factors: ~12 round trips to L2 / HBM, ~10 us per
+// node at batch sizes whose work planes exceed L2).  The host therefore flattens everything index-like into one 48-byte
+// record per node, stored in level order (tn_prepare), and a view loads the record (round trip 1), then ALL operands the
+// node function will ask for, unconditionally and side by side (round trip 2); the node functions of tpl_tn_core.h run
+// unchanged on top and find their operands in registers.  Nodes with more than two children fall through to the generic
+// accessors for the extra children.
+constexpr int TREE_REC_INTS = 12;            // i rs ds p | prs pds coff nch | ch0 ch1 cds0 cds1
+
+struct TreeRec {
+    int i, rs, ds, p, prs, pds, coff, nch, ch0, ch1, cds0, cds1;
+};
+__device__ __forceinline__ TreeRec tree_rec_load(const int* recs, int k) {
+    const int4* r = reinterpret_cast<const int4*>(recs + (size_t)k * TREE_REC_INTS);
+    const int4 q0 = __ldg(r), q1 = __ldg(r + 1), q2 = __ldg(r + 2);
+    TreeRec t = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+    return t;
+}
+
+struct RecBase : DevView {
+    TreeRec t;
+    __device__ RecBase(const DevView& v, const TreeRec& rec) : DevView(v), t(rec) {}
+    __device__ int parent(int n) const { return n == t.i ? t.p : DevView::parent(n); }
+    __device__ int child_begin(int n) const { return n == t.i ? t.coff : DevView::child_begin(n); }
+    __device__ int child_end(int n) const { return n == t.i ? t.coff + t.nch : DevView::child_end(n); }
+    __device__ int child(int j) const {
+        const int q = j - t.coff;
+        return (q == 0 && t.nch > 0) ? t.ch0 : ((q == 1 && t.nch > 1) ? t.ch1 : DevView::child(j));
+    }
+    __device__ int rslot(int n) const { return n == t.i ? t.rs : (n == t.p ? t.prs : DevView::rslot(n)); }
+    __device__ int dslot(int n) const {
+        return n == t.i ? t.ds : (n == t.p ? t.pds : (n == t.ch0 ? t.cds0 : (n == t.ch1 ? t.cds1 : DevView::dslot(n))));
+    }
+    __device__ unsigned long long mask_word(int n) const { return a.lanemask[(size_t)(b >> 6) * a.mask_stride + n]; }
+};
+
+
 __global__ void __launch_bounds__(32 * OPT_WY) tn_diag_kernel(TnArgs a) {
     const int b = blockIdx.x * 32 + threadIdx.x;
     const int B = a.o.B;
@@ -266,6 +304,107 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_setup_kernel(TnArgs a) {
     }
 }
 
+// hess_node for the ordinary node - not the root, not a child of the root, no or two children (99.9 % of a tree) - written
+// against a 64-byte host-built index record (node order) so that ALL rows the node needs (its own, its parent's, its
+// children's X and P rows) are requested side by side: one round trip to HBM per node instead of the three to four that
+// the accessor chain of the generic function serialises (own rows -> parent -> children), which is what bound this
+// kernel (long-scoreboard stalls, 0.26-0.47 of the HBM rate).  Same arithmetic, in the same order, as hess_node.
+constexpr int HV_REC_INTS = 16;              // i rs ds p | prs pds nch fast | ch0 ch1 cds0 cds1 | crs0 crs1 - -
+
+__device__ __forceinline__ void hess_node_fast(const TnArgs& a, const int4 q0, const int4 q1, const int4 q2, const int4 q3, int B, int b,
+                                               double lam, double mu, double& vw, double& vv) {
+    const int i = q0.x, rs = q0.y, ds = q0.z, p = q0.w, prs = q1.x, pds = q1.y, nch = q1.z;
+    const int ch[2] = {q2.x, q2.y}, cds[2] = {q2.z, q2.w}, crs[2] = {q3.x, q3.y};
+    const size_t Bs = (size_t)B;
+    const double* __restrict__ X = a.X;
+    const double* __restrict__ Pv = a.Pv;
+    // ---- every load first ----
+    bool mi = false, mp = false, mc[2] = {false, false};
+    if (a.lanemask) {
+        const unsigned long long* mw = a.lanemask + (size_t)(b >> 6) * a.mask_stride;
+        const unsigned long long wi = mw[i], wp = mw[p], w0 = nch ? mw[ch[0]] : 0ull, w1 = nch ? mw[ch[1]] : 0ull;
+        mi = (wi >> (b & 63)) & 1ull; mp = (wp >> (b & 63)) & 1ull; mc[0] = (w0 >> (b & 63)) & 1ull; mc[1] = (w1 >> (b & 63)) & 1ull;
+    }
+    const double r = X[(size_t)rs * Bs + b], v_rs = Pv[(size_t)rs * Bs + b];
+    const double h = ds >= 0 ? X[(size_t)ds * Bs + b] : a.t.hfix[i];
+    const double v_ds = ds >= 0 ? Pv[(size_t)ds * Bs + b] : 0.0;
+    const double rp = X[(size_t)prs * Bs + b], v_prs = Pv[(size_t)prs * Bs + b];
+    const double hp = pds >= 0 ? X[(size_t)pds * Bs + b] : a.t.hfix[p];
+    const double v_pds = pds >= 0 ? Pv[(size_t)pds * Bs + b] : 0.0;
+    double rc[2] = {0.0, 0.0}, hc[2] = {0.0, 0.0}, v_crs[2] = {0.0, 0.0}, v_cds[2] = {0.0, 0.0}, cc[2] = {0.0, 0.0}, sc_crs[2] = {0.0, 0.0}, sc_cds[2] = {0.0, 0.0};
+    if (nch) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            rc[k] = X[(size_t)crs[k] * Bs + b];
+            v_crs[k] = Pv[(size_t)crs[k] * Bs + b];
+            hc[k] = cds[k] >= 0 ? X[(size_t)cds[k] * Bs + b] : a.t.hfix[ch[k]];
+            v_cds[k] = cds[k] >= 0 ? Pv[(size_t)cds[k] * Bs + b] : 0.0;
+            cc[k] = a.t.c[ch[k]];
+            sc_crs[k] = a.sc[crs[k]];
+            sc_cds[k] = cds[k] >= 0 ? a.sc[cds[k]] : 0.0;
+        }
+    }
+    const double sc_rs = a.sc[rs], sc_ds = ds >= 0 ? a.sc[ds] : 0.0, sc_prs = a.sc[prs], sc_pds = pds >= 0 ? a.sc[pds] : 0.0;
+    const double c = a.t.c[i];
+    const double gx = a.Gx[(size_t)rs * Bs + b];
+    const bool damp = mu > 0.0;
+    const double dg_rs = damp ? a.DG[(size_t)rs * Bs + b] : 0.0, dg_ds = (damp && ds >= 0) ? a.DG[(size_t)ds * Bs + b] : 0.0;
+    const double pmn = ds >= 0 ? a.pmin_n[i] : -1.0, pmx = ds >= 0 ? a.pmax_n[i] : -1.0;
+    // ---- hess_node, same order of operations ----
+    const bool rfree = !mi;
+    const double lam2 = 2.0 * lam;
+    const double vr = rfree ? sc_rs * r * v_rs : 0.0;
+    const double vh = ds >= 0 ? sc_ds * v_ds : 0.0;
+    double w_r = 0.0, w_h = 0.0;
+    if (!mi) {
+        const double vrp = !mp ? sc_prs * rp * v_prs : 0.0;
+        const double vhp = pds >= 0 ? sc_pds * v_pds : 0.0;
+        const double d = safe_duration(hp - h);
+        const double dv = vhp - vh;
+        w_r = (c / (r * r)) * vr + dv;
+        w_h = -((c / (d * d)) * dv + vr);
+        w_r += lam2 * (vr - vrp);
+    }
+    if (nch) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (mc[k]) continue;
+            const double vrc = sc_crs[k] * rc[k] * v_crs[k];
+            const double vhc = cds[k] >= 0 ? sc_cds[k] * v_cds[k] : 0.0;
+            if (ds >= 0) {
+                const double dc = safe_duration(h - hc[k]);
+                w_h += (cc[k] / (dc * dc)) * (vh - vhc) + vrc;
+            }
+            if (rfree) w_r -= lam2 * (vrc - vr);
+        }
+    }
+    if (ds >= 0) {
+        double bar = 0.0;
+        if (pmn != -1.0) { const double q = h - pmn; if (q > 0.0) bar += 2.0 / (q * q * q); }
+        if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) bar += 2.0 / (q * q * q); }
+        w_h += a.pb * bar * vh;
+    }
+    vw = 0.0;
+    vv = 0.0;
+    {
+        double W = 0.0;
+        if (rfree) {
+            W = sc_rs * r * w_r + gx * sc_rs * sc_rs * r * v_rs;
+            if (damp) W += mu * fabs(dg_rs) * v_rs;
+            vw += v_rs * W;
+            vv += v_rs * v_rs;
+        }
+        a.Hp[(size_t)rs * Bs + b] = W;
+    }
+    if (ds >= 0) {
+        double W = sc_ds * w_h;
+        if (damp) W += mu * fabs(dg_ds) * v_ds;
+        vw += v_ds * W;
+        vv += v_ds * v_ds;
+        a.Hp[(size_t)ds * Bs + b] = W;
+    }
+}
+
 __global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int b = blockIdx.x * 32 + tx;
@@ -277,9 +416,12 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
     if (active) {
         DevView V = {a, B, b, a.Pv, a.Hp, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, a.mu[b]};
         const int i0 = blockIdx.y * a.nodes_per_chunk, i1 = min(a.t.n, i0 + a.nodes_per_chunk);
+        const int4* recs = reinterpret_cast<const int4*>(a.hv_rec);
         for (int i = i0 + ty; i < i1; i += OPT_WY) {
             double vw, vv;
-            hess_node(V, i, vw, vv);
+            const int4 q1 = __ldg(recs + 4 * (size_t)i + 1);
+            if (q1.w) hess_node_fast(a, __ldg(recs + 4 * (size_t)i), q1, __ldg(recs + 4 * (size_t)i + 2), __ldg(recs + 4 * (size_t)i + 3), B, b, V.lam, V.mu, vw, vv);
+            else hess_node(V, i, vw, vv);
             v[0] += vw;
             v[1] += vv;
         }
@@ -334,42 +476,6 @@ template <bool FACTOR>
 __device__ __forceinline__ double tree_lane_mu(const TnArgs& a, int b) {
     return FACTOR ? lane_mu_eff(a, b, lane_decision(a, b)) : a.mu[b];
 }
-
-// ---- record views: the sweeps are LATENCY bound (one warp = one node x 32 vectors, a chain of dependent loads
-// node -> slots -> parent -> parent's slots -> rows -> children -> children's factors: ~12 round trips to L2 / HBM, ~10 us per
-// node at batch sizes whose work planes exceed L2).  The host therefore flattens everything index-like into one 48-byte
-// record per node, stored in level order (tn_prepare), and a view loads the record (round trip 1), then ALL operands the
-// node function will ask for, unconditionally and side by side (round trip 2); the node functions of tpl_tn_core.h run
-// unchanged on top and find their operands in registers.  Nodes with more than two children fall through to the generic
-// accessors for the extra children.
-constexpr int TREE_REC_INTS = 12;            // i rs ds p | prs pds coff nch | ch0 ch1 cds0 cds1
-
-struct TreeRec {
-    int i, rs, ds, p, prs, pds, coff, nch, ch0, ch1, cds0, cds1;
-};
-__device__ __forceinline__ TreeRec tree_rec_load(const TnArgs& a, int k) {
-    const int4* r = reinterpret_cast<const int4*>(a.lev_rec + (size_t)k * TREE_REC_INTS);
-    const int4 q0 = __ldg(r), q1 = __ldg(r + 1), q2 = __ldg(r + 2);
-    TreeRec t = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-    return t;
-}
-
-struct RecBase : DevView {
-    TreeRec t;
-    __device__ RecBase(const DevView& v, const TreeRec& rec) : DevView(v), t(rec) {}
-    __device__ int parent(int n) const { return n == t.i ? t.p : DevView::parent(n); }
-    __device__ int child_begin(int n) const { return n == t.i ? t.coff : DevView::child_begin(n); }
-    __device__ int child_end(int n) const { return n == t.i ? t.coff + t.nch : DevView::child_end(n); }
-    __device__ int child(int j) const {
-        const int q = j - t.coff;
-        return (q == 0 && t.nch > 0) ? t.ch0 : ((q == 1 && t.nch > 1) ? t.ch1 : DevView::child(j));
-    }
-    __device__ int rslot(int n) const { return n == t.i ? t.rs : (n == t.p ? t.prs : DevView::rslot(n)); }
-    __device__ int dslot(int n) const {
-        return n == t.i ? t.ds : (n == t.p ? t.pds : (n == t.ch0 ? t.cds0 : (n == t.ch1 ? t.cds1 : DevView::dslot(n))));
-    }
-    __device__ unsigned long long mask_word(int n) const { return a.lanemask[(size_t)(b >> 6) * a.mask_stride + n]; }
-};
 
 // the point-only part of the factorisation (tree_local_node): every node independently
 struct LocalView : RecBase {
@@ -516,27 +622,35 @@ struct DownView : RecBase {
 
 template <bool FACTOR>
 __device__ __forceinline__ void tree_up_at(const TnArgs& a, const DevView& V, int k) {
-    const TreeRec rec = tree_rec_load(a, k);
+    const TreeRec rec = tree_rec_load(a.lev_rec, k);
     UpView<FACTOR> U(V, rec);
     if (FACTOR) tree_pivot_node(U, rec.i);
     tree_up_node(U, rec.i);
 }
 __device__ __forceinline__ void tree_down_at(const TnArgs& a, const DevView& V, int k) {
-    const TreeRec rec = tree_rec_load(a, k);
+    const TreeRec rec = tree_rec_load(a.lev_rec, k);
     DownView D(V, rec);
     tree_down_node(D, rec.i);
 }
 
-// the point-only part of the factorisation for every node (no dependence between nodes): one launch before the sweeps
+// the point-only part of the factorisation for every node (no dependence between nodes): one launch before the sweeps.
+// REC: through the record view (few vector groups: the launch is latency bound); otherwise through the plain accessors,
+// which cost fewer instructions and registers when there are enough warps to hide the load chains (measured: the views
+// halve the throughput of the node-indexed kernels at thousands of vectors)
+template <bool REC>
 __global__ void __launch_bounds__(32 * OPT_WY) tn_tree_local_kernel(TnArgs a) {
     const int b = blockIdx.x * 32 + threadIdx.x;
     if (!tree_lane_active<true>(a, b)) return;
     DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, tree_lane_mu<true>(a, b)};
     const int k0 = blockIdx.y * TREE_NODES_PER_BLOCK, k1 = min(a.t.n, k0 + TREE_NODES_PER_BLOCK);
     for (int k = k0 + threadIdx.y; k < k1; k += OPT_WY) {
-        const TreeRec rec = tree_rec_load(a, k);
-        LocalView L(V, rec);
-        tree_local_node(L, rec.i);
+        if (REC) {
+            const TreeRec rec = tree_rec_load(a.lev_rec, k);
+            LocalView L(V, rec);
+            tree_local_node(L, rec.i);
+        } else {
+            tree_local_node(V, k);
+        }
     }
 }
 
