@@ -730,7 +730,6 @@ def main():
         if parity["f_rel"] > 1e-10 or parity["g_rel"] > 1e-8:
             raise SystemExit("bench.py: the bench vectors fail the parity gate against the oracle: %r" % (parity,))
 
-    plp.set_timing(True)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -743,6 +742,12 @@ def main():
     if dist is not None:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
+    # per-kernel durations for the roofline: the same K steps again, right behind the timed region, with CUDA events recorded
+    # inside the library around the main kernel (kept out of the timed region: two more event records per step)
+    plp.set_timing(True)
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
     cnt, main_ms, fin_ms = plp.get_timing()
     plp.set_timing(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -803,7 +808,10 @@ def main():
                              "kernel": {4: "pl_desc_kernel", 3: "pl_persist_kernel", 2: "pl_tile_kernel",
                                         1: "pl_main_kernel"}.get(plp.last_kernel_generation(), "?"),
                              "kernel_ms": main_ms / max(cnt, 1), "finalize_ms": fin_ms / max(cnt, 1),
-                             "algorithmic_bytes_per_launch": bytes_per_eval * B}}
+                             "algorithmic_bytes_per_launch": bytes_per_eval * B,
+                             "frac_of_whole_step": bytes_per_eval * B / (ms / args.steps * 1e-3) / 1e9 / peak,
+                             "how": "kernel_ms: CUDA events around the main kernel, %d launches right behind the timed region; "
+                                    "frac_of_whole_step: the timed region itself (main + finalize kernels per step)" % max(cnt, 1)}}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 r = cpu_reference_rate(flat, np.ascontiguousarray(Xh[:, 0]))

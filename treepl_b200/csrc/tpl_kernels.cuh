@@ -300,6 +300,43 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const __grid
     const int tx = threadIdx.x, seg = threadIdx.y;
     const int lane = blockIdx.x * 32 + tx;
     const bool active = lane < B;
+    // ---- sparse rows, spread over the 32 segment threads of each vector ----
+    // The barrier sum is order dependent in the reference (accumulator reset on inf, :983-991), so the
+    // segment threads only FETCH: the dependent  slot -> X row  loads run 32-wide, the terms land in
+    // shared memory, and one thread per vector then accumulates them in ascending node order.
+    constexpr int FIN_BAR = 48;                                          // barrier rows staged in shared memory
+    constexpr int FIN_RC = 8;                                            // root children staged in shared memory
+    __shared__ double s_bh[FIN_BAR][32];                                 // date of barrier row k
+    __shared__ double s_pmn[FIN_BAR], s_pmx[FIN_BAR];
+    __shared__ double s_rc[FIN_RC][32];                                  // rate of root child j (as the objective sees it)
+    __shared__ int s_rcs[FIN_RC];                                        // its rate row (-1: none)
+    __shared__ unsigned char s_rcm[FIN_RC][32];                          // masked for this vector
+    const double* __restrict__ X = a.X;
+    int bnd_bad = 0;
+    if (active) {
+        for (int k = seg; k < t.nbnd; k += FIN_SEGS) {                   // set_durations :887-896
+            const double h = X[(size_t)t.bnd_ds[k] * B + lane];          // fixed dates are checked on the host
+            if (h < t.bnd_min[k] || h > t.bnd_max[k]) bnd_bad = 1;
+        }
+        if (!LF) {
+            for (int k = seg; k < t.nbar && k < FIN_BAR; k += FIN_SEGS) {
+                const int ds = t.bar_ds[k];
+                s_bh[k][tx] = (ds >= 0) ? X[(size_t)ds * B + lane] : t.bar_hfix[k];
+                if (tx == 0) { s_pmn[k] = t.bar_pmin[k]; s_pmx[k] = t.bar_pmax[k]; }
+            }
+            const int nrc = t.child_off[1] - t.child_off[0];
+            for (int j = seg; j < nrc && j < FIN_RC; j += FIN_SEGS) {
+                const int ch = t.children[t.child_off[0] + j];
+                const bool mc = is_masked<MASKMODE>(a, ch, lane);
+                const int crs = t.rslot[ch];
+                s_rc[j][tx] = (crs >= 0) ? X[(size_t)crs * B + lane] : t.rfix[ch];
+                s_rcm[j][tx] = mc ? 1 : 0;
+                if (tx == 0) s_rcs[j] = crs;
+            }
+        }
+    }
+
+    // (everything above reads X only; the objective partials and gradient rows of the main kernel are read from here on)
     if (a.part_mode == 1) {
         // generation-3 partials: CTA c owned work items [c W / G, (c+1) W / G) of the chunk-major list
         // (chunk k = items [k ntiles, (k+1) ntiles)); slot 1 if the CTA had started in the previous chunk
@@ -310,9 +347,17 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const __grid
         const int g0 = seg * len, g1 = min(a.p_ncta, g0 + len);
         double ll = 0.0, su = 0.0;
         int bad = 0;
+        const bool small = (G + 1) * W < 0x7fffffffLL;        // 32-bit divisions (the usual case) cost a fifth of 64-bit ones
         if (active)
             for (int c = g0; c < g1; c++) {
-                const long long lo = c * W / G, hi = (c + 1) * W / G;
+                long long lo, hi;
+                if (small) {
+                    lo = (unsigned)(c * (int)W) / (unsigned)G;
+                    hi = (unsigned)((c + 1) * (int)W) / (unsigned)G;
+                } else {
+                    lo = c * W / G;
+                    hi = (c + 1) * W / G;
+                }
                 if (lo < c1 && hi > c0 && lo < hi) {
                     const size_t o = ((size_t)c * 2 + (lo < c0 ? 1 : 0)) * a.p_nwarps * 64 + l;
                     for (int wv = 0; wv < a.p_nwarps; wv++) {
@@ -361,42 +406,6 @@ __global__ void __launch_bounds__(32 * FIN_SEGS) pl_finalize_kernel(const __grid
         s_sum[2][seg][tx] = gr;
         s_bad[seg][tx] = bad;
     }
-    // ---- sparse rows, spread over the 32 segment threads of each vector ----
-    // The barrier sum is order dependent in the reference (accumulator reset on inf, :983-991), so the
-    // segment threads only FETCH: the dependent  slot -> X row  loads run 32-wide, the terms land in
-    // shared memory, and one thread per vector then accumulates them in ascending node order.
-    constexpr int FIN_BAR = 48;                                          // barrier rows staged in shared memory
-    constexpr int FIN_RC = 8;                                            // root children staged in shared memory
-    __shared__ double s_bh[FIN_BAR][32];                                 // date of barrier row k
-    __shared__ double s_pmn[FIN_BAR], s_pmx[FIN_BAR];
-    __shared__ double s_rc[FIN_RC][32];                                  // rate of root child j (as the objective sees it)
-    __shared__ int s_rcs[FIN_RC];                                        // its rate row (-1: none)
-    __shared__ unsigned char s_rcm[FIN_RC][32];                          // masked for this vector
-    const double* __restrict__ X = a.X;
-    int bnd_bad = 0;
-    if (active) {
-        for (int k = seg; k < t.nbnd; k += FIN_SEGS) {                   // set_durations :887-896
-            const double h = X[(size_t)t.bnd_ds[k] * B + lane];          // fixed dates are checked on the host
-            if (h < t.bnd_min[k] || h > t.bnd_max[k]) bnd_bad = 1;
-        }
-        if (!LF) {
-            for (int k = seg; k < t.nbar && k < FIN_BAR; k += FIN_SEGS) {
-                const int ds = t.bar_ds[k];
-                s_bh[k][tx] = (ds >= 0) ? X[(size_t)ds * B + lane] : t.bar_hfix[k];
-                if (tx == 0) { s_pmn[k] = t.bar_pmin[k]; s_pmx[k] = t.bar_pmax[k]; }
-            }
-            const int nrc = t.child_off[1] - t.child_off[0];
-            for (int j = seg; j < nrc && j < FIN_RC; j += FIN_SEGS) {
-                const int ch = t.children[t.child_off[0] + j];
-                const bool mc = is_masked<MASKMODE>(a, ch, lane);
-                const int crs = t.rslot[ch];
-                s_rc[j][tx] = (crs >= 0) ? X[(size_t)crs * B + lane] : t.rfix[ch];
-                s_rcm[j][tx] = mc ? 1 : 0;
-                if (tx == 0) s_rcs[j] = crs;
-            }
-        }
-    }
-
     s_bad[seg][tx] |= bnd_bad;
     __syncthreads();
     __shared__ int s_dead[32];                                           // AD: barrier sum was inf/NaN -> no barrier gradient
