@@ -183,6 +183,17 @@ typedef struct tpl_opt_result {
 int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, const double* lower, const double* upper,
                        int mode, const tpl_opt_options* opts, int* status, int* iters, tpl_opt_result* result);
 
+/* The same optimisation for a cross-validation job: vector b starts from column start_col[b] of the host matrix
+ * Xstart [P][K] (K <= B: e.g. the full-data optimum of the vector's smoothing value - what every fold of the reference's
+ * CV loop starts from, main.cpp:681,702-704), so K columns instead of B cross the bus and the batch is expanded on the
+ * device; and only `nprobe` rows of every optimised vector come back: probe_out[j][b] = X[probe_rows[j][b]][b]
+ * (host [nprobe][B] each, probe_rows = -1 -> 0) - the rows the fold's chi-square needs (main.cpp:737-793).  Xout
+ * (host [P][B]) may be NULL.  Method 1 only; everything else as tpl_optimize_batch. */
+int tpl_optimize_batch_cols(tpl_engine* e, int B, int K, const double* Xstart, const int* start_col, double* F,
+                            const double* lower, const double* upper, int mode, const tpl_opt_options* opts, int* status,
+                            int* iters, tpl_opt_result* result, int nprobe, const int* probe_rows, double* probe_out,
+                            double* Xout);
+
 /* ---- batched simulated annealing ------------------------------------------------------------------
  * siman_calc_par::optimize (siman_calc_par.cpp:80-229) for B chains at once, one GPU thread per chain: the reference's
  * proposal (one parameter scaled by 1 + u, rates and dates with probability 1/2 each), acceptance rule, cooling, step-size

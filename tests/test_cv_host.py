@@ -74,6 +74,26 @@ def test_single_tip_scoring_of_all_lanes_equals_the_per_fold_formula():
     assert np.array_equal(got, want)
 
 
+def test_probe_based_scoring_equals_the_per_fold_formula():
+    """What the CV driver does since the fold optima stay on the device: cv.fold_probe_rows picks the X rows a fold's chi-square
+    needs, cv.chisq_from_probes scores from them == cv.group_chisq on the whole vector, bit for bit (ragged random groups and
+    single-tip folds, incl. children of the root)."""
+    flat, tips = _m1155()
+    n = len(flat["parents"])
+    fp, P = tf.generate_param_order_vector(flat["free"], lf=False)
+    rng = np.random.RandomState(2)
+    x = cv.start_vector(flat, P, n - 1)
+    rnd = cv.sample_random_groups(flat, tips, n_groups=4, frac=0.2, seed=5)
+    for groups, randomcv in (([[int(t)] for t in tips], False), (rnd + [rnd[0][:3]], True)):
+        B = len(groups)
+        X = x[:, None] * np.exp(0.1 * rng.randn(P, B))
+        rows, ptips = cv.fold_probe_rows(flat, groups, fp)
+        probes = np.where(rows >= 0, X[np.maximum(rows, 0), np.arange(B)[None, :]], 0.0)       # what cols_probe_kernel returns
+        got = cv.chisq_from_probes(flat, probes, rows, ptips, randomcv)
+        want = np.array([cv.group_chisq(flat, X[:, b], groups[b], fp, randomcv) for b in range(B)])
+        assert np.array_equal(got, want)
+
+
 def test_smoothing_grid_follows_the_reference_fixups():
     """main.cpp:275-284 (swap start/stop, invert a step > 1 in float) and :668,814 (while(curcv >= cvstop) curcv *= step)."""
     import pytest

@@ -177,7 +177,7 @@ struct tpl_engine {
         PinBuf<int> h_done;
         // truncated Newton
         DevBuf<double> R, ZZ, Pv, Hp, Minv, DG, pmin_n, pmax_n, tn_part, tn_lane_d;
-        DevBuf<int> tn_lane_i, tn_lev_nodes, tn_lev_off, tn_lev_rec, tn_hv_rec;
+        DevBuf<int> tn_lane_i, tn_lev_nodes, tn_lev_off, tn_lev_rec, tn_hv_rec, tn_cols, tn_probe_rows;
         DevBuf<double> tn_tw;
         std::vector<int> tn_lev_off_host;
         // annealer

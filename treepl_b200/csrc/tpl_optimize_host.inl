@@ -107,6 +107,33 @@ int run_optimizer(tpl_engine* e, tplopt::OptArgs a, int B, int mode, int max_ste
 
 // ---- batched truncated Newton (tpl_tn_core.h / tpl_tn.cuh) ---------------------------------------------------------
 
+// tpl_optimize_batch_cols: the B start vectors are columns of a small host matrix and only a few rows per vector return
+struct ColsIO {
+    int K;                       // columns of Xstart
+    const double* Xstart;        // host [P][K]
+    const int* start_col;        // host [B]
+    int nprobe;
+    const int* probe_rows;       // host [nprobe][B], -1 = none
+    double* probe_out;           // host [nprobe][B]
+    double* Xout;                // host [P][B] or null
+};
+
+__global__ void cols_expand_kernel(int P, int B, int K, const double* __restrict__ Xs, const int* __restrict__ col, double* __restrict__ X) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int c = col[b];
+    for (int p = blockIdx.y; p < P; p += gridDim.y) X[(size_t)p * B + b] = Xs[(size_t)p * K + c];
+}
+
+__global__ void cols_probe_kernel(int B, int nprobe, const double* __restrict__ X, const int* __restrict__ rows, double* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    for (int j = blockIdx.y; j < nprobe; j += gridDim.y) {
+        const int r = rows[(size_t)j * B + b];
+        out[(size_t)j * B + b] = r >= 0 ? X[(size_t)r * B + b] : 0.0;
+    }
+}
+
 // index record of node i for the kernels' record views (tpl_tn.cuh::TreeRec)
 static void tn_fill_record(const tpl_engine* e, int i, int* r) {
     const int n = e->n;
@@ -122,7 +149,7 @@ static void tn_fill_record(const tpl_engine* e, int i, int* r) {
 
 // work space, tree operands and chunking of the truncated-Newton kernels; uploads lo / hi / sc and X
 int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>& lo, const std::vector<double>& hi,
-               const std::vector<double>& sc, int nr, const tpl_opt_options& o, tpltn::TnArgs& a) {
+               const std::vector<double>& sc, int nr, const tpl_opt_options& o, tpltn::TnArgs& a, const ColsIO* io = nullptr) {
     using namespace tpltn;
     if (e->lf_mode) return fail(TPL_ERR_ARG, "truncated Newton needs the PL layout (one rate per branch)");
     if (e->cv_any) return fail(TPL_ERR_ARG, "truncated Newton takes CV masks per vector (tpl_batch_configure), not set_cv_nodes");
@@ -157,7 +184,20 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
     CK(cudaMemcpyAsync(w.lo.p, lo.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(w.hi.p, hi.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(w.sc.p, sc.data(), sizeof(double) * P, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(w.X.p, X, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
+    if (io) {
+        // start vectors = columns of a [P][K] matrix: K columns cross the bus, the batch is expanded on the device
+        // (w.Hp as the staging buffer: it is zeroed below, after the expansion)
+        if (io->K < 1 || (size_t)io->K > (size_t)B) return fail(TPL_ERR_ARG, "start columns: need 1 <= K <= B");
+        for (int b = 0; b < B; b++)
+            if (io->start_col[b] < 0 || io->start_col[b] >= io->K) return fail(TPL_ERR_ARG, "start_col out of range");
+        CK(w.tn_cols.ensure((size_t)B));
+        CK(cudaMemcpyAsync(w.Hp.p, io->Xstart, sizeof(double) * (size_t)P * io->K, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w.tn_cols.p, io->start_col, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+        cols_expand_kernel<<<dim3((B + 127) / 128, std::min(P, 1024)), 128, 0, s>>>(P, B, io->K, w.Hp.p, w.tn_cols.p, w.X.p);
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaMemcpyAsync(w.X.p, X, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
+    }
     CK(cudaMemsetAsync(w.tn_lane_d.p, 0, sizeof(double) * 14 * B, s));
     CK(cudaMemsetAsync(w.tn_lane_i.p, 0, sizeof(int) * (8 * (size_t)B + 1 + 6 * (size_t)groups), s));     // st = TS_INIT, t = 0
     for (DevBuf<double>* buf : {&w.Gz, &w.D, &w.R, &w.ZZ, &w.Pv, &w.Hp, &w.Minv, &w.DG, &w.Gx})
@@ -285,11 +325,11 @@ void tn_launch_tree_solve(const tpltn::TnArgs& a, const std::vector<int>& loff, 
 
 int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<double>& lo, const std::vector<double>& hi,
                 const std::vector<double>& sc, int nr, int mode, const tpl_opt_options& o, int* status, int* iters,
-                tpl_opt_result* result) {
+                tpl_opt_result* result, const ColsIO* io = nullptr) {
     using namespace tpltn;
     if (mode != TPL_GRAD_AD) return fail(TPL_ERR_ARG, "truncated Newton differentiates the AD objective (TPL_GRAD_AD)");
     TnArgs a;
-    int prc = tn_prepare(e, B, X, lo, hi, sc, nr, o, a);
+    int prc = tn_prepare(e, B, X, lo, hi, sc, nr, o, a, io);
     if (prc != TPL_OK) return prc;
     const int P = e->numparams;
     const size_t PB = (size_t)P * B;
@@ -370,7 +410,20 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
     launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(ev1, s));
-    CK(cudaMemcpyAsync(X, w.X.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
+    if (io) {
+        if (io->nprobe > 0) {          // only the probed rows of every vector return to the host (w.Hp as the gather buffer)
+            const size_t np = (size_t)io->nprobe * B;
+            if (np > PB) return fail(TPL_ERR_ARG, "more probes than parameters");
+            CK(w.tn_probe_rows.ensure(np));
+            CK(cudaMemcpyAsync(w.tn_probe_rows.p, io->probe_rows, sizeof(int) * np, cudaMemcpyHostToDevice, s));
+            cols_probe_kernel<<<dim3((B + 127) / 128, std::min(io->nprobe, 1024)), 128, 0, s>>>(B, io->nprobe, w.X.p, w.tn_probe_rows.p, w.Hp.p);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(io->probe_out, w.Hp.p, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
+        }
+        if (io->Xout) CK(cudaMemcpyAsync(io->Xout, w.X.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
+    } else {
+        CK(cudaMemcpyAsync(X, w.X.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaMemcpyAsync(F, w.Fout.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
     if (status) CK(cudaMemcpyAsync(status, a.flag, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
     std::vector<double> tlog(B);
@@ -399,10 +452,33 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
 
 }  // namespace
 
+static int optimize_batch_impl(tpl_engine* e, int B, double* X, double* F, const double* lower, const double* upper,
+                               int mode, const tpl_opt_options* opts, int* status, int* iters, tpl_opt_result* result, const ColsIO* io);
+
 extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, const double* lower, const double* upper,
                                   int mode, const tpl_opt_options* opts, int* status, int* iters, tpl_opt_result* result) {
+    if (!X) return fail(TPL_ERR_ARG, "tpl_optimize_batch: null X");
+    return optimize_batch_impl(e, B, X, F, lower, upper, mode, opts, status, iters, result, nullptr);
+}
+
+extern "C" int tpl_optimize_batch_cols(tpl_engine* e, int B, int K, const double* Xstart, const int* start_col, double* F,
+                                       const double* lower, const double* upper, int mode, const tpl_opt_options* opts, int* status,
+                                       int* iters, tpl_opt_result* result, int nprobe, const int* probe_rows, double* probe_out,
+                                       double* Xout) {
+    if (!Xstart || !start_col || nprobe < 0 || (nprobe > 0 && (!probe_rows || !probe_out)))
+        return fail(TPL_ERR_ARG, "tpl_optimize_batch_cols: null argument");
+    if (!opts || opts->method != 1) return fail(TPL_ERR_ARG, "tpl_optimize_batch_cols: method 1 (truncated Newton) only");
+    if (e && e->have_fp)
+        for (size_t k = 0; k < (size_t)nprobe * (size_t)std::max(B, 0); k++)
+            if (probe_rows[k] >= e->numparams) return fail(TPL_ERR_ARG, "probe row out of range");
+    const ColsIO io = {K, Xstart, start_col, nprobe, probe_rows, probe_out, Xout};
+    return optimize_batch_impl(e, B, nullptr, F, lower, upper, mode, opts, status, iters, result, &io);
+}
+
+static int optimize_batch_impl(tpl_engine* e, int B, double* X, double* F, const double* lower, const double* upper,
+                               int mode, const tpl_opt_options* opts, int* status, int* iters, tpl_opt_result* result, const ColsIO* io) {
     using namespace tplopt;
-    if (!e || !X || !F || !lower || !upper || B < 1) return fail(TPL_ERR_ARG, "tpl_optimize_batch: null or B < 1");
+    if (!e || !F || !lower || !upper || B < 1) return fail(TPL_ERR_ARG, "tpl_optimize_batch: null or B < 1");
     if (!e->have_fp) return fail(TPL_ERR_STATE, "set_freeparams has not been called");
     CK(cudaSetDevice(e->device));
     int rc = sync_device_tree(e);
@@ -439,7 +515,8 @@ extern "C" int tpl_optimize_batch(tpl_engine* e, int B, double* X, double* F, co
         }
         if (!(lo[p] <= hi[p])) return fail(TPL_ERR_ARG, "empty bound interval");
     }
-    if (o.method == 1) return optimize_tn(e, B, X, F, lo, hi, sc, nr, mode, o, status, iters, result);
+    if (o.method == 1) return optimize_tn(e, B, X, F, lo, hi, sc, nr, mode, o, status, iters, result, io);
+    if (io) return fail(TPL_ERR_ARG, "start columns / probes need method 1");
     if (o.method != 0) return fail(TPL_ERR_ARG, "method must be 0 (L-BFGS) or 1 (truncated Newton)");
     const size_t PB = (size_t)P * B;
     tpl_engine::OptWork& w = e->opt;

@@ -172,6 +172,53 @@ def single_tip_chisq(flat, X, tips, freeparams):
         return np.where((d < 1e-100) | (expe < 1e-100), 0.0, (c - expe) ** 2 / expe)
 
 
+def fold_probe_rows(flat, lane_groups, freeparams):
+    """The X rows a fold's chi-square needs (src/main.cpp:737-793), per lane: for the j-th pruned tip of lane b,
+    rows[2 j, b] = rate row of its parent (a child of the root: of its LAST sibling), rows[2 j + 1, b] = date row of its
+    parent (-1: the parent's date is fixed).  -> (rows [2 L, B] int32, tips [L, B] int64, -1 = padding), L = longest group."""
+    n = len(flat["parents"])
+    par = np.asarray(flat["parents"])
+    fp = np.asarray(freeparams)
+    B = len(lane_groups)
+    L = max((len(g) for g in lane_groups), default=0)
+    tips = -np.ones((L, B), dtype=np.int64)
+    for b, g in enumerate(lane_groups):
+        tips[: len(g), b] = g
+    valid = tips >= 0
+    t = np.where(valid, tips, 0)
+    p = par[t]
+    rnode = p.copy()
+    root_kids = np.flatnonzero(par == 0)
+    for j, b in zip(*np.nonzero(valid & (p == 0))):       # child of the root: the rate of its LAST sibling (main.cpp:741-746)
+        rnode[j, b] = [k for k in root_kids if k != tips[j, b]][-1]
+    rows = -np.ones((2 * L, B), dtype=np.int32)
+    rows[0::2] = np.where(valid, fp[rnode], -1)
+    rows[1::2] = np.where(valid, fp[n + p], -1)
+    return rows, tips
+
+
+def chisq_from_probes(flat, probes, rows, tips, randomcv):
+    """chi-square term of every lane from the probed rows (same arithmetic, tip by tip in group order, as group_chisq)."""
+    par = np.asarray(flat["parents"])
+    valid = tips >= 0
+    t = np.where(valid, tips, 0)
+    p = par[t]
+    r = np.where(rows[0::2] >= 0, probes[0::2], 0.0)
+    hp = np.where(rows[1::2] >= 0, probes[1::2], flat["start_dates"][p])
+    d = hp - flat["start_dates"][t]
+    d = np.where(d == 0, 2.2250738585072014e-308, d)
+    expe = r * d
+    c = flat["c"][t]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        terms = np.where((d < 1e-100) | (expe < 1e-100), 0.0, (c - expe) ** 2 / expe)
+    terms = np.where(valid, terms, 0.0)
+    total = np.zeros(tips.shape[1])
+    for j in range(tips.shape[0]):                         # tip order, fixed
+        total = total + terms[j]
+    cnt = valid.sum(axis=0)
+    return total / np.maximum(cnt, 1) if randomcv else total
+
+
 def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_pen=False, max_iter=3000, verbose=False,
                    history=8, dist=None, **opt):
     """-> dict(chisq per smoothing value, best smoothing, timings).  groups: list of folds, each a list of tip node
@@ -220,14 +267,30 @@ def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_p
     lane_k, lane_g = lane_item // T, lane_item % T
     lam2 = np.asarray(smoothing_grid, dtype=np.float64)[lane_k]
     masks = [groups[g] for g in lane_g]
-    X0 = np.ascontiguousarray(Xfull[:, lane_k])
     plp.batch_configure(B2p, lane_smoothing=lam2, masks=masks)
-    Xcv, Fcv, info2 = _minimize_together(dist, dev, plp, X0, lo, hi, nr, dscale, max_iter, history, verbose, **opt)
+    # every fold starts from the full-data optimum of its smoothing value (main.cpp:681,702-704): the K optima cross the bus
+    # once and are expanded on the device; only the rows the chi-square needs come back (tpl_optimize_batch_cols)
+    rows, ptips = fold_probe_rows(flat, masks, fp)
+    opt2 = dict(opt)
+    opt2.setdefault("method", 1)
+    err, res2 = None, None
+    try:
+        if opt2["method"] != 1:
+            raise ValueError("the CV driver's fold phase needs method 1")
+        Fcv, probes, _, oi = plp.optimize_batch_cols(Xfull, lane_k.astype(np.int32), lo, hi, probe_rows=rows, max_steps=20 * max_iter,
+                                                     date_scale=dscale, use_graph=1, **opt2)
+        bad = np.nonzero(oi["status"] == 4)[0]
+        if bad.size:
+            raise ValueError("start point infeasible for vectors %s" % bad.tolist()[:8])
+        res2 = (Fcv, probes, oi)
+    except (ValueError, eng.EngineError) as ex:
+        err = ex
+    cvshard.raise_together(err, dist=dist, device=dev)
+    Fcv, probes, oi = res2
+    info2 = {"iterations": int(oi["iterations"].max()), "nfev": oi["steps"], "converged": (oi["status"] >= 1) & (oi["status"] <= 3),
+             "device_ms": oi["device_ms"], "launches": oi["launches"], "cg_iterations": oi["cg_iterations"]}
     t2 = time.perf_counter()
-    if all(len(g) == 1 for g in groups):
-        local = single_tip_chisq(flat, Xcv[:, :B2], np.array([groups[g][0] for g in lane_g[:B2]], dtype=np.int64), fp)
-    else:
-        local = np.array([group_chisq(flat, Xcv[:, b], groups[lane_g[b]], fp, randomcv) for b in range(B2)])
+    local = chisq_from_probes(flat, probes, rows, ptips, randomcv)[:B2]
     full, _ = cvshard.gather_fold_scores(local, n_items, dist=dist, device=dev)
     terms = full.reshape(K, T)
     chisq = np.zeros(K)

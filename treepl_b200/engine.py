@@ -100,6 +100,8 @@ def load_library():
     L.tpl_optimize_batch.argtypes = [vp, ci, dp, dp, dp, dp, ci, C.POINTER(OptOptions), ip, ip, C.POINTER(OptResult)]
     L.tpl_anneal_batch.restype = ci
     L.tpl_anneal_batch.argtypes = [vp, ci, dp, dp, C.POINTER(AnnealOptions), ip, ip]
+    L.tpl_optimize_batch_cols.restype = ci
+    L.tpl_optimize_batch_cols.argtypes = [vp, ci, ci, dp, ip, dp, dp, dp, ci, C.POINTER(OptOptions), ip, ip, C.POINTER(OptResult), ci, ip, dp, dp]
     L.tpl_debug_hessvec.restype = ci
     L.tpl_debug_hessvec.argtypes = [vp, ci, dp, dp, dp, dp, dp]
     L.tpl_debug_treesolve.restype = ci
@@ -119,7 +121,7 @@ EXPORTED_SYMBOLS = (
     "tpl_calc_function_gradient", "tpl_calc_pl_grad", "tpl_get_rates", "tpl_get_dates", "tpl_get_durations",
     "tpl_batch_configure", "tpl_calc_pl_grad_batch", "tpl_calc_pl_grad_batch_dev", "tpl_last_launch_count",
     "tpl_host_alloc", "tpl_host_free", "tpl_device_sm", "tpl_debug_math", "tpl_set_timing", "tpl_get_timing", "tpl_debug_force_kernel",
-    "tpl_last_kernel_generation", "tpl_optimize_batch", "tpl_debug_hessvec", "tpl_debug_treesolve", "tpl_anneal_batch",
+    "tpl_last_kernel_generation", "tpl_optimize_batch", "tpl_optimize_batch_cols", "tpl_debug_hessvec", "tpl_debug_treesolve", "tpl_anneal_batch",
 )
 
 
@@ -381,6 +383,39 @@ class PLCalcParallel:
                                                _ip(status), _ip(iters), C.byref(res)))
         return X, F, {"steps": res.steps, "n_done": res.n_done, "launches": res.launches, "device_ms": res.device_ms,
                       "mean_log10_step": res.mean_log10_step, "cg_iterations": res.cg_iterations, "status": status, "iterations": iters}
+
+    def optimize_batch_cols(self, Xstart, start_col, lower, upper, probe_rows=None, want_x=False, mode=GRAD_AD, **options):
+        """tpl_optimize_batch_cols: vector b starts from column start_col[b] of Xstart [P, K]; probe_rows [nprobe, B] (X row
+        per vector, -1 = none) selects what returns -> (F [B], probes [nprobe, B], X [P, B] or None, info)."""
+        Xs = _f64(Xstart)
+        P, K = Xs.shape
+        if P != self.numparams:
+            raise ValueError("Xstart has %d rows, engine expects %d" % (P, self.numparams))
+        col = _i32(start_col)
+        B = col.shape[0]
+        lo, hi = _f64(lower), _f64(upper)
+        assert lo.shape[0] == P and hi.shape[0] == P
+        rows = _i32(probe_rows) if probe_rows is not None else np.zeros((0, B), dtype=np.int32)
+        assert rows.ndim == 2 and rows.shape[1] == B
+        nprobe = rows.shape[0]
+        probes = np.zeros((nprobe, B))
+        X = np.zeros((P, B)) if want_x else None
+        F = np.zeros(B)
+        status = np.zeros(B, dtype=np.int32)
+        iters = np.zeros(B, dtype=np.int32)
+        o = OptOptions()
+        options.setdefault("method", 1)
+        for k, v in options.items():
+            if not hasattr(o, k):
+                raise TypeError("unknown optimiser option %r" % k)
+            setattr(o, k, v)
+        res = OptResult()
+        self._check(self._L.tpl_optimize_batch_cols(self._h, B, K, _dp(Xs), _ip(col), _dp(F), _dp(lo), _dp(hi), int(mode), C.byref(o),
+                                                    _ip(status), _ip(iters), C.byref(res), nprobe, _ip(rows) if nprobe else None,
+                                                    _dp(probes) if nprobe else None, _dp(X) if want_x else None))
+        return F, probes, X, {"steps": res.steps, "n_done": res.n_done, "launches": res.launches, "device_ms": res.device_ms,
+                              "mean_log10_step": res.mean_log10_step, "cg_iterations": res.cg_iterations, "status": status,
+                              "iterations": iters}
 
     def anneal_batch(self, X0, **options):
         """Batched simulated annealing (tpl_anneal_batch): X0 [P, B] feasible starts -> (X, F, status, iterations).
