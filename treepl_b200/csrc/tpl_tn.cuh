@@ -361,8 +361,8 @@ __device__ __forceinline__ void hess_node_fast(const TnArgs& a, const int4 q0, c
         const double vhp = pds >= 0 ? sc_pds * v_pds : 0.0;
         const double d = safe_duration(hp - h);
         const double dv = vhp - vh;
-        w_r = (c / (r * r)) * vr + dv;
-        w_h = -((c / (d * d)) * dv + vr);
+        w_r = (c * tn_rcp(r * r)) * vr + dv;
+        w_h = -((c * tn_rcp(d * d)) * dv + vr);
         w_r += lam2 * (vr - vrp);
     }
     if (nch) {
@@ -373,7 +373,7 @@ __device__ __forceinline__ void hess_node_fast(const TnArgs& a, const int4 q0, c
             const double vhc = cds[k] >= 0 ? sc_cds[k] * v_cds[k] : 0.0;
             if (ds >= 0) {
                 const double dc = safe_duration(h - hc[k]);
-                w_h += (cc[k] / (dc * dc)) * (vh - vhc) + vrc;
+                w_h += (cc[k] * tn_rcp(dc * dc)) * (vh - vhc) + vrc;
             }
             if (rfree) w_r -= lam2 * (vrc - vr);
         }
@@ -416,11 +416,18 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
     if (active) {
         DevView V = {a, B, b, a.Pv, a.Hp, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, a.mu[b]};
         const int i0 = blockIdx.y * a.nodes_per_chunk, i1 = min(a.t.n, i0 + a.nodes_per_chunk);
+        // the record of the NEXT node is requested before this node's rows: its round trip overlaps this node's work instead of
+        // heading the next node's chain (per node: record -> rows -> arithmetic; the kernel's rate is warps in flight / that latency)
         const int4* recs = reinterpret_cast<const int4*>(a.hv_rec);
-        for (int i = i0 + ty; i < i1; i += OPT_WY) {
+        int i = i0 + ty;
+        int4 n0, n1, n2, n3;
+        if (i < i1) { n0 = __ldg(recs + 4 * (size_t)i); n1 = __ldg(recs + 4 * (size_t)i + 1); n2 = __ldg(recs + 4 * (size_t)i + 2); n3 = __ldg(recs + 4 * (size_t)i + 3); }
+        for (; i < i1; i += OPT_WY) {
+            const int4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
+            const int inext = i + OPT_WY;
+            if (inext < i1) { n0 = __ldg(recs + 4 * (size_t)inext); n1 = __ldg(recs + 4 * (size_t)inext + 1); n2 = __ldg(recs + 4 * (size_t)inext + 2); n3 = __ldg(recs + 4 * (size_t)inext + 3); }
             double vw, vv;
-            const int4 q1 = __ldg(recs + 4 * (size_t)i + 1);
-            if (q1.w) hess_node_fast(a, __ldg(recs + 4 * (size_t)i), q1, __ldg(recs + 4 * (size_t)i + 2), __ldg(recs + 4 * (size_t)i + 3), B, b, V.lam, V.mu, vw, vv);
+            if (q1.w) hess_node_fast(a, q0, q1, q2, q3, B, b, V.lam, V.mu, vw, vv);
             else hess_node(V, i, vw, vv);
             v[0] += vw;
             v[1] += vv;

@@ -195,10 +195,21 @@ TPL_HD void node_values(const View& V, int i, bool& rfree, double& r, double& h,
 
 TPL_HD double safe_duration(double d) { return d > 2.2250738585072014e-308 ? d : 2.2250738585072014e-308; }
 
-// correctly rounded reciprocal: one MUFU seed + Newton on the device (about half the dependent chain of a division),
-// 1.0 / x on the host - the same value, so the CPU emulation stays bit-compatible with the kernels
+// Reciprocal for the Hessian entries (c / r^2, c / d^2, 1 / det).  The node-indexed kernels are bound by the latency of one
+// warp's instruction chain per node, and an IEEE fp64 division is ~25 dependent instructions: on the device an ordinary
+// operand (2^-400 .. 2^400) takes the MUFU.RCP64H seed + two Newton steps (5 instructions, <= 2 ulp - the preconditioner
+// and the CG products tolerate far more), anything else the correctly rounded reciprocal.  Host: 1.0 / x.
 TPL_HD double tn_rcp(double x) {
 #ifdef __CUDA_ARCH__
+    const unsigned e = ((unsigned)__double2hiint(x)) >> 20;
+    if ((e - 623u) < 800u) {
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+        double t = fma(-x, y, 1.0);
+        y = fma(y, t, y);
+        t = fma(-x, y, 1.0);
+        return fma(y, t, y);
+    }
     return __drcp_rn(x);
 #else
     return 1.0 / x;
@@ -223,8 +234,8 @@ TPL_HD void hess_node(View& V, int i, double& vw, double& vv) {
         const double d = safe_duration(hp - h);
         const double c = V.c(i);
         const double dv = vhp - vh;
-        w_r = (c / (r * r)) * vr + dv;
-        w_h = -((c / (d * d)) * dv + vr);
+        w_r = (c * tn_rcp(r * r)) * vr + dv;
+        w_h = -((c * tn_rcp(d * d)) * dv + vr);
         if (p != 0) {
             w_r += lam2 * (vr - vrp);
         } else {                                             // child of the root: variance term over ALL root children
@@ -251,7 +262,7 @@ TPL_HD void hess_node(View& V, int i, double& vw, double& vv) {
         node_values(V, ch, cfree, rc, hc, vrc, vhc);
         if (ds >= 0) {
             const double dc = safe_duration(h - hc);
-            w_h += (V.c(ch) / (dc * dc)) * (vh - vhc) + vrc;
+            w_h += (V.c(ch) * tn_rcp(dc * dc)) * (vh - vhc) + vrc;
         }
         if (rfree && i != 0 && !mi) w_r -= lam2 * (vrc - vr);
     }
@@ -304,8 +315,8 @@ TPL_HD void diag_node(View& V, int i) {
         const double hp = pds >= 0 ? V.x(pds) : V.hfix(p);
         const double d = safe_duration(hp - h);
         const double c = V.c(i);
-        H_r = c / (r * r);
-        H_h = c / (d * d);
+        H_r = c * tn_rcp(r * r);
+        H_h = c * tn_rcp(d * d);
         if (p != 0) H_r += lam2;
         else H_r += root_child_curvature(V, i, r);
     }
@@ -316,7 +327,7 @@ TPL_HD void diag_node(View& V, int i) {
             const int cds = V.dslot(ch);
             const double hc = cds >= 0 ? V.x(cds) : V.hfix(ch);
             const double dc = safe_duration(h - hc);
-            H_h += V.c(ch) / (dc * dc);
+            H_h += V.c(ch) * tn_rcp(dc * dc);
         }
         if (rfree && i != 0 && !mi) H_r += lam2;
     }
