@@ -116,3 +116,41 @@ def test_pruned_tip_on_the_root_keeps_the_full_data_rate():
             want = cv.loocv_chisq(flat, x[:, None], [tip], fp)[0]
             got = res["terms"][k, g]
             assert abs(got - want) <= 2e-3 * max(abs(want), 1e-3), (lam, tip, got, want)
+
+
+def test_start_columns_and_probes_equal_the_expanded_batch():
+    """tpl_optimize_batch_cols (start vectors = columns of a [P, K] matrix expanded on the device, only probed rows returned)
+    == tpl_optimize_batch on the batch expanded by the host, bit for bit: optima, objectives, status, probes."""
+    flat = Golden("M1155").flat
+    n = len(flat["parents"])
+    fp, P = eng.generate_param_order_vector(flat["free"], lf=False)
+    lo, hi = batchopt.reference_bounds(flat, fp, P)
+    x0 = cv.start_vector(flat, P, n - 1)
+    rng = np.random.RandomState(4)
+    K, B = 3, 14
+    Xs = np.repeat(x0[:, None], K, axis=1)
+    Xs[: n - 1] *= np.exp(0.2 * rng.randn(n - 1, K))
+    col = rng.randint(0, K, size=B).astype(np.int32)
+    lam = 10.0 ** rng.uniform(-1, 3, size=B)
+    tips = np.flatnonzero(flat["child_counts"] == 0)
+    masks = [[int(tips[(5 + 3 * b) % len(tips)])] if b % 3 else [] for b in range(B)]
+    rows = rng.randint(-1, P, size=(5, B)).astype(np.int32)
+    par = flat["parents"]
+    dscale = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))
+    plp = eng.PLCalcParallel.from_flat(flat, device=0)
+    plp.set_freeparams(P, False, fp)
+    plp.batch_configure(B, lane_smoothing=lam, masks=masks)
+    X1, F1, i1 = plp.optimize_batch(np.ascontiguousarray(Xs[:, col]), lo, hi, method=1, date_scale=dscale, max_steps=4000)
+    F2, probes, X2, i2 = plp.optimize_batch_cols(Xs, col, lo, hi, probe_rows=rows, want_x=True, date_scale=dscale, max_steps=4000)
+    assert ((i1["status"] >= 1) & (i1["status"] <= 3)).all()
+    assert np.array_equal(F1, F2) and np.array_equal(X1, X2) and np.array_equal(i1["status"], i2["status"])
+    want = np.where(rows >= 0, X1[np.maximum(rows, 0), np.arange(B)[None, :]], 0.0)
+    assert np.array_equal(probes, want)
+    # without probes and without X only the objectives return
+    F3, p3, X3, _ = plp.optimize_batch_cols(Xs, col, lo, hi, date_scale=dscale, max_steps=4000)
+    assert np.array_equal(F3, F1) and p3.shape == (0, B) and X3 is None
+    with pytest.raises(eng.EngineError):
+        plp.optimize_batch_cols(Xs, col + K, lo, hi, date_scale=dscale)            # column index out of range
+    with pytest.raises(eng.EngineError):
+        plp.optimize_batch_cols(Xs, col, lo, hi, method=0)                         # L-BFGS has no start-column entry
+    plp.close()

@@ -271,24 +271,26 @@ def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_p
     # every fold starts from the full-data optimum of its smoothing value (main.cpp:681,702-704): the K optima cross the bus
     # once and are expanded on the device; only the rows the chi-square needs come back (tpl_optimize_batch_cols)
     rows, ptips = fold_probe_rows(flat, masks, fp)
-    opt2 = dict(opt)
-    opt2.setdefault("method", 1)
-    err, res2 = None, None
-    try:
-        if opt2["method"] != 1:
-            raise ValueError("the CV driver's fold phase needs method 1")
-        Fcv, probes, _, oi = plp.optimize_batch_cols(Xfull, lane_k.astype(np.int32), lo, hi, probe_rows=rows, max_steps=20 * max_iter,
-                                                     date_scale=dscale, use_graph=1, **opt2)
-        bad = np.nonzero(oi["status"] == 4)[0]
-        if bad.size:
-            raise ValueError("start point infeasible for vectors %s" % bad.tolist()[:8])
-        res2 = (Fcv, probes, oi)
-    except (ValueError, eng.EngineError) as ex:
-        err = ex
-    cvshard.raise_together(err, dist=dist, device=dev)
-    Fcv, probes, oi = res2
-    info2 = {"iterations": int(oi["iterations"].max()), "nfev": oi["steps"], "converged": (oi["status"] >= 1) & (oi["status"] <= 3),
-             "device_ms": oi["device_ms"], "launches": oi["launches"], "cg_iterations": oi["cg_iterations"]}
+    if opt.get("method", 1) == 1:
+        err, res2 = None, None
+        try:
+            Fcv, probes, _, oi = plp.optimize_batch_cols(Xfull, lane_k.astype(np.int32), lo, hi, probe_rows=rows, max_steps=20 * max_iter,
+                                                         date_scale=dscale, use_graph=1, **opt)
+            bad = np.nonzero(oi["status"] == 4)[0]
+            if bad.size:
+                raise ValueError("start point infeasible for vectors %s" % bad.tolist()[:8])
+            res2 = (Fcv, probes, oi)
+        except (ValueError, eng.EngineError) as ex:
+            err = ex
+        cvshard.raise_together(err, dist=dist, device=dev)
+        Fcv, probes, oi = res2
+        info2 = {"iterations": int(oi["iterations"].max()), "nfev": oi["steps"], "converged": (oi["status"] >= 1) & (oi["status"] <= 3),
+                 "device_ms": oi["device_ms"], "launches": oi["launches"], "cg_iterations": oi["cg_iterations"]}
+    else:
+        # method 0 (L-BFGS) has no start-column entry: the batch is expanded and read back on the host
+        Xcv, Fcv, info2 = _minimize_together(dist, dev, plp, np.ascontiguousarray(Xfull[:, lane_k]), lo, hi, nr, dscale, max_iter, history,
+                                             verbose, **opt)
+        probes = np.where(rows >= 0, Xcv[np.maximum(rows, 0), np.arange(B2p)[None, :]], 0.0)
     t2 = time.perf_counter()
     local = chisq_from_probes(flat, probes, rows, ptips, randomcv)[:B2]
     full, _ = cvshard.gather_fold_scores(local, n_items, dist=dist, device=dev)
