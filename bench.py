@@ -70,8 +70,10 @@ def build_problem(tips, seed=1):
         return {k: z[k] for k in z.files}
     ft, _, _ = tf.synth_problem(tips, seed=seed, ncal=16)
     d = ft.as_dict()
-    try:
-        np.savez(cache, **d)
+    try:        # atomic: the ranks of a multi-GPU run build the same tree side by side and must never read a half-written cache
+        tmp = "%s.%d.tmp.npz" % (cache, os.getpid())
+        np.savez(tmp, **d)
+        os.replace(tmp, cache)
     except OSError:
         pass
     return d
