@@ -617,7 +617,15 @@ def run_sweep(args):
         for _ in range(reps):
             q.calc_pl_grad(x, eng.GRAD_ANALYTIC)
         us = 1e6 * (time.perf_counter() - t) / reps
-        row = {"tree": name, "N": int(len(fl["parents"])), "P": int(Pk), "b200_callback_us": us,
+        # the same callback as the reference's function_plcp issues it through the C++ mirror: calc_pl, then calc_gradient
+        # (optimize_tnc.cpp:83-86) - one evaluation, the gradient rides along with calc_pl once the pair pattern is seen
+        for _ in range(3):
+            q.calc_pl(x); q.calc_gradient(x)
+        t = time.perf_counter()
+        for _ in range(reps):
+            q.calc_pl(x); q.calc_gradient(x)
+        pair_us = 1e6 * (time.perf_counter() - t) / reps
+        row = {"tree": name, "N": int(len(fl["parents"])), "P": int(Pk), "b200_callback_us": us, "b200_calc_pl_then_calc_gradient_us": pair_us,
                "kernel_generation": q.last_kernel_generation(), "launches_per_call": q.last_launch_count()}
         q.close()
         if rb.available():

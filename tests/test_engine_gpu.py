@@ -457,3 +457,45 @@ def test_smallest_trees():
                     f, g = o.calc_pl_and_gradient(xb) if mode == eng.GRAD_ANALYTIC else o.calc_function_gradient(xb)
                     assert close_f(F[b], f) and rel_err(G[:, b], g) < G_TOL
         plp.close()
+
+
+def test_gradient_computed_with_calc_pl_for_callback_pairs():
+    """calc_pl -> calc_gradient pairs (every TNC / NLopt callback, optimize_tnc.cpp:75-105): from the second pair on calc_pl
+    computes the analytic gradient in the same launch and calc_gradient returns it without another evaluation - the same
+    numbers, bit for bit; calc_pl twice in a row (the annealer) switches that off; a state change between the two calls
+    (smoothing, CV mask) forces a fresh evaluation."""
+    gd = Golden("M1155")
+    flat = gd.flat
+    n = len(flat["parents"])
+    fp, P = eng.generate_param_order_vector(flat["free"], lf=False)
+    rng = np.random.RandomState(3)
+    plp = eng.PLCalcParallel.from_flat(flat)
+    x0 = plp.set_freeparams(P, False, fp)
+    plp.smoothing = 10.0
+    xs = []
+    for _ in range(4):
+        x = x0.copy()
+        x[: n - 1] = 0.01 * np.exp(0.3 * rng.randn(n - 1))
+        xs.append(x)
+    ref = eng.PLCalcParallel.from_flat(flat)                 # never sees a pair twice: always the two-evaluation path
+    ref.set_freeparams(P, False, fp)
+    ref.smoothing = 10.0
+    want = [ref.calc_pl_grad(x, eng.GRAD_ANALYTIC) for x in xs]
+    ref.close()
+    for k, x in enumerate(xs):                               # pair 0 arms the speculation, pairs 1.. use it
+        f = plp.calc_pl(x)
+        g = plp.calc_gradient(x)
+        assert f == want[k][0] and np.array_equal(g, want[k][1])
+    # the annealer's pattern: objective only; the next pair is again exact
+    for x in xs[:3]:
+        assert plp.calc_pl(x) == plp.calc_pl(x)
+    f = plp.calc_pl(xs[3])
+    assert f == want[3][0] and np.array_equal(plp.calc_gradient(xs[3]), want[3][1])
+    # a state change between calc_pl and calc_gradient: the gradient of the NEW objective at the same point
+    f = plp.calc_pl(xs[0]); plp.calc_gradient(xs[0])        # arm
+    f = plp.calc_pl(xs[1])
+    plp.smoothing = 1000.0
+    g = plp.calc_gradient(xs[1])
+    f2, g2 = plp.calc_pl_grad(xs[1], eng.GRAD_ANALYTIC)
+    assert np.array_equal(g, g2) and not np.array_equal(g, want[1][1])
+    plp.close()

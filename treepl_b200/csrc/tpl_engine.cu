@@ -123,6 +123,13 @@ struct tpl_engine {
     // last calc_pl vector = contents of the pinned staging buffer h_X (the member state is the
     // scatter of it over the base member values; materialised lazily, only when someone reads it)
     bool last_x_valid = false;
+    // calc_pl -> calc_gradient pairs (every TNC / NLopt callback, optimize_tnc.cpp:75-105): once the pattern has been seen,
+    // calc_pl computes the analytic gradient in the same launch and calc_gradient returns it from the pinned buffer; a second
+    // calc_pl in a row (the annealer, siman_calc_par.cpp:154) switches the speculation off again
+    bool spec_grad = false, g_cached = false;
+    int pl_since_grad = 0;
+    double g_lambda = 0.0, g_pb = 0.0;
+    bool g_logpen = false;
     // ---- device tree ----
     DevBuf<int> d_parent, d_rslot, d_dslot, d_child_off, d_children, d_bar_ds;
     DevBuf<double> d_bar_hfix;
@@ -743,12 +750,14 @@ int eval_device(tpl_engine* e, int B, const double* dX, double* dF, double* dG, 
 }
 
 // single point: host x -> device, evaluate, bring f (and g) back
-double eval_point(tpl_engine* e, const double* x, double* g, int mode, bool keep_state) {
+double eval_point(tpl_engine* e, const double* x, double* g, int mode, bool keep_state, bool spec_g = false) {
     const double nan = std::numeric_limits<double>::quiet_NaN();
     g_err.clear();      // a NaN RESULT is legal (the reference propagates NaN); callers tell it from a failure by tpl_last_error()
     if (!e || !x) { fail(TPL_ERR_ARG, "null argument"); return nan; }
     if (!e->have_fp) { fail(TPL_ERR_STATE, "set_freeparams has not been called"); return nan; }
     if (cudaSetDevice(e->device) != cudaSuccess) { fail(TPL_ERR_CUDA, "cudaSetDevice failed"); return nan; }
+    e->g_cached = false;
+    const bool want_g = g != nullptr || spec_g;
     const int P = e->numparams;
     if (!keep_state && e->last_x_valid && x != e->h_X.p) materialize_state(e);   // h_X is about to be overwritten
     if (e->h_X.ensure(P) != cudaSuccess || e->h_G.ensure(P) != cudaSuccess || e->h_F.ensure(1) != cudaSuccess ||
@@ -762,14 +771,18 @@ double eval_point(tpl_engine* e, const double* x, double* g, int mode, bool keep
         fail(TPL_ERR_CUDA, "H2D copy failed");
         return nan;
     }
-    if (eval_device(e, 1, e->d_X.p, e->d_F.p, g ? e->d_G.p : nullptr, mode, false, s) != TPL_OK) return nan;
+    if (eval_device(e, 1, e->d_X.p, e->d_F.p, want_g ? e->d_G.p : nullptr, mode, false, s) != TPL_OK) return nan;
     cudaMemcpyAsync(e->h_F.p, e->d_F.p, sizeof(double), cudaMemcpyDeviceToHost, s);
-    if (g) cudaMemcpyAsync(e->h_G.p, e->d_G.p, sizeof(double) * P, cudaMemcpyDeviceToHost, s);
+    if (want_g) cudaMemcpyAsync(e->h_G.p, e->d_G.p, sizeof(double) * P, cudaMemcpyDeviceToHost, s);
     cudaError_t err = cudaStreamSynchronize(s);
     if (err != cudaSuccess) { fail(TPL_ERR_CUDA, std::string("evaluation failed: ") + cudaGetErrorString(err)); return nan; }
     double f = e->h_F.p[0];
     if (e->static_bad) f = TPL_LARGE;
     if (keep_state) e->last_x_valid = true;
+    if (want_g && mode == TPL_GRAD_ANALYTIC && keep_state) {      // h_G = analytic gradient at the state calc_pl just left
+        e->g_cached = true;
+        e->g_lambda = e->smoothing; e->g_pb = e->pb; e->g_logpen = e->log_pen;
+    }
     if (g) {
         const bool infeasible = (f == TPL_LARGE);
         if (mode == TPL_GRAD_AD && infeasible) {
@@ -921,12 +934,26 @@ int tpl_numparams(const tpl_engine* e) { return e ? e->numparams : TPL_ERR_ARG; 
 int tpl_device_sm(const tpl_engine* e) { return e ? e->sm : TPL_ERR_ARG; }
 int tpl_last_launch_count(const tpl_engine* e) { return e ? e->last_launches : 0; }
 
-double tpl_calc_pl(tpl_engine* e, const double* x) { return eval_point(e, x, nullptr, TPL_GRAD_ANALYTIC, true); }
+double tpl_calc_pl(tpl_engine* e, const double* x) {
+    if (e && ++e->pl_since_grad > 1) e->spec_grad = false;           // calc_pl twice in a row: nobody is asking for gradients
+    return eval_point(e, x, nullptr, TPL_GRAD_ANALYTIC, true, e && e->spec_grad);
+}
 
 int tpl_calc_gradient(tpl_engine* e, const double* x, double* g) {
     if (!e || !g) return fail(TPL_ERR_ARG, "null");
     if (!e->last_x_valid) return fail(TPL_ERR_STATE, "calc_gradient needs a preceding calc_pl (it differentiates at the engine state)");
     (void)x;
+    e->spec_grad = true;
+    e->pl_since_grad = 0;
+    if (e->g_cached && !e->topo_dirty && !e->slots_dirty && !e->state_dirty && e->g_lambda == e->smoothing && e->g_pb == e->pb &&
+        e->g_logpen == e->log_pen) {
+        // the preceding calc_pl already computed it (same launch, same kernels as the path below)
+        const int P = e->numparams;
+        memcpy(g, e->h_G.p, sizeof(double) * P);
+        if (e->lf_mode && std::isnan(g[0]))
+            for (int i = 0; i < P; i++) g[i] = 1000000;               // calc_lf_gradient :680-687
+        return TPL_OK;
+    }
     double f = eval_point(e, e->h_X.p, g, TPL_GRAD_ANALYTIC, true);
     return std::isnan(f) && !g_err.empty() ? TPL_ERR_CUDA : TPL_OK;
 }
