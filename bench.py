@@ -279,12 +279,7 @@ def load_big_test():
 def restart_vectors(flat, P, ks, jitter=0.3, seed=1):
     """the start vectors of cv.multistart, [len(ks), P] (start k depends on (seed, k) only)"""
     from treepl_b200 import cv
-    nr = len(flat["parents"]) - 1
-    x0 = cv.start_vector(flat, P, nr)
-    X0 = np.repeat(x0[None, :], len(ks), axis=0)
-    for j, k in enumerate(ks):
-        X0[j, :nr] *= np.exp(jitter * np.random.RandomState(seed * 1000003 + k).randn(nr))
-    return X0
+    return np.ascontiguousarray(cv.restart_starts(flat, P, ks, jitter, seed).T)
 
 
 class Ranks:

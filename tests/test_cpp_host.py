@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SRC = r'''
 #include <cstdio>
+#include <cstring>
 #include <vector>
 #include "treepl_b200/host/pl_calc_b200.h"
 int main() {
@@ -45,6 +46,15 @@ int main() {
         std::vector<int> status(B);
         tpl_opt_result r = plp.optimize_batch(B, X.data(), F.data(), lo.data(), up.data(), TPL_GRAD_AD, nullptr, status.data());
         printf("OPT F=%.6f F0=%.6f status=%d steps=%d\n", F[0], f01, status[0], r.steps);
+        // the same two problems through the CV entry: start columns of a one-column matrix, probes of rows 0 and np - 1
+        tpl_opt_options oo;
+        memset(&oo, 0, sizeof(oo));
+        oo.method = 1;
+        std::vector<double> X1(np), F2(B), probes(2 * B);
+        for (int p = 0; p < np; p++) X1[p] = x[p];
+        std::vector<int> col(B, 0), rows = {0, 0, np - 1, np - 1};
+        plp.optimize_batch_cols(B, 1, X1.data(), col.data(), F2.data(), lo.data(), up.data(), TPL_GRAD_AD, &oo, 2, rows.data(), probes.data());
+        printf("COLS dF=%.3e dP0=%.3e dP1=%.3e\n", F2[0] - F[0], probes[0] - X[0], probes[2] - X[(np - 1) * B]);
     } catch (const std::exception& ex) {
         printf("EXCEPTION %s\n", ex.what());
         return 3;
@@ -101,3 +111,6 @@ def test_cpp_host_mirror_on_the_gpu():
     assert abs(float(first[1].split("=")[1]) - f) <= 1e-6 and abs(float(first[3].split("=")[1]) - g[0]) <= 1e-5 * abs(g[0]), (res.stdout, f, g[0])
     opt = [ln for ln in res.stdout.splitlines() if ln.startswith("OPT ")][0].split()
     assert float(opt[1].split("=")[1]) < float(opt[2].split("=")[1]) and opt[3] in ("status=1", "status=2", "status=3"), res.stdout
+    # the CV entry (start columns + probes) through the mirror: the same optimum, the probed rows of it
+    cols = [ln for ln in res.stdout.splitlines() if ln.startswith("COLS ")][0].split()
+    assert all(float(t.split("=")[1]) == 0.0 for t in cols[1:]), res.stdout

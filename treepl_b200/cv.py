@@ -316,6 +316,18 @@ def loocv(flat, smoothing_grid, tips, **kw):
     return cross_validate(flat, smoothing_grid, [[int(t)] for t in tips], randomcv=False, **kw)
 
 
+def restart_starts(flat, P, ks, jitter=0.3, seed=1):
+    """Start vectors [P, len(ks)] of the multi-start job: rates jittered log-normally around the clock-like start, feasible start
+    dates.  Start k depends on (seed, k) only (one random stream per start), so the set of starts is the same for every world
+    size - and for the reference arm of the benchmark, which optimises the first few of them on the CPU."""
+    nr = len(flat["parents"]) - 1
+    x0 = start_vector(flat, P, nr)
+    J = np.stack([np.random.RandomState(seed * 1000003 + k).randn(nr) for k in ks])          # [len(ks), nr]
+    X0 = np.repeat(x0[:, None], len(ks), axis=1)
+    X0[:nr] *= np.exp(jitter * J).T
+    return X0
+
+
 def multistart(flat, smoothing, n_starts, jitter=0.3, seed=1, device=0, dist=None, log_pen=False, **opt):
     """n_starts independent optimisations from random starts (rates jittered log-normally around the clock-like
     start, feasible start dates), sharded over the ranks; the global best is exchanged with
@@ -338,9 +350,7 @@ def multistart(flat, smoothing, n_starts, jitter=0.3, seed=1, device=0, dist=Non
     B = max(2, len(mine) + (len(mine) % 2))
     x0 = start_vector(flat, P, nr)
     ks = [mine[min(b, len(mine) - 1)] if mine else 0 for b in range(B)]
-    J = np.stack([np.random.RandomState(seed * 1000003 + k).randn(nr) for k in ks])          # [B, nr], one stream per start
-    X0 = np.repeat(x0[:, None], B, axis=1)
-    X0[:nr] *= np.exp(jitter * J).T
+    X0 = restart_starts(flat, P, ks, jitter, seed)
     plp.batch_configure(B)
     par = flat["parents"]
     dscale = float(np.median(np.maximum(flat["start_dates"][par[1:]] - flat["start_dates"][1:], 1e-12)))

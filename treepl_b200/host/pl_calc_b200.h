@@ -196,6 +196,19 @@ public:
         return res;
     }
 
+    // The fold loop of a CV run (main.cpp:689-801): vector b starts from column start_col[b] of Xstart [P][K] (the full-data
+    // optimum of its smoothing value, main.cpp:679-681) and only the rows its chi-square needs come back:
+    // probe_out[j][b] = X[probe_rows[j][b]][b] (main.cpp:737-793).  Truncated Newton (opts->method = 1) only.
+    tpl_opt_result optimize_batch_cols(int B, int K, const double* Xstart, const int* start_col, double* F, const double* lower,
+                                       const double* upper, int mode, const tpl_opt_options* opts, int nprobe, const int* probe_rows,
+                                       double* probe_out, double* Xout = nullptr, int* status = nullptr, int* iters = nullptr) {
+        sync_members();
+        tpl_opt_result res;
+        check(tpl_optimize_batch_cols(e_, B, K, Xstart, start_col, F, lower, upper, mode, opts, status, iters, &res, nprobe, probe_rows,
+                                      probe_out, Xout));
+        return res;
+    }
+
     // B annealing chains at once (siman_calc_par::optimize, siman_calc_par.cpp:80-229): X [P][B] in/out, F [B] out
     void anneal_batch(int B, double* X, double* F, const tpl_anneal_options* opts = nullptr, int* status = nullptr,
                       int* iterations = nullptr) {
