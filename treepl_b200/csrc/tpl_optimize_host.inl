@@ -204,6 +204,8 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
         CK(cudaMemsetAsync(buf->p, 0, sizeof(double) * PB, s));
     CK(cudaStreamSynchronize(s));       // pen_min / pen_max uploads read host vectors of the engine; lo / hi / sc are the caller's
     a.o.P = P; a.o.B = B; a.o.nr = nr;
+    a.pack_shift = 5;                               // B <= 16: sub-warps of the next power of two >= B lanes (tpl_tn.cuh::node_lane)
+    if (B <= 16) { a.pack_shift = 0; while ((1 << a.pack_shift) < B) a.pack_shift++; }
     a.o.max_ls = o.max_ls > 0 ? o.max_ls : 40;
     a.o.max_cg = o.max_cg > 0 ? o.max_cg : 500;     // a cap of 100 truncates stiff solves (large smoothing x large rates) into crawling
     a.o.patience = o.patience > 0 ? o.patience : 3;

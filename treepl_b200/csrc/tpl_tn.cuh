@@ -47,6 +47,7 @@ struct TnArgs {
     const double* Ft;                        // [B]
     int *st, *ls, *cgit, *flag, *stall, *iters, *ncg, *act;
     double *F0, *t_, *gd, *rz, *rz0, *tol2, *alpha, *beta, *gmax, *tlog, *gdtmp, *mu;
+    int pack_shift;                          // node-indexed kernels at B <= 16: a warp carries 32 >> pack_shift nodes x (1 << pack_shift) vectors
     int row_chunks, rows_per_chunk;          // row-indexed kernels
     int node_chunks, nodes_per_chunk;        // node-indexed kernels
     double *part_setup, *part_hv, *part_upd, *part_gd, *part_tm;
@@ -78,8 +79,10 @@ __device__ __forceinline__ Lane lane_of(const TnArgs& a, int b) {
 // Per-vector reduction across the blocks (blockIdx.y) of a 32-vector group.  v[k]: this thread's partial; bit k of MAXM /
 // MINM selects max / min instead of sum.  Returns true in the last block to arrive, with the group totals in v[] of the
 // ty == 0 threads.  Deterministic: partials are combined in chunk order, then in ty order.
+// pack_shift < 5 (node-indexed kernels at B <= 16, see node_lane below): the 32 >> pack_shift sub-warps of a warp hold
+// partials of the SAME vectors (different nodes); they are folded in sub-warp order, and the totals land in sub-warp 0.
 template <int K, unsigned MAXM, unsigned MINM>
-__device__ __forceinline__ bool group_reduce(double (&v)[K], double* part, int* counter, int B, int b) {
+__device__ __forceinline__ bool group_reduce(double (&v)[K], double* part, int* counter, int B, int b, int pack_shift = 5) {
     __shared__ double red[OPT_WY][K][32];
     __shared__ int s_last;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -91,11 +94,13 @@ __device__ __forceinline__ bool group_reduce(double (&v)[K], double* part, int* 
 #pragma unroll
     for (int k = 0; k < K; k++) red[ty][k][tx] = v[k];
     __syncthreads();
-    if (ty == 0 && b < B) {
+    const int lpw = 1 << pack_shift, npw = 32 >> pack_shift, sub = tx >> pack_shift;
+    if (ty == 0 && sub == 0 && b < B) {
 #pragma unroll
         for (int k = 0; k < K; k++) {
             double x = red[0][k][tx];
-            for (int y = 1; y < OPT_WY; y++) x = comb(k, x, red[y][k][tx]);
+            for (int y = 0; y < OPT_WY; y++)
+                for (int q = (y == 0 ? 1 : 0); q < npw; q++) x = comb(k, x, red[y][k][q * lpw + tx]);
             part[((size_t)blockIdx.y * K + k) * B + b] = x;
         }
     }
@@ -124,6 +129,22 @@ __device__ __forceinline__ bool group_reduce(double (&v)[K], double* part, int* 
     }
     if (tx == 0 && ty == 0) counter[blockIdx.x] = 0;        // ready for the next launch
     return true;
+}
+
+// Thread mapping of the node-indexed kernels.  Normally a warp is one node x 32 vectors (tx = vector).  With 16 or fewer
+// vectors most of those lanes would idle - and these kernels are bound by the latency of one node's chain per warp - so the
+// warp is cut into sub-warps of LPW = 1 << pack_shift lanes (LPW >= B, one vector group only) that work on 32 / LPW different
+// nodes at once: `b` = the vector, `sub` = which of the warp's nodes, `npw` = nodes per warp.
+struct NodeLane {
+    int b, sub, npw;
+};
+__device__ __forceinline__ NodeLane node_lane(const TnArgs& a) {
+    const int sh = a.pack_shift;                 // 5: no packing
+    NodeLane l;
+    l.b = blockIdx.x * 32 + (threadIdx.x & ((1 << sh) - 1));
+    l.sub = threadIdx.x >> sh;
+    l.npw = 32 >> sh;
+    return l;
 }
 
 struct DevView {
@@ -246,14 +267,15 @@ struct RecBase : DevView {
 
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_diag_kernel(TnArgs a) {
-    const int b = blockIdx.x * 32 + threadIdx.x;
+    const NodeLane nl = node_lane(a);
+    const int b = nl.b;
     const int B = a.o.B;
     if (b >= B) return;
     const int dec = lane_decision(a, b);
     if (dec != DEC_ACCEPT && dec != DEC_INIT) return;
     DevView V = {a, B, b, a.Pv, a.DG, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, 0.0};
     const int i0 = blockIdx.y * a.nodes_per_chunk, i1 = min(a.t.n, i0 + a.nodes_per_chunk);
-    for (int i = i0 + threadIdx.y; i < i1; i += OPT_WY) diag_node(V, i);
+    for (int i = i0 + threadIdx.y * nl.npw + nl.sub; i < i1; i += OPT_WY * nl.npw) diag_node(V, i);
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_setup_kernel(TnArgs a) {
@@ -406,8 +428,9 @@ __device__ __forceinline__ void hess_node_fast(const TnArgs& a, const int4 q0, c
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int b = blockIdx.x * 32 + tx;
+    const int ty = threadIdx.y;
+    const NodeLane nl = node_lane(a);
+    const int b = nl.b;
     const int B = a.o.B;
     // a vector whose CG solve ended in an earlier sub-iteration of this step waits for the line-search set-up
     const bool active = b < B && a.st[b] == TS_CG && !(a.act[b] & ACT_FIN);
@@ -419,12 +442,13 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
         // the record of the NEXT node is requested before this node's rows: its round trip overlaps this node's work instead of
         // heading the next node's chain (per node: record -> rows -> arithmetic; the kernel's rate is warps in flight / that latency)
         const int4* recs = reinterpret_cast<const int4*>(a.hv_rec);
-        int i = i0 + ty;
+        const int istep = OPT_WY * nl.npw;
+        int i = i0 + ty * nl.npw + nl.sub;
         int4 n0, n1, n2, n3;
         if (i < i1) { n0 = __ldg(recs + 4 * (size_t)i); n1 = __ldg(recs + 4 * (size_t)i + 1); n2 = __ldg(recs + 4 * (size_t)i + 2); n3 = __ldg(recs + 4 * (size_t)i + 3); }
-        for (; i < i1; i += OPT_WY) {
+        for (; i < i1; i += istep) {
             const int4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
-            const int inext = i + OPT_WY;
+            const int inext = i + istep;
             if (inext < i1) { n0 = __ldg(recs + 4 * (size_t)inext); n1 = __ldg(recs + 4 * (size_t)inext + 1); n2 = __ldg(recs + 4 * (size_t)inext + 2); n3 = __ldg(recs + 4 * (size_t)inext + 3); }
             double vw, vv;
             if (q1.w) hess_node_fast(a, q0, q1, q2, q3, B, b, V.lam, V.mu, vw, vv);
@@ -433,8 +457,8 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
             v[1] += vv;
         }
     }
-    if (!group_reduce<2, 0u, 0u>(v, a.part_hv, a.cnt_hv, B, b)) return;
-    if (ty == 0 && active) phase_hv(lane_of(a, b), v, a.o);
+    if (!group_reduce<2, 0u, 0u>(v, a.part_hv, a.cnt_hv, B, b, a.pack_shift)) return;
+    if (ty == 0 && nl.sub == 0 && active) phase_hv(lane_of(a, b), v, a.o);
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_update_kernel(TnArgs a) {
@@ -646,11 +670,12 @@ __device__ __forceinline__ void tree_down_at(const TnArgs& a, const DevView& V, 
 // halve the throughput of the node-indexed kernels at thousands of vectors)
 template <bool REC>
 __global__ void __launch_bounds__(32 * OPT_WY) tn_tree_local_kernel(TnArgs a) {
-    const int b = blockIdx.x * 32 + threadIdx.x;
+    const NodeLane nl = node_lane(a);
+    const int b = nl.b;
     if (!tree_lane_active<true>(a, b)) return;
     DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, tree_lane_mu<true>(a, b)};
     const int k0 = blockIdx.y * TREE_NODES_PER_BLOCK, k1 = min(a.t.n, k0 + TREE_NODES_PER_BLOCK);
-    for (int k = k0 + threadIdx.y; k < k1; k += OPT_WY) {
+    for (int k = k0 + threadIdx.y * nl.npw + nl.sub; k < k1; k += OPT_WY * nl.npw) {
         if (REC) {
             const TreeRec rec = tree_rec_load(a.lev_rec, k);
             LocalView L(V, rec);
@@ -663,40 +688,44 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_tree_local_kernel(TnArgs a) {
 
 template <bool FACTOR>
 __global__ void __launch_bounds__(32 * OPT_WY) tn_tree_up_kernel(TnArgs a, int level) {
-    const int b = blockIdx.x * 32 + threadIdx.x;
+    const NodeLane nl = node_lane(a);
+    const int b = nl.b;
     if (!tree_lane_active<FACTOR>(a, b)) return;
     DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, tree_lane_mu<FACTOR>(a, b)};
     const int k0 = a.lev_off[level] + blockIdx.y * TREE_NODES_PER_BLOCK;
     const int k1 = min(a.lev_off[level + 1], k0 + TREE_NODES_PER_BLOCK);
-    for (int k = k0 + threadIdx.y; k < k1; k += OPT_WY) tree_up_at<FACTOR>(a, V, k);
+    for (int k = k0 + threadIdx.y * nl.npw + nl.sub; k < k1; k += OPT_WY * nl.npw) tree_up_at<FACTOR>(a, V, k);
 }
 
 template <bool FACTOR>
 __global__ void __launch_bounds__(32 * OPT_WY) tn_tree_down_kernel(TnArgs a, int level) {
-    const int b = blockIdx.x * 32 + threadIdx.x;
+    const NodeLane nl = node_lane(a);
+    const int b = nl.b;
     if (!tree_lane_active<FACTOR>(a, b)) return;
     DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, tree_lane_mu<FACTOR>(a, b)};
     const int k0 = a.lev_off[level] + blockIdx.y * TREE_NODES_PER_BLOCK;
     const int k1 = min(a.lev_off[level + 1], k0 + TREE_NODES_PER_BLOCK);
-    for (int k = k0 + threadIdx.y; k < k1; k += OPT_WY) tree_down_at(a, V, k);
+    for (int k = k0 + threadIdx.y * nl.npw + nl.sub; k < k1; k += OPT_WY * nl.npw) tree_down_at(a, V, k);
 }
 
 // the narrow levels [nlev_wide, nlev): up to the root and back down inside one block per vector group
 template <bool FACTOR>
 __global__ void __launch_bounds__(32 * TREE_TOP_WY) tn_tree_top_kernel(TnArgs a) {
-    const int b = blockIdx.x * 32 + threadIdx.x;
+    const NodeLane nl = node_lane(a);
+    const int b = nl.b;
     const bool active = tree_lane_active<FACTOR>(a, b);
     if (!__syncthreads_or(active)) return;
     DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[min(b, a.o.B - 1)] : a.lambda, a.pb, a.log_pen != 0,
                  active ? tree_lane_mu<FACTOR>(a, b) : 0.0};
+    const int first = threadIdx.y * nl.npw + nl.sub, stride = TREE_TOP_WY * nl.npw;
     for (int level = a.nlev_wide; level < a.nlev; level++) {
         if (active)
-            for (int k = a.lev_off[level] + threadIdx.y; k < a.lev_off[level + 1]; k += TREE_TOP_WY) tree_up_at<FACTOR>(a, V, k);
+            for (int k = a.lev_off[level] + first; k < a.lev_off[level + 1]; k += stride) tree_up_at<FACTOR>(a, V, k);
         __syncthreads();
     }
     for (int level = a.nlev - 1; level >= a.nlev_wide; level--) {
         if (active)
-            for (int k = a.lev_off[level] + threadIdx.y; k < a.lev_off[level + 1]; k += TREE_TOP_WY) tree_down_at(a, V, k);
+            for (int k = a.lev_off[level] + first; k < a.lev_off[level + 1]; k += stride) tree_down_at(a, V, k);
         __syncthreads();
     }
 }
@@ -772,15 +801,16 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_gd_kernel(TnArgs a) {
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_stepmax_kernel(TnArgs a) {
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int b = blockIdx.x * 32 + tx;
+    const int ty = threadIdx.y;
+    const NodeLane nl = node_lane(a);
+    const int b = nl.b;
     const int B = a.o.B;
     const bool active = b < B && a.st[b] == TS_CG && (a.act[b] & ACT_FIN);
     if (!__syncthreads_or(active)) return;
     double v[1] = {1e300};
     if (active) {
         const int i0 = max(1, blockIdx.y * a.nodes_per_chunk), i1 = min(a.t.n, (blockIdx.y + 1) * a.nodes_per_chunk);
-        for (int i = i0 + ty; i < i1; i += OPT_WY) {
+        for (int i = i0 + ty * nl.npw + nl.sub; i < i1; i += OPT_WY * nl.npw) {
             const int pa = a.t.parent[i];
             const int ri = a.t.dslot[i], rp = a.t.dslot[pa];
             double zi, di = 0.0, zp, dp = 0.0;
@@ -789,13 +819,13 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_stepmax_kernel(TnArgs a) {
             v[0] = fmin(v[0], tplopt::branch_step_limit(zi, di, zp, dp));
             if (ri >= 0) v[0] = fmin(v[0], tplopt::bound_step_limit(a.Z[(size_t)ri * B + b], a.S[(size_t)ri * B + b], a.lo[ri], a.hi[ri]));
         }
-        if (blockIdx.y == 0 && ty == 0) {            // the root's own date (no branch above it)
+        if (blockIdx.y == 0 && ty == 0 && nl.sub == 0) {            // the root's own date (no branch above it)
             const int r0 = a.t.dslot[0];
             if (r0 >= 0) v[0] = fmin(v[0], tplopt::bound_step_limit(a.Z[(size_t)r0 * B + b], a.S[(size_t)r0 * B + b], a.lo[r0], a.hi[r0]));
         }
     }
-    if (!group_reduce<1, 0u, 1u>(v, a.part_tm, a.cnt_tm, B, b)) return;
-    if (ty == 0 && active)
+    if (!group_reduce<1, 0u, 1u>(v, a.part_tm, a.cnt_tm, B, b, a.pack_shift)) return;
+    if (ty == 0 && nl.sub == 0 && active)
         if (phase_finish(lane_of(a, b), a.gdtmp[b], v[0], a.o)) atomicAdd(a.ndone, 1);
 }
 
