@@ -284,7 +284,8 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
         for (int i = 0; i < n; i++) nodes[fill[height[i]]++] = i;
         a.nlev = hmax + 1;
         a.nlev_wide = 0;
-        const int wide_min = o.tree_wide_min > 0 ? o.tree_wide_min : 4 * tpltn::TREE_TOP_WY;
+        // a level is worth its own launch when it fills the top kernel's block several times over: 16 warps x (nodes per warp)
+        const int wide_min = o.tree_wide_min > 0 ? o.tree_wide_min : 4 * tpltn::TREE_TOP_WY * (32 >> a.pack_shift);
         while (a.nlev_wide < a.nlev && off[a.nlev_wide + 1] - off[a.nlev_wide] >= wide_min) a.nlev_wide++;
         // one index record per node, in level order: what the sweeps' record views load first (tpl_tn.cuh)
         std::vector<int> recs((size_t)n * tpltn::TREE_REC_INTS, -1);
