@@ -377,7 +377,8 @@ def job_restarts(rk, runs=1, warm=0, config4=False):
             "converged": int(rk.vsum(res["local_converged"])), "best_objective": res["best"], "winner_rank": res["winner_rank"],
             "objective_spread_rank0": [float(np.min(res["local_objectives"])), float(np.max(res["local_objectives"]))],
             "gpu_launches": int(res["launches"]) * rk.world, "batched_evaluations": res["nfev"],
-            "hessian_vector_products_rank0": res["cg_iterations"], "n_local": res["n_local"]}
+            "hessian_vector_products_rank0": res["cg_iterations"], "n_local": res["n_local"],
+            "seconds": {"optimize_rank0": res["optimize_seconds"], "device_rank0": 1e-3 * (res["device_ms"] or 0.0)}}
 
 
 def job_cv100k(rk, tips_n, cv_steps, warm=0):

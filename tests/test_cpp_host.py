@@ -50,11 +50,12 @@ int main() {
         tpl_opt_options oo;
         memset(&oo, 0, sizeof(oo));
         oo.method = 1;
-        std::vector<double> X1(np), F2(B), probes(2 * B);
-        for (int p = 0; p < np; p++) X1[p] = x[p];
+        std::vector<double> X1(np), F2(B), probes(2 * B), Xm(np * B), Fm(B);
+        for (int p = 0; p < np; p++) { X1[p] = x[p]; Xm[p * B] = Xm[p * B + 1] = x[p]; }
+        plp.optimize_batch(B, Xm.data(), Fm.data(), lo.data(), up.data(), TPL_GRAD_AD, &oo);          // truncated Newton, expanded batch
         std::vector<int> col(B, 0), rows = {0, 0, np - 1, np - 1};
         plp.optimize_batch_cols(B, 1, X1.data(), col.data(), F2.data(), lo.data(), up.data(), TPL_GRAD_AD, &oo, 2, rows.data(), probes.data());
-        printf("COLS dF=%.3e dP0=%.3e dP1=%.3e\n", F2[0] - F[0], probes[0] - X[0], probes[2] - X[(np - 1) * B]);
+        printf("COLS dF=%.3e dP0=%.3e dP1=%.3e\n", F2[0] - Fm[0], probes[0] - Xm[0], probes[2] - Xm[(np - 1) * B]);
     } catch (const std::exception& ex) {
         printf("EXCEPTION %s\n", ex.what());
         return 3;
