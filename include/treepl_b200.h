@@ -54,6 +54,11 @@ int tpl_create(tpl_engine** out, int device, int numnodes,
 /* pl_calc_parallel::delete_ad_arrays + destructor (main.cpp:798) */
 void tpl_destroy(tpl_engine* e);
 
+/* Device memory of destroyed engines is kept by the library for the next engine of the process (a CV run builds one
+ * engine per phase, each with tens of GB of work space; cudaMalloc / cudaFree of that size cost tenths of a second).
+ * This returns every cached block to the driver.  The cache is also emptied before an allocation failure is reported. */
+int tpl_release_cached_memory(void);
+
 /* message of the last failing call on this thread.  The evaluation entry points that return a double (tpl_calc_pl,
  * tpl_calc_function_gradient, tpl_calc_pl_grad) clear it on entry: NaN with an EMPTY message is a NaN objective (the
  * reference propagates NaN to its wrappers), NaN with a message is a failure. */

@@ -107,6 +107,7 @@ int tpl_get_durations(tpl_engine* e, double* out) { memcpy(out, e->plp.durations
 int tpl_batch_configure(tpl_engine*, int, const double*, const int*, const int*) { return fail(TPL_ERR_STATE, "CPU conformance double: no batched path"); }
 int tpl_calc_pl_grad_batch(tpl_engine*, int, const double*, double*, double*, int) { return fail(TPL_ERR_STATE, "CPU conformance double: no batched path"); }
 int tpl_optimize_batch(tpl_engine*, int, double*, double*, const double*, const double*, int, const tpl_opt_options*, int*, int*, tpl_opt_result*) { return fail(TPL_ERR_STATE, "CPU conformance double: no batched path"); }
+int tpl_release_cached_memory(void) { return TPL_OK; }
 int tpl_optimize_batch_cols(tpl_engine*, int, int, const double*, const int*, double*, const double*, const double*, int, const tpl_opt_options*, int*, int*, tpl_opt_result*, int, const int*, double*, double*) { return fail(TPL_ERR_STATE, "CPU conformance double: no batched path"); }
 int tpl_anneal_batch(tpl_engine*, int, double*, double*, const tpl_anneal_options*, int*, int*) { return fail(TPL_ERR_STATE, "CPU conformance double: no batched path"); }
 

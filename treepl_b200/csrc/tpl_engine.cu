@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -39,19 +40,81 @@ int fail(int code, const std::string& msg) {
             return fail(TPL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));         \
     } while (0)
 
+// Device memory blocks outlive the engine that allocated them: a CV run or a multi-start job builds one engine per phase and
+// per call, each with tens of GB of work space, and cudaMalloc / cudaFree of blocks that size cost 0.1-0.6 s per engine
+// (more when several ranks of a box allocate at once: the driver serialises them).  Freed blocks are kept per device and
+// handed to the next request of a similar size; tpl_release_cached_memory() returns them to the driver, and so does an
+// allocation failure before it is reported.
+struct DevPool {
+    struct Blk { void* p; size_t bytes; int dev; };
+    std::mutex m;
+    std::vector<Blk> blocks;
+    void* take(size_t bytes, int dev, size_t* got) {
+        std::lock_guard<std::mutex> g(m);
+        int best = -1;
+        for (int k = 0; k < (int)blocks.size(); k++) {
+            const Blk& b = blocks[k];
+            if (b.dev != dev || b.bytes < bytes || b.bytes > std::max(2 * bytes, bytes + (size_t)(1 << 20))) continue;
+            if (best < 0 || b.bytes < blocks[best].bytes) best = k;
+        }
+        if (best < 0) return nullptr;
+        void* p = blocks[best].p;
+        *got = blocks[best].bytes;
+        blocks.erase(blocks.begin() + best);
+        return p;
+    }
+    void give(void* p, size_t bytes, int dev) {
+        std::lock_guard<std::mutex> g(m);
+        blocks.push_back({p, bytes, dev});
+    }
+    void trim(int dev) {                       // dev < 0: every device
+        std::lock_guard<std::mutex> g(m);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (size_t k = 0; k < blocks.size();) {
+            if (dev >= 0 && blocks[k].dev != dev) { k++; continue; }
+            cudaSetDevice(blocks[k].dev);
+            cudaFree(blocks[k].p);
+            blocks.erase(blocks.begin() + k);
+        }
+        cudaSetDevice(cur);
+    }
+};
+DevPool& dev_pool() { static DevPool* pool = new DevPool(); return *pool; }    // never destroyed: no cudaFree after the runtime is gone
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
-    size_t cap = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
+    size_t cap = 0;            // elements the caller may use (the block may be larger)
+    size_t bytes = 0;          // size of the block as allocated
+    int dev = 0;
+    void release() {
+        if (p) dev_pool().give(p, bytes, dev);
+        p = nullptr;
+        cap = bytes = 0;
+    }
+    ~DevBuf() { release(); }
     cudaError_t ensure(size_t n) {
         if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
-        if (e == cudaSuccess) cap = n;
-        return e;
+        release();
+        cudaGetDevice(&dev);
+        const size_t want = n * sizeof(T);
+        size_t got = 0;
+        void* q = dev_pool().take(want, dev, &got);
+        if (!q) {
+            cudaError_t e = cudaMalloc(&q, want);
+            if (e != cudaSuccess) {            // give the cached blocks back and try once more
+                cudaGetLastError();
+                dev_pool().trim(dev);
+                e = cudaMalloc(&q, want);
+                if (e != cudaSuccess) return e;
+            }
+            got = want;
+        }
+        p = (T*)q;
+        bytes = got;
+        cap = got / sizeof(T);
+        return cudaSuccess;
     }
     cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
         cudaError_t e = ensure(v.size() ? v.size() : 1);
@@ -861,7 +924,13 @@ void tpl_destroy(tpl_engine* e) {
     if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
     for (int k = 0; k < 3; k++) if (e->pstream[k]) { cudaStreamSynchronize(e->pstream[k]); cudaStreamDestroy(e->pstream[k]); }
     for (auto& v : e->ev) cudaEventDestroy(v);
+    cudaDeviceSynchronize();            // the engine's blocks go back to the process-wide cache: nothing may still be using them
     delete e;
+}
+
+int tpl_release_cached_memory(void) {
+    dev_pool().trim(-1);
+    return TPL_OK;
 }
 
 int tpl_set_smoothing(tpl_engine* e, double s) { if (!e) return fail(TPL_ERR_ARG, "null"); e->smoothing = s; return TPL_OK; }

@@ -24,6 +24,9 @@
 //   tn_tree_top_kernel<FACTOR>   narrow levels: up to the root, then back down
 //   tn_tree_down_kernel<FACTOR>  one wide level: back substitution -> ZZ rows
 //   tn_pc_finish_kernel<FACTOR>  row-indexed    [p = zz] and r.zz                                        -> phase_setup / phase_update
+// The node-indexed kernels are latency bound (one warp = one node's dependent chain): the sweeps read host-built index
+// records through "record views" that fetch all operands of a node side by side, tn_hv_kernel has a hand-specialised fast
+// path on its own records, and with 16 or fewer vectors a warp carries several nodes at once (node_lane).  DESIGN.md 8.1.
 #pragma once
 #include "tpl_kernels.cuh"
 #include "tpl_lbfgs.cuh"

@@ -54,6 +54,11 @@ class EngineError(RuntimeError):
     pass
 
 
+def release_cached_memory():
+    """tpl_release_cached_memory: give the device memory kept from closed engines back to the driver"""
+    load_library().tpl_release_cached_memory()
+
+
 def lib_path():
     return _build.LIB
 
@@ -121,7 +126,7 @@ EXPORTED_SYMBOLS = (
     "tpl_calc_function_gradient", "tpl_calc_pl_grad", "tpl_get_rates", "tpl_get_dates", "tpl_get_durations",
     "tpl_batch_configure", "tpl_calc_pl_grad_batch", "tpl_calc_pl_grad_batch_dev", "tpl_last_launch_count",
     "tpl_host_alloc", "tpl_host_free", "tpl_device_sm", "tpl_debug_math", "tpl_set_timing", "tpl_get_timing", "tpl_debug_force_kernel",
-    "tpl_last_kernel_generation", "tpl_optimize_batch", "tpl_optimize_batch_cols", "tpl_debug_hessvec", "tpl_debug_treesolve", "tpl_anneal_batch",
+    "tpl_last_kernel_generation", "tpl_release_cached_memory", "tpl_optimize_batch", "tpl_optimize_batch_cols", "tpl_debug_hessvec", "tpl_debug_treesolve", "tpl_anneal_batch",
 )
 
 
