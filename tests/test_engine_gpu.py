@@ -499,3 +499,38 @@ def test_gradient_computed_with_calc_pl_for_callback_pairs():
     f2, g2 = plp.calc_pl_grad(xs[1], eng.GRAD_ANALYTIC)
     assert np.array_equal(g, g2) and not np.array_equal(g, want[1][1])
     plp.close()
+
+
+def test_device_blocks_of_closed_engines_are_reused_and_can_be_released():
+    """Work space of a closed engine stays with the library for the next engine of the process (tens of GB for a large CV
+    batch: cudaMalloc / cudaFree of that size cost tenths of a second per engine); tpl_release_cached_memory returns it."""
+    import torch
+    from treepl_b200 import batchopt, cv
+    gd = Golden("big_test")
+    flat = gd.flat
+    n = len(flat["parents"])
+    fp, P = eng.generate_param_order_vector(flat["free"], lf=False)
+    lo, hi = batchopt.reference_bounds(flat, fp, P)
+    x0 = cv.start_vector(flat, P, n - 1)
+    B = 256
+    X0 = np.repeat(x0[:, None], B, axis=1)
+    eng.release_cached_memory()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+
+    def run():
+        plp = eng.PLCalcParallel.from_flat(flat)
+        plp.set_freeparams(P, False, fp)
+        plp.batch_configure(B)
+        X, F, info = plp.optimize_batch(X0, lo, hi, method=1, max_steps=4)
+        plp.close()
+        return F
+
+    F1 = run()
+    held = free0 - torch.cuda.mem_get_info()[0]
+    assert held > 300e6, held                                  # ~12 [P][B] arrays + the tree work planes are still held
+    F2 = run()                                                 # the second engine runs in the first one's blocks
+    assert np.array_equal(F1, F2)
+    assert free0 - torch.cuda.mem_get_info()[0] <= held + 64e6
+    eng.release_cached_memory()
+    assert free0 - torch.cuda.mem_get_info()[0] < 64e6
