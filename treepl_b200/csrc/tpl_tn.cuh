@@ -134,7 +134,7 @@ __device__ __forceinline__ bool group_reduce(double (&v)[K], double* part, int* 
     return true;
 }
 
-// Thread mapping of the node-indexed kernels.  Normally a warp is one node x 32 vectors (tx = vector).  With 16 or fewer
+// Thread mapping of the optimiser kernels.  Normally a warp is one node (or row) x 32 vectors (tx = vector).  With 16 or fewer
 // vectors most of those lanes would idle - and these kernels are bound by the latency of one node's chain per warp - so the
 // warp is cut into sub-warps of LPW = 1 << pack_shift lanes (LPW >= B, one vector group only) that work on 32 / LPW different
 // nodes at once: `b` = the vector, `sub` = which of the warp's nodes, `npw` = nodes per warp.
@@ -197,11 +197,12 @@ __device__ __forceinline__ double lane_mu_eff(const TnArgs& a, int b, int dec) {
 
 // Z = clamp(w / sc), S = 0
 __global__ void __launch_bounds__(32 * OPT_WY) tn_init_kernel(TnArgs a) {
-    const int b = blockIdx.x * 32 + threadIdx.x;
+    const NodeLane nl = node_lane(a);           // B <= 16: a warp carries several rows (as the node-indexed kernels carry nodes)
+    const int b = nl.b;
     if (b >= a.o.B) return;
-    if (blockIdx.y == 0 && threadIdx.y == 0) a.act[b] = ACT_TRIAL;      // the first trial point is the start itself (t = 0)
+    if (blockIdx.y == 0 && threadIdx.y == 0 && nl.sub == 0) a.act[b] = ACT_TRIAL;      // the first trial point is the start itself (t = 0)
     const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(a.o.P, p0 + a.rows_per_chunk);
-    for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
+    for (int p = p0 + threadIdx.y * nl.npw + nl.sub; p < p1; p += OPT_WY * nl.npw) {
         const size_t i = (size_t)p * a.o.B + b;
         const double x = a.X[i];
         const double w = p < a.o.nr ? log(x) : x;
@@ -211,7 +212,8 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_init_kernel(TnArgs a) {
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_trial_kernel(TnArgs a) {
-    const int b = blockIdx.x * 32 + threadIdx.x;
+    const NodeLane nl = node_lane(a);
+    const int b = nl.b;
     const int B = a.o.B, P = a.o.P, nr = a.o.nr;
     if (b >= B) return;
     const int act = a.act[b];
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_trial_kernel(TnArgs a) {
     const bool sd = (act & ACT_SD) != 0;
     const double t = a.t_[b];
     const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
-    for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
+    for (int p = p0 + threadIdx.y * nl.npw + nl.sub; p < p1; p += OPT_WY * nl.npw) {
         const size_t i = (size_t)p * B + b;
         double s;
         if (sd) {
@@ -282,8 +284,9 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_diag_kernel(TnArgs a) {
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_setup_kernel(TnArgs a) {
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int b = blockIdx.x * 32 + tx;
+    const int ty = threadIdx.y;
+    const NodeLane nl = node_lane(a);
+    const int b = nl.b;
     const int B = a.o.B, P = a.o.P, nr = a.o.nr;
     int dec = DEC_SKIP;
     double t = 0.0;
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_setup_kernel(TnArgs a) {
     if (dec == DEC_ACCEPT || dec == DEC_INIT) {
         const double mu = lane_mu_eff(a, b, dec);
         const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
-        for (int p = p0 + ty; p < p1; p += OPT_WY) {
+        for (int p = p0 + ty * nl.npw + nl.sub; p < p1; p += OPT_WY * nl.npw) {
             const size_t i = (size_t)p * B + b;
             const double lo = a.lo[p], hi = a.hi[p];
             double z = a.Z[i];
@@ -317,8 +320,8 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_setup_kernel(TnArgs a) {
             v[2] = fma(gp, gp, v[2]);
         }
     }
-    if (!group_reduce<3, 2u, 0u>(v, a.part_setup, a.cnt_setup, B, b)) return;
-    if (ty == 0 && b < B) {
+    if (!group_reduce<3, 2u, 0u>(v, a.part_setup, a.cnt_setup, B, b, a.pack_shift)) return;
+    if (ty == 0 && nl.sub == 0 && b < B) {
         if (a.precond && (dec == DEC_ACCEPT || dec == DEC_INIT)) {
             // r.M^-1 r comes from the tree solve (tn_pc_finish_kernel runs phase_setup); the decision inputs stay untouched
             a.gmax_tmp[b] = v[1];
@@ -465,8 +468,9 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_update_kernel(TnArgs a) {
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int b = blockIdx.x * 32 + tx;
+    const int ty = threadIdx.y;
+    const NodeLane nl = node_lane(a);
+    const int b = nl.b;
     const int B = a.o.B, P = a.o.P;
     const bool active = b < B && a.st[b] == TS_CG && (a.act[b] & ACT_CG);
     if (!__syncthreads_or(active)) return;
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_update_kernel(TnArgs a) {
     if (active) {
         const double alpha = a.alpha[b];
         const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
-        for (int p = p0 + ty; p < p1; p += OPT_WY) {
+        for (int p = p0 + ty * nl.npw + nl.sub; p < p1; p += OPT_WY * nl.npw) {
             const size_t i = (size_t)p * B + b;
             const double pv = a.Pv[i];
             a.S[i] = fma(alpha, pv, a.S[i]);
@@ -486,8 +490,8 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_update_kernel(TnArgs a) {
         }
     }
     if (a.precond) return;                       // zz = M^-1 r and r.zz follow from the tree sweeps
-    if (!group_reduce<1, 0u, 0u>(v, a.part_upd, a.cnt_upd, B, b)) return;
-    if (ty == 0 && active) phase_update(lane_of(a, b), v, a.o);
+    if (!group_reduce<1, 0u, 0u>(v, a.part_upd, a.cnt_upd, B, b, a.pack_shift)) return;
+    if (ty == 0 && nl.sub == 0 && active) phase_update(lane_of(a, b), v, a.o);
 }
 
 // ---- tree preconditioner sweeps ------------------------------------------------------------------------------------------
@@ -736,23 +740,24 @@ __global__ void __launch_bounds__(32 * TREE_TOP_WY) tn_tree_top_kernel(TnArgs a)
 // after the sweeps: [p = zz,] r.zz -> the state machine that the Jacobi path runs inside tn_setup / tn_update
 template <bool FACTOR>
 __global__ void __launch_bounds__(32 * OPT_WY) tn_pc_finish_kernel(TnArgs a) {
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int b = blockIdx.x * 32 + tx;
+    const int ty = threadIdx.y;
+    const NodeLane nl = node_lane(a);
+    const int b = nl.b;
     const int B = a.o.B, P = a.o.P;
     const bool active = tree_lane_active<FACTOR>(a, b);
     if (!__syncthreads_or(active)) return;
     double v[1] = {0.0};
     if (active) {
         const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
-        for (int p = p0 + ty; p < p1; p += OPT_WY) {
+        for (int p = p0 + ty * nl.npw + nl.sub; p < p1; p += OPT_WY * nl.npw) {
             const size_t i = (size_t)p * B + b;
             const double zz = a.ZZ[i];
             if (FACTOR) a.Pv[i] = zz;
             v[0] = fma(a.R[i], zz, v[0]);
         }
     }
-    if (!group_reduce<1, 0u, 0u>(v, a.part_pc, a.cnt_pc, B, b)) return;
-    if (ty == 0 && active) {
+    if (!group_reduce<1, 0u, 0u>(v, a.part_pc, a.cnt_pc, B, b, a.pack_shift)) return;
+    if (ty == 0 && nl.sub == 0 && active) {
         if (FACTOR) {
             const double red[3] = {v[0], a.gmax_tmp[b], a.gg_tmp[b]};
             if (phase_setup(lane_of(a, b), a.Ft[b], red, a.o)) atomicAdd(a.ndone, 1);
@@ -763,21 +768,23 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_pc_finish_kernel(TnArgs a) {
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_dir_kernel(TnArgs a) {
-    const int b = blockIdx.x * 32 + threadIdx.x;
+    const NodeLane nl = node_lane(a);
+    const int b = nl.b;
     const int B = a.o.B, P = a.o.P;
     if (b >= B) return;
     if (a.st[b] != TS_CG || !(a.act[b] & ACT_DIR)) return;
     const double beta = a.beta[b];
     const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
-    for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
+    for (int p = p0 + threadIdx.y * nl.npw + nl.sub; p < p1; p += OPT_WY * nl.npw) {
         const size_t i = (size_t)p * B + b;
         a.Pv[i] = fma(beta, a.Pv[i], a.ZZ[i]);
     }
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_gd_kernel(TnArgs a) {
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int b = blockIdx.x * 32 + tx;
+    const int ty = threadIdx.y;
+    const NodeLane nl = node_lane(a);
+    const int b = nl.b;
     const int B = a.o.B, P = a.o.P;
     int act = 0;
     if (b < B && a.st[b] == TS_CG) act = a.act[b];
@@ -787,7 +794,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_gd_kernel(TnArgs a) {
     if (active) {
         const bool takep = (act & ACT_TAKEP) != 0;
         const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(P, p0 + a.rows_per_chunk);
-        for (int p = p0 + ty; p < p1; p += OPT_WY) {
+        for (int p = p0 + ty * nl.npw + nl.sub; p < p1; p += OPT_WY * nl.npw) {
             const size_t i = (size_t)p * B + b;
             double s;
             if (takep) {
@@ -799,8 +806,8 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_gd_kernel(TnArgs a) {
             v[0] = fma(a.Gz[i], s, v[0]);
         }
     }
-    if (!group_reduce<1, 0u, 0u>(v, a.part_gd, a.cnt_gd, B, b)) return;
-    if (ty == 0 && active) a.gdtmp[b] = v[0];
+    if (!group_reduce<1, 0u, 0u>(v, a.part_gd, a.cnt_gd, B, b, a.pack_shift)) return;
+    if (ty == 0 && nl.sub == 0 && active) a.gdtmp[b] = v[0];
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_stepmax_kernel(TnArgs a) {
@@ -833,11 +840,12 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_stepmax_kernel(TnArgs a) {
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_final_kernel(TnArgs a, double* F) {
-    const int b = blockIdx.x * 32 + threadIdx.x;
+    const NodeLane nl = node_lane(a);
+    const int b = nl.b;
     if (b >= a.o.B) return;
-    if (blockIdx.y == 0 && threadIdx.y == 0) F[b] = a.F0[b];
+    if (blockIdx.y == 0 && threadIdx.y == 0 && nl.sub == 0) F[b] = a.F0[b];
     const int p0 = blockIdx.y * a.rows_per_chunk, p1 = min(a.o.P, p0 + a.rows_per_chunk);
-    for (int p = p0 + threadIdx.y; p < p1; p += OPT_WY) {
+    for (int p = p0 + threadIdx.y * nl.npw + nl.sub; p < p1; p += OPT_WY * nl.npw) {
         const size_t i = (size_t)p * a.o.B + b;
         a.X[i] = tplopt::to_param(p < a.o.nr, a.Z[i], a.sc[p]);
     }
