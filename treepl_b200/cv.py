@@ -274,8 +274,10 @@ def cross_validate(flat, smoothing_grid, groups, randomcv=False, device=0, log_p
     if opt.get("method", 1) == 1:
         err, res2 = None, None
         try:
-            Fcv, probes, _, oi = plp.optimize_batch_cols(Xfull, lane_k.astype(np.int32), lo, hi, probe_rows=rows, max_steps=20 * max_iter,
-                                                         date_scale=dscale, use_graph=1, **opt)
+            # only the columns this rank's vectors start from (never more columns than vectors)
+            used, col = np.unique(lane_k, return_inverse=True)
+            Fcv, probes, _, oi = plp.optimize_batch_cols(np.ascontiguousarray(Xfull[:, used]), col.astype(np.int32), lo, hi, probe_rows=rows,
+                                                         max_steps=20 * max_iter, date_scale=dscale, use_graph=1, **opt)
             bad = np.nonzero(oi["status"] == 4)[0]
             if bad.size:
                 raise ValueError("start point infeasible for vectors %s" % bad.tolist()[:8])
