@@ -26,8 +26,10 @@ def _engine(pr, flat):
 
 
 @pytest.mark.parametrize("name,lams,masked", [("test", [0.1, 10.0], False), ("M1155", [10.0, 0.1, 1000.0, 1.0], True),
-                                              ("big_test", [1.0] * 33, True)])
+                                              ("big_test", [1.0] * 33, True), ("M1155", [10.0, 0.1] * 20, True),
+                                              ("pl4203", [100.0] * 17, False)])
 def test_hessvec_kernel_equals_cpu_emulation(name, lams, masked):
+    """B <= 16: lane-packed tn_hv_kernel; B > 16: the tiled shared-memory kernel (tn_hv_tile_kernel)."""
     sim = TS.load_sim()
     flat = Golden(name).flat
     n = len(flat["parents"])
