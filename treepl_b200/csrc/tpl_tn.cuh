@@ -271,6 +271,61 @@ struct RecBase : DevView {
 };
 
 
+// diag_node for the ordinary node (same records and the same idea as hess_node_fast below: every row requested before the
+// first is used); same arithmetic, in the same order, as diag_node
+__device__ __forceinline__ void diag_node_fast(const TnArgs& a, const int4 q0, const int4 q1, const int4 q2, int B, int b, double lam) {
+    const int i = q0.x, rs = q0.y, ds = q0.z, pds = q1.y, nch = q1.z, p = q0.w;
+    const int ch[2] = {q2.x, q2.y}, cds[2] = {q2.z, q2.w};
+    const size_t Bs = (size_t)B;
+    bool mi = false, mc[2] = {false, false};
+    if (a.lanemask) {
+        const unsigned long long* mw = a.lanemask + (size_t)(b >> 6) * a.mask_stride;
+        const unsigned long long wi = mw[i], w0 = nch ? mw[ch[0]] : 0ull, w1 = nch ? mw[ch[1]] : 0ull;
+        mi = (wi >> (b & 63)) & 1ull; mc[0] = (w0 >> (b & 63)) & 1ull; mc[1] = (w1 >> (b & 63)) & 1ull;
+    }
+    const double r = a.X[(size_t)rs * Bs + b];
+    const double h = ds >= 0 ? a.X[(size_t)ds * Bs + b] : a.t.hfix[i];
+    const double hp = pds >= 0 ? a.X[(size_t)pds * Bs + b] : a.t.hfix[p];
+    double hc[2] = {0.0, 0.0}, cc[2] = {0.0, 0.0};
+    if (nch && ds >= 0) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            hc[k] = cds[k] >= 0 ? a.X[(size_t)cds[k] * Bs + b] : a.t.hfix[ch[k]];
+            cc[k] = a.t.c[ch[k]];
+        }
+    }
+    const double c = a.t.c[i];
+    const double gx = a.Gx[(size_t)rs * Bs + b];
+    const double sc_rs = a.sc[rs], sc_ds = ds >= 0 ? a.sc[ds] : 0.0;
+    const double pmn = ds >= 0 ? a.pmin_n[i] : -1.0, pmx = ds >= 0 ? a.pmax_n[i] : -1.0;
+    const bool rfree = !mi;
+    const double lam2 = 2.0 * lam;
+    double H_r = 0.0, H_h = 0.0;
+    if (!mi) {
+        const double d = safe_duration(hp - h);
+        H_r = c * tn_rcp(r * r);
+        H_h = c * tn_rcp(d * d);
+        H_r += lam2;
+    }
+    if (nch) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (mc[k]) continue;
+            if (ds >= 0) {
+                const double dc = safe_duration(h - hc[k]);
+                H_h += cc[k] * tn_rcp(dc * dc);
+            }
+            if (rfree) H_r += lam2;
+        }
+    }
+    if (ds >= 0) {
+        if (pmn != -1.0) { const double q = h - pmn; if (q > 0.0) H_h += a.pb * 2.0 / (q * q * q); }
+        if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) H_h += a.pb * 2.0 / (q * q * q); }
+    }
+    a.DG[(size_t)rs * Bs + b] = rfree ? sc_rs * sc_rs * r * r * H_r + gx * sc_rs * sc_rs * r : 0.0;
+    if (ds >= 0) a.DG[(size_t)ds * Bs + b] = sc_ds * sc_ds * H_h;
+}
+
 __global__ void __launch_bounds__(32 * OPT_WY) tn_diag_kernel(TnArgs a) {
     const NodeLane nl = node_lane(a);
     const int b = nl.b;
@@ -280,7 +335,12 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_diag_kernel(TnArgs a) {
     if (dec != DEC_ACCEPT && dec != DEC_INIT) return;
     DevView V = {a, B, b, a.Pv, a.DG, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, 0.0};
     const int i0 = blockIdx.y * a.nodes_per_chunk, i1 = min(a.t.n, i0 + a.nodes_per_chunk);
-    for (int i = i0 + threadIdx.y * nl.npw + nl.sub; i < i1; i += OPT_WY * nl.npw) diag_node(V, i);
+    const int4* recs = reinterpret_cast<const int4*>(a.hv_rec);
+    for (int i = i0 + threadIdx.y * nl.npw + nl.sub; i < i1; i += OPT_WY * nl.npw) {
+        const int4 q1 = __ldg(recs + 4 * (size_t)i + 1);
+        if (q1.w) diag_node_fast(a, __ldg(recs + 4 * (size_t)i), q1, __ldg(recs + 4 * (size_t)i + 2), B, b, V.lam);
+        else diag_node(V, i);
+    }
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_setup_kernel(TnArgs a) {
@@ -820,14 +880,20 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_stepmax_kernel(TnArgs a) {
     double v[1] = {1e300};
     if (active) {
         const int i0 = max(1, blockIdx.y * a.nodes_per_chunk), i1 = min(a.t.n, (blockIdx.y + 1) * a.nodes_per_chunk);
+        // index record first (node, parent and their date rows in one 32-byte load), then all four rows side by side
+        const int4* recs = reinterpret_cast<const int4*>(a.hv_rec);
+        const size_t Bs = (size_t)B;
         for (int i = i0 + ty * nl.npw + nl.sub; i < i1; i += OPT_WY * nl.npw) {
-            const int pa = a.t.parent[i];
-            const int ri = a.t.dslot[i], rp = a.t.dslot[pa];
-            double zi, di = 0.0, zp, dp = 0.0;
-            if (ri >= 0) { const double sc = a.sc[ri]; zi = a.Z[(size_t)ri * B + b] * sc; di = a.S[(size_t)ri * B + b] * sc; } else zi = a.t.hfix[i];
-            if (rp >= 0) { const double sc = a.sc[rp]; zp = a.Z[(size_t)rp * B + b] * sc; dp = a.S[(size_t)rp * B + b] * sc; } else zp = a.t.hfix[pa];
+            const int4 q0 = __ldg(recs + 4 * (size_t)i), q1 = __ldg(recs + 4 * (size_t)i + 1);
+            const int pa = q0.w, ri = q0.z, rp = q1.y;
+            const double z_i = ri >= 0 ? a.Z[(size_t)ri * Bs + b] : 0.0, s_i = ri >= 0 ? a.S[(size_t)ri * Bs + b] : 0.0;
+            const double z_p = rp >= 0 ? a.Z[(size_t)rp * Bs + b] : 0.0, s_p = rp >= 0 ? a.S[(size_t)rp * Bs + b] : 0.0;
+            const double sc_i = ri >= 0 ? a.sc[ri] : 0.0, sc_p = rp >= 0 ? a.sc[rp] : 0.0;
+            const double lo_i = ri >= 0 ? a.lo[ri] : 0.0, hi_i = ri >= 0 ? a.hi[ri] : 0.0;
+            const double zi = ri >= 0 ? z_i * sc_i : a.t.hfix[i], di = ri >= 0 ? s_i * sc_i : 0.0;
+            const double zp = rp >= 0 ? z_p * sc_p : a.t.hfix[pa], dp = rp >= 0 ? s_p * sc_p : 0.0;
             v[0] = fmin(v[0], tplopt::branch_step_limit(zi, di, zp, dp));
-            if (ri >= 0) v[0] = fmin(v[0], tplopt::bound_step_limit(a.Z[(size_t)ri * B + b], a.S[(size_t)ri * B + b], a.lo[ri], a.hi[ri]));
+            if (ri >= 0) v[0] = fmin(v[0], tplopt::bound_step_limit(z_i, s_i, lo_i, hi_i));
         }
         if (blockIdx.y == 0 && ty == 0 && nl.sub == 0) {            // the root's own date (no branch above it)
             const int r0 = a.t.dslot[0];
