@@ -880,20 +880,14 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_stepmax_kernel(TnArgs a) {
     double v[1] = {1e300};
     if (active) {
         const int i0 = max(1, blockIdx.y * a.nodes_per_chunk), i1 = min(a.t.n, (blockIdx.y + 1) * a.nodes_per_chunk);
-        // index record first (node, parent and their date rows in one 32-byte load), then all four rows side by side
-        const int4* recs = reinterpret_cast<const int4*>(a.hv_rec);
-        const size_t Bs = (size_t)B;
         for (int i = i0 + ty * nl.npw + nl.sub; i < i1; i += OPT_WY * nl.npw) {
-            const int4 q0 = __ldg(recs + 4 * (size_t)i), q1 = __ldg(recs + 4 * (size_t)i + 1);
-            const int pa = q0.w, ri = q0.z, rp = q1.y;
-            const double z_i = ri >= 0 ? a.Z[(size_t)ri * Bs + b] : 0.0, s_i = ri >= 0 ? a.S[(size_t)ri * Bs + b] : 0.0;
-            const double z_p = rp >= 0 ? a.Z[(size_t)rp * Bs + b] : 0.0, s_p = rp >= 0 ? a.S[(size_t)rp * Bs + b] : 0.0;
-            const double sc_i = ri >= 0 ? a.sc[ri] : 0.0, sc_p = rp >= 0 ? a.sc[rp] : 0.0;
-            const double lo_i = ri >= 0 ? a.lo[ri] : 0.0, hi_i = ri >= 0 ? a.hi[ri] : 0.0;
-            const double zi = ri >= 0 ? z_i * sc_i : a.t.hfix[i], di = ri >= 0 ? s_i * sc_i : 0.0;
-            const double zp = rp >= 0 ? z_p * sc_p : a.t.hfix[pa], dp = rp >= 0 ? s_p * sc_p : 0.0;
+            const int pa = a.t.parent[i];
+            const int ri = a.t.dslot[i], rp = a.t.dslot[pa];
+            double zi, di = 0.0, zp, dp = 0.0;
+            if (ri >= 0) { const double sc = a.sc[ri]; zi = a.Z[(size_t)ri * B + b] * sc; di = a.S[(size_t)ri * B + b] * sc; } else zi = a.t.hfix[i];
+            if (rp >= 0) { const double sc = a.sc[rp]; zp = a.Z[(size_t)rp * B + b] * sc; dp = a.S[(size_t)rp * B + b] * sc; } else zp = a.t.hfix[pa];
             v[0] = fmin(v[0], tplopt::branch_step_limit(zi, di, zp, dp));
-            if (ri >= 0) v[0] = fmin(v[0], tplopt::bound_step_limit(z_i, s_i, lo_i, hi_i));
+            if (ri >= 0) v[0] = fmin(v[0], tplopt::bound_step_limit(a.Z[(size_t)ri * B + b], a.S[(size_t)ri * B + b], a.lo[ri], a.hi[ri]));
         }
         if (blockIdx.y == 0 && ty == 0 && nl.sub == 0) {            // the root's own date (no branch above it)
             const int r0 = a.t.dslot[0];
