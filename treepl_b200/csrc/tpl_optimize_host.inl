@@ -309,7 +309,7 @@ void tn_launch_tree_solve(const tpltn::TnArgs& a, const std::vector<int>& loff, 
         const dim3 lg(groups, (a.t.n + TREE_NODES_PER_BLOCK - 1) / TREE_NODES_PER_BLOCK);
         if (groups < 32) tn_tree_local_kernel<true><<<lg, blk, 0, s>>>(a); else tn_tree_local_kernel<false><<<lg, blk, 0, s>>>(a);
     }
-    for (int l = 0; l < a.nlev_wide; l++) {
+    for (int l = factor ? 1 : 0; l < a.nlev_wide; l++) {      // a factorising sweep finishes level 0 (the tips) in the local kernel
         const dim3 g(groups, (loff[l + 1] - loff[l] + TREE_NODES_PER_BLOCK - 1) / TREE_NODES_PER_BLOCK);
         if (factor) tn_tree_up_kernel<true><<<g, blk, 0, s>>>(a, l); else tn_tree_up_kernel<false><<<g, blk, 0, s>>>(a, l);
     }
@@ -377,7 +377,7 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
         CK(cudaGetLastError());
         return TPL_OK;
     };
-    const int per_step = 7 + 3 * cg_per_step + (1 + cg_per_step) * tree_launches + (a.precond ? 1 : 0);
+    const int per_step = 7 + 3 * cg_per_step + (1 + cg_per_step) * tree_launches + (a.precond && a.nlev_wide == 0 ? 1 : 0);
     int steps = 0;
     int rc = one_step();               // first step outside any capture: sizes the evaluation work space
     if (rc != TPL_OK) return rc;

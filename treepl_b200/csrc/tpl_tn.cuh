@@ -19,7 +19,8 @@
 // Tree preconditioner (tpl_tn_core.h::tree_*_node; TnArgs::precond): zz = M^-1 r by one leaf-to-root and one root-to-leaf
 // sweep over HEIGHT levels (a node's children sit on lower levels; level sizes never increase): one launch per wide
 // level, and ONE block per 32-vector group for all the narrow top levels (block-level barriers between levels):
-//   tn_tree_local_kernel         FACTOR only, all nodes at once: the node's own block of H_z and its coupling with the parent
+//   tn_tree_local_kernel         FACTOR only, all nodes at once: the node's own block of H_z and its coupling with the parent;
+//                                for the childless nodes (level 0) also their pivot step and forward substitution
 //   tn_tree_up_kernel<FACTOR>    one wide level: [pivot step: S_i, K_i, T_i] + forward substitution
 //   tn_tree_top_kernel<FACTOR>   narrow levels: up to the root, then back down
 //   tn_tree_down_kernel<FACTOR>  one wide level: back substitution -> ZZ rows
@@ -742,13 +743,23 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_tree_local_kernel(TnArgs a) {
     if (!tree_lane_active<true>(a, b)) return;
     DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, tree_lane_mu<true>(a, b)};
     const int k0 = blockIdx.y * TREE_NODES_PER_BLOCK, k1 = min(a.t.n, k0 + TREE_NODES_PER_BLOCK);
+    // A node WITHOUT children (height level 0: the tips, half of the tree) depends on nobody: its pivot step and its forward
+    // substitution are finished right here, and the factorising sweep starts at level 1 (one launch less, and the largest).
     for (int k = k0 + threadIdx.y * nl.npw + nl.sub; k < k1; k += OPT_WY * nl.npw) {
         if (REC) {
             const TreeRec rec = tree_rec_load(a.lev_rec, k);
             LocalView L(V, rec);
             tree_local_node(L, rec.i);
+            if (rec.nch == 0) {
+                tree_pivot_node(L, rec.i);
+                tree_up_node(L, rec.i);
+            }
         } else {
             tree_local_node(V, k);
+            if (V.child_begin(k) == V.child_end(k)) {
+                tree_pivot_node(V, k);
+                tree_up_node(V, k);
+            }
         }
     }
 }
@@ -785,7 +796,7 @@ __global__ void __launch_bounds__(32 * TREE_TOP_WY) tn_tree_top_kernel(TnArgs a)
     DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[min(b, a.o.B - 1)] : a.lambda, a.pb, a.log_pen != 0,
                  active ? tree_lane_mu<FACTOR>(a, b) : 0.0};
     const int first = threadIdx.y * nl.npw + nl.sub, stride = TREE_TOP_WY * nl.npw;
-    for (int level = a.nlev_wide; level < a.nlev; level++) {
+    for (int level = max(a.nlev_wide, FACTOR ? 1 : 0); level < a.nlev; level++) {    // level 0 of a factorising sweep: tn_tree_local_kernel
         if (active)
             for (int k = a.lev_off[level] + first; k < a.lev_off[level + 1]; k += stride) tree_up_at<FACTOR>(a, V, k);
         __syncthreads();
