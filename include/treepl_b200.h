@@ -173,7 +173,9 @@ typedef struct tpl_opt_options {
                            * nearest zero-duration boundary (ratio test over the branches); 0 = 0.9, < 0 = off */
     int tree_wide_min;  /* method 1, tree preconditioner: a height level with at least this many nodes gets its own launch per
                          * sweep; the narrower levels above are walked inside one block per 32-vector group (0 = 64) */
-    int reserved;
+    int tree_coop;      /* method 1, tree preconditioner: the wide levels of a sweep run as ONE cooperative launch with grid
+                         * barriers between the levels (0 = where it was measured to pay: 16+ vectors in at most 6 groups of 32; 1 = always where
+                         * the device supports it; -1 = one launch per level) */
 } tpl_opt_options;
 
 typedef struct tpl_opt_result {

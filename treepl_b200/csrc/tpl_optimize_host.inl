@@ -287,6 +287,9 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
         // a level is worth its own launch when it fills the top kernel's block several times over: 16 warps x (nodes per warp)
         const int wide_min = o.tree_wide_min > 0 ? o.tree_wide_min : 4 * tpltn::TREE_TOP_WY * (32 >> a.pack_shift);
         while (a.nlev_wide < a.nlev && off[a.nlev_wide + 1] - off[a.nlev_wide] >= wide_min) a.nlev_wide++;
+        // measured (scratch A/B on one B200): the single launch wins 5-15 % where the sweeps are latency bound
+        // (16+ vectors in up to ~6 groups) and loses 1-7 % at 2-5 vectors and at 32+ groups, where a level fills the device anyway
+        a.coop_levels = o.tree_coop < 0 ? 0 : (o.tree_coop > 0 ? 1 : (B >= 16 && (B + 31) / 32 <= 6));
         // one index record per node, in level order: what the sweeps' record views load first (tpl_tn.cuh)
         std::vector<int> recs((size_t)n * tpltn::TREE_REC_INTS, -1);
         for (int k = 0; k < n; k++) tn_fill_record(e, nodes[k], recs.data() + (size_t)k * tpltn::TREE_REC_INTS);
@@ -301,29 +304,69 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
     return TPL_OK;
 }
 
-// zz = M^-1 r through the block-tree factorisation: wide levels one launch each, the narrow top in one block per group
-void tn_launch_tree_solve(const tpltn::TnArgs& a, const std::vector<int>& loff, int groups, cudaStream_t s, bool factor, bool finish) {
+// wide levels [l_first, l_last) of one sweep: ONE cooperative launch with grid barriers between the levels when the device
+// supports it (and there is more than one level), else one launch per level
+template <bool FACTOR, bool DOWN>
+int tn_launch_levels(const tpltn::TnArgs& a, const std::vector<int>& loff, int groups, int l_first, int l_last, cudaStream_t s) {
+    using namespace tpltn;
+    if (l_last <= l_first) return 0;
+    const dim3 blk(32, tplopt::OPT_WY);
+    static int resident = -1;                       // blocks of this kernel that fit the device at once (per instantiation)
+    static int coop = -1;
+    if (coop < 0) {
+        int dev = 0, sms = 0, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tn_tree_levels_kernel<FACTOR, DOWN>, 32 * tplopt::OPT_WY, 0);
+        resident = occ * sms;
+        if (resident < 1) coop = 0;
+    }
+    if (coop && a.coop_levels && l_last - l_first >= 2) {
+        const int npw = 32 >> a.pack_shift;
+        long long most = 1;
+        for (int l = l_first; l < l_last; l++) most = std::max(most, (long long)((loff[l + 1] - loff[l] + npw - 1) / npw) * groups);
+        const int blocks = (int)std::min<long long>(resident, (most + tplopt::OPT_WY - 1) / tplopt::OPT_WY);
+        TnArgs aa = a;
+        int lf = l_first, ll = l_last, gr = groups;
+        void* args[] = {&aa, &lf, &ll, &gr};
+        if (cudaLaunchCooperativeKernel((void*)tn_tree_levels_kernel<FACTOR, DOWN>, dim3(blocks), blk, args, 0, s) == cudaSuccess) return 1;
+        cudaGetLastError();
+        coop = 0;                                   // not launchable here: per-level launches from now on
+    }
+    for (int q = 0; q < l_last - l_first; q++) {
+        const int l = DOWN ? l_last - 1 - q : l_first + q;
+        const dim3 g(groups, (loff[l + 1] - loff[l] + TREE_NODES_PER_BLOCK - 1) / TREE_NODES_PER_BLOCK);
+        if (DOWN) tn_tree_down_kernel<FACTOR><<<g, blk, 0, s>>>(a, l);
+        else tn_tree_up_kernel<FACTOR><<<g, blk, 0, s>>>(a, l);
+    }
+    return l_last - l_first;
+}
+
+// zz = M^-1 r through the block-tree factorisation: the wide levels of a sweep in one cooperative launch (or one launch each), the
+// narrow top in one block per group.  -> number of launches
+int tn_launch_tree_solve(const tpltn::TnArgs& a, const std::vector<int>& loff, int groups, cudaStream_t s, bool factor, bool finish) {
     using namespace tpltn;
     const dim3 blk(32, tplopt::OPT_WY), tblk(32, TREE_TOP_WY);
+    int nl = 0;
     if (factor) {
         const dim3 lg(groups, (a.t.n + TREE_NODES_PER_BLOCK - 1) / TREE_NODES_PER_BLOCK);
         if (groups < 32) tn_tree_local_kernel<true><<<lg, blk, 0, s>>>(a); else tn_tree_local_kernel<false><<<lg, blk, 0, s>>>(a);
+        nl++;
     }
-    for (int l = factor ? 1 : 0; l < a.nlev_wide; l++) {      // a factorising sweep finishes level 0 (the tips) in the local kernel
-        const dim3 g(groups, (loff[l + 1] - loff[l] + TREE_NODES_PER_BLOCK - 1) / TREE_NODES_PER_BLOCK);
-        if (factor) tn_tree_up_kernel<true><<<g, blk, 0, s>>>(a, l); else tn_tree_up_kernel<false><<<g, blk, 0, s>>>(a, l);
-    }
+    // a factorising sweep finishes level 0 (the tips) in the local kernel
+    nl += factor ? tn_launch_levels<true, false>(a, loff, groups, 1, a.nlev_wide, s) : tn_launch_levels<false, false>(a, loff, groups, 0, a.nlev_wide, s);
     if (a.nlev > a.nlev_wide) {
         if (factor) tn_tree_top_kernel<true><<<groups, tblk, 0, s>>>(a); else tn_tree_top_kernel<false><<<groups, tblk, 0, s>>>(a);
+        nl++;
     }
-    for (int l = a.nlev_wide - 1; l >= 0; l--) {
-        const dim3 g(groups, (loff[l + 1] - loff[l] + TREE_NODES_PER_BLOCK - 1) / TREE_NODES_PER_BLOCK);
-        if (factor) tn_tree_down_kernel<true><<<g, blk, 0, s>>>(a, l); else tn_tree_down_kernel<false><<<g, blk, 0, s>>>(a, l);
-    }
+    nl += factor ? tn_launch_levels<true, true>(a, loff, groups, 0, a.nlev_wide, s) : tn_launch_levels<false, true>(a, loff, groups, 0, a.nlev_wide, s);
     if (finish) {
         const dim3 rgrd(groups, a.row_chunks);
         if (factor) tn_pc_finish_kernel<true><<<rgrd, blk, 0, s>>>(a); else tn_pc_finish_kernel<false><<<rgrd, blk, 0, s>>>(a);
+        nl++;
     }
+    return nl;
 }
 
 int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<double>& lo, const std::vector<double>& hi,
@@ -357,8 +400,8 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
     tn_trial_kernel<<<rgrd, blk, 0, s>>>(a);
     launches += 2;
     CK(cudaGetLastError());
-    const int tree_launches = a.precond ? 2 * a.nlev_wide + (a.nlev > a.nlev_wide ? 1 : 0) + 1 : 0;     // + 1 more (local blocks) when factorising
-    auto tree_solve = [&](bool factor) { tn_launch_tree_solve(a, w.tn_lev_off_host, groups, s, factor, true); };
+    int step_launches = 0;                                  // kernels of one optimiser step, counted while the first one is enqueued
+    auto tree_solve = [&](bool factor) { step_launches += tn_launch_tree_solve(a, w.tn_lev_off_host, groups, s, factor, true); };
     auto one_step = [&]() -> int {
         int rc = eval_device(e, B, a.X, const_cast<double*>(a.Ft), const_cast<double*>(a.Gx), mode, true, s);
         if (rc != TPL_OK) return rc;
@@ -377,10 +420,10 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
         CK(cudaGetLastError());
         return TPL_OK;
     };
-    const int per_step = 7 + 3 * cg_per_step + (1 + cg_per_step) * tree_launches + (a.precond && a.nlev_wide == 0 ? 1 : 0);
     int steps = 0;
     int rc = one_step();               // first step outside any capture: sizes the evaluation work space
     if (rc != TPL_OK) return rc;
+    const int per_step = 5 + e->last_launches + 3 * cg_per_step + step_launches;
     steps++;
     launches += per_step;
     GraphGuard gg(e);

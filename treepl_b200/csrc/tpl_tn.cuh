@@ -29,6 +29,8 @@
 // records through "record views" that fetch all operands of a node side by side, tn_hv_kernel has a hand-specialised fast
 // path on its own records, and with 16 or fewer vectors a warp carries several nodes at once (node_lane).  DESIGN.md 8.1.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "tpl_kernels.cuh"
 #include "tpl_lbfgs.cuh"
 #include "tpl_tn_core.h"
@@ -66,6 +68,7 @@ struct TnArgs {
     const int* lev_rec;                      // [n][TREE_REC_INTS] index record of node lev_nodes[k] (tpl_tn.cuh: record views)
     const int* hv_rec;                       // [n][HV_REC_INTS] index record of node i for hess_node_fast
     int nlev, nlev_wide;                     // levels [0, nlev_wide): one launch each; [nlev_wide, nlev): tn_tree_top_kernel
+    int coop_levels;                         // host side: the wide levels of a sweep run as ONE cooperative launch (tn_tree_levels_kernel)
     double *gmax_tmp, *gg_tmp;               // [B] reductions of the set-up pass kept until the solve has produced r.zz
     double* part_pc;
     int* cnt_pc;
@@ -162,8 +165,9 @@ struct DevView {
     __device__ double dg(int row) const { return a.DG[(size_t)row * B + b]; }
     __device__ bool fr(int row) const { return a.Minv[(size_t)row * B + b] > 0.0; }       // free variable of this solve
     __device__ double rhs(int row) const { return a.R[(size_t)row * B + b]; }
-    __device__ double outv(int row) const { return W[(size_t)row * B + b]; }
-    __device__ double tw(int q, int i) const { return a.TW[((size_t)q * a.t.n + i) * B + b]; }
+    // the sweeps read what OTHER blocks wrote earlier in the same (cooperative) launch: past L1
+    __device__ double outv(int row) const { return __ldcg(W + (size_t)row * B + b); }
+    __device__ double tw(int q, int i) const { return __ldcg(a.TW + ((size_t)q * a.t.n + i) * B + b); }
     __device__ void tw_put(int q, int i, double val) { a.TW[((size_t)q * a.t.n + i) * B + b] = val; }
     __device__ int parent(int i) const { return a.t.parent[i]; }
     __device__ int child_begin(int i) const { return a.t.child_off[i]; }
@@ -655,21 +659,21 @@ struct UpView : RecBase {
         rhs_ds = t.ds >= 0 ? a.R[(size_t)t.ds * Bs + b] : 0.0;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            k0[q] = h0 ? a.TW[((size_t)(TW_K + q) * n + t.ch0) * Bs + b] : 0.0;
-            k1[q] = h1 ? a.TW[((size_t)(TW_K + q) * n + t.ch1) * Bs + b] : 0.0;
+            k0[q] = h0 ? __ldcg(a.TW + ((size_t)(TW_K + q) * n + t.ch0) * Bs + b) : 0.0;
+            k1[q] = h1 ? __ldcg(a.TW + ((size_t)(TW_K + q) * n + t.ch1) * Bs + b) : 0.0;
         }
 #pragma unroll
         for (int q = 0; q < 2; q++) {
-            y0[q] = h0 ? a.TW[((size_t)(TW_Y + q) * n + t.ch0) * Bs + b] : 0.0;
-            y1[q] = h1 ? a.TW[((size_t)(TW_Y + q) * n + t.ch1) * Bs + b] : 0.0;
+            y0[q] = h0 ? __ldcg(a.TW + ((size_t)(TW_Y + q) * n + t.ch0) * Bs + b) : 0.0;
+            y1[q] = h1 ? __ldcg(a.TW + ((size_t)(TW_Y + q) * n + t.ch1) * Bs + b) : 0.0;
         }
         if (PIVOT) {
 #pragma unroll
-            for (int q = 0; q < 7; q++) loc[q] = a.TW[((size_t)(TW_L + q) * n + t.i) * Bs + b];
+            for (int q = 0; q < 7; q++) loc[q] = __ldcg(a.TW + ((size_t)(TW_L + q) * n + t.i) * Bs + b);
 #pragma unroll
             for (int q = 0; q < 3; q++) {
-                t0[q] = h0 ? a.TW[((size_t)(TW_T + q) * n + t.ch0) * Bs + b] : 0.0;
-                t1[q] = h1 ? a.TW[((size_t)(TW_T + q) * n + t.ch1) * Bs + b] : 0.0;
+                t0[q] = h0 ? __ldcg(a.TW + ((size_t)(TW_T + q) * n + t.ch0) * Bs + b) : 0.0;
+                t1[q] = h1 ? __ldcg(a.TW + ((size_t)(TW_T + q) * n + t.ch1) * Bs + b) : 0.0;
             }
         }
     }
@@ -700,13 +704,13 @@ struct DownView : RecBase {
     __device__ DownView(const DevView& v, const TreeRec& rec) : RecBase(v, rec) {
         const size_t Bs = (size_t)B, n = (size_t)a.t.n;
 #pragma unroll
-        for (int q = 0; q < 3; q++) sS[q] = a.TW[((size_t)(TW_S + q) * n + t.i) * Bs + b];
+        for (int q = 0; q < 3; q++) sS[q] = __ldcg(a.TW + ((size_t)(TW_S + q) * n + t.i) * Bs + b);
 #pragma unroll
-        for (int q = 0; q < 4; q++) sK[q] = a.TW[((size_t)(TW_K + q) * n + t.i) * Bs + b];
+        for (int q = 0; q < 4; q++) sK[q] = __ldcg(a.TW + ((size_t)(TW_K + q) * n + t.i) * Bs + b);
 #pragma unroll
-        for (int q = 0; q < 2; q++) sY[q] = a.TW[((size_t)(TW_Y + q) * n + t.i) * Bs + b];
-        o_prs = t.prs >= 0 ? W[(size_t)t.prs * Bs + b] : 0.0;
-        o_pds = t.pds >= 0 ? W[(size_t)t.pds * Bs + b] : 0.0;
+        for (int q = 0; q < 2; q++) sY[q] = __ldcg(a.TW + ((size_t)(TW_Y + q) * n + t.i) * Bs + b);
+        o_prs = t.prs >= 0 ? __ldcg(W + (size_t)t.prs * Bs + b) : 0.0;
+        o_pds = t.pds >= 0 ? __ldcg(W + (size_t)t.pds * Bs + b) : 0.0;
     }
     __device__ double outv(int row) const { return row == t.prs ? o_prs : (row == t.pds ? o_pds : DevView::outv(row)); }
     __device__ double tw(int q, int n) const {
@@ -784,6 +788,32 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_tree_down_kernel(TnArgs a, int
     const int k0 = a.lev_off[level] + blockIdx.y * TREE_NODES_PER_BLOCK;
     const int k1 = min(a.lev_off[level + 1], k0 + TREE_NODES_PER_BLOCK);
     for (int k = k0 + threadIdx.y * nl.npw + nl.sub; k < k1; k += OPT_WY * nl.npw) tree_down_at(a, V, k);
+}
+
+// SEVERAL wide levels in ONE cooperative launch, a grid-wide barrier between levels (2.7 us on a B200 with 1,184 blocks)
+// instead of a kernel boundary (10-12 us): the sweeps of a latency-bound optimiser step are 130 launches otherwise.
+// Work item = (32-vector group, warp-slot of the level's node list); items are dealt round-robin to all warps of the grid.
+// DOWN: levels l_last - 1 ... l_first, back substitution; otherwise l_first ... l_last - 1, [pivot +] forward substitution.
+template <bool FACTOR, bool DOWN>
+__global__ void __launch_bounds__(32 * OPT_WY) tn_tree_levels_kernel(TnArgs a, int l_first, int l_last, int groups) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int sh = a.pack_shift, npw = 32 >> sh, sub = threadIdx.x >> sh, bl = threadIdx.x & ((1 << sh) - 1);
+    const long long warp0 = (long long)blockIdx.x * OPT_WY + threadIdx.y, nwarps = (long long)gridDim.x * OPT_WY;
+    for (int s = 0; s < l_last - l_first; s++) {
+        const int level = DOWN ? l_last - 1 - s : l_first + s;
+        const int k0 = a.lev_off[level], k1 = a.lev_off[level + 1];
+        const long long items = (long long)((k1 - k0 + npw - 1) / npw) * groups;
+        for (long long it = warp0; it < items; it += nwarps) {
+            const int g = (int)(it % groups), k = k0 + (int)(it / groups) * npw + sub;
+            const int b = g * 32 + bl;
+            if (k < k1 && tree_lane_active<FACTOR>(a, b)) {
+                DevView V = {a, a.o.B, b, a.Pv, a.ZZ, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, tree_lane_mu<FACTOR>(a, b)};
+                if (DOWN) tree_down_at(a, V, k);
+                else tree_up_at<FACTOR>(a, V, k);
+            }
+        }
+        if (s + 1 < l_last - l_first) grid.sync();
+    }
 }
 
 // the narrow levels [nlev_wide, nlev): up to the root and back down inside one block per vector group
