@@ -176,6 +176,10 @@ typedef struct tpl_opt_options {
     int tree_coop;      /* method 1, tree preconditioner: the wide levels of a sweep run as ONE cooperative launch with grid
                          * barriers between the levels (0 = where it was measured to pay: 16+ vectors in at most 6 groups of 32; 1 = always where
                          * the device supports it; -1 = one launch per level) */
+    int hv_pipe;        /* method 1: Hessian-vector product through the software-pipelined kernel (operand rows staged in shared
+                         * memory by cp.async, three nodes per warp in flight) for batches of more than 16 vectors (0 = yes,
+                         * -1 = the register-staged kernel everywhere) */
+    int reserved;
 } tpl_opt_options;
 
 typedef struct tpl_opt_result {
@@ -236,7 +240,8 @@ int tpl_set_timing(tpl_engine* e, int on);
 int tpl_get_timing(tpl_engine* e, double* main_ms, double* finalize_ms);
 
 /* test hooks: pin the kernel generation (0 = automatic, 1 = generic "pull" kernel, 2 = shared-memory
- * tile kernel whenever it is legal), and report which one the last evaluation used              */
+ * tile kernel whenever it is legal; 5 = automatic generation, but the host-buffer pipeline of tpl_calc_pl_grad_batch in
+ * uniform 64-vector pieces), and report which one the last evaluation used              */
 int tpl_debug_force_kernel(tpl_engine* e, int generation);
 int tpl_last_kernel_generation(const tpl_engine* e);
 

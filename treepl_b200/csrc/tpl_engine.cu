@@ -248,6 +248,7 @@ struct tpl_engine {
         // truncated Newton
         DevBuf<double> R, ZZ, Pv, Hp, Minv, DG, pmin_n, pmax_n, tn_part, tn_lane_d;
         DevBuf<int> tn_lane_i, tn_lev_nodes, tn_lev_off, tn_lev_rec, tn_hv_rec, tn_cols, tn_probe_rows;
+        DevBuf<double> tn_hv_const;
         DevBuf<double> tn_tw;
         std::vector<int> tn_lev_off_host;
         // annealer
@@ -1109,8 +1110,25 @@ int tpl_calc_pl_grad_batch(tpl_engine* e, int B, const double* X, double* F, dou
         // 64-vector sub-batches (512-byte rows of the 2-D copies) measured best: 32 shortens the pipeline's fill and
         // drain but its 256-byte rows copy slower (14.4 k vs 16.5 k evals/s), 128 lengthens fill and drain (14.2 k).
         // Per-vector CV masks are addressed in 64-vector words, so masked batches never go below 64.
+        // (Half-size first and last pieces, to shorten the fill and drain, lose for the same reason: B = 256 15.8 k against 16.7 k.)
+        // A ragged tail shorter than 32 vectors would run the generic kernel: the last two pieces share the remainder instead.
         const int SB = 64;
-        const int nsub = (B + SB - 1) / SB;
+        std::vector<std::pair<int, int>> pieces;       // (first vector, vectors)
+        {
+            int off = 0;
+            while (B - off > 2 * SB) { pieces.emplace_back(off, SB); off += SB; }
+            const int rest = B - off;                  // 2 ... 128
+            const bool masked = e->cfg_mask && e->cfg_B == B;          // mask words cover 64 vectors: pieces start at multiples of 64
+            if (rest > SB && rest < SB + SB / 2 && !masked && e->force_gen != 5) {
+                const int first = ((rest / 2) + 1) & ~1;
+                pieces.emplace_back(off, first);
+                pieces.emplace_back(off + first, rest - first);
+            } else {
+                pieces.emplace_back(off, std::min(SB, rest));
+                if (rest > SB) pieces.emplace_back(off + SB, rest - SB);
+            }
+        }
+        const int nsub = (int)pieces.size();
         for (int k = 0; k < 3; k++) {
             if (!e->pstream[k]) CK(cudaStreamCreateWithFlags(&e->pstream[k], cudaStreamNonBlocking));
             CK(e->p_X[k].ensure((size_t)P * SB));
@@ -1123,8 +1141,8 @@ int tpl_calc_pl_grad_batch(tpl_engine* e, int B, const double* X, double* F, dou
         CK(cudaStreamSynchronize(e->stream));
         for (int sidx = 0; sidx < nsub; sidx++) {
             const int k = sidx % 3;
-            const int off = sidx * SB;
-            const int nl = std::min(SB, B - off);
+            const int off = pieces[sidx].first;
+            const int nl = pieces[sidx].second;
             cudaStream_t st = e->pstream[k];
             CK(cudaMemcpy2DAsync(e->p_X[k].p, (size_t)nl * 8, X + off, (size_t)B * 8, (size_t)nl * 8, P,
                                  cudaMemcpyHostToDevice, st));
@@ -1156,7 +1174,7 @@ int tpl_calc_pl_grad_batch(tpl_engine* e, int B, const double* X, double* F, dou
 }
 
 int tpl_debug_force_kernel(tpl_engine* e, int gen) {
-    if (!e || gen < 0 || gen > 4) return fail(TPL_ERR_ARG, "bad argument");
+    if (!e || gen < 0 || gen > 5) return fail(TPL_ERR_ARG, "bad argument");
     e->force_gen = gen;
     return TPL_OK;
 }

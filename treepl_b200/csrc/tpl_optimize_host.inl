@@ -148,10 +148,24 @@ static void tn_fill_record(const tpl_engine* e, int i, int* r) {
 }
 
 // work space, tree operands and chunking of the truncated-Newton kernels; uploads lo / hi / sc and X
+// tn_hv_pipe_kernel needs 105 KB of dynamic shared memory per block: opt in once per process
+bool tn_hv_pipe_ready() {
+    static int ok = -1;
+    if (ok < 0) ok = cudaFuncSetAttribute(tpltn::tn_hv_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tpltn::HVP_SMEM) == cudaSuccess ? 1 : 0;
+    if (!ok) cudaGetLastError();
+    return ok == 1;
+}
+// Hp = H p: the software-pipelined kernel for full 32-vector groups, the register-staged one for packed lanes (B <= 16)
+void tn_launch_hv(const tpltn::TnArgs& a, dim3 ngrd, dim3 blk, cudaStream_t s) {
+    if (a.hv_pipe) tpltn::tn_hv_pipe_kernel<<<ngrd, blk, tpltn::HVP_SMEM, s>>>(a);
+    else tpltn::tn_hv_kernel<<<ngrd, blk, 0, s>>>(a);
+}
+
 int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>& lo, const std::vector<double>& hi,
                const std::vector<double>& sc, int nr, const tpl_opt_options& o, tpltn::TnArgs& a, const ColsIO* io = nullptr) {
     using namespace tpltn;
     if (e->lf_mode) return fail(TPL_ERR_ARG, "truncated Newton needs the PL layout (one rate per branch)");
+    if ((double)e->numparams * (double)B >= 4.0e9) return fail(TPL_ERR_ARG, "truncated Newton: P * B must stay below 2^32 elements (32-bit element offsets in the node kernels)");
     if (e->cv_any) return fail(TPL_ERR_ARG, "truncated Newton takes CV masks per vector (tpl_batch_configure), not set_cv_nodes");
     const int P = e->numparams, n = e->n;
     const size_t PB = (size_t)P * B;
@@ -261,6 +275,35 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
             r[7] = fast ? 1 : 0;
         }
         CK(w.tn_hv_rec.upload(hrec, s));
+        // constant record of the same nodes for tn_hv_pipe_kernel (one 128-byte fetch instead of ~13 dependent broadcast loads):
+        // scales of the eight rows (a fixed date in the place of the scale of a date row that does not exist), c of the node and
+        // of its children, calibration penalties
+        a.hv_const = nullptr;
+        a.hv_pipe = 0;
+        if (o.hv_pipe >= 0 && a.pack_shift == 5 && tn_hv_pipe_ready()) {
+            std::vector<double> hc((size_t)n * tpltn::HV_CONST, 0.0);
+            for (int i = 0; i < n; i++) {
+                const int* r = hrec.data() + (size_t)i * tpltn::HV_REC_INTS;
+                if (!r[7]) continue;
+                double* q = hc.data() + (size_t)i * tpltn::HV_CONST;
+                const int pa = r[3];
+                q[0] = sc[r[1]];
+                q[1] = r[2] >= 0 ? sc[r[2]] : e->dates[i];
+                q[2] = sc[r[4]];
+                q[3] = r[5] >= 0 ? sc[r[5]] : e->dates[pa];
+                for (int j = 0; j < 2 && j < r[6]; j++) {
+                    q[4 + 2 * j] = sc[r[12 + j]];
+                    q[5 + 2 * j] = r[10 + j] >= 0 ? sc[r[10 + j]] : e->dates[r[8 + j]];
+                    q[9 + j] = e->c[r[8 + j]];
+                }
+                q[8] = e->c[i];
+                q[11] = e->pen_min[i];
+                q[12] = e->pen_max[i];
+            }
+            CK(w.tn_hv_const.upload(hc, s));
+            a.hv_const = w.tn_hv_const.p;
+            a.hv_pipe = 1;
+        }
         CK(cudaStreamSynchronize(s));
         a.hv_rec = w.tn_hv_rec.p;
     }
@@ -409,7 +452,7 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
         tn_setup_kernel<<<rgrd, blk, 0, s>>>(a);
         if (a.precond) tree_solve(true);
         for (int k = 0; k < cg_per_step; k++) {
-            tn_hv_kernel<<<ngrd, blk, 0, s>>>(a);
+            tn_launch_hv(a, ngrd, blk, s);
             tn_update_kernel<<<rgrd, blk, 0, s>>>(a);
             if (a.precond) tree_solve(false);
             tn_dir_kernel<<<rgrd, blk, 0, s>>>(a);
@@ -720,7 +763,7 @@ extern "C" int tpl_debug_hessvec(tpl_engine* e, int B, const double* X, const do
     tn_diag_kernel<<<ngrd, blk, 0, s>>>(a);                     // st = TS_INIT and a finite objective: every vector "accepts"
     std::vector<int> cg(B, TS_CG);
     CK(cudaMemcpyAsync(a.st, cg.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
-    tn_hv_kernel<<<ngrd, blk, 0, s>>>(a);
+    tn_launch_hv(a, ngrd, blk, s);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(W, w.Hp.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(DG, w.DG.p, sizeof(double) * PB, cudaMemcpyDeviceToHost, s));

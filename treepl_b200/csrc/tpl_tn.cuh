@@ -67,6 +67,8 @@ struct TnArgs {
     const int* lev_off;                      // [nlev + 1]
     const int* lev_rec;                      // [n][TREE_REC_INTS] index record of node lev_nodes[k] (tpl_tn.cuh: record views)
     const int* hv_rec;                       // [n][HV_REC_INTS] index record of node i for hess_node_fast
+    int hv_pipe;                             // host side: tn_hv_pipe_kernel instead of tn_hv_kernel
+    const double* hv_const;                  // [n][HV_CONST] per-node constants of tn_hv_pipe_kernel (scales, c, calibration penalties, fixed dates)
     int nlev, nlev_wide;                     // levels [0, nlev_wide): one launch each; [nlev_wide, nlev): tn_tree_top_kernel
     int coop_levels;                         // host side: the wide levels of a sweep run as ONE cooperative launch (tn_tree_levels_kernel)
     double *gmax_tmp, *gg_tmp;               // [B] reductions of the set-up pass kept until the solve has produced r.zz
@@ -162,13 +164,15 @@ struct DevView {
     double lam, pb;
     bool log_pen;
     double mu;                                   // Levenberg-Marquardt damping of this vector
-    __device__ double dg(int row) const { return a.DG[(size_t)row * B + b]; }
-    __device__ bool fr(int row) const { return a.Minv[(size_t)row * B + b] > 0.0; }       // free variable of this solve
-    __device__ double rhs(int row) const { return a.R[(size_t)row * B + b]; }
+    // element offset in a [P][B] plane: 32-bit (tn_prepare refuses P * B >= 2^32), one IMAD instead of a 64-bit multiply-add chain
+    __device__ unsigned ix(int row) const { return (unsigned)row * (unsigned)B + (unsigned)b; }
+    __device__ double dg(int row) const { return a.DG[ix(row)]; }
+    __device__ bool fr(int row) const { return a.Minv[ix(row)] > 0.0; }       // free variable of this solve
+    __device__ double rhs(int row) const { return a.R[ix(row)]; }
     // the sweeps read what OTHER blocks wrote earlier in the same (cooperative) launch: past L1
-    __device__ double outv(int row) const { return __ldcg(W + (size_t)row * B + b); }
-    __device__ double tw(int q, int i) const { return __ldcg(a.TW + ((size_t)q * a.t.n + i) * B + b); }
-    __device__ void tw_put(int q, int i, double val) { a.TW[((size_t)q * a.t.n + i) * B + b] = val; }
+    __device__ double outv(int row) const { return __ldcg(W + ix(row)); }
+    __device__ double tw(int q, int i) const { return __ldcg(a.TW + (size_t)q * ((size_t)a.t.n * B) + ix(i)); }
+    __device__ void tw_put(int q, int i, double val) { a.TW[(size_t)q * ((size_t)a.t.n * B) + ix(i)] = val; }
     __device__ int parent(int i) const { return a.t.parent[i]; }
     __device__ int child_begin(int i) const { return a.t.child_off[i]; }
     __device__ int child_end(int i) const { return a.t.child_off[i + 1]; }
@@ -185,10 +189,10 @@ struct DevView {
         return (a.lanemask[(size_t)(b >> 6) * a.mask_stride + i] >> (b & 63)) & 1ull;
     }
     __device__ double sc(int row) const { return a.sc[row]; }
-    __device__ double x(int row) const { return a.X[(size_t)row * B + b]; }
-    __device__ double v(int row) const { return Vv[(size_t)row * B + b]; }
-    __device__ double gx(int row) const { return a.Gx[(size_t)row * B + b]; }
-    __device__ void put(int row, double val) { W[(size_t)row * B + b] = val; }
+    __device__ double x(int row) const { return a.X[ix(row)]; }
+    __device__ double v(int row) const { return Vv[ix(row)]; }
+    __device__ double gx(int row) const { return a.Gx[ix(row)]; }
+    __device__ void put(int row, double val) { W[ix(row)] = val; }
 };
 
 __device__ __forceinline__ int lane_decision(const TnArgs& a, int b) {
@@ -288,19 +292,19 @@ __device__ __forceinline__ void diag_node_fast(const TnArgs& a, const int4 q0, c
         const unsigned long long wi = mw[i], w0 = nch ? mw[ch[0]] : 0ull, w1 = nch ? mw[ch[1]] : 0ull;
         mi = (wi >> (b & 63)) & 1ull; mc[0] = (w0 >> (b & 63)) & 1ull; mc[1] = (w1 >> (b & 63)) & 1ull;
     }
-    const double r = a.X[(size_t)rs * Bs + b];
-    const double h = ds >= 0 ? a.X[(size_t)ds * Bs + b] : a.t.hfix[i];
-    const double hp = pds >= 0 ? a.X[(size_t)pds * Bs + b] : a.t.hfix[p];
+    const double r = a.X[(unsigned)rs * (unsigned)B + (unsigned)b];
+    const double h = ds >= 0 ? a.X[(unsigned)ds * (unsigned)B + (unsigned)b] : a.t.hfix[i];
+    const double hp = pds >= 0 ? a.X[(unsigned)pds * (unsigned)B + (unsigned)b] : a.t.hfix[p];
     double hc[2] = {0.0, 0.0}, cc[2] = {0.0, 0.0};
     if (nch && ds >= 0) {
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            hc[k] = cds[k] >= 0 ? a.X[(size_t)cds[k] * Bs + b] : a.t.hfix[ch[k]];
+            hc[k] = cds[k] >= 0 ? a.X[(unsigned)cds[k] * (unsigned)B + (unsigned)b] : a.t.hfix[ch[k]];
             cc[k] = a.t.c[ch[k]];
         }
     }
     const double c = a.t.c[i];
-    const double gx = a.Gx[(size_t)rs * Bs + b];
+    const double gx = a.Gx[(unsigned)rs * (unsigned)B + (unsigned)b];
     const double sc_rs = a.sc[rs], sc_ds = ds >= 0 ? a.sc[ds] : 0.0;
     const double pmn = ds >= 0 ? a.pmin_n[i] : -1.0, pmx = ds >= 0 ? a.pmax_n[i] : -1.0;
     const bool rfree = !mi;
@@ -327,8 +331,8 @@ __device__ __forceinline__ void diag_node_fast(const TnArgs& a, const int4 q0, c
         if (pmn != -1.0) { const double q = h - pmn; if (q > 0.0) H_h += a.pb * 2.0 / (q * q * q); }
         if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) H_h += a.pb * 2.0 / (q * q * q); }
     }
-    a.DG[(size_t)rs * Bs + b] = rfree ? sc_rs * sc_rs * r * r * H_r + gx * sc_rs * sc_rs * r : 0.0;
-    if (ds >= 0) a.DG[(size_t)ds * Bs + b] = sc_ds * sc_ds * H_h;
+    a.DG[(unsigned)rs * (unsigned)B + (unsigned)b] = rfree ? sc_rs * sc_rs * r * r * H_r + gx * sc_rs * sc_rs * r : 0.0;
+    if (ds >= 0) a.DG[(unsigned)ds * (unsigned)B + (unsigned)b] = sc_ds * sc_ds * H_h;
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_diag_kernel(TnArgs a) {
@@ -404,77 +408,52 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_setup_kernel(TnArgs a) {
 // kernel (long-scoreboard stalls, 0.26-0.47 of the HBM rate).  Same arithmetic, in the same order, as hess_node.
 constexpr int HV_REC_INTS = 16;              // i rs ds p | prs pds nch fast | ch0 ch1 cds0 cds1 | crs0 crs1 - -
 
-__device__ __forceinline__ void hess_node_fast(const TnArgs& a, const int4 q0, const int4 q1, const int4 q2, const int4 q3, int B, int b,
-                                               double lam, double mu, double& vw, double& vv) {
-    const int i = q0.x, rs = q0.y, ds = q0.z, p = q0.w, prs = q1.x, pds = q1.y, nch = q1.z;
-    const int ch[2] = {q2.x, q2.y}, cds[2] = {q2.z, q2.w}, crs[2] = {q3.x, q3.y};
-    const size_t Bs = (size_t)B;
-    const double* __restrict__ X = a.X;
-    const double* __restrict__ Pv = a.Pv;
-    // ---- every load first ----
-    bool mi = false, mp = false, mc[2] = {false, false};
-    if (a.lanemask) {
-        const unsigned long long* mw = a.lanemask + (size_t)(b >> 6) * a.mask_stride;
-        const unsigned long long wi = mw[i], wp = mw[p], w0 = nch ? mw[ch[0]] : 0ull, w1 = nch ? mw[ch[1]] : 0ull;
-        mi = (wi >> (b & 63)) & 1ull; mp = (wp >> (b & 63)) & 1ull; mc[0] = (w0 >> (b & 63)) & 1ull; mc[1] = (w1 >> (b & 63)) & 1ull;
-    }
-    const double r = X[(size_t)rs * Bs + b], v_rs = Pv[(size_t)rs * Bs + b];
-    const double h = ds >= 0 ? X[(size_t)ds * Bs + b] : a.t.hfix[i];
-    const double v_ds = ds >= 0 ? Pv[(size_t)ds * Bs + b] : 0.0;
-    const double rp = X[(size_t)prs * Bs + b], v_prs = Pv[(size_t)prs * Bs + b];
-    const double hp = pds >= 0 ? X[(size_t)pds * Bs + b] : a.t.hfix[p];
-    const double v_pds = pds >= 0 ? Pv[(size_t)pds * Bs + b] : 0.0;
-    double rc[2] = {0.0, 0.0}, hc[2] = {0.0, 0.0}, v_crs[2] = {0.0, 0.0}, v_cds[2] = {0.0, 0.0}, cc[2] = {0.0, 0.0}, sc_crs[2] = {0.0, 0.0}, sc_cds[2] = {0.0, 0.0};
-    if (nch) {
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            rc[k] = X[(size_t)crs[k] * Bs + b];
-            v_crs[k] = Pv[(size_t)crs[k] * Bs + b];
-            hc[k] = cds[k] >= 0 ? X[(size_t)cds[k] * Bs + b] : a.t.hfix[ch[k]];
-            v_cds[k] = cds[k] >= 0 ? Pv[(size_t)cds[k] * Bs + b] : 0.0;
-            cc[k] = a.t.c[ch[k]];
-            sc_crs[k] = a.sc[crs[k]];
-            sc_cds[k] = cds[k] >= 0 ? a.sc[cds[k]] : 0.0;
-        }
-    }
-    const double sc_rs = a.sc[rs], sc_ds = ds >= 0 ? a.sc[ds] : 0.0, sc_prs = a.sc[prs], sc_pds = pds >= 0 ? a.sc[pds] : 0.0;
-    const double c = a.t.c[i];
-    const double gx = a.Gx[(size_t)rs * Bs + b];
+// everything hess_node reads for an ordinary node and one vector
+struct HvOperands {
+    double r, v_rs, h, v_ds, rp, v_prs, hp, v_pds;
+    double rc[2], hc[2], v_crs[2], v_cds[2], cc[2], sc_crs[2], sc_cds[2];
+    double sc_rs, sc_ds, sc_prs, sc_pds, c, gx, dg_rs, dg_ds, pmn, pmx;
+    bool mi, mp, mc[2];
+};
+
+// hess_node on loaded operands: same arithmetic, in the same order.  rs / ds: the node's own rows (ds < 0: no date row);
+// pds, cds: only their sign is used.  -> Hp rows written, vw = v.Hv and vv = v.v contributions returned.
+// Element offsets row * B + b are 32-bit here (tn_prepare refuses P * B >= 2^32: eleven such planes do not fit any GPU).
+__device__ __forceinline__ void hess_node_fast_math(const TnArgs& a, const HvOperands& o, int rs, int ds, int pds, int nch, int cds0, int cds1,
+                                                    unsigned Bs, unsigned b, double lam, double mu, double& vw, double& vv) {
+    const int cds[2] = {cds0, cds1};
     const bool damp = mu > 0.0;
-    const double dg_rs = damp ? a.DG[(size_t)rs * Bs + b] : 0.0, dg_ds = (damp && ds >= 0) ? a.DG[(size_t)ds * Bs + b] : 0.0;
-    const double pmn = ds >= 0 ? a.pmin_n[i] : -1.0, pmx = ds >= 0 ? a.pmax_n[i] : -1.0;
-    // ---- hess_node, same order of operations ----
-    const bool rfree = !mi;
+    const bool rfree = !o.mi;
     const double lam2 = 2.0 * lam;
-    const double vr = rfree ? sc_rs * r * v_rs : 0.0;
-    const double vh = ds >= 0 ? sc_ds * v_ds : 0.0;
+    const double vr = rfree ? o.sc_rs * o.r * o.v_rs : 0.0;
+    const double vh = ds >= 0 ? o.sc_ds * o.v_ds : 0.0;
     double w_r = 0.0, w_h = 0.0;
-    if (!mi) {
-        const double vrp = !mp ? sc_prs * rp * v_prs : 0.0;
-        const double vhp = pds >= 0 ? sc_pds * v_pds : 0.0;
-        const double d = safe_duration(hp - h);
+    if (!o.mi) {
+        const double vrp = !o.mp ? o.sc_prs * o.rp * o.v_prs : 0.0;
+        const double vhp = pds >= 0 ? o.sc_pds * o.v_pds : 0.0;
+        const double d = safe_duration(o.hp - o.h);
         const double dv = vhp - vh;
-        w_r = (c * tn_rcp(r * r)) * vr + dv;
-        w_h = -((c * tn_rcp(d * d)) * dv + vr);
+        w_r = (o.c * tn_rcp(o.r * o.r)) * vr + dv;
+        w_h = -((o.c * tn_rcp(d * d)) * dv + vr);
         w_r += lam2 * (vr - vrp);
     }
     if (nch) {
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            if (mc[k]) continue;
-            const double vrc = sc_crs[k] * rc[k] * v_crs[k];
-            const double vhc = cds[k] >= 0 ? sc_cds[k] * v_cds[k] : 0.0;
+            if (o.mc[k]) continue;
+            const double vrc = o.sc_crs[k] * o.rc[k] * o.v_crs[k];
+            const double vhc = cds[k] >= 0 ? o.sc_cds[k] * o.v_cds[k] : 0.0;
             if (ds >= 0) {
-                const double dc = safe_duration(h - hc[k]);
-                w_h += (cc[k] * tn_rcp(dc * dc)) * (vh - vhc) + vrc;
+                const double dc = safe_duration(o.h - o.hc[k]);
+                w_h += (o.cc[k] * tn_rcp(dc * dc)) * (vh - vhc) + vrc;
             }
             if (rfree) w_r -= lam2 * (vrc - vr);
         }
     }
     if (ds >= 0) {
         double bar = 0.0;
-        if (pmn != -1.0) { const double q = h - pmn; if (q > 0.0) bar += 2.0 / (q * q * q); }
-        if (pmx != -1.0) { const double q = pmx - h; if (q > 0.0) bar += 2.0 / (q * q * q); }
+        if (o.pmn != -1.0) { const double q = o.h - o.pmn; if (q > 0.0) bar += 2.0 / (q * q * q); }
+        if (o.pmx != -1.0) { const double q = o.pmx - o.h; if (q > 0.0) bar += 2.0 / (q * q * q); }
         w_h += a.pb * bar * vh;
     }
     vw = 0.0;
@@ -482,20 +461,64 @@ __device__ __forceinline__ void hess_node_fast(const TnArgs& a, const int4 q0, c
     {
         double W = 0.0;
         if (rfree) {
-            W = sc_rs * r * w_r + gx * sc_rs * sc_rs * r * v_rs;
-            if (damp) W += mu * fabs(dg_rs) * v_rs;
-            vw += v_rs * W;
-            vv += v_rs * v_rs;
+            W = o.sc_rs * o.r * w_r + o.gx * o.sc_rs * o.sc_rs * o.r * o.v_rs;
+            if (damp) W += mu * fabs(o.dg_rs) * o.v_rs;
+            vw += o.v_rs * W;
+            vv += o.v_rs * o.v_rs;
         }
-        a.Hp[(size_t)rs * Bs + b] = W;
+        a.Hp[(unsigned)rs * Bs + b] = W;
     }
     if (ds >= 0) {
-        double W = sc_ds * w_h;
-        if (damp) W += mu * fabs(dg_ds) * v_ds;
-        vw += v_ds * W;
-        vv += v_ds * v_ds;
-        a.Hp[(size_t)ds * Bs + b] = W;
+        double W = o.sc_ds * w_h;
+        if (damp) W += mu * fabs(o.dg_ds) * o.v_ds;
+        vw += o.v_ds * W;
+        vv += o.v_ds * o.v_ds;
+        a.Hp[(unsigned)ds * Bs + b] = W;
     }
+}
+
+__device__ __forceinline__ void hess_node_fast(const TnArgs& a, const int4 q0, const int4 q1, const int4 q2, const int4 q3, int B, int b,
+                                               double lam, double mu, double& vw, double& vv) {
+    const int i = q0.x, rs = q0.y, ds = q0.z, p = q0.w, prs = q1.x, pds = q1.y, nch = q1.z;
+    const int ch[2] = {q2.x, q2.y}, cds[2] = {q2.z, q2.w}, crs[2] = {q3.x, q3.y};
+    const unsigned Bs = (unsigned)B, bu = (unsigned)b;
+    const double* __restrict__ X = a.X;
+    const double* __restrict__ Pv = a.Pv;
+    HvOperands o;
+    // ---- every load first ----
+    o.mi = false; o.mp = false; o.mc[0] = o.mc[1] = false;
+    if (a.lanemask) {
+        const unsigned long long* mw = a.lanemask + (size_t)(b >> 6) * a.mask_stride;
+        const unsigned long long wi = mw[i], wp = mw[p], w0 = nch ? mw[ch[0]] : 0ull, w1 = nch ? mw[ch[1]] : 0ull;
+        o.mi = (wi >> (b & 63)) & 1ull; o.mp = (wp >> (b & 63)) & 1ull; o.mc[0] = (w0 >> (b & 63)) & 1ull; o.mc[1] = (w1 >> (b & 63)) & 1ull;
+    }
+    o.r = X[(unsigned)rs * Bs + bu]; o.v_rs = Pv[(unsigned)rs * Bs + bu];
+    o.h = ds >= 0 ? X[(unsigned)ds * Bs + bu] : a.t.hfix[i];
+    o.v_ds = ds >= 0 ? Pv[(unsigned)ds * Bs + bu] : 0.0;
+    o.rp = X[(unsigned)prs * Bs + bu]; o.v_prs = Pv[(unsigned)prs * Bs + bu];
+    o.hp = pds >= 0 ? X[(unsigned)pds * Bs + bu] : a.t.hfix[p];
+    o.v_pds = pds >= 0 ? Pv[(unsigned)pds * Bs + bu] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) { o.rc[k] = o.hc[k] = o.v_crs[k] = o.v_cds[k] = o.cc[k] = o.sc_crs[k] = o.sc_cds[k] = 0.0; }
+    if (nch) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            o.rc[k] = X[(unsigned)crs[k] * Bs + bu];
+            o.v_crs[k] = Pv[(unsigned)crs[k] * Bs + bu];
+            o.hc[k] = cds[k] >= 0 ? X[(unsigned)cds[k] * Bs + bu] : a.t.hfix[ch[k]];
+            o.v_cds[k] = cds[k] >= 0 ? Pv[(unsigned)cds[k] * Bs + bu] : 0.0;
+            o.cc[k] = a.t.c[ch[k]];
+            o.sc_crs[k] = a.sc[crs[k]];
+            o.sc_cds[k] = cds[k] >= 0 ? a.sc[cds[k]] : 0.0;
+        }
+    }
+    o.sc_rs = a.sc[rs]; o.sc_ds = ds >= 0 ? a.sc[ds] : 0.0; o.sc_prs = a.sc[prs]; o.sc_pds = pds >= 0 ? a.sc[pds] : 0.0;
+    o.c = a.t.c[i];
+    o.gx = a.Gx[(unsigned)rs * Bs + bu];
+    const bool damp = mu > 0.0;
+    o.dg_rs = damp ? a.DG[(unsigned)rs * Bs + bu] : 0.0; o.dg_ds = (damp && ds >= 0) ? a.DG[(unsigned)ds * Bs + bu] : 0.0;
+    o.pmn = ds >= 0 ? a.pmin_n[i] : -1.0; o.pmx = ds >= 0 ? a.pmax_n[i] : -1.0;
+    hess_node_fast_math(a, o, rs, ds, pds, nch, cds[0], cds[1], Bs, bu, lam, mu, vw, vv);
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
@@ -516,11 +539,11 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
         const int istep = OPT_WY * nl.npw;
         int i = i0 + ty * nl.npw + nl.sub;
         int4 n0, n1, n2, n3;
-        if (i < i1) { n0 = __ldg(recs + 4 * (size_t)i); n1 = __ldg(recs + 4 * (size_t)i + 1); n2 = __ldg(recs + 4 * (size_t)i + 2); n3 = __ldg(recs + 4 * (size_t)i + 3); }
+        if (i < i1) { n0 = __ldg(recs + 4 * (unsigned)i); n1 = __ldg(recs + 4 * (unsigned)i + 1); n2 = __ldg(recs + 4 * (unsigned)i + 2); n3 = __ldg(recs + 4 * (unsigned)i + 3); }
         for (; i < i1; i += istep) {
             const int4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
             const int inext = i + istep;
-            if (inext < i1) { n0 = __ldg(recs + 4 * (size_t)inext); n1 = __ldg(recs + 4 * (size_t)inext + 1); n2 = __ldg(recs + 4 * (size_t)inext + 2); n3 = __ldg(recs + 4 * (size_t)inext + 3); }
+            if (inext < i1) { n0 = __ldg(recs + 4 * (unsigned)inext); n1 = __ldg(recs + 4 * (unsigned)inext + 1); n2 = __ldg(recs + 4 * (unsigned)inext + 2); n3 = __ldg(recs + 4 * (unsigned)inext + 3); }
             double vw, vv;
             if (q1.w) hess_node_fast(a, q0, q1, q2, q3, B, b, V.lam, V.mu, vw, vv);
             else hess_node(V, i, vw, vv);
@@ -530,6 +553,156 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_hv_kernel(TnArgs a) {
     }
     if (!group_reduce<2, 0u, 0u>(v, a.part_hv, a.cnt_hv, B, b, a.pack_shift)) return;
     if (ty == 0 && nl.sub == 0 && active) phase_hv(lane_of(a, b), v, a.o);
+}
+
+// ---- tn_hv_pipe_kernel: the same product with the operand rows staged ASYNCHRONOUSLY in shared memory ----
+// tn_hv_kernel keeps one node per warp in flight: record -> ~19 row loads held in registers -> ~100 dependent fp64 instructions,
+// 16 warps per SM at 118 registers; its rate is warps in flight / latency of that chain (0.31-0.33 of the HBM rate at 64 vectors
+// on the 100k-tip tree).  Here every warp runs its own software pipeline with cp.async: while it computes node k from shared
+// memory, the operand rows of nodes k+1 and k+2 and the records of node k+3 are on the wire - three times the bytes in flight
+// per SM without a register to hold them.  A lane copies, and later reads, only its own vector's 8 bytes of each row, so the row
+// ring needs no barrier at all; the per-node records (64-byte index record, 128-byte constant record built by the host, four
+// CV-mask words) are copied by the first lanes and read by all after cp.async.wait_group + __syncwarp.
+//   ring per warp: 3 row slots x 16 rows x 32 lanes x 8 B + 4 record slots x 224 B = 13,184 B; 8 warps = 105,472 B per block,
+//   two blocks per SM.  Groups are committed in the order R(k+3), W(k+2) per iteration, so "wait_group 2" at the top of
+//   iteration k has R(k+2) and W(k) complete and leaves W(k+1), R(k+3) (and then W(k+2)) pending.
+// Nodes outside the fast path (root, its children, polytomies) take hess_node on global memory as before.
+constexpr int HV_CONST = 16;                 // sc_rs, sc_ds|hfix_i, sc_prs, sc_pds|hfix_p, sc_crs0, sc_cds0|hfix_c0, sc_crs1, sc_cds1|hfix_c1, c, cc0, cc1, pmn, pmx
+constexpr int HVP_ROWS = 16, HVP_WSLOTS = 3, HVP_RSLOTS = 4;
+constexpr int HVP_REC_BYTES = HV_REC_INTS * 4 + HV_CONST * 8 + 32;       // 224
+constexpr int HVP_WARP_BYTES = HVP_WSLOTS * HVP_ROWS * 32 * 8 + HVP_RSLOTS * HVP_REC_BYTES;
+constexpr int HVP_SMEM = OPT_WY * HVP_WARP_BYTES;
+
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(32 * OPT_WY, 2) tn_hv_pipe_kernel(TnArgs a) {
+    extern __shared__ __align__(16) unsigned char hvp_smem[];
+    const int ty = threadIdx.y, tx = threadIdx.x;
+    const int B = a.o.B;
+    const int b = blockIdx.x * 32 + tx;
+    const bool active = b < B && a.st[b] == TS_CG && !(a.act[b] & ACT_FIN);
+    if (!__syncthreads_or(active)) return;
+    double v[2] = {0.0, 0.0};
+    unsigned char* wbase = hvp_smem + (size_t)ty * HVP_WARP_BYTES;
+    double* wrows = reinterpret_cast<double*>(wbase);                                  // [HVP_WSLOTS][HVP_ROWS][32]
+    unsigned char* rrecs = wbase + HVP_WSLOTS * HVP_ROWS * 32 * 8;                      // [HVP_RSLOTS][HVP_REC_BYTES]
+    const unsigned Bs = (unsigned)B, bu = (unsigned)b;
+    const double* __restrict__ X = a.X;
+    const double* __restrict__ Pv = a.Pv;
+    const int i0 = blockIdx.y * a.nodes_per_chunk, i1 = min(a.t.n, i0 + a.nodes_per_chunk);
+    const int m = i0 + ty < i1 ? (i1 - i0 - ty + OPT_WY - 1) / OPT_WY : 0;               // this warp's nodes: i0 + ty + OPT_WY k
+    const unsigned long long* mw = a.lanemask ? a.lanemask + (size_t)(b >> 6) * a.mask_stride : nullptr;   // (b >> 6 is warp uniform)
+    const double lam = active ? (a.lane_lambda ? a.lane_lambda[b] : a.lambda) : 0.0, mu = active ? a.mu[b] : 0.0;
+    DevView V = {a, B, b, a.Pv, a.Hp, lam, a.pb, a.log_pen != 0, mu};
+
+    auto issue_rec = [&](int k) {             // R(k): index record (lanes 0-3) and constant record (lanes 4-11), 16 bytes each
+        if (k < m) {
+            const int i = i0 + ty + OPT_WY * k;
+            unsigned char* dst = rrecs + (k % HVP_RSLOTS) * HVP_REC_BYTES;
+            if (tx < 4) cp_async16(dst + 16 * tx, reinterpret_cast<const unsigned char*>(a.hv_rec + (size_t)i * HV_REC_INTS) + 16 * tx);
+            else if (tx < 12) cp_async16(dst + 16 * tx, reinterpret_cast<const unsigned char*>(a.hv_const + (size_t)i * HV_CONST) + 16 * (tx - 4));
+        }
+        cp_async_commit();
+    };
+    auto issue_rows = [&](int k) {            // W(k): the 16 operand rows of node k (record already in shared memory), mask words
+        if (k < m) {
+            const unsigned char* rec = rrecs + (k % HVP_RSLOTS) * HVP_REC_BYTES;
+            const int4 q0 = *reinterpret_cast<const int4*>(rec), q1 = *reinterpret_cast<const int4*>(rec + 16);
+            if (q1.w) {
+                const int4 q2 = *reinterpret_cast<const int4*>(rec + 32), q3 = *reinterpret_cast<const int4*>(rec + 48);
+                if (active) {
+                    double* dst = wrows + (size_t)(k % HVP_WSLOTS) * HVP_ROWS * 32 + tx;
+                    const int rows[8] = {q0.y, q0.z, q1.x, q1.y, q3.x, q2.z, q3.y, q2.w};      // rs ds prs pds crs0 cds0 crs1 cds1
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (rows[q] >= 0 && (q < 4 || q1.z)) {
+                            const unsigned off = (unsigned)rows[q] * Bs + bu;
+                            cp_async8(dst + (2 * q) * 32, X + off);
+                            cp_async8(dst + (2 * q + 1) * 32, Pv + off);
+                        }
+                    }
+                }
+                if (mw && tx < 4) {
+                    const int nd = tx == 0 ? q0.x : (tx == 1 ? q0.w : (tx == 2 ? q2.x : q2.y));   // i p ch0 ch1
+                    if (tx < 2 || q1.z) cp_async8(const_cast<unsigned char*>(rec) + HV_REC_INTS * 4 + HV_CONST * 8 + 8 * tx, mw + nd);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    issue_rec(0); issue_rec(1); issue_rec(2);
+    cp_async_wait<2>(); __syncwarp();
+    issue_rows(0);
+    cp_async_wait<2>(); __syncwarp();
+    issue_rows(1);
+    for (int k = 0; k < m; k++) {
+        __syncwarp();                                         // every lane is done with node k-1 (its record slot is reused below)
+        issue_rec(k + 3);
+        cp_async_wait<2>();
+        __syncwarp();                                         // R(k+2), W(k) visible to all lanes
+        issue_rows(k + 2);
+        const unsigned char* rec = rrecs + (k % HVP_RSLOTS) * HVP_REC_BYTES;
+        const int4 q0 = *reinterpret_cast<const int4*>(rec), q1 = *reinterpret_cast<const int4*>(rec + 16);
+        if (!active) continue;
+        double vw, vv;
+        if (q1.w) {
+            const int4 q2 = *reinterpret_cast<const int4*>(rec + 32);
+            const double* cst = reinterpret_cast<const double*>(rec + HV_REC_INTS * 4);
+            const unsigned long long* mk = reinterpret_cast<const unsigned long long*>(rec + HV_REC_INTS * 4 + HV_CONST * 8);
+            const double* w = wrows + (size_t)(k % HVP_WSLOTS) * HVP_ROWS * 32 + tx;
+            const int rs = q0.y, ds = q0.z, pds = q1.y, nch = q1.z, cds0 = q2.z, cds1 = q2.w;
+            HvOperands o;
+            o.mi = o.mp = o.mc[0] = o.mc[1] = false;
+            if (mw) {
+                o.mi = (mk[0] >> (b & 63)) & 1ull; o.mp = (mk[1] >> (b & 63)) & 1ull;
+                if (nch) { o.mc[0] = (mk[2] >> (b & 63)) & 1ull; o.mc[1] = (mk[3] >> (b & 63)) & 1ull; }
+            }
+            o.r = w[0 * 32]; o.v_rs = w[1 * 32];
+            o.h = ds >= 0 ? w[2 * 32] : cst[1];
+            o.v_ds = ds >= 0 ? w[3 * 32] : 0.0;
+            o.rp = w[4 * 32]; o.v_prs = w[5 * 32];
+            o.hp = pds >= 0 ? w[6 * 32] : cst[3];
+            o.v_pds = pds >= 0 ? w[7 * 32] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 2; q++) { o.rc[q] = o.hc[q] = o.v_crs[q] = o.v_cds[q] = o.cc[q] = o.sc_crs[q] = o.sc_cds[q] = 0.0; }
+            if (nch) {
+                const int cds[2] = {cds0, cds1};
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    o.rc[q] = w[(8 + 4 * q) * 32];
+                    o.v_crs[q] = w[(9 + 4 * q) * 32];
+                    o.hc[q] = cds[q] >= 0 ? w[(10 + 4 * q) * 32] : cst[5 + 2 * q];
+                    o.v_cds[q] = cds[q] >= 0 ? w[(11 + 4 * q) * 32] : 0.0;
+                    o.cc[q] = cst[9 + q];
+                    o.sc_crs[q] = cst[4 + 2 * q];
+                    o.sc_cds[q] = cds[q] >= 0 ? cst[5 + 2 * q] : 0.0;
+                }
+            }
+            o.sc_rs = cst[0]; o.sc_ds = ds >= 0 ? cst[1] : 0.0; o.sc_prs = cst[2]; o.sc_pds = pds >= 0 ? cst[3] : 0.0;
+            o.c = cst[8];
+            o.gx = a.Gx[(unsigned)rs * Bs + bu];
+            const bool damp = mu > 0.0;
+            o.dg_rs = damp ? a.DG[(unsigned)rs * Bs + bu] : 0.0; o.dg_ds = (damp && ds >= 0) ? a.DG[(unsigned)ds * Bs + bu] : 0.0;
+            o.pmn = ds >= 0 ? cst[11] : -1.0; o.pmx = ds >= 0 ? cst[12] : -1.0;
+            hess_node_fast_math(a, o, rs, ds, pds, nch, cds0, cds1, Bs, bu, lam, mu, vw, vv);
+        } else {
+            hess_node(V, q0.x, vw, vv);
+        }
+        v[0] += vw;
+        v[1] += vv;
+    }
+    cp_async_wait<0>();
+    if (!group_reduce<2, 0u, 0u>(v, a.part_hv, a.cnt_hv, B, b, 5)) return;
+    if (ty == 0 && active) phase_hv(lane_of(a, b), v, a.o);
 }
 
 __global__ void __launch_bounds__(32 * OPT_WY) tn_update_kernel(TnArgs a) {
@@ -594,17 +767,17 @@ struct LocalView : RecBase {
             const unsigned long long w_0 = h0 ? mask_word(t.ch0) : 0ull, w_1 = h1 ? mask_word(t.ch1) : 0ull;
             m_i = (w_i >> (b & 63)) & 1ull; m_p = (w_p >> (b & 63)) & 1ull; m_c0 = (w_0 >> (b & 63)) & 1ull; m_c1 = (w_1 >> (b & 63)) & 1ull;
         }
-        r_i = t.rs >= 0 ? a.X[(size_t)t.rs * Bs + b] : a.t.rfix[t.i];
-        h_i = t.ds >= 0 ? a.X[(size_t)t.ds * Bs + b] : a.t.hfix[t.i];
-        x_prs = t.prs >= 0 ? a.X[(size_t)t.prs * Bs + b] : 0.0;
-        h_p = t.pds >= 0 ? a.X[(size_t)t.pds * Bs + b] : (hp ? a.t.hfix[t.p] : 0.0);
-        h_c0 = t.cds0 >= 0 ? a.X[(size_t)t.cds0 * Bs + b] : (h0 ? a.t.hfix[t.ch0] : 0.0);
-        h_c1 = t.cds1 >= 0 ? a.X[(size_t)t.cds1 * Bs + b] : (h1 ? a.t.hfix[t.ch1] : 0.0);
-        f_rs = t.rs >= 0 ? a.Minv[(size_t)t.rs * Bs + b] : 0.0;
-        f_ds = t.ds >= 0 ? a.Minv[(size_t)t.ds * Bs + b] : 0.0;
-        f_prs = t.prs >= 0 ? a.Minv[(size_t)t.prs * Bs + b] : 0.0;
-        f_pds = t.pds >= 0 ? a.Minv[(size_t)t.pds * Bs + b] : 0.0;
-        gx_rs = t.rs >= 0 ? a.Gx[(size_t)t.rs * Bs + b] : 0.0;
+        r_i = t.rs >= 0 ? a.X[(unsigned)t.rs * (unsigned)B + (unsigned)b] : a.t.rfix[t.i];
+        h_i = t.ds >= 0 ? a.X[(unsigned)t.ds * (unsigned)B + (unsigned)b] : a.t.hfix[t.i];
+        x_prs = t.prs >= 0 ? a.X[(unsigned)t.prs * (unsigned)B + (unsigned)b] : 0.0;
+        h_p = t.pds >= 0 ? a.X[(unsigned)t.pds * (unsigned)B + (unsigned)b] : (hp ? a.t.hfix[t.p] : 0.0);
+        h_c0 = t.cds0 >= 0 ? a.X[(unsigned)t.cds0 * (unsigned)B + (unsigned)b] : (h0 ? a.t.hfix[t.ch0] : 0.0);
+        h_c1 = t.cds1 >= 0 ? a.X[(unsigned)t.cds1 * (unsigned)B + (unsigned)b] : (h1 ? a.t.hfix[t.ch1] : 0.0);
+        f_rs = t.rs >= 0 ? a.Minv[(unsigned)t.rs * (unsigned)B + (unsigned)b] : 0.0;
+        f_ds = t.ds >= 0 ? a.Minv[(unsigned)t.ds * (unsigned)B + (unsigned)b] : 0.0;
+        f_prs = t.prs >= 0 ? a.Minv[(unsigned)t.prs * (unsigned)B + (unsigned)b] : 0.0;
+        f_pds = t.pds >= 0 ? a.Minv[(unsigned)t.pds * (unsigned)B + (unsigned)b] : 0.0;
+        gx_rs = t.rs >= 0 ? a.Gx[(unsigned)t.rs * (unsigned)B + (unsigned)b] : 0.0;
         sc_rs = t.rs >= 0 ? a.sc[t.rs] : 0.0;
         sc_ds = t.ds >= 0 ? a.sc[t.ds] : 0.0;
         sc_prs = t.prs >= 0 ? a.sc[t.prs] : 0.0;
@@ -631,7 +804,7 @@ struct LocalView : RecBase {
         return DevView::hfix(n);
     }
     __device__ bool fr(int row) const {
-        return (row == t.rs ? f_rs : (row == t.ds ? f_ds : (row == t.prs ? f_prs : (row == t.pds ? f_pds : a.Minv[(size_t)row * B + b])))) > 0.0;
+        return (row == t.rs ? f_rs : (row == t.ds ? f_ds : (row == t.prs ? f_prs : (row == t.pds ? f_pds : a.Minv[(unsigned)row * (unsigned)B + (unsigned)b])))) > 0.0;
     }
     __device__ double sc(int row) const {
         return row == t.rs ? sc_rs : (row == t.ds ? sc_ds : (row == t.prs ? sc_prs : (row == t.pds ? sc_pds : DevView::sc(row))));
@@ -653,32 +826,32 @@ struct UpView : RecBase {
         const size_t Bs = (size_t)B, n = (size_t)a.t.n;
         const bool h0 = t.nch > 0, h1 = t.nch > 1;
         m_i = a.lanemask ? ((mask_word(t.i) >> (b & 63)) & 1ull) : false;
-        f_rs = t.rs >= 0 ? a.Minv[(size_t)t.rs * Bs + b] : 0.0;
-        f_ds = t.ds >= 0 ? a.Minv[(size_t)t.ds * Bs + b] : 0.0;
-        rhs_rs = t.rs >= 0 ? a.R[(size_t)t.rs * Bs + b] : 0.0;
-        rhs_ds = t.ds >= 0 ? a.R[(size_t)t.ds * Bs + b] : 0.0;
+        f_rs = t.rs >= 0 ? a.Minv[(unsigned)t.rs * (unsigned)B + (unsigned)b] : 0.0;
+        f_ds = t.ds >= 0 ? a.Minv[(unsigned)t.ds * (unsigned)B + (unsigned)b] : 0.0;
+        rhs_rs = t.rs >= 0 ? a.R[(unsigned)t.rs * (unsigned)B + (unsigned)b] : 0.0;
+        rhs_ds = t.ds >= 0 ? a.R[(unsigned)t.ds * (unsigned)B + (unsigned)b] : 0.0;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            k0[q] = h0 ? __ldcg(a.TW + ((size_t)(TW_K + q) * n + t.ch0) * Bs + b) : 0.0;
-            k1[q] = h1 ? __ldcg(a.TW + ((size_t)(TW_K + q) * n + t.ch1) * Bs + b) : 0.0;
+            k0[q] = h0 ? __ldcg(a.TW + (size_t)(TW_K + q) * (n * Bs) + ((unsigned)t.ch0 * (unsigned)B + (unsigned)b)) : 0.0;
+            k1[q] = h1 ? __ldcg(a.TW + (size_t)(TW_K + q) * (n * Bs) + ((unsigned)t.ch1 * (unsigned)B + (unsigned)b)) : 0.0;
         }
 #pragma unroll
         for (int q = 0; q < 2; q++) {
-            y0[q] = h0 ? __ldcg(a.TW + ((size_t)(TW_Y + q) * n + t.ch0) * Bs + b) : 0.0;
-            y1[q] = h1 ? __ldcg(a.TW + ((size_t)(TW_Y + q) * n + t.ch1) * Bs + b) : 0.0;
+            y0[q] = h0 ? __ldcg(a.TW + (size_t)(TW_Y + q) * (n * Bs) + ((unsigned)t.ch0 * (unsigned)B + (unsigned)b)) : 0.0;
+            y1[q] = h1 ? __ldcg(a.TW + (size_t)(TW_Y + q) * (n * Bs) + ((unsigned)t.ch1 * (unsigned)B + (unsigned)b)) : 0.0;
         }
         if (PIVOT) {
 #pragma unroll
-            for (int q = 0; q < 7; q++) loc[q] = __ldcg(a.TW + ((size_t)(TW_L + q) * n + t.i) * Bs + b);
+            for (int q = 0; q < 7; q++) loc[q] = __ldcg(a.TW + (size_t)(TW_L + q) * (n * Bs) + ((unsigned)t.i * (unsigned)B + (unsigned)b));
 #pragma unroll
             for (int q = 0; q < 3; q++) {
-                t0[q] = h0 ? __ldcg(a.TW + ((size_t)(TW_T + q) * n + t.ch0) * Bs + b) : 0.0;
-                t1[q] = h1 ? __ldcg(a.TW + ((size_t)(TW_T + q) * n + t.ch1) * Bs + b) : 0.0;
+                t0[q] = h0 ? __ldcg(a.TW + (size_t)(TW_T + q) * (n * Bs) + ((unsigned)t.ch0 * (unsigned)B + (unsigned)b)) : 0.0;
+                t1[q] = h1 ? __ldcg(a.TW + (size_t)(TW_T + q) * (n * Bs) + ((unsigned)t.ch1 * (unsigned)B + (unsigned)b)) : 0.0;
             }
         }
     }
     __device__ bool masked(int n) const { return n == t.i ? m_i : DevView::masked(n); }
-    __device__ bool fr(int row) const { return (row == t.rs ? f_rs : (row == t.ds ? f_ds : a.Minv[(size_t)row * B + b])) > 0.0; }
+    __device__ bool fr(int row) const { return (row == t.rs ? f_rs : (row == t.ds ? f_ds : a.Minv[(unsigned)row * (unsigned)B + (unsigned)b])) > 0.0; }
     __device__ double rhs(int row) const { return row == t.rs ? rhs_rs : (row == t.ds ? rhs_ds : DevView::rhs(row)); }
     __device__ double tw(int q, int n) const {
         if (PIVOT && n == t.i && q < TW_L + 7) return loc[q - TW_L];          // tree_pivot_node reads its local block first
@@ -704,13 +877,13 @@ struct DownView : RecBase {
     __device__ DownView(const DevView& v, const TreeRec& rec) : RecBase(v, rec) {
         const size_t Bs = (size_t)B, n = (size_t)a.t.n;
 #pragma unroll
-        for (int q = 0; q < 3; q++) sS[q] = __ldcg(a.TW + ((size_t)(TW_S + q) * n + t.i) * Bs + b);
+        for (int q = 0; q < 3; q++) sS[q] = __ldcg(a.TW + (size_t)(TW_S + q) * (n * Bs) + ((unsigned)t.i * (unsigned)B + (unsigned)b));
 #pragma unroll
-        for (int q = 0; q < 4; q++) sK[q] = __ldcg(a.TW + ((size_t)(TW_K + q) * n + t.i) * Bs + b);
+        for (int q = 0; q < 4; q++) sK[q] = __ldcg(a.TW + (size_t)(TW_K + q) * (n * Bs) + ((unsigned)t.i * (unsigned)B + (unsigned)b));
 #pragma unroll
-        for (int q = 0; q < 2; q++) sY[q] = __ldcg(a.TW + ((size_t)(TW_Y + q) * n + t.i) * Bs + b);
-        o_prs = t.prs >= 0 ? __ldcg(W + (size_t)t.prs * Bs + b) : 0.0;
-        o_pds = t.pds >= 0 ? __ldcg(W + (size_t)t.pds * Bs + b) : 0.0;
+        for (int q = 0; q < 2; q++) sY[q] = __ldcg(a.TW + (size_t)(TW_Y + q) * (n * Bs) + ((unsigned)t.i * (unsigned)B + (unsigned)b));
+        o_prs = t.prs >= 0 ? __ldcg(W + ((unsigned)t.prs * (unsigned)B + (unsigned)b)) : 0.0;
+        o_pds = t.pds >= 0 ? __ldcg(W + ((unsigned)t.pds * (unsigned)B + (unsigned)b)) : 0.0;
     }
     __device__ double outv(int row) const { return row == t.prs ? o_prs : (row == t.pds ? o_pds : DevView::outv(row)); }
     __device__ double tw(int q, int n) const {
@@ -925,14 +1098,14 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_stepmax_kernel(TnArgs a) {
             const int pa = a.t.parent[i];
             const int ri = a.t.dslot[i], rp = a.t.dslot[pa];
             double zi, di = 0.0, zp, dp = 0.0;
-            if (ri >= 0) { const double sc = a.sc[ri]; zi = a.Z[(size_t)ri * B + b] * sc; di = a.S[(size_t)ri * B + b] * sc; } else zi = a.t.hfix[i];
-            if (rp >= 0) { const double sc = a.sc[rp]; zp = a.Z[(size_t)rp * B + b] * sc; dp = a.S[(size_t)rp * B + b] * sc; } else zp = a.t.hfix[pa];
+            if (ri >= 0) { const double sc = a.sc[ri]; zi = a.Z[(unsigned)ri * (unsigned)B + (unsigned)b] * sc; di = a.S[(unsigned)ri * (unsigned)B + (unsigned)b] * sc; } else zi = a.t.hfix[i];
+            if (rp >= 0) { const double sc = a.sc[rp]; zp = a.Z[(unsigned)rp * (unsigned)B + (unsigned)b] * sc; dp = a.S[(unsigned)rp * (unsigned)B + (unsigned)b] * sc; } else zp = a.t.hfix[pa];
             v[0] = fmin(v[0], tplopt::branch_step_limit(zi, di, zp, dp));
-            if (ri >= 0) v[0] = fmin(v[0], tplopt::bound_step_limit(a.Z[(size_t)ri * B + b], a.S[(size_t)ri * B + b], a.lo[ri], a.hi[ri]));
+            if (ri >= 0) v[0] = fmin(v[0], tplopt::bound_step_limit(a.Z[(unsigned)ri * (unsigned)B + (unsigned)b], a.S[(unsigned)ri * (unsigned)B + (unsigned)b], a.lo[ri], a.hi[ri]));
         }
         if (blockIdx.y == 0 && ty == 0 && nl.sub == 0) {            // the root's own date (no branch above it)
             const int r0 = a.t.dslot[0];
-            if (r0 >= 0) v[0] = fmin(v[0], tplopt::bound_step_limit(a.Z[(size_t)r0 * B + b], a.S[(size_t)r0 * B + b], a.lo[r0], a.hi[r0]));
+            if (r0 >= 0) v[0] = fmin(v[0], tplopt::bound_step_limit(a.Z[(unsigned)r0 * (unsigned)B + (unsigned)b], a.S[(unsigned)r0 * (unsigned)B + (unsigned)b], a.lo[r0], a.hi[r0]));
         }
     }
     if (!group_reduce<1, 0u, 1u>(v, a.part_tm, a.cnt_tm, B, b, a.pack_shift)) return;

@@ -36,7 +36,7 @@ class OptOptions(C.Structure):
     """tpl_opt_options (include/treepl_b200.h); 0 = library default"""
     _fields_ = [("history", C.c_int), ("max_steps", C.c_int), ("patience", C.c_int), ("max_ls", C.c_int),
                 ("check_every", C.c_int), ("use_graph", C.c_int), ("method", C.c_int), ("max_cg", C.c_int), ("cg_per_step", C.c_int), ("precond", C.c_int), ("ftol", C.c_double), ("gtol", C.c_double),
-                ("armijo", C.c_double), ("date_scale", C.c_double), ("boundary_frac", C.c_double), ("tree_wide_min", C.c_int), ("tree_coop", C.c_int)]
+                ("armijo", C.c_double), ("date_scale", C.c_double), ("boundary_frac", C.c_double), ("tree_wide_min", C.c_int), ("tree_coop", C.c_int), ("hv_pipe", C.c_int), ("reserved", C.c_int)]
 
 
 class AnnealOptions(C.Structure):
@@ -368,7 +368,7 @@ class PLCalcParallel:
         """Device-resident batched L-BFGS (tpl_optimize_batch): X0 [P, B] feasible start vectors ->
         (X [P, B], F [B], info).  options: fields of tpl_opt_options (history, max_steps, patience, max_ls,
         check_every, use_graph, method (0 L-BFGS, 1 truncated Newton), max_cg, cg_per_step, precond, ftol, gtol, armijo, date_scale, boundary_frac,
-        tree_wide_min, tree_coop)."""
+        tree_wide_min, tree_coop, hv_pipe)."""
         X = _f64(X0).copy()
         P, B = X.shape
         if P != self.numparams:
