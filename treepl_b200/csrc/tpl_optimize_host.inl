@@ -151,13 +151,16 @@ static void tn_fill_record(const tpl_engine* e, int i, int* r) {
 // tn_hv_pipe_kernel needs 105 KB of dynamic shared memory per block: opt in once per process
 bool tn_hv_pipe_ready() {
     static int ok = -1;
-    if (ok < 0) ok = cudaFuncSetAttribute(tpltn::tn_hv_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tpltn::HVP_SMEM) == cudaSuccess ? 1 : 0;
+    if (ok < 0)
+        ok = (cudaFuncSetAttribute(tpltn::tn_hv_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tpltn::HVP_SMEM) == cudaSuccess &&
+              cudaFuncSetAttribute(tpltn::tn_hv_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tpltn::HVP_SMEM) == cudaSuccess) ? 1 : 0;
     if (!ok) cudaGetLastError();
     return ok == 1;
 }
 // Hp = H p: the software-pipelined kernel for full 32-vector groups, the register-staged one for packed lanes (B <= 16)
 void tn_launch_hv(const tpltn::TnArgs& a, dim3 ngrd, dim3 blk, cudaStream_t s) {
-    if (a.hv_pipe) tpltn::tn_hv_pipe_kernel<<<ngrd, blk, tpltn::HVP_SMEM, s>>>(a);
+    if (a.hv_pipe && a.lanemask) tpltn::tn_hv_pipe_kernel<true><<<ngrd, blk, tpltn::HVP_SMEM, s>>>(a);
+    else if (a.hv_pipe) tpltn::tn_hv_pipe_kernel<false><<<ngrd, blk, tpltn::HVP_SMEM, s>>>(a);
     else tpltn::tn_hv_kernel<<<ngrd, blk, 0, s>>>(a);
 }
 
@@ -186,10 +189,15 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_node, tn_hv_kernel, 32 * WY, 0);
     one_wave(occ_row, P, WY, &a.row_chunks, &a.rows_per_chunk);
     one_wave(occ_node, n, WY, &a.node_chunks, &a.nodes_per_chunk);
+    int occ_diag = 1, occ_tm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_diag, tn_diag_kernel, 32 * WY, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tm, tn_stepmax_kernel, 32 * WY, 0);
+    one_wave(occ_diag, n, WY, &a.diag_chunks, &a.diag_nodes_per_chunk);
+    one_wave(occ_tm, n, WY, &a.tm_chunks, &a.tm_nodes_per_chunk);
     CK(w.Z.ensure(PB)); CK(w.Gz.ensure(PB)); CK(w.D.ensure(PB)); CK(w.X.ensure(PB)); CK(w.Gx.ensure(PB));
     CK(w.R.ensure(PB)); CK(w.ZZ.ensure(PB)); CK(w.Pv.ensure(PB)); CK(w.Hp.ensure(PB)); CK(w.Minv.ensure(PB)); CK(w.DG.ensure(PB));
     CK(w.lo.ensure(P)); CK(w.hi.ensure(P)); CK(w.sc.ensure(P)); CK(w.Ft.ensure(B)); CK(w.Fout.ensure(B)); CK(w.h_done.ensure(1));
-    const size_t npart = (size_t)(3 + 1 + 1 + 1) * a.row_chunks * B + (size_t)(2 + 1) * a.node_chunks * B;
+    const size_t npart = (size_t)(3 + 1 + 1 + 1) * a.row_chunks * B + (size_t)2 * a.node_chunks * B + (size_t)a.tm_chunks * B;
     CK(w.tn_part.ensure(npart));
     CK(w.tn_lane_d.ensure((size_t)14 * B));
     CK(w.tn_lane_i.ensure((size_t)8 * B + 1 + 6 * (size_t)groups));
@@ -255,7 +263,7 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
     a.part_upd = pp; pp += (size_t)a.row_chunks * B;
     a.part_gd = pp; pp += (size_t)a.row_chunks * B;
     a.part_hv = pp; pp += (size_t)2 * a.node_chunks * B;
-    a.part_tm = pp; pp += (size_t)a.node_chunks * B;
+    a.part_tm = pp; pp += (size_t)a.tm_chunks * B;
     a.part_pc = pp;
     {   // index records (node order) of the Hessian-vector kernel's fast path: every non-root node whose parent is not the root,
         // with no or exactly two children (rates exist for all of them in the PL layout)
@@ -266,7 +274,8 @@ int tn_prepare(tpl_engine* e, int B, const double* X, const std::vector<double>&
             const int c0 = e->child_off[i], nc = e->child_off[i + 1] - c0;
             r[0] = i; r[1] = e->freeparams[i]; r[2] = e->freeparams[n + i]; r[3] = pa;
             r[4] = pa >= 0 ? e->freeparams[pa] : -1; r[5] = pa >= 0 ? e->freeparams[n + pa] : -1; r[6] = nc;
-            bool fast = i != 0 && pa != 0 && (nc == 0 || nc == 2) && r[1] >= 0 && r[4] >= 0;
+            // two shapes only: a tip without a date row, or an internal node with two children and a date row
+            bool fast = i != 0 && pa != 0 && ((nc == 0 && r[2] < 0) || (nc == 2 && r[2] >= 0)) && r[1] >= 0 && r[4] >= 0;
             for (int j = 0; j < 2 && j < nc; j++) {
                 const int ch = e->children[c0 + j];
                 r[8 + j] = ch; r[10 + j] = e->freeparams[n + ch]; r[12 + j] = e->freeparams[ch];
@@ -448,7 +457,7 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
     auto one_step = [&]() -> int {
         int rc = eval_device(e, B, a.X, const_cast<double*>(a.Ft), const_cast<double*>(a.Gx), mode, true, s);
         if (rc != TPL_OK) return rc;
-        tn_diag_kernel<<<ngrd, blk, 0, s>>>(a);
+        tn_diag_kernel<<<dim3(groups, a.diag_chunks), blk, 0, s>>>(a);
         tn_setup_kernel<<<rgrd, blk, 0, s>>>(a);
         if (a.precond) tree_solve(true);
         for (int k = 0; k < cg_per_step; k++) {
@@ -458,7 +467,7 @@ int optimize_tn(tpl_engine* e, int B, double* X, double* F, const std::vector<do
             tn_dir_kernel<<<rgrd, blk, 0, s>>>(a);
         }
         tn_gd_kernel<<<rgrd, blk, 0, s>>>(a);
-        tn_stepmax_kernel<<<ngrd, blk, 0, s>>>(a);
+        tn_stepmax_kernel<<<dim3(groups, a.tm_chunks), blk, 0, s>>>(a);
         tn_trial_kernel<<<rgrd, blk, 0, s>>>(a);
         CK(cudaGetLastError());
         return TPL_OK;
@@ -760,7 +769,7 @@ extern "C" int tpl_debug_hessvec(tpl_engine* e, int B, const double* X, const do
     const dim3 blk(32, tplopt::OPT_WY);
     const dim3 ngrd((B + 31) / 32, a.node_chunks);
     CK(cudaMemcpyAsync(w.Pv.p, V, sizeof(double) * PB, cudaMemcpyHostToDevice, s));
-    tn_diag_kernel<<<ngrd, blk, 0, s>>>(a);                     // st = TS_INIT and a finite objective: every vector "accepts"
+    tn_diag_kernel<<<dim3((B + 31) / 32, a.diag_chunks), blk, 0, s>>>(a);                     // st = TS_INIT and a finite objective: every vector "accepts"
     std::vector<int> cg(B, TS_CG);
     CK(cudaMemcpyAsync(a.st, cg.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
     tn_launch_hv(a, ngrd, blk, s);

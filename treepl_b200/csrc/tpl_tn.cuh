@@ -56,6 +56,8 @@ struct TnArgs {
     int pack_shift;                          // node-indexed kernels at B <= 16: a warp carries 32 >> pack_shift nodes x (1 << pack_shift) vectors
     int row_chunks, rows_per_chunk;          // row-indexed kernels
     int node_chunks, nodes_per_chunk;        // node-indexed kernels
+    int diag_chunks, diag_nodes_per_chunk;   // tn_diag_kernel and tn_stepmax_kernel need a third / half of the Hessian-vector kernel's registers:
+    int tm_chunks, tm_nodes_per_chunk;       // their grids are sized by their OWN occupancy (these kernels are bound by warps in flight)
     double *part_setup, *part_hv, *part_upd, *part_gd, *part_tm;
     int *cnt_setup, *cnt_hv, *cnt_upd, *cnt_gd, *cnt_tm;      // [groups] arrival counters, zero between launches
     int* ndone;
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_diag_kernel(TnArgs a) {
     const int dec = lane_decision(a, b);
     if (dec != DEC_ACCEPT && dec != DEC_INIT) return;
     DevView V = {a, B, b, a.Pv, a.DG, a.lane_lambda ? a.lane_lambda[b] : a.lambda, a.pb, a.log_pen != 0, 0.0};
-    const int i0 = blockIdx.y * a.nodes_per_chunk, i1 = min(a.t.n, i0 + a.nodes_per_chunk);
+    const int i0 = blockIdx.y * a.diag_nodes_per_chunk, i1 = min(a.t.n, i0 + a.diag_nodes_per_chunk);
     const int4* recs = reinterpret_cast<const int4*>(a.hv_rec);
     for (int i = i0 + threadIdx.y * nl.npw + nl.sub; i < i1; i += OPT_WY * nl.npw) {
         const int4 q1 = __ldg(recs + 4 * (size_t)i + 1);
@@ -583,6 +585,44 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// One fast-path node from the staged rows.  The host marks a node fast only in two shapes - a tip (no children, no date row) or an
+// internal node with two children and a date row - and tn_hv_pipe_kernel's issue step fills the slot of every row that does not
+// exist (the fixed date of a tip child or of a calibrated parent, with a zero direction entry), so nothing here depends on the
+// record at run time: the class is a template parameter and hess_node_fast_math folds to straight-line code.
+template <bool INTERNAL, bool MASK>
+__device__ __forceinline__ void hvp_node(const TnArgs& a, const unsigned char* rec, const double* w, unsigned Bs, unsigned bu, int b,
+                                         double lam, double mu, double& vw, double& vv) {
+    const int rs = reinterpret_cast<const int*>(rec)[1], ds = reinterpret_cast<const int*>(rec)[2];
+    const double2* c2 = reinterpret_cast<const double2*>(rec + HV_REC_INTS * 4);
+    HvOperands o;
+    o.mi = o.mp = o.mc[0] = o.mc[1] = false;
+    if (MASK) {
+        const unsigned long long* mk = reinterpret_cast<const unsigned long long*>(rec + HV_REC_INTS * 4 + HV_CONST * 8);
+        o.mi = (mk[0] >> (b & 63)) & 1ull; o.mp = (mk[1] >> (b & 63)) & 1ull;
+        if (INTERNAL) { o.mc[0] = (mk[2] >> (b & 63)) & 1ull; o.mc[1] = (mk[3] >> (b & 63)) & 1ull; }
+    }
+    const double2 s0 = c2[0], s1 = c2[1], k4 = c2[4];            // (sc_rs, sc_ds | hfix) (sc_prs, sc_pds | hfix) (c, cc0)
+    o.r = w[0 * 32]; o.v_rs = w[1 * 32]; o.h = w[2 * 32]; o.v_ds = INTERNAL ? w[3 * 32] : 0.0;
+    o.rp = w[4 * 32]; o.v_prs = w[5 * 32]; o.hp = w[6 * 32]; o.v_pds = w[7 * 32];
+    o.sc_rs = s0.x; o.sc_ds = INTERNAL ? s0.y : 0.0; o.sc_prs = s1.x; o.sc_pds = s1.y; o.c = k4.x;
+#pragma unroll
+    for (int q = 0; q < 2; q++) { o.rc[q] = o.hc[q] = o.v_crs[q] = o.v_cds[q] = o.cc[q] = o.sc_crs[q] = o.sc_cds[q] = 0.0; }
+    o.pmn = o.pmx = -1.0;
+    if (INTERNAL) {
+        const double2 s2 = c2[2], s3 = c2[3], k5 = c2[5], k6 = c2[6];   // (sc_crs0, sc_cds0 | hfix) (sc_crs1, sc_cds1 | hfix) (cc1, pmn) (pmx, -)
+        o.rc[0] = w[8 * 32]; o.v_crs[0] = w[9 * 32]; o.hc[0] = w[10 * 32]; o.v_cds[0] = w[11 * 32];
+        o.rc[1] = w[12 * 32]; o.v_crs[1] = w[13 * 32]; o.hc[1] = w[14 * 32]; o.v_cds[1] = w[15 * 32];
+        o.sc_crs[0] = s2.x; o.sc_cds[0] = s2.y; o.sc_crs[1] = s3.x; o.sc_cds[1] = s3.y;
+        o.cc[0] = k4.y; o.cc[1] = k5.x; o.pmn = k5.y; o.pmx = k6.x;
+    }
+    o.gx = a.Gx[(unsigned)rs * Bs + bu];
+    const bool damp = mu > 0.0;
+    o.dg_rs = damp ? a.DG[(unsigned)rs * Bs + bu] : 0.0;
+    o.dg_ds = (INTERNAL && damp) ? a.DG[(unsigned)ds * Bs + bu] : 0.0;
+    hess_node_fast_math(a, o, rs, INTERNAL ? ds : -1, 0, INTERNAL ? 2 : 0, 0, 0, Bs, bu, lam, mu, vw, vv);
+}
+
+template <bool MASK>
 __global__ void __launch_bounds__(32 * OPT_WY, 2) tn_hv_pipe_kernel(TnArgs a) {
     extern __shared__ __align__(16) unsigned char hvp_smem[];
     const int ty = threadIdx.y, tx = threadIdx.x;
@@ -599,7 +639,7 @@ __global__ void __launch_bounds__(32 * OPT_WY, 2) tn_hv_pipe_kernel(TnArgs a) {
     const double* __restrict__ Pv = a.Pv;
     const int i0 = blockIdx.y * a.nodes_per_chunk, i1 = min(a.t.n, i0 + a.nodes_per_chunk);
     const int m = i0 + ty < i1 ? (i1 - i0 - ty + OPT_WY - 1) / OPT_WY : 0;               // this warp's nodes: i0 + ty + OPT_WY k
-    const unsigned long long* mw = a.lanemask ? a.lanemask + (size_t)(b >> 6) * a.mask_stride : nullptr;   // (b >> 6 is warp uniform)
+    const unsigned long long* mw = MASK ? a.lanemask + (size_t)(b >> 6) * a.mask_stride : nullptr;   // (b >> 6 is warp uniform)
     const double lam = active ? (a.lane_lambda ? a.lane_lambda[b] : a.lambda) : 0.0, mu = active ? a.mu[b] : 0.0;
     DevView V = {a, B, b, a.Pv, a.Hp, lam, a.pb, a.log_pen != 0, mu};
 
@@ -612,27 +652,44 @@ __global__ void __launch_bounds__(32 * OPT_WY, 2) tn_hv_pipe_kernel(TnArgs a) {
         }
         cp_async_commit();
     };
-    auto issue_rows = [&](int k) {            // W(k): the 16 operand rows of node k (record already in shared memory), mask words
+    // W(k): the operand rows of node k (its records are in shared memory): X and P entries of the rows rs ds prs pds crs0 cds0 crs1 cds1
+    // land in ring rows 2q (X) and 2q + 1 (P); a row that does not exist gets its fixed date and a zero direction entry instead
+    auto issue_rows = [&](int k) {
         if (k < m) {
-            const unsigned char* rec = rrecs + (k % HVP_RSLOTS) * HVP_REC_BYTES;
+            unsigned char* rec = rrecs + (k % HVP_RSLOTS) * HVP_REC_BYTES;
             const int4 q0 = *reinterpret_cast<const int4*>(rec), q1 = *reinterpret_cast<const int4*>(rec + 16);
             if (q1.w) {
-                const int4 q2 = *reinterpret_cast<const int4*>(rec + 32), q3 = *reinterpret_cast<const int4*>(rec + 48);
+                const int4 q2 = *reinterpret_cast<const int4*>(rec + 32);
                 if (active) {
-                    double* dst = wrows + (size_t)(k % HVP_WSLOTS) * HVP_ROWS * 32 + tx;
-                    const int rows[8] = {q0.y, q0.z, q1.x, q1.y, q3.x, q2.z, q3.y, q2.w};      // rs ds prs pds crs0 cds0 crs1 cds1
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        if (rows[q] >= 0 && (q < 4 || q1.z)) {
-                            const unsigned off = (unsigned)rows[q] * Bs + bu;
+                    const double* cst = reinterpret_cast<const double*>(rec + HV_REC_INTS * 4);
+                    double* dst = wrows + (k % HVP_WSLOTS) * (HVP_ROWS * 32) + tx;
+                    auto row = [&](int q, int r, double fixed) {
+                        if (r >= 0) {
+                            const unsigned off = (unsigned)r * Bs + bu;
                             cp_async8(dst + (2 * q) * 32, X + off);
                             cp_async8(dst + (2 * q + 1) * 32, Pv + off);
+                        } else {
+                            dst[(2 * q) * 32] = fixed;
+                            dst[(2 * q + 1) * 32] = 0.0;
                         }
+                    };
+                    row(0, q0.y, 0.0);
+                    row(2, q1.x, 0.0);
+                    row(3, q1.y, cst[3]);
+                    if (q1.z) {
+                        const int2 q3 = *reinterpret_cast<const int2*>(rec + 48);
+                        row(1, q0.z, 0.0);
+                        row(4, q3.x, 0.0);
+                        row(5, q2.z, cst[5]);
+                        row(6, q3.y, 0.0);
+                        row(7, q2.w, cst[7]);
+                    } else {
+                        dst[2 * 32] = cst[1];                 // the tip's date
                     }
                 }
-                if (mw && tx < 4) {
+                if (MASK && tx < 4) {
                     const int nd = tx == 0 ? q0.x : (tx == 1 ? q0.w : (tx == 2 ? q2.x : q2.y));   // i p ch0 ch1
-                    if (tx < 2 || q1.z) cp_async8(const_cast<unsigned char*>(rec) + HV_REC_INTS * 4 + HV_CONST * 8 + 8 * tx, mw + nd);
+                    if (tx < 2 || q1.z) cp_async8(rec + HV_REC_INTS * 4 + HV_CONST * 8 + 8 * tx, mw + nd);
                 }
             }
         }
@@ -650,52 +707,16 @@ __global__ void __launch_bounds__(32 * OPT_WY, 2) tn_hv_pipe_kernel(TnArgs a) {
         cp_async_wait<2>();
         __syncwarp();                                         // R(k+2), W(k) visible to all lanes
         issue_rows(k + 2);
-        const unsigned char* rec = rrecs + (k % HVP_RSLOTS) * HVP_REC_BYTES;
-        const int4 q0 = *reinterpret_cast<const int4*>(rec), q1 = *reinterpret_cast<const int4*>(rec + 16);
         if (!active) continue;
+        const unsigned char* rec = rrecs + (k % HVP_RSLOTS) * HVP_REC_BYTES;
+        const int fast = reinterpret_cast<const int*>(rec)[7], nch = reinterpret_cast<const int*>(rec)[6];
+        const double* w = wrows + (k % HVP_WSLOTS) * (HVP_ROWS * 32) + tx;
         double vw, vv;
-        if (q1.w) {
-            const int4 q2 = *reinterpret_cast<const int4*>(rec + 32);
-            const double* cst = reinterpret_cast<const double*>(rec + HV_REC_INTS * 4);
-            const unsigned long long* mk = reinterpret_cast<const unsigned long long*>(rec + HV_REC_INTS * 4 + HV_CONST * 8);
-            const double* w = wrows + (size_t)(k % HVP_WSLOTS) * HVP_ROWS * 32 + tx;
-            const int rs = q0.y, ds = q0.z, pds = q1.y, nch = q1.z, cds0 = q2.z, cds1 = q2.w;
-            HvOperands o;
-            o.mi = o.mp = o.mc[0] = o.mc[1] = false;
-            if (mw) {
-                o.mi = (mk[0] >> (b & 63)) & 1ull; o.mp = (mk[1] >> (b & 63)) & 1ull;
-                if (nch) { o.mc[0] = (mk[2] >> (b & 63)) & 1ull; o.mc[1] = (mk[3] >> (b & 63)) & 1ull; }
-            }
-            o.r = w[0 * 32]; o.v_rs = w[1 * 32];
-            o.h = ds >= 0 ? w[2 * 32] : cst[1];
-            o.v_ds = ds >= 0 ? w[3 * 32] : 0.0;
-            o.rp = w[4 * 32]; o.v_prs = w[5 * 32];
-            o.hp = pds >= 0 ? w[6 * 32] : cst[3];
-            o.v_pds = pds >= 0 ? w[7 * 32] : 0.0;
-#pragma unroll
-            for (int q = 0; q < 2; q++) { o.rc[q] = o.hc[q] = o.v_crs[q] = o.v_cds[q] = o.cc[q] = o.sc_crs[q] = o.sc_cds[q] = 0.0; }
-            if (nch) {
-                const int cds[2] = {cds0, cds1};
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    o.rc[q] = w[(8 + 4 * q) * 32];
-                    o.v_crs[q] = w[(9 + 4 * q) * 32];
-                    o.hc[q] = cds[q] >= 0 ? w[(10 + 4 * q) * 32] : cst[5 + 2 * q];
-                    o.v_cds[q] = cds[q] >= 0 ? w[(11 + 4 * q) * 32] : 0.0;
-                    o.cc[q] = cst[9 + q];
-                    o.sc_crs[q] = cst[4 + 2 * q];
-                    o.sc_cds[q] = cds[q] >= 0 ? cst[5 + 2 * q] : 0.0;
-                }
-            }
-            o.sc_rs = cst[0]; o.sc_ds = ds >= 0 ? cst[1] : 0.0; o.sc_prs = cst[2]; o.sc_pds = pds >= 0 ? cst[3] : 0.0;
-            o.c = cst[8];
-            o.gx = a.Gx[(unsigned)rs * Bs + bu];
-            const bool damp = mu > 0.0;
-            o.dg_rs = damp ? a.DG[(unsigned)rs * Bs + bu] : 0.0; o.dg_ds = (damp && ds >= 0) ? a.DG[(unsigned)ds * Bs + bu] : 0.0;
-            o.pmn = ds >= 0 ? cst[11] : -1.0; o.pmx = ds >= 0 ? cst[12] : -1.0;
-            hess_node_fast_math(a, o, rs, ds, pds, nch, cds0, cds1, Bs, bu, lam, mu, vw, vv);
+        if (fast) {
+            if (nch) hvp_node<true, MASK>(a, rec, w, Bs, bu, b, lam, mu, vw, vv);
+            else hvp_node<false, MASK>(a, rec, w, Bs, bu, b, lam, mu, vw, vv);
         } else {
-            hess_node(V, q0.x, vw, vv);
+            hess_node(V, reinterpret_cast<const int*>(rec)[0], vw, vv);
         }
         v[0] += vw;
         v[1] += vv;
@@ -1093,7 +1114,7 @@ __global__ void __launch_bounds__(32 * OPT_WY) tn_stepmax_kernel(TnArgs a) {
     if (!__syncthreads_or(active)) return;
     double v[1] = {1e300};
     if (active) {
-        const int i0 = max(1, blockIdx.y * a.nodes_per_chunk), i1 = min(a.t.n, (blockIdx.y + 1) * a.nodes_per_chunk);
+        const int i0 = max(1, blockIdx.y * a.tm_nodes_per_chunk), i1 = min(a.t.n, (blockIdx.y + 1) * a.tm_nodes_per_chunk);
         for (int i = i0 + ty * nl.npw + nl.sub; i < i1; i += OPT_WY * nl.npw) {
             const int pa = a.t.parent[i];
             const int ri = a.t.dslot[i], rp = a.t.dslot[pa];
