@@ -403,7 +403,9 @@ int tn_launch_tree_solve(const tpltn::TnArgs& a, const std::vector<int>& loff, i
     int nl = 0;
     if (factor) {
         const dim3 lg(groups, (a.t.n + TREE_NODES_PER_BLOCK - 1) / TREE_NODES_PER_BLOCK);
-        if (groups < 32) tn_tree_local_kernel<true><<<lg, blk, 0, s>>>(a); else tn_tree_local_kernel<false><<<lg, blk, 0, s>>>(a);
+        // record view only for a single vector group: from two groups on the plain accessors (72 registers, three blocks per SM) are
+        // as fast or faster since the element offsets are 32-bit (100k tips / 64 vectors -1.8 %, 128 restarts -2.2 %, one group +0.8 %)
+        if (groups < 2) tn_tree_local_kernel<true><<<lg, blk, 0, s>>>(a); else tn_tree_local_kernel<false><<<lg, blk, 0, s>>>(a);
         nl++;
     }
     // a factorising sweep finishes level 0 (the tips) in the local kernel
