@@ -534,3 +534,39 @@ def test_device_blocks_of_closed_engines_are_reused_and_can_be_released():
     assert free0 - torch.cuda.mem_get_info()[0] <= held + 64e6
     eng.release_cached_memory()
     assert free0 - torch.cuda.mem_get_info()[0] < 64e6
+
+
+@pytest.mark.parametrize("B", [130, 162, 200, 256])
+def test_host_buffer_pipeline_handles_ragged_batches(B):
+    """tpl_calc_pl_grad_batch with host buffers evaluates B >= 128 vectors as pipelined pieces of up to 64 (copies of piece k+1
+    and k-1 overlap the kernels of piece k); a ragged tail is shared between the last two pieces so that none falls below the
+    32 vectors the descriptor kernel needs.  Every vector must equal its evaluation in a small, unpipelined batch (gradient rows
+    are written once by their owner: bitwise; the objective's partial sums are grouped per launch: to rounding) and the oracle."""
+    gd = Golden("big_test")
+    flat = gd.flat
+    n = len(flat["parents"])
+    fp, P = eng.generate_param_order_vector(flat["free"], lf=False)
+    plp = eng.PLCalcParallel.from_flat(flat)
+    x0 = plp.set_freeparams(P, False, fp)
+    plp.smoothing = 3.0
+    rng = np.random.RandomState(B)
+    X = np.repeat(x0[:, None], B, axis=1)
+    X[: n - 1, :] = 0.005 * np.exp(0.3 * rng.randn(n - 1, B))
+    lam = 10.0 ** rng.uniform(-1, 2, B)
+    plp.batch_configure(B, lane_smoothing=lam)
+    F, G = plp.calc_pl_grad_batch(X, mode=eng.GRAD_AD)
+    assert np.isfinite(F).all() and (F < 1e15).all()
+    o = plo.OracleProblem(flat)
+    o.set_freeparams(False)
+    for lo_b in (0, B - 40):                                    # the head and the ragged tail
+        sub = slice(lo_b, lo_b + 40)
+        plp.batch_configure(40, lane_smoothing=lam[sub])
+        Fs, Gs = plp.calc_pl_grad_batch(np.ascontiguousarray(X[:, sub]), mode=eng.GRAD_AD)
+        assert np.allclose(F[sub], Fs, rtol=1e-13, atol=0)
+        assert np.array_equal(G[:, sub], Gs)
+    for b in (0, B - 1, B - 33):
+        o.set_smoothing(lam[b])
+        f, g = o.calc_function_gradient(np.ascontiguousarray(X[:, b]))
+        assert close_f(F[b], f), (b, F[b], f)
+        assert rel_err(G[:, b], g) < G_TOL
+    plp.close()
