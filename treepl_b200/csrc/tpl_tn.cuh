@@ -934,8 +934,10 @@ __device__ __forceinline__ void tree_down_at(const TnArgs& a, const DevView& V, 
 // REC: through the record view (few vector groups: the launch is latency bound); otherwise through the plain accessors,
 // which cost fewer instructions and registers when there are enough warps to hide the load chains (measured: the views
 // halve the throughput of the node-indexed kernels at thousands of vectors)
+// (the plain variant at four blocks per SM - 64 registers, no spills: this kernel is bound by its dependent loads, long scoreboard
+// 69 % of the stall samples; -2...3 % per optimisation.  Forcing the factorising sweeps to three blocks per SM spills and loses.)
 template <bool REC>
-__global__ void __launch_bounds__(32 * OPT_WY) tn_tree_local_kernel(TnArgs a) {
+__global__ void __launch_bounds__(32 * OPT_WY, REC ? 2 : 4) tn_tree_local_kernel(TnArgs a) {
     const NodeLane nl = node_lane(a);
     const int b = nl.b;
     if (!tree_lane_active<true>(a, b)) return;
