@@ -1097,11 +1097,50 @@ int tpl_calc_pl_grad_batch_dev(tpl_engine* e, int B, const double* dX, double* d
     return eval_device(e, B, dX, dF, dG, mode, true, s);
 }
 
+// Would eval_device pick the descriptor kernel (generation 4) for this batch?  (same conditions as there)
+static bool batch_takes_desc_kernel(const tpl_engine* e, int B, int mode) {
+    if (e->force_gen != 0 && e->force_gen != 4) return false;
+    const bool lanemask = e->cfg_mask && e->cfg_B == B;
+    const int maskmode = lanemask ? 2 : (e->cv_any ? 1 : 0);
+    const bool tile_legal = e->gen2_ok && !e->lf_mode && maskmode != 1 && (B % 2 == 0) && (double)e->numparams * (double)B < 2.0e9;
+    const int nchunks2 = (B + tpl::TILE_LANES - 1) / tpl::TILE_LANES;
+    const long long W = (long long)nchunks2 * e->ntiles2;
+    const int G = (int)std::min<long long>(e->num_sms, W);
+    const bool stages = tpl::desc_kernel_smem(e->tile_hrows, 2) <= e->max_smem;
+    return tile_legal && B >= 32 && e->gen4_ok && nchunks2 <= G && stages && !(e->log_pen && mode == TPL_GRAD_ANALYTIC);
+}
+
+// The device's address of a PINNED (cudaMallocHost / cudaHostRegister / tpl_host_alloc) host buffer, or null for pageable memory
+static void* mapped_host_pointer(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 int tpl_calc_pl_grad_batch(tpl_engine* e, int B, const double* X, double* F, double* G, int mode) {
     if (!e || !X || !F || B < 1) return fail(TPL_ERR_ARG, "null or B < 1");
     if (!e->have_fp) return fail(TPL_ERR_STATE, "set_freeparams has not been called");
     CK(cudaSetDevice(e->device));
     const int P = e->numparams;
+    // Zero-copy: when X and G are pinned host buffers and the batch takes the descriptor kernel - which reads every X row once (TMA)
+    // and writes every G row once - the kernels work ON the host buffers through their device mapping.  The same 2 x 8 P B bytes
+    // cross PCIe, but inside the kernel: reads and writes overlap from the first tile to the last (full duplex for the whole step,
+    // no fill and drain of a copy pipeline, no staging copies in HBM).  F and the sparse rows of the finalize kernel go the same way.
+    // tpl_debug_force_kernel(e, 5) keeps the staged pipeline below (A/B and tests).
+    if (G && B >= 32 && batch_takes_desc_kernel(e, B, mode)) {
+        double* mX = static_cast<double*>(mapped_host_pointer(X));
+        double* mG = static_cast<double*>(mapped_host_pointer(G));
+        if (mX && mG) {
+            CK(e->d_F.ensure(B));
+            cudaStream_t s = e->stream;
+            int rc = eval_device(e, B, mX, e->d_F.p, mG, mode, true, s);
+            if (rc != TPL_OK) return rc;
+            CK(cudaMemcpyAsync(F, e->d_F.p, B * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (e->static_bad) for (int b = 0; b < B; b++) F[b] = TPL_LARGE;
+            return TPL_OK;
+        }
+    }
     if (B >= 128 && B % 2 == 0 && !e->lf_mode) {
         // Pipelined: 64-vector sub-batches on three streams, so that the upload of sub-batch k+1, the kernels
         // of sub-batch k and the download of sub-batch k-1 overlap (PCIe is full duplex; a single H2D -> kernel

@@ -9,6 +9,7 @@ Here every (smoothing value, fold) pair is one vector of the batch: per-vector s
 """
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -320,13 +321,30 @@ def loocv(flat, smoothing_grid, tips, **kw):
 
 def restart_starts(flat, P, ks, jitter=0.3, seed=1):
     """Start vectors [P, len(ks)] of the multi-start job: rates jittered log-normally around the clock-like start, feasible start
-    dates.  Start k depends on (seed, k) only (one random stream per start), so the set of starts is the same for every world
-    size - and for the reference arm of the benchmark, which optimises the first few of them on the CPU."""
+    dates.  Start k depends on (seed, k) only (one counter-based Philox stream per start, key = (seed, k)), so the set of starts
+    is the same for every world size - and for the reference arm of the benchmark, which optimises the first few of them on the
+    CPU.  Blocks of starts are drawn and exponentiated on a few threads (numpy releases the GIL in both): 1,024 starts of the
+    9,313-node tree cost 0.75 s of the job's 1.4 s when drawn one Mersenne-Twister stream after the other."""
+    from concurrent.futures import ThreadPoolExecutor
+
     nr = len(flat["parents"]) - 1
     x0 = start_vector(flat, P, nr)
-    J = np.stack([np.random.RandomState(seed * 1000003 + k).randn(nr) for k in ks])          # [len(ks), nr]
-    X0 = np.repeat(x0[:, None], len(ks), axis=1)
-    X0[:nr] *= np.exp(jitter * J).T
+    ks = list(ks)
+    X0 = np.empty((P, len(ks)))
+    X0[nr:] = x0[nr:, None]
+
+    def block(lo):
+        hi = min(len(ks), lo + 16)
+        J = np.stack([np.random.Generator(np.random.Philox(key=[int(seed), int(k)])).standard_normal(nr) for k in ks[lo:hi]])
+        X0[:nr, lo:hi] = x0[:nr, None] * np.exp(jitter * J).T
+
+    starts = range(0, len(ks), 16)
+    if len(ks) <= 32:
+        for lo in starts:
+            block(lo)
+    else:
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            list(ex.map(block, starts))
     return X0
 
 
