@@ -129,7 +129,9 @@ int tpl_get_durations(tpl_engine* e, double* out);
 int tpl_batch_configure(tpl_engine* e, int B, const double* lane_smoothing,
                         const int* mask_off, const int* mask_nodes);
 
-/* host buffers: X[P*B] in, F[B] and G[P*B] out (G may be NULL: objective only) */
+/* host buffers: X[P*B] in, F[B] and G[P*B] out (G may be NULL: objective only).  Any host memory works; with 128 or more vectors
+ * the batch moves as pipelined 64-vector pieces (upload, kernels and download of neighbouring pieces overlap), and PINNED buffers
+ * (tpl_host_alloc, cudaMallocHost, cudaHostRegister) of 32 ... 126 vectors are evaluated in place over PCIe, without staging copies. */
 int tpl_calc_pl_grad_batch(tpl_engine* e, int B, const double* X, double* F, double* G, int mode);
 
 /* device buffers, asynchronous on `cuda_stream` (a cudaStream_t, NULL = the engine's stream).

@@ -570,3 +570,48 @@ def test_host_buffer_pipeline_handles_ragged_batches(B):
         assert close_f(F[b], f), (b, F[b], f)
         assert rel_err(G[:, b], g) < G_TOL
     plp.close()
+
+
+def test_pinned_host_buffers_are_evaluated_in_place():
+    """tpl_calc_pl_grad_batch on PINNED host buffers (tpl_host_alloc), 32 <= B < 128: the descriptor kernel reads X from and
+    writes G to the host buffers through their device mapping (no staging copies).  Bitwise equal to the staged path on pageable
+    buffers of the same batch."""
+    import ctypes as C
+    gd = Golden("big_test")
+    flat = gd.flat
+    n = len(flat["parents"])
+    fp, P = eng.generate_param_order_vector(flat["free"], lf=False)
+    plp = eng.PLCalcParallel.from_flat(flat)
+    x0 = plp.set_freeparams(P, False, fp)
+    plp.smoothing = 2.0
+    B = 64
+    rng = np.random.RandomState(11)
+    X = np.repeat(x0[:, None], B, axis=1)
+    X[: n - 1, :] = 0.005 * np.exp(0.3 * rng.randn(n - 1, B))
+    plp.batch_configure(B)
+    F0, G0 = plp.calc_pl_grad_batch(X, mode=eng.GRAD_AD)             # pageable numpy buffers: staged
+    assert plp.last_kernel_generation() == 4
+    L = plp._L
+    nb = P * B * 8
+    px, pg, pf = L.tpl_host_alloc(nb), L.tpl_host_alloc(nb), L.tpl_host_alloc(B * 8)
+    assert px and pg and pf
+    try:
+        Xp = np.ctypeslib.as_array(C.cast(px, C.POINTER(C.c_double)), shape=(P, B))
+        Gp = np.ctypeslib.as_array(C.cast(pg, C.POINTER(C.c_double)), shape=(P, B))
+        Fp = np.ctypeslib.as_array(C.cast(pf, C.POINTER(C.c_double)), shape=(B,))
+        Xp[:] = X
+        Gp[:] = -7.0
+        dp = C.POINTER(C.c_double)
+        rc = L.tpl_calc_pl_grad_batch(plp._h, B, C.cast(px, dp), C.cast(pf, dp), C.cast(pg, dp), eng.GRAD_AD)
+        assert rc >= 0, L.tpl_last_error()
+        assert np.array_equal(Fp, F0)
+        assert np.array_equal(Gp, G0)
+        assert np.array_equal(Xp, X)                                 # inputs untouched
+        plp.force_kernel(5)                                          # pinned buffers through the staged path
+        Gp[:] = -7.0
+        rc = L.tpl_calc_pl_grad_batch(plp._h, B, C.cast(px, dp), C.cast(pf, dp), C.cast(pg, dp), eng.GRAD_AD)
+        assert rc >= 0
+        assert np.array_equal(Fp, F0) and np.array_equal(Gp, G0)
+    finally:
+        L.tpl_host_free(px); L.tpl_host_free(pg); L.tpl_host_free(pf)
+        plp.close()

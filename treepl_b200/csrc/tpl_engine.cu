@@ -1122,12 +1122,13 @@ int tpl_calc_pl_grad_batch(tpl_engine* e, int B, const double* X, double* F, dou
     if (!e->have_fp) return fail(TPL_ERR_STATE, "set_freeparams has not been called");
     CK(cudaSetDevice(e->device));
     const int P = e->numparams;
-    // Zero-copy: when X and G are pinned host buffers and the batch takes the descriptor kernel - which reads every X row once (TMA)
-    // and writes every G row once - the kernels work ON the host buffers through their device mapping.  The same 2 x 8 P B bytes
-    // cross PCIe, but inside the kernel: reads and writes overlap from the first tile to the last (full duplex for the whole step,
-    // no fill and drain of a copy pipeline, no staging copies in HBM).  F and the sparse rows of the finalize kernel go the same way.
-    // tpl_debug_force_kernel(e, 5) keeps the staged pipeline below (A/B and tests).
-    if (G && B >= 32 && batch_takes_desc_kernel(e, B, mode)) {
+    // Zero-copy for batches too small to pipeline (B < 128): when X and G are pinned host buffers and the batch takes the descriptor
+    // kernel - which reads every X row once (TMA) and writes every G row once - the kernels work ON the host buffers through their
+    // device mapping, so reads and writes cross PCIe at the same time instead of one after the other: 12.4 k against 9.5 k evals/s at
+    // B = 64 on the 100k-tip tree.  From 128 vectors on the staged pipeline below is faster (B = 256: 16.5 k against 15.3 k; the
+    // kernel's reads of host memory - 512-byte row segments, halo rows a second time - reach ~40 GB/s, the copy engine 47-55).
+    // Results are bitwise those of the device-buffer entry.  tpl_debug_force_kernel(e, 5) switches this path off (tests).
+    if (G && B >= 32 && B < 128 && batch_takes_desc_kernel(e, B, mode)) {
         double* mX = static_cast<double*>(mapped_host_pointer(X));
         double* mG = static_cast<double*>(mapped_host_pointer(G));
         if (mX && mG) {
