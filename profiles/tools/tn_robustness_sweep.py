@@ -3,7 +3,9 @@
 smoothing values 10^4 ... 10^-3, clock-like start, one vector per smoothing value; prints one JSON object per tree with the
 status histogram (index = status code: 0 step cap, 1 gradient converged, 2 objective converged, 3 step/stall, 4 infeasible
 start, 5 non-finite), steps, wall seconds, Newton iterations and the largest relative projected gradient.
-    python profiles/tools/tn_robustness_sweep.py > profiles/r02_tn_sweep.json          (needs a B200)"""
+    python profiles/tools/tn_robustness_sweep.py [copies] > profiles/r02_tn_sweep.json          (needs a B200)
+copies (default 1): every smoothing value that many times - 2 makes a 32-vector batch, which takes the software-pipelined
+Hessian-vector kernel and the cooperative level sweeps instead of the small-batch forms."""
 import json
 import os
 import sys
@@ -22,7 +24,7 @@ for name in ("M1155", "big_test", "clock", "pl4203", "test", "test_two_cal", "vi
     flat = dict(Golden(name).flat)
     n = len(flat["parents"])
     fp, P = eng.generate_param_order_vector(flat["free"], lf=False)
-    lams = 10.0 ** np.linspace(4, -3, 16)
+    lams = np.repeat(10.0 ** np.linspace(4, -3, 16), int(sys.argv[1]) if len(sys.argv) > 1 else 1)
     for log_pen in (False, True):
         plp = eng.PLCalcParallel.from_flat(flat, device=0)
         plp.set_log_pen(log_pen)
