@@ -148,14 +148,21 @@ static void tn_fill_record(const tpl_engine* e, int i, int* r) {
 }
 
 // work space, tree operands and chunking of the truncated-Newton kernels; uploads lo / hi / sc and X
-// tn_hv_pipe_kernel needs 105 KB of dynamic shared memory per block: opt in once per process
+// tn_hv_pipe_kernel needs 105 KB of dynamic shared memory per block: opt in once per DEVICE (function attributes belong to the
+// device's context; a process may hold engines on several GPUs)
 bool tn_hv_pipe_ready() {
-    static int ok = -1;
-    if (ok < 0)
-        ok = (cudaFuncSetAttribute(tpltn::tn_hv_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tpltn::HVP_SMEM) == cudaSuccess &&
-              cudaFuncSetAttribute(tpltn::tn_hv_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tpltn::HVP_SMEM) == cudaSuccess) ? 1 : 0;
-    if (!ok) cudaGetLastError();
-    return ok == 1;
+    static std::mutex mu;
+    static int ok[64];                              // 0 unknown, 1 ready, -1 not available
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return false; }
+    std::lock_guard<std::mutex> lk(mu);
+    if (ok[dev] == 0) {
+        const bool set = cudaFuncSetAttribute(tpltn::tn_hv_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tpltn::HVP_SMEM) == cudaSuccess &&
+                         cudaFuncSetAttribute(tpltn::tn_hv_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tpltn::HVP_SMEM) == cudaSuccess;
+        if (!set) cudaGetLastError();
+        ok[dev] = set ? 1 : -1;
+    }
+    return ok[dev] == 1;
 }
 // Hp = H p: the software-pipelined kernel for full 32-vector groups, the register-staged one for packed lanes (B <= 16)
 void tn_launch_hv(const tpltn::TnArgs& a, dim3 ngrd, dim3 blk, cudaStream_t s) {
@@ -363,18 +370,23 @@ int tn_launch_levels(const tpltn::TnArgs& a, const std::vector<int>& loff, int g
     using namespace tpltn;
     if (l_last <= l_first) return 0;
     const dim3 blk(32, tplopt::OPT_WY);
-    static int resident = -1;                       // blocks of this kernel that fit the device at once (per instantiation)
-    static int coop = -1;
-    if (coop < 0) {
-        int dev = 0, sms = 0, occ = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    // per device (a process may hold engines on several GPUs): blocks of this kernel that fit the device at once, and whether it
+    // launches cooperatively at all; 0 = not asked yet
+    static int resident_of[64], coop_of[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = std::min(std::max(dev, 0), 63);
+    if (coop_of[dev] == 0) {
+        int sms = 0, occ = 0, sup = 0;
+        cudaDeviceGetAttribute(&sup, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tn_tree_levels_kernel<FACTOR, DOWN>, 32 * tplopt::OPT_WY, 0);
-        resident = occ * sms;
-        if (resident < 1) coop = 0;
+        resident_of[dev] = occ * sms;
+        coop_of[dev] = (sup && resident_of[dev] >= 1) ? 1 : -1;
     }
-    if (coop && a.coop_levels && l_last - l_first >= 2) {
+    const int resident = resident_of[dev];
+    int& coop = coop_of[dev];
+    if (coop > 0 && a.coop_levels && l_last - l_first >= 2) {
         const int npw = 32 >> a.pack_shift;
         long long most = 1;
         for (int l = l_first; l < l_last; l++) most = std::max(most, (long long)((loff[l + 1] - loff[l] + npw - 1) / npw) * groups);
@@ -384,7 +396,7 @@ int tn_launch_levels(const tpltn::TnArgs& a, const std::vector<int>& loff, int g
         void* args[] = {&aa, &lf, &ll, &gr};
         if (cudaLaunchCooperativeKernel((void*)tn_tree_levels_kernel<FACTOR, DOWN>, dim3(blocks), blk, args, 0, s) == cudaSuccess) return 1;
         cudaGetLastError();
-        coop = 0;                                   // not launchable here: per-level launches from now on
+        coop = -1;                                  // not launchable here: per-level launches from now on
     }
     for (int q = 0; q < l_last - l_first; q++) {
         const int l = DOWN ? l_last - 1 - q : l_first + q;
