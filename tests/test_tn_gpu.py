@@ -292,3 +292,30 @@ def test_random_subsample_cv_end_to_end():
     gz[: pr.nr] *= r["x"][: pr.nr]
     assert np.abs(gz).max() <= 1e-6 * abs(f[0])
     plp.close()
+
+
+def test_engines_on_two_devices_of_one_process():
+    """The C ABI lets one process hold engines on several GPUs (tpl_create's device argument).  Kernel attributes (the pipelined
+    Hessian-vector kernel's shared-memory opt-in) and the cooperative-launch state are per device: the same 40-vector
+    optimisation on device 0 and device 1 gives bitwise the same optimum.  Needs two visible GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    flat = dict(Golden("pl4203").flat)
+    n = len(flat["parents"])
+    fp, P = eng.generate_param_order_vector(flat["free"], lf=False)
+    lo, hi = batchopt.reference_bounds(flat, fp, P)
+    x0 = cv.start_vector(flat, P, n - 1)
+    B = 40
+    lam = 10.0 ** np.linspace(2, -1, B)
+    out = []
+    for dev in (1, 0, 1):
+        plp = eng.PLCalcParallel.from_flat(flat, device=dev)
+        plp.set_freeparams(P, False, fp)
+        plp.batch_configure(B, lane_smoothing=lam)
+        X, F, info = plp.optimize_batch(np.repeat(x0[:, None], B, axis=1), lo, hi, method=1, max_steps=4000)
+        assert ((info["status"] >= 1) & (info["status"] <= 3)).all()
+        out.append((X, F))
+        plp.close()
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[2][1])
