@@ -367,7 +367,7 @@ def job_restarts(rk, runs=1, warm=0, config4=False):
     lam, lp = (0.0001, True) if config4 else (1.0, False)
     times, res = [], None
     for s in range(warm + runs):
-        res, dt = rk.timed(lambda: cv.multistart(flat, lam, N_STARTS, device=rk.local, dist=rk.dist, check_every=50, log_pen=lp))
+        res, dt = rk.timed(lambda: cv.multistart(flat, lam, N_STARTS, device=rk.local, dist=rk.dist, check_every=10, log_pen=lp))
         if s >= warm:
             times.append(dt)
     val = sum(times) / len(times)
