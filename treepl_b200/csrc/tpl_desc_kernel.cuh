@@ -384,9 +384,11 @@ pl_desc_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ TileA
 #pragma unroll
                         for (int l = 0; l < 2; l++) {
                             const double d = hp[l] - h[l];
-                            ok = ok && in_range400(r[l]) && in_range400(d);
-                            if (MODE == 0 && !tip) ok = ok && (__double2hiint(h[l]) >= 0);   // h < 0 -> LARGE (:74-78)
                             const double xx = r[l] * d;
+                            // r > 0, d > 0, both finite and r d ordinary <=> r's sign bit clear and r d in the ordinary range
+                            // (one exponent test + one sign test instead of two exponent tests)
+                            ok = ok && in_range400(xx) && (__double2hiint(r[l]) >= 0);
+                            if (MODE == 0 && !tip) ok = ok && (__double2hiint(h[l]) >= 0);   // h < 0 -> LARGE (:74-78)
                             const double ac = cl.x * fast_rcp(xx);
                             g_r[l] = fma(-ac, d, d);                                         // d - c/r
                             g_h[l] = -fma(-ac, r[l], r[l]);                                  // -(r - c/d)
@@ -416,8 +418,9 @@ pl_desc_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ TileA
 #pragma unroll
                                 for (int l = 0; l < 2; l++) {
                                     const double dc = h[l] - hca[kk][l];
-                                    ok = ok && in_range400(rca[kk][l]) && in_range400(dc);
-                                    const double acn = cca[kk] * fast_rcp(rca[kk][l] * dc);
+                                    const double xc = rca[kk][l] * dc;
+                                    ok = ok && in_range400(xc) && (__double2hiint(rca[kk][l]) >= 0);
+                                    const double acn = cca[kk] * fast_rcp(xc);
                                     const double dlt = fma(-acn, rca[kk][l], rca[kk][l]);     // r_ch - c_ch/d_ch
                                     const double dq = rca[kk][l] - r[l];
                                     if (!MASK || !((mca[kk] >> l) & 1u)) {
